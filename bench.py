@@ -1,0 +1,405 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the GenPC geometric hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (config.workload = "C2"): batched Chamfer fwd+bwd, B=32 per GPU, 2048 x 16384 points (PCN shape,
+BASELINE.json configs[1]); a step = one forward + backward pass over one batch; metric = directed
+point-pair evaluations per second (2*B*N*M per step), whole job over all ranks (weak scaling: every rank
+owns its own 32 scans, no data-path collective).
+
+Printed keys beyond the base contract:
+  roofline      dominant kernel (nn_scan_kernel): FP32-pipe bound -> achieved/peak in TFLOP/s (8 FLOP/pair)
+  roofline_bwd  gradient scatter kernel: HBM bound -> GB/s against MEASURED_PEAKS.json
+  cpu_baseline  the oracle port (OpenMP, all host cores) and torch.cdist on the same workload sample
+  ref_cuda_ext  the unmodified reference CUDA extension (oracle/_ref) on the same GPU and inputs
+  e2e           same metric through the public API from pinned HOST buffers (H2D + D2H inside the timing)
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+B, N, M = 32, 2048, 16384
+FLOP_PER_PAIR = 8            # 3 sub, 3 mul, 2 add
+FP32_NOMINAL_TFLOPS = 74.4   # 148 SM x 128 lanes x 2 x 1.965 GHz (not in MEASURED_PEAKS.json)
+L2_FLUSH_BYTES = 256 << 20
+
+
+def env_int(k, d):
+    return int(os.environ.get(k, d))
+
+
+class ClockSampler:
+    """Samples SM clock + throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40,
+                 "hw_power_brake_slowdown": 0x80, "sw_power_cap": 0x4}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for n, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def start(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join()
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+def make_inputs(rank):
+    from genpc_b200.synthetic import pcn_batch
+
+    part, comp = pcn_batch(1000 * rank, B, N, M)
+    return part, comp
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return j.get("hbm_gbs", 6650.0), "measured"
+    return 6650.0, "fallback"
+
+
+def measured_fp32_peak():
+    p = os.path.join(ROOT, "profiles", "fp32_peak_b200.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p))
+        except Exception:
+            return None
+    return None
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU baselines (rank 0, N=1 only) -- oracle/ is used here strictly as the thing that is timed beside us
+# ---------------------------------------------------------------------------------------------------
+def cpu_baseline(part, comp, budget_b=None):
+    import oracle
+
+    cores = os.cpu_count()
+    nb = budget_b or B
+    a, b = part[:nb], comp[:nb]
+    t0 = time.perf_counter()
+    d1, d2, i1, i2 = oracle.chamfer_forward(a, b)
+    g1 = np.full(d1.shape, 1.0 / d1.size, np.float32)
+    g2 = np.full(d2.shape, 1.0 / d2.size, np.float32)
+    oracle.chamfer_backward(a, b, g1, g2, i1, i2)
+    dt = time.perf_counter() - t0
+    pairs = 2.0 * nb * N * M
+    out = {"value": pairs / dt, "unit": "pairs/s", "cores": cores, "kind": "port",
+           "sample": f"oracle C port (OpenMP), fwd+bwd on {nb} of the {B} scans of C2, {dt:.2f} s"}
+    # the reference's stated CPU path (BASELINE.json): torch.cdist (no-mm) + min both ways
+    try:
+        torch.set_num_threads(cores)
+        nb2 = min(nb, 4)
+        ta, tb = torch.from_numpy(part[:nb2]), torch.from_numpy(comp[:nb2])
+        t0 = time.perf_counter()
+        D = torch.cdist(ta, tb, compute_mode="donot_use_mm_for_euclid_dist")
+        D.min(2), D.min(1)
+        dt2 = time.perf_counter() - t0
+        out["torch_cdist"] = {"value": 2.0 * nb2 * N * M / dt2, "unit": "pairs/s", "cores": torch.get_num_threads(),
+                              "sample": f"torch.cdist(no-mm)+min both ways, forward only, {nb2} scans, {dt2:.2f} s"}
+    except Exception as e:  # pragma: no cover
+        out["torch_cdist"] = {"error": str(e)}
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# The reference's stock path: dist_chamfer_3D.py:26-64 restated around the UNMODIFIED extension
+# (the file itself cannot be imported on Python 3.12: importlib.find_loader, :6)
+# ---------------------------------------------------------------------------------------------------
+def make_ref_function(ext):
+    class RefChamfer(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, xyz1, xyz2):
+            batchsize, n, _ = xyz1.size()
+            _, m, _ = xyz2.size()
+            device = xyz1.device
+            dist1 = torch.zeros(batchsize, n).to(device)            # CPU alloc + H2D, as the reference (:33-42)
+            dist2 = torch.zeros(batchsize, m).to(device)
+            idx1 = torch.zeros(batchsize, n).type(torch.IntTensor).to(device)
+            idx2 = torch.zeros(batchsize, m).type(torch.IntTensor).to(device)
+            torch.cuda.set_device(device)
+            ext.forward(xyz1, xyz2, dist1, dist2, idx1, idx2)
+            ctx.save_for_backward(xyz1, xyz2, idx1, idx2)
+            return dist1, dist2, idx1, idx2
+
+        @staticmethod
+        def backward(ctx, graddist1, graddist2, gradidx1, gradidx2):
+            xyz1, xyz2, idx1, idx2 = ctx.saved_tensors
+            graddist1 = graddist1.contiguous()
+            graddist2 = graddist2.contiguous()
+            device = graddist1.device
+            gradxyz1 = torch.zeros(xyz1.size()).to(device)           # (:56-60)
+            gradxyz2 = torch.zeros(xyz2.size()).to(device)
+            ext.backward(xyz1, xyz2, gradxyz1, gradxyz2, graddist1, graddist2, idx1, idx2)
+            return gradxyz1, gradxyz2
+
+    return lambda a, b: RefChamfer.apply(a.contiguous(), b.contiguous())
+
+
+def chamfer_l2_loss(fn, a, b):
+    """utils/loss_util.py:31-33 chamfer_l2 = mean(d1) + mean(d2)."""
+    d1, d2, _, _ = fn(a, b)
+    return torch.mean(d1) + torch.mean(d2)
+
+
+def run_gpu_arm(args, fn, rank, world, dev, part, comp, tag):
+    """Times K steps device-resident (`value`) and K steps end-to-end from pinned host buffers (`e2e`)."""
+    import torch.distributed as dist
+
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+    a = torch.from_numpy(part).to(dev).requires_grad_(True)
+    b = torch.from_numpy(comp).to(dev).requires_grad_(True)
+    ha, hb = torch.from_numpy(part).pin_memory(), torch.from_numpy(comp).pin_memory()
+    hloss = torch.zeros(1).pin_memory()
+
+    def step_resident():
+        a.grad = None
+        b.grad = None
+        loss = chamfer_l2_loss(fn, a, b)
+        loss.backward()
+        return loss
+
+    def step_e2e():
+        da = ha.to(dev, non_blocking=True).requires_grad_(True)
+        db = hb.to(dev, non_blocking=True).requires_grad_(True)
+        loss = chamfer_l2_loss(fn, da, db)
+        loss.backward()
+        hloss.copy_(loss.detach(), non_blocking=True)
+        return loss
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(step, K, W):
+        for _ in range(W):
+            flush.zero_()
+            step()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+        barrier()
+        for i in range(K):
+            flush.zero_()  # L2 flush between timed iterations, outside the event bracket
+            ev[i][0].record()
+            step()
+            ev[i][1].record()
+        barrier()
+        ms = sum(e0.elapsed_time(e1) for e0, e1 in ev)
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    sampler = ClockSampler(dev.index)
+    sampler.start()
+    ms_res = timed(step_resident, args.steps, args.warmup)
+    clocks = sampler.stop()
+    ms_e2e = timed(step_e2e, args.steps, args.warmup)
+    pairs_per_step = 2.0 * B * N * M * world
+    res = {
+        "value": pairs_per_step * args.steps / (ms_res * 1e-3),
+        "ms_per_step": ms_res / args.steps,
+        "e2e": {"value": pairs_per_step * args.steps / (ms_e2e * 1e-3), "unit": "pairs/s",
+                "h2d_bytes_per_step": int(ha.numel() * 4 + hb.numel() * 4), "d2h_bytes_per_step": 4,
+                "ms_per_step": ms_e2e / args.steps},
+        "clocks": clocks,
+    }
+    return res, (a, b, flush)
+
+
+def time_kernels_ours(dev, a, b, flush, iters=20):
+    """CUDA-event time of the forward op (memset + nn_scan_kernel + unpack; the scan is >98 % of it) and of
+    the backward op (chamfer_grad_kernel) on the launching stream, L2 flushed before each."""
+    from genpc_b200 import chamfer_3D
+
+    a, b = a.detach(), b.detach()
+    d1 = torch.zeros(B, N, device=dev); d2 = torch.zeros(B, M, device=dev)
+    i1 = torch.zeros(B, N, dtype=torch.int32, device=dev); i2 = torch.zeros(B, M, dtype=torch.int32, device=dev)
+    g1 = torch.full((B, N), 1.0 / (B * N), device=dev); g2 = torch.full((B, M), 1.0 / (B * M), device=dev)
+    gx1 = torch.zeros_like(a); gx2 = torch.zeros_like(b)
+    tf, tb = [], []
+    for it in range(iters + 3):
+        flush.zero_()
+        e0, e1, e2, e3 = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        e0.record()
+        chamfer_3D.forward(a, b, d1, d2, i1, i2)
+        e1.record()
+        gx1.zero_(); gx2.zero_()
+        flush.zero_()
+        e2.record()
+        chamfer_3D.backward(a, b, gx1, gx2, g1, g2, i1, i2)
+        e3.record()
+        torch.cuda.synchronize(dev)
+        if it >= 3:
+            tf.append(e0.elapsed_time(e1)); tb.append(e2.elapsed_time(e3))
+    return sum(tf) / len(tf), sum(tb) / len(tb)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank, local, world = env_int("RANK", 0), env_int("LOCAL_RANK", 0), env_int("WORLD_SIZE", 1)
+
+    if not torch.cuda.is_available():
+        if args.impl == "reference":
+            # no GPU: the reference's CUDA extension cannot run; time the CPU port instead
+            part, comp = make_inputs(0)
+            cb = cpu_baseline(part, comp, budget_b=4)
+            print(json.dumps({"impl": "reference", "metric": "chamfer_fwd_bwd_point_pairs_per_sec",
+                              "value": cb["value"], "unit": "pairs/s", "n_gpus": 0, "cpu_baseline": cb,
+                              "e2e": {"value": cb["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0,
+                                      "d2h_bytes_per_step": 0}}))
+            return
+        raise SystemExit("bench.py: no CUDA device (genpc_b200 has no CPU fallback)")
+
+    dev = torch.device(f"cuda:{local}")
+    torch.cuda.set_device(dev)
+    if world > 1:
+        import torch.distributed as dist
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    part, comp = make_inputs(rank)
+    hbm_peak, peak_src = peaks()
+
+    line = {"metric": "chamfer_fwd_bwd_point_pairs_per_sec", "unit": "pairs/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "C2: batched Chamfer3D fwd+bwd, B=32 per GPU, 2048 x 16384 pts (PCN shape), "
+                                   "loss = chamfer_l2", "B_per_gpu": B, "N": N, "M": M,
+                       "pairs_per_step_per_gpu": 2 * B * N * M, "parallelism": f"dp{world} (independent scans)",
+                       "l2": "flushed (256 MiB write) before every timed step"}}
+
+    if args.impl == "reference":
+        import oracle
+
+        ext = oracle.load_ref_ext("chamfer_3D")
+        if ext is None:
+            if rank == 0:
+                cb = cpu_baseline(part, comp)
+                line.update({"impl": "reference", "value": cb["value"], "cpu_baseline": cb, "ms_per_step": None,
+                             "e2e": {"value": cb["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0,
+                                     "d2h_bytes_per_step": 0},
+                             "note": "oracle/_ref not built: timed the CPU port"})
+                print(json.dumps(line))
+            return
+        res, _ = run_gpu_arm(args, make_ref_function(ext), rank, world, dev, part, comp, "reference")
+        line.update(res)
+        line.update({"impl": "reference", "gpu_launches": 4 * args.steps,
+                     "note": "UNMODIFIED reference chamfer_3D CUDA extension (oracle/_ref, built from "
+                             "/root/reference sources for sm_100a) through dist_chamfer_3D.py's stock flow "
+                             "(CPU-allocated outputs + .to(device)); the reference has no CPU implementation"})
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(part, comp)
+        if rank == 0:
+            print(json.dumps(line))
+        if world > 1:
+            torch.distributed.destroy_process_group()
+        return
+
+    from genpc_b200.loss_functions import chamfer_3DDist
+
+    mod = chamfer_3DDist()
+    res, (a, b, flush) = run_gpu_arm(args, lambda x, y: mod(x, y), rank, world, dev, part, comp, "ours")
+    line.update(res)
+    line["gpu_launches"] = 3 * args.steps  # nn_scan_kernel + nn_unpack_kernel + chamfer_grad_kernel per step
+    if rank == 0:
+        t_fwd, t_bwd = time_kernels_ours(dev, a, b, flush)
+        flops = 2.0 * B * N * M * FLOP_PER_PAIR
+        ach = flops / (t_fwd * 1e-3) / 1e12
+        m = measured_fp32_peak()
+        line["roofline"] = {"bound": "fp32", "kernel": "nn_scan_kernel", "achieved": ach,
+                            "peak": FP32_NOMINAL_TFLOPS, "unit": "TFLOP/s", "frac": ach / FP32_NOMINAL_TFLOPS,
+                            "peak_source": "nominal FFMA peak 148x128x2x1.965 GHz (MEASURED_PEAKS.json has no FP32 "
+                                           "figure; measured issue rates in profiles/fp32_peak_b200.json)",
+                            "ms": t_fwd, "pairs_per_s": 2.0 * B * N * M / (t_fwd * 1e-3), "traffic": None}
+        if m and "nn_mix_packed" in m:
+            line["roofline"]["measured_mix_peak_tflops"] = m["nn_mix_packed"].get("tflops")
+        bwd_bytes = 44.0 * B * (N + M)
+        gbs = bwd_bytes / (t_bwd * 1e-3) / 1e9
+        line["roofline_bwd"] = {"bound": "hbm", "kernel": "chamfer_grad_kernel", "achieved": gbs, "peak": hbm_peak,
+                                "unit": "GB/s", "frac": gbs / hbm_peak, "peak_source": peak_src, "ms": t_bwd,
+                                "traffic": None}
+        if world == 1:
+            try:
+                import oracle
+
+                ext = oracle.load_ref_ext("chamfer_3D")
+                if ext is not None:
+                    d1 = torch.zeros(B, N, device=dev); d2 = torch.zeros(B, M, device=dev)
+                    i1 = torch.zeros(B, N, dtype=torch.int32, device=dev)
+                    i2 = torch.zeros(B, M, dtype=torch.int32, device=dev)
+                    ts = []
+                    for it in range(6):
+                        flush.zero_()
+                        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        e0.record(); ext.forward(a.detach(), b.detach(), d1, d2, i1, i2); e1.record()
+                        torch.cuda.synchronize(dev)
+                        if it >= 2:
+                            ts.append(e0.elapsed_time(e1))
+                    t_ref = sum(ts) / len(ts)
+                    line["ref_cuda_ext"] = {"fwd_ms": t_ref, "pairs_per_s": 2.0 * B * N * M / (t_ref * 1e-3),
+                                            "speedup_fwd_kernel": t_ref / t_fwd}
+            except Exception as e:  # pragma: no cover
+                line["ref_cuda_ext"] = {"error": str(e)}
+            if not args.no_cpu_baseline:
+                line["cpu_baseline"] = cpu_baseline(part, comp)
+        print(json.dumps(line))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,69 @@
+"""ctypes binding of libgenpc_b200.so (the C ABI in include/genpc_b200.h).
+
+There is NO CPU fallback: if the CUDA library is missing or a call fails, this module raises.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgenpc_b200.so")
+_lib = None
+
+_vp = ctypes.c_void_p
+_int = ctypes.c_int
+_flt = ctypes.c_float
+_sz = ctypes.c_size_t
+
+
+class GenpcError(RuntimeError):
+    pass
+
+
+_SIGNATURES = {
+    "genpc_version": (ctypes.c_char_p, []),
+    "genpc_chamfer_workspace_bytes": (_sz, [_int, _int, _int]),
+    "genpc_chamfer_forward": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _int, _vp, _sz, _vp]),
+    "genpc_chamfer_backward": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _int, _vp]),
+}
+
+
+def lib():
+    """Load the shared library (built by `python -m genpc_b200.csrc.build` / __graft_entry__.build())."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise GenpcError(
+                f"{LIB_PATH} is missing: build it with `python -m genpc_b200.csrc.build` "
+                "(genpc_b200 has no CPU fallback)")
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(L, name)  # AttributeError if the symbol is not exported
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        if rc > 0:
+            raise GenpcError(f"{what}: CUDA error {rc}")
+        names = {-1: "shape violation", -2: "workspace missing/too small", -3: "index range"}
+        raise GenpcError(f"{what}: {names.get(rc, rc)}")
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def current_stream(device):
+    import torch
+
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if not t.is_cuda:
+            raise GenpcError("genpc_b200 runs on CUDA tensors only (no CPU fallback); got a CPU tensor")

@@ -1,0 +1,269 @@
+// chamfer.cu -- Chamfer3D nearest-neighbour forward / backward for sm_100a.
+//
+// Replaces the reference's NmDistanceKernel / NmDistanceGradKernel (chamfer3D.cu:12-195).
+// Design:
+//   * one launch covers BOTH directions; a work item is (direction, batch, 256*QT queries, NN_SPAN targets),
+//     so B=1 problems still fill 148 SMs (the reference runs 16 CTAs at B=1);
+//   * targets are staged once per item into shared memory as SoA x[]/y[]/z[] (NaN padded), read back
+//     with broadcast LDS.128, and evaluated two at a time on the packed FP32 pipe (FADD2/FMUL2/FFMA2);
+//   * the running minimum is a single FMNMX3 per two pairs; the arg-min is NOT tracked per pair:
+//     only the id of the 16-target chunk that lowered the minimum is kept (strict `<`, so the earliest
+//     chunk wins ties) and the exact lowest index is recovered by re-scanning that one chunk;
+//   * per-item results are merged across target splits with one packed 64-bit atomicMin per query
+//     ((dist_bits << 32) | idx: unsigned order == dist ascending, then idx ascending == the reference's
+//     lowest-index tie rule), then unpacked to dist/idx.
+#include "common.cuh"
+
+namespace genpc {
+
+constexpr int NN_THREADS = 256;
+constexpr int NN_SPAN = 1024;  // targets per work item (12 KB of shared memory)
+constexpr int NN_CHUNK = 16;   // index-recovery granularity
+
+struct NNDir {
+    const float *q;            // queries  [B][nq][3]
+    const float *t;            // targets  [B][mt][3]
+    unsigned long long *out;   // packed   [B][nq]
+    int nq, mt, qtiles, tsplits, items;
+};
+struct NNParams {
+    NNDir dir[2];
+};
+
+template <int QT>
+__global__ void __launch_bounds__(NN_THREADS, 2) nn_scan_kernel(const NNParams p) {
+    __shared__ __align__(16) float s[3][NN_SPAN];
+    const int tid = threadIdx.x;
+    int item = blockIdx.x;
+    const int d = (item >= p.dir[0].items) ? 1 : 0;
+    if (d) item -= p.dir[0].items;
+    NNDir D;  // field-wise select keeps the parameters in constant memory (no local copy)
+    D.q = d ? p.dir[1].q : p.dir[0].q;
+    D.t = d ? p.dir[1].t : p.dir[0].t;
+    D.out = d ? p.dir[1].out : p.dir[0].out;
+    D.nq = d ? p.dir[1].nq : p.dir[0].nq;
+    D.mt = d ? p.dir[1].mt : p.dir[0].mt;
+    D.qtiles = d ? p.dir[1].qtiles : p.dir[0].qtiles;
+    D.tsplits = d ? p.dir[1].tsplits : p.dir[0].tsplits;
+    const int ts = item % D.tsplits;
+    const int rest = item / D.tsplits;
+    const int qt = rest % D.qtiles;
+    const int b = rest / D.qtiles;
+    const int t0 = ts * NN_SPAN;
+    const int cnt = min(NN_SPAN, D.mt - t0);
+
+    // ---- stage targets: coalesced AoS read -> SoA shared, NaN padding (NaN never wins a min) ----
+    {
+        const float *tg = D.t + ((size_t)b * D.mt + t0) * 3;
+        const float qnan = __int_as_float(0x7fc00000);
+        const int lim = cnt * 3;
+        for (int i = tid; i < NN_SPAN * 3; i += NN_THREADS) {
+            const int k = i / 3, c = i - k * 3;
+            s[c][k] = (i < lim) ? __ldg(tg + i) : qnan;
+        }
+    }
+    // ---- queries into registers (negated, duplicated for the packed pipe) ----
+    float2 nqx[QT], nqy[QT], nqz[QT];
+    float best[QT];
+    int bchunk[QT];
+    const int jbase = qt * (NN_THREADS * QT) + tid;
+#pragma unroll
+    for (int q = 0; q < QT; ++q) {
+        const int j = jbase + q * NN_THREADS;
+        float x = 0.f, y = 0.f, z = 0.f;
+        if (j < D.nq) {
+            const float *qp = D.q + ((size_t)b * D.nq + j) * 3;
+            x = __ldg(qp), y = __ldg(qp + 1), z = __ldg(qp + 2);
+        }
+        nqx[q] = make_float2(-x, -x);
+        nqy[q] = make_float2(-y, -y);
+        nqz[q] = make_float2(-z, -z);
+        best[q] = __int_as_float(0x7f800000);
+        bchunk[q] = 0;
+    }
+    __syncthreads();
+
+    const int nchunks = (cnt + NN_CHUNK - 1) / NN_CHUNK;
+    const float4 *sx4 = reinterpret_cast<const float4 *>(s[0]);
+    const float4 *sy4 = reinterpret_cast<const float4 *>(s[1]);
+    const float4 *sz4 = reinterpret_cast<const float4 *>(s[2]);
+    for (int c = 0; c < nchunks; ++c) {
+        float cm[QT];
+#pragma unroll
+        for (int q = 0; q < QT; ++q) cm[q] = __int_as_float(0x7f800000);
+#pragma unroll
+        for (int kk = 0; kk < NN_CHUNK / 4; ++kk) {
+            const float4 X = sx4[c * (NN_CHUNK / 4) + kk];
+            const float4 Y = sy4[c * (NN_CHUNK / 4) + kk];
+            const float4 Z = sz4[c * (NN_CHUNK / 4) + kk];
+#pragma unroll
+            for (int q = 0; q < QT; ++q) {
+                const float2 a = sqdist_ref_x2(nqx[q], nqy[q], nqz[q], make_float2(X.x, X.y),
+                                               make_float2(Y.x, Y.y), make_float2(Z.x, Z.y));
+                const float2 e = sqdist_ref_x2(nqx[q], nqy[q], nqz[q], make_float2(X.z, X.w),
+                                               make_float2(Y.z, Y.w), make_float2(Z.z, Z.w));
+                cm[q] = fmin3(cm[q], a.x, a.y);
+                cm[q] = fmin3(cm[q], e.x, e.y);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < QT; ++q) {
+            if (cm[q] < best[q]) {  // strict: the earliest chunk keeps ties
+                best[q] = cm[q];
+                bchunk[q] = c;
+            }
+        }
+    }
+
+    // ---- recover the exact (lowest) index inside the winning chunk, merge across target splits ----
+#pragma unroll
+    for (int q = 0; q < QT; ++q) {
+        const int j = jbase + q * NN_THREADS;
+        if (j >= D.nq) continue;
+        const float qx = -nqx[q].x, qy = -nqy[q].x, qz = -nqz[q].x;
+        const int cb = bchunk[q] * NN_CHUNK;
+        int kbest = 0;
+#pragma unroll
+        for (int k = NN_CHUNK - 1; k >= 0; --k) {
+            const float dd = sqdist_ref(qx, qy, qz, s[0][cb + k], s[1][cb + k], s[2][cb + k]);
+            if (dd == best[q]) kbest = k;
+        }
+        atomicMin(D.out + (size_t)b * D.nq + j, pack_dist_idx(best[q], t0 + cb + kbest));
+    }
+}
+
+__global__ void nn_unpack_kernel(const unsigned long long *__restrict__ packed, float *__restrict__ dist1,
+                                 int *__restrict__ idx1, size_t n1, float *__restrict__ dist2,
+                                 int *__restrict__ idx2, size_t n2) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n1 + n2) return;
+    const unsigned long long w = packed[i];
+    const float dv = __uint_as_float((unsigned int)(w >> 32));
+    const int iv = (int)(unsigned int)(w & 0xffffffffu);
+    if (i < n1) {
+        dist1[i] = dv;
+        idx1[i] = iv;
+    } else {
+        dist2[i - n1] = dv;
+        idx2[i - n1] = iv;
+    }
+}
+
+// Backward: one thread per (direction, batch, point); same six terms as NmDistanceGradKernel
+// (chamfer3D.cu:155-174): g = 2*grad; own += g*(p - nn); nn's -= g*(p - nn).
+__global__ void chamfer_grad_kernel(const float *__restrict__ xyz1, const float *__restrict__ xyz2,
+                                    const float *__restrict__ gd1, const float *__restrict__ gd2,
+                                    const int *__restrict__ idx1, const int *__restrict__ idx2,
+                                    float *gx1, float *gx2, int B, int N, int M) {
+    const size_t n1 = (size_t)B * N, n2 = (size_t)B * M;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n1 + n2) return;
+    const float *a, *o, *gd;
+    const int *idx;
+    float *ga, *go;
+    int na, no;
+    if (i < n1) {
+        a = xyz1, o = xyz2, gd = gd1, idx = idx1, ga = gx1, go = gx2, na = N, no = M;
+    } else {
+        i -= n1;
+        a = xyz2, o = xyz1, gd = gd2, idx = idx2, ga = gx2, go = gx1, na = M, no = N;
+    }
+    const size_t b = i / na;
+    const float x1 = __ldg(a + i * 3), y1 = __ldg(a + i * 3 + 1), z1 = __ldg(a + i * 3 + 2);
+    const int j2 = __ldg(idx + i);
+    const size_t t = b * no + j2;
+    const float x2 = __ldg(o + t * 3), y2 = __ldg(o + t * 3 + 1), z2 = __ldg(o + t * 3 + 2);
+    const float g = __fmul_rn(__ldg(gd + i), 2.f);
+    const float tx = __fmul_rn(g, __fsub_rn(x1, x2));
+    const float ty = __fmul_rn(g, __fsub_rn(y1, y2));
+    const float tz = __fmul_rn(g, __fsub_rn(z1, z2));
+    atomicAdd(ga + i * 3 + 0, tx);
+    atomicAdd(ga + i * 3 + 1, ty);
+    atomicAdd(ga + i * 3 + 2, tz);
+    atomicAdd(go + t * 3 + 0, -tx);
+    atomicAdd(go + t * 3 + 1, -ty);
+    atomicAdd(go + t * 3 + 2, -tz);
+}
+
+static int pick_qt(int nq) {
+    // queries per thread: large tiles amortise the shared-memory reads, small clouds keep lanes busy
+    if (nq >= 4 * NN_THREADS) return 4;
+    if (nq >= 2 * NN_THREADS) return 2;
+    return 1;
+}
+
+static void fill_dir(NNDir &D, const float *q, const float *t, unsigned long long *out, int B, int nq, int mt,
+                     int QT) {
+    D.q = q, D.t = t, D.out = out, D.nq = nq, D.mt = mt;
+    D.qtiles = (nq + NN_THREADS * QT - 1) / (NN_THREADS * QT);
+    D.tsplits = (mt + NN_SPAN - 1) / NN_SPAN;
+    D.items = B * D.qtiles * D.tsplits;
+}
+
+}  // namespace genpc
+
+using namespace genpc;
+
+extern "C" size_t genpc_chamfer_workspace_bytes(int B, int N, int M) {
+    if (B < 0 || N < 0 || M < 0) return 0;
+    return ((size_t)B * N + (size_t)B * M) * sizeof(unsigned long long);
+}
+
+extern "C" int genpc_chamfer_forward(const float *xyz1, const float *xyz2, float *dist1, float *dist2,
+                                     int *idx1, int *idx2, int B, int N, int M, void *workspace,
+                                     size_t workspace_bytes, genpc_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (B < 0 || N < 0 || M < 0) return GENPC_ERR_SHAPE;
+    const size_t n1 = (size_t)B * N, n2 = (size_t)B * M;
+    if (n1 + n2 == 0) return GENPC_OK;
+    if (N == 0 || M == 0) {
+        // the reference's kernels write nothing in this case; outputs keep the zeros they were allocated with
+        if (n1) {
+            cudaMemsetAsync(dist1, 0, n1 * 4, stream);
+            cudaMemsetAsync(idx1, 0, n1 * 4, stream);
+        }
+        if (n2) {
+            cudaMemsetAsync(dist2, 0, n2 * 4, stream);
+            cudaMemsetAsync(idx2, 0, n2 * 4, stream);
+        }
+        GENPC_CHECK_LAUNCH();
+        return GENPC_OK;
+    }
+    if (workspace == nullptr || workspace_bytes < genpc_chamfer_workspace_bytes(B, N, M)) return GENPC_ERR_WORKSPACE;
+    unsigned long long *packed = (unsigned long long *)workspace;
+    cudaError_t e = cudaMemsetAsync(packed, 0xff, (n1 + n2) * 8, stream);
+    if (e != cudaSuccess) return (int)e;
+
+    const int QT = pick_qt(N < M ? N : M);
+    NNParams p;
+    fill_dir(p.dir[0], xyz1, xyz2, packed, B, N, M, QT);
+    fill_dir(p.dir[1], xyz2, xyz1, packed + n1, B, M, N, QT);
+    const long long items = (long long)p.dir[0].items + p.dir[1].items;
+    if (items > 0x7fffffffLL) return GENPC_ERR_RANGE;
+    switch (QT) {
+        case 4: nn_scan_kernel<4><<<(unsigned)items, NN_THREADS, 0, stream>>>(p); break;
+        case 2: nn_scan_kernel<2><<<(unsigned)items, NN_THREADS, 0, stream>>>(p); break;
+        default: nn_scan_kernel<1><<<(unsigned)items, NN_THREADS, 0, stream>>>(p); break;
+    }
+    GENPC_CHECK_LAUNCH();
+    const size_t tot = n1 + n2;
+    nn_unpack_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(packed, dist1, idx1, n1, dist2, idx2, n2);
+    GENPC_CHECK_LAUNCH();
+    return GENPC_OK;
+}
+
+extern "C" int genpc_chamfer_backward(const float *xyz1, const float *xyz2, const float *graddist1,
+                                      const float *graddist2, const int *idx1, const int *idx2,
+                                      float *gradxyz1, float *gradxyz2, int B, int N, int M,
+                                      genpc_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (B < 0 || N < 0 || M < 0) return GENPC_ERR_SHAPE;
+    const size_t tot = (size_t)B * N + (size_t)B * M;
+    if (tot == 0 || N == 0 || M == 0) return GENPC_OK;
+    chamfer_grad_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(xyz1, xyz2, graddist1, graddist2, idx1,
+                                                                            idx2, gradxyz1, gradxyz2, B, N, M);
+    GENPC_CHECK_LAUNCH();
+    return GENPC_OK;
+}
+
+extern "C" const char *genpc_version(void) { return "genpc_b200 0.1 sm_100a"; }

@@ -1,0 +1,48 @@
+"""Drop-in for the reference's loss_functions/Chamfer3D/dist_chamfer_3D.py (:26-74).
+
+Same classes, same call signature and return tuple; the differences are the two the reference gets wrong
+for a device-resident pipeline: outputs are allocated on the device instead of on
+the CPU followed by .to(device) (:33-42, :56-60), and kernels go to the current stream.
+"""
+import torch
+from torch import nn
+from torch.autograd import Function
+
+from ... import chamfer_3D
+
+
+# Chamfer's distance module -- GPU tensors only (as the reference, :25)
+class chamfer_3DFunction(Function):
+    @staticmethod
+    def forward(ctx, xyz1, xyz2):
+        batchsize, n, _ = xyz1.size()
+        _, m, _ = xyz2.size()
+        device = xyz1.device
+        dist1 = torch.zeros(batchsize, n, device=device)
+        dist2 = torch.zeros(batchsize, m, device=device)
+        idx1 = torch.zeros(batchsize, n, dtype=torch.int32, device=device)
+        idx2 = torch.zeros(batchsize, m, dtype=torch.int32, device=device)
+        chamfer_3D.forward(xyz1, xyz2, dist1, dist2, idx1, idx2)
+        ctx.save_for_backward(xyz1, xyz2, idx1, idx2)
+        ctx.mark_non_differentiable(idx1, idx2)
+        return dist1, dist2, idx1, idx2
+
+    @staticmethod
+    def backward(ctx, graddist1, graddist2, gradidx1, gradidx2):
+        xyz1, xyz2, idx1, idx2 = ctx.saved_tensors
+        graddist1 = graddist1.contiguous()
+        graddist2 = graddist2.contiguous()
+        gradxyz1 = torch.zeros_like(xyz1)
+        gradxyz2 = torch.zeros_like(xyz2)
+        chamfer_3D.backward(xyz1, xyz2, gradxyz1, gradxyz2, graddist1, graddist2, idx1, idx2)
+        return gradxyz1, gradxyz2
+
+
+class chamfer_3DDist(nn.Module):
+    def __init__(self):
+        super(chamfer_3DDist, self).__init__()
+
+    def forward(self, input1, input2):
+        input1 = input1.contiguous()
+        input2 = input2.contiguous()
+        return chamfer_3DFunction.apply(input1, input2)

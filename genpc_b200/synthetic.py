@@ -1,0 +1,56 @@
+"""Seeded synthetic shapes standing in for the generators' outputs (InstantMesh / TRELLIS meshes are out of
+scope, BASELINE.json north_star).  numpy only; used by bench.py, smoke() and the tests -- not a hot path."""
+import numpy as np
+
+
+def superquadric(seed, n, exps=None):
+    """n points on a superquadric surface, normalised like normalize_numpy(range=0.5)
+    (reference utils/dataUtils.py:561-581): centred, longest bbox side = 1 -> coords in [-0.5, 0.5]."""
+    rng = np.random.default_rng(seed)
+    e1, e2 = exps if exps is not None else rng.uniform(0.3, 1.6, size=2)
+    ax = rng.uniform(0.4, 1.0, size=3)
+    eta = rng.uniform(-np.pi / 2, np.pi / 2, n)
+    om = rng.uniform(-np.pi, np.pi, n)
+
+    def f(w, e):
+        return np.sign(w) * np.abs(w) ** e
+
+    x = ax[0] * f(np.cos(eta), e1) * f(np.cos(om), e2)
+    y = ax[1] * f(np.cos(eta), e1) * f(np.sin(om), e2)
+    z = ax[2] * f(np.sin(eta), e1)
+    p = np.stack([x, y, z], 1)
+    lo, hi = p.min(0), p.max(0)
+    p = (p - (lo + hi) / 2) / (hi - lo).max()
+    return p.astype(np.float32)
+
+
+def partial_view(points, seed, n_out):
+    """Subset visible from a random direction (front half along the view axis), resampled to n_out."""
+    rng = np.random.default_rng(seed + 7919)
+    v = rng.standard_normal(3)
+    v /= np.linalg.norm(v)
+    depth = points @ v
+    vis = np.nonzero(depth > np.quantile(depth, 0.45))[0]
+    sel = rng.choice(vis, size=n_out, replace=len(vis) < n_out)
+    return points[sel].astype(np.float32)
+
+
+def rigid_perturb(points, seed, max_rot_deg=30.0, max_t=0.1, scale_range=(0.7, 1.3)):
+    """Known ground-truth pose for the registration workload: p' = s R p + t."""
+    rng = np.random.default_rng(seed + 104729)
+    axis = rng.standard_normal(3)
+    axis /= np.linalg.norm(axis)
+    ang = np.deg2rad(rng.uniform(-max_rot_deg, max_rot_deg))
+    K = np.array([[0, -axis[2], axis[1]], [axis[2], 0, -axis[0]], [-axis[1], axis[0], 0]])
+    R = np.eye(3) + np.sin(ang) * K + (1 - np.cos(ang)) * K @ K
+    t = rng.standard_normal(3)
+    t *= rng.uniform(0, max_t) / np.linalg.norm(t)
+    s = rng.uniform(*scale_range)
+    return (s * points @ R.T + t).astype(np.float32), (R.astype(np.float32), t.astype(np.float32), np.float32(s))
+
+
+def pcn_batch(seed0, B, n_partial=2048, n_complete=16384):
+    """BASELINE config C2: B shapes, complete = n_complete surface samples, partial = n_partial visible points."""
+    comp = np.stack([superquadric(seed0 + b, n_complete) for b in range(B)])
+    part = np.stack([partial_view(comp[b], seed0 + b, n_partial) for b in range(B)])
+    return part, comp

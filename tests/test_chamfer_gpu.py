@@ -1,0 +1,154 @@
+"""GPU parity: libgenpc_b200's Chamfer forward/backward (through the C ABI via the reference-shaped Python
+API) against the CPU oracle, against the UNMODIFIED reference extension (oracle/_ref, when built) and
+against the committed golden vectors.  Bit-exact dist/idx; gradients within 1e-5 relative."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from util import lattice_cloud, rand_cloud, shape_cloud
+
+pytestmark = pytest.mark.gpu
+
+SHAPES = [(1, 1, 1), (1, 5, 3), (2, 37, 513), (3, 600, 64), (1, 1025, 1023), (2, 2048, 16384),
+          (1, 255, 4097), (4, 1000, 1000), (1, 16384, 16384), (1, 3, 70000)]
+
+
+def run_ours(a, b, dev):
+    from genpc_b200.loss_functions import chamfer_3DDist
+
+    d1, d2, i1, i2 = chamfer_3DDist()(torch.from_numpy(a).to(dev), torch.from_numpy(b).to(dev))
+    return d1.cpu().numpy(), d2.cpu().numpy(), i1.cpu().numpy(), i2.cpu().numpy()
+
+
+@pytest.mark.parametrize("B,N,M", SHAPES)
+def test_forward_bit_exact_vs_oracle(cuda, B, N, M):
+    a, b = rand_cloud(B * 7 + N, B, N), rand_cloud(M + 1, B, M)
+    got = run_ours(a, b, cuda)
+    exp = oracle.chamfer_forward(a, b)
+    for g, e, name in zip(got, exp, ("dist1", "dist2", "idx1", "idx2")):
+        assert g.dtype == e.dtype, name
+        assert np.array_equal(g.view(np.int32), e.view(np.int32)), f"{name} differs ({(g != e).sum()} entries)"
+
+
+@pytest.mark.parametrize("B,N,M", [(2, 300, 2000), (1, 5000, 5000), (3, 1024, 1024)])
+def test_ties_lowest_index(cuda, B, N, M):
+    a, b = lattice_cloud(1, B, N), lattice_cloud(2, B, M)
+    got = run_ours(a, b, cuda)
+    exp = oracle.chamfer_forward(a, b)
+    for g, e in zip(got, exp):
+        assert np.array_equal(g, e)
+
+
+def test_shape_clouds_and_negative_coords(cuda):
+    a, b = shape_cloud(3, 2, 2048), shape_cloud(4, 2, 16384)
+    got = run_ours(a, b, cuda)
+    exp = oracle.chamfer_forward(a, b)
+    for g, e in zip(got, exp):
+        assert np.array_equal(g, e)
+
+
+def test_self_distance(cuda):
+    a = rand_cloud(5, 2, 3000)
+    d1, d2, i1, i2 = run_ours(a, a, cuda)
+    assert (d1 == 0).all() and (d2 == 0).all()
+    assert (i1 == np.arange(3000)).all() and (i2 == np.arange(3000)).all()
+
+
+def test_empty_clouds(cuda):
+    from genpc_b200.loss_functions import chamfer_3DDist
+
+    d1, d2, i1, i2 = chamfer_3DDist()(torch.zeros(2, 0, 3, device=cuda), torch.rand(2, 5, 3, device=cuda))
+    assert d1.shape == (2, 0) and d2.shape == (2, 5) and (d2 == 0).all() and (i2 == 0).all()
+
+
+@pytest.mark.parametrize("B,N,M", [(2, 90, 150), (4, 2048, 16384), (1, 7000, 300)])
+def test_backward_vs_oracle(cuda, B, N, M):
+    from genpc_b200.loss_functions import chamfer_3DDist
+
+    a, b = shape_cloud(6, B, N), shape_cloud(7, B, M)
+    rng = np.random.default_rng(0)
+    g1 = rng.standard_normal((B, N)).astype(np.float32)
+    g2 = rng.standard_normal((B, M)).astype(np.float32)
+    ta = torch.from_numpy(a).to(cuda).requires_grad_(True)
+    tb = torch.from_numpy(b).to(cuda).requires_grad_(True)
+    d1, d2, i1, i2 = chamfer_3DDist()(ta, tb)
+    (d1 * torch.from_numpy(g1).to(cuda)).sum().add((d2 * torch.from_numpy(g2).to(cuda)).sum()).backward()
+    e1, e2 = oracle.chamfer_backward(a, b, g1, g2, i1.cpu().numpy(), i2.cpu().numpy())
+    # tolerance: 1e-5 relative (north_star) on the gradient scale of each cloud
+    for got, exp in ((ta.grad.cpu().numpy(), e1), (tb.grad.cpu().numpy(), e2)):
+        scale = np.abs(exp).max()
+        assert np.abs(got - exp).max() <= 1e-5 * scale + 1e-12
+
+
+def test_full_size_properties_c2(cuda):
+    """BASELINE config C2 (B=32, 2048 x 16384): size-independent properties instead of the oracle."""
+    from genpc_b200.loss_functions import chamfer_3DDist
+
+    g = torch.Generator(device="cpu").manual_seed(0)
+    a = torch.rand(32, 2048, 3, generator=g).to(cuda)
+    b = torch.rand(32, 16384, 3, generator=g).to(cuda)
+    d1, d2, i1, i2 = chamfer_3DDist()(a, b)
+    # (1) distance recomputed from the returned index (same rounding order) is bit-identical
+    def redo(q, t, idx):
+        nn = torch.gather(t, 1, idx.long()[..., None].expand(-1, -1, 3))
+        dx, dy, dz = (nn - q).unbind(-1)
+        return torch.addcmul(torch.addcmul(dy * dy, dx, dx), dz, dz)  # may or may not fuse: compare loosely
+    assert torch.allclose(redo(a, b, i1), d1, rtol=1e-6, atol=0)
+    assert torch.allclose(redo(b, a, i2), d2, rtol=1e-6, atol=0)
+    # (2) no other target is closer (checked with cdist on a slice in float64)
+    D = torch.cdist(a[:2].double(), b[:2].double()) ** 2
+    assert torch.allclose(D.min(2).values.float(), d1[:2], rtol=1e-5)
+    assert torch.allclose(D.min(1).values.float(), d2[:2], rtol=1e-5)
+    # (3) permutation equivariance of the targets: permuting b permutes idx1 consistently
+    perm = torch.randperm(16384, generator=g).to(cuda)
+    d1p, _, i1p, _ = chamfer_3DDist()(a, b[:, perm])
+    assert torch.equal(d1p, d1)
+    assert torch.equal(torch.gather(b[:, perm], 1, i1p.long()[..., None].expand(-1, -1, 3)),
+                       torch.gather(b, 1, i1.long()[..., None].expand(-1, -1, 3)))
+
+
+def test_vs_reference_extension(cuda):
+    """The unmodified reference chamfer_3D extension on the same GPU and inputs (oracle/_ref)."""
+    ref = oracle.load_ref_ext("chamfer_3D")
+    if ref is None:
+        pytest.skip("oracle/_ref/chamfer_3D not built (needs /root/reference at build time)")
+    from genpc_b200 import chamfer_3D as ours
+
+    for (B, N, M, seed) in [(2, 2048, 16384, 0), (1, 5000, 777, 1), (3, 513, 1025, 2)]:
+        a = torch.from_numpy(shape_cloud(seed, B, N)).to(cuda)
+        b = torch.from_numpy(shape_cloud(seed + 100, B, M)).to(cuda)
+        outs = []
+        for mod in (ref, ours):
+            d1 = torch.zeros(B, N, device=cuda); d2 = torch.zeros(B, M, device=cuda)
+            i1 = torch.zeros(B, N, dtype=torch.int32, device=cuda); i2 = torch.zeros(B, M, dtype=torch.int32, device=cuda)
+            mod.forward(a, b, d1, d2, i1, i2)
+            torch.cuda.synchronize()
+            g1 = torch.randn(B, N, generator=torch.Generator().manual_seed(seed)).to(cuda)
+            g2 = torch.randn(B, M, generator=torch.Generator().manual_seed(seed + 1)).to(cuda)
+            gx1 = torch.zeros_like(a); gx2 = torch.zeros_like(b)
+            mod.backward(a, b, gx1, gx2, g1, g2, i1, i2)
+            torch.cuda.synchronize()
+            outs.append((d1, d2, i1, i2, gx1, gx2))
+        r, o = outs
+        for k in range(4):
+            assert torch.equal(r[k], o[k]), f"output {k} differs from the reference extension"
+        for k in (4, 5):
+            scale = r[k].abs().max()
+            assert (r[k] - o[k]).abs().max() <= 1e-5 * scale
+
+
+def test_golden_vectors(cuda):
+    """tests/golden/chamfer_ref_*.npz: outputs of the reference extension (made by tests/golden/make_golden.py)."""
+    import glob
+
+    files = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "chamfer_ref_*.npz")))
+    if not files:
+        pytest.skip("no golden vectors committed yet")
+    for f in files:
+        z = np.load(f)
+        got = run_ours(z["xyz1"], z["xyz2"], cuda)
+        for g, name in zip(got, ("dist1", "dist2", "idx1", "idx2")):
+            assert np.array_equal(g, z[name]), f"{os.path.basename(f)}:{name}"
