@@ -1,0 +1,175 @@
+// fps.cu -- farthest point sampling for sm_100a: one persistent CTA per cloud.
+//
+// Replaces the reference's CPU call `fpsample.fps_sampling(xyz, K)` (main.py:21-22, reg_xyz.py:215,
+// DepthPrompting.py:88-90; un-vendored Rust package -> semantics defined by oracle_fps):
+// start index given, running distance +inf, d = fma(dz,dz,fma(dx,dx,dy*dy)), next = arg-max of the
+// running distance with the LOWEST index on ties.
+//
+// The K picks are strictly sequential, so the kernel is a latency machine: the cloud lives in registers
+// (PPT points + running distances per thread, 1024 threads), each pick costs one distance update per
+// point, two REDUX warp reductions (max of the value bits, then min index among the lanes that hold it),
+// ONE __syncthreads (double-buffered 32-entry exchange), and the same two REDUX again.
+// Clouds larger than 1024*PPT_MAX points fall back to a global-memory loop with the same arithmetic.
+#include "common.cuh"
+
+namespace genpc {
+
+constexpr int FPS_THREADS = 1024;
+constexpr int FPS_WARPS = FPS_THREADS / 32;
+
+__device__ __forceinline__ void fps_block_argmax(float best, int best_i, unsigned (*sval)[FPS_WARPS],
+                                                 int (*sidx)[FPS_WARPS], int parity, int lane, int warp,
+                                                 int &winner) {
+    // running distances are >= 0 (or -1 for padding, mapped to 0 bits below) -> bit pattern orders like the float
+    unsigned vb = best < 0.f ? 0u : __float_as_uint(best) + 1u;  // +1 keeps real 0.0 above the padding
+    unsigned wmax = __reduce_max_sync(0xffffffffu, vb);
+    int cand = (vb == wmax) ? best_i : 0x7fffffff;
+    int wmin = __reduce_min_sync(0xffffffffu, cand);
+    if (lane == 0) {
+        sval[parity][warp] = wmax;
+        sidx[parity][warp] = wmin;
+    }
+    __syncthreads();
+    unsigned v2 = sval[parity][lane];
+    int i2 = sidx[parity][lane];
+    unsigned bmax = __reduce_max_sync(0xffffffffu, v2);
+    int c2 = (v2 == bmax) ? i2 : 0x7fffffff;
+    winner = __reduce_min_sync(0xffffffffu, c2);
+}
+
+template <int PPT, bool CREG>
+__global__ void __launch_bounds__(FPS_THREADS, 1) fps_reg_kernel(const float *__restrict__ xyz, int N, int K,
+                                                                   int start, int *__restrict__ idx_out,
+                                                                   float *__restrict__ seq_out) {
+    __shared__ unsigned sval[2][FPS_WARPS];
+    __shared__ int sidx[2][FPS_WARPS];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float *p = xyz + (size_t)b * N * 3;
+    // running distances always live in registers; coordinates too when the cloud is small (CREG),
+    // otherwise they are re-read through L1 (196 KB for 16384 points fits the 228 KB L1 of one SM).
+    constexpr int CP = CREG ? PPT : 1;
+    float px[CP], py[CP], pz[CP], run[PPT];
+#pragma unroll
+    for (int k = 0; k < PPT; ++k) {
+        const int i = tid + k * FPS_THREADS;
+        if (CREG) px[k % CP] = py[k % CP] = pz[k % CP] = 0.f;
+        if (i < N) {
+            if (CREG) px[k % CP] = __ldg(p + i * 3), py[k % CP] = __ldg(p + i * 3 + 1), pz[k % CP] = __ldg(p + i * 3 + 2);
+            run[k] = __int_as_float(0x7f800000);
+        } else {
+            run[k] = -1.f;  // padding: never selected (distances are >= 0)
+        }
+    }
+    int cur = start;
+    for (int s = 0; s < K; ++s) {
+        if (tid == 0) idx_out[(size_t)b * K + s] = cur;
+        const float lx = __ldg(p + cur * 3), ly = __ldg(p + cur * 3 + 1), lz = __ldg(p + cur * 3 + 2);
+        float best = -2.f;
+        int best_i = 0x7fffffff;
+#pragma unroll
+        for (int k = 0; k < PPT; ++k) {
+            float x, y, z;
+            if (CREG) {
+                x = px[k % CP], y = py[k % CP], z = pz[k % CP];
+            } else {
+                const int i = min(tid + k * FPS_THREADS, N - 1);
+                x = __ldg(p + i * 3), y = __ldg(p + i * 3 + 1), z = __ldg(p + i * 3 + 2);
+            }
+            const float dx = __fsub_rn(x, lx), dy = __fsub_rn(y, ly), dz = __fsub_rn(z, lz);
+            const float d = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+            const float r = (run[k] < d) ? run[k] : d;  // as oracle_fps; padding (-1) stays -1
+            run[k] = r;
+            if (r > best) {  // strict: k ascending == index ascending -> lowest index kept
+                best = r;
+                best_i = tid + k * FPS_THREADS;
+            }
+        }
+        int winner;
+        fps_block_argmax(best, best_i, sval, sidx, s & 1, lane, warp, winner);
+        if (seq_out != nullptr && tid == 0) {
+            if (s == 0) seq_out[(size_t)b * K] = __int_as_float(0x7f800000);
+            if (s + 1 < K) {
+                // the winner's running distance: max value bits - 1
+                unsigned m = 0;
+#pragma unroll
+                for (int w = 0; w < FPS_WARPS; ++w) m = max(m, sval[s & 1][w]);
+                seq_out[(size_t)b * K + s + 1] = __uint_as_float(m - 1u);
+            }
+        }
+        cur = winner;
+    }
+}
+
+// Generic fallback: points and running distances stay in global memory (L2-resident for any realistic N).
+__global__ void __launch_bounds__(FPS_THREADS, 1) fps_gmem_kernel(const float *__restrict__ xyz, int N, int K,
+                                                                    int start, int *__restrict__ idx_out,
+                                                                    float *__restrict__ seq_out,
+                                                                    float *__restrict__ run_ws) {
+    __shared__ unsigned sval[2][FPS_WARPS];
+    __shared__ int sidx[2][FPS_WARPS];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float *p = xyz + (size_t)b * N * 3;
+    float *run = run_ws + (size_t)b * N;
+    for (int i = tid; i < N; i += FPS_THREADS) run[i] = __int_as_float(0x7f800000);
+    int cur = start;
+    for (int s = 0; s < K; ++s) {
+        if (tid == 0) idx_out[(size_t)b * K + s] = cur;
+        const float lx = __ldg(p + cur * 3), ly = __ldg(p + cur * 3 + 1), lz = __ldg(p + cur * 3 + 2);
+        float best = -2.f;
+        int best_i = 0x7fffffff;
+        for (int i = tid; i < N; i += FPS_THREADS) {
+            const float dx = __fsub_rn(__ldg(p + i * 3), lx), dy = __fsub_rn(__ldg(p + i * 3 + 1), ly),
+                        dz = __fsub_rn(__ldg(p + i * 3 + 2), lz);
+            const float d = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+            const float rv = run[i];
+            const float r = (rv < d) ? rv : d;
+            run[i] = r;
+            if (r > best) {
+                best = r;
+                best_i = i;
+            }
+        }
+        int winner;
+        fps_block_argmax(best, best_i, sval, sidx, s & 1, lane, warp, winner);
+        if (seq_out != nullptr && tid == 0) {
+            if (s == 0) seq_out[(size_t)b * K] = __int_as_float(0x7f800000);
+            if (s + 1 < K) {
+                unsigned m = 0;
+                for (int w = 0; w < FPS_WARPS; ++w) m = max(m, sval[s & 1][w]);
+                seq_out[(size_t)b * K + s + 1] = __uint_as_float(m - 1u);
+            }
+        }
+        cur = winner;
+    }
+}
+
+}  // namespace genpc
+
+using namespace genpc;
+
+extern "C" size_t genpc_fps_workspace_bytes(int B, int N, int K) {
+    if (B < 0 || N < 0) return 0;
+    return (N > FPS_THREADS * 32) ? (size_t)B * N * sizeof(float) : 0;
+}
+
+extern "C" int genpc_fps(const float *xyz, int B, int N, int K, int start, int *idx_out, float *seq_out,
+                         void *workspace, size_t workspace_bytes, genpc_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (B < 0 || N <= 0 || K < 0 || K > N || start < 0 || start >= N) return GENPC_ERR_SHAPE;
+    if (B == 0 || K == 0) return GENPC_OK;
+    const int ppt = (N + FPS_THREADS - 1) / FPS_THREADS;
+#define FPS_LAUNCH(P) fps_reg_kernel<P, (P <= 4)><<<B, FPS_THREADS, 0, stream>>>(xyz, N, K, start, idx_out, seq_out)
+    if (ppt <= 1) FPS_LAUNCH(1);
+    else if (ppt <= 2) FPS_LAUNCH(2);
+    else if (ppt <= 4) FPS_LAUNCH(4);
+    else if (ppt <= 8) FPS_LAUNCH(8);
+    else if (ppt <= 16) FPS_LAUNCH(16);
+    else if (ppt <= 32) FPS_LAUNCH(32);
+    else {
+        if (workspace == nullptr || workspace_bytes < genpc_fps_workspace_bytes(B, N, K)) return GENPC_ERR_WORKSPACE;
+        fps_gmem_kernel<<<B, FPS_THREADS, 0, stream>>>(xyz, N, K, start, idx_out, seq_out, (float *)workspace);
+    }
+#undef FPS_LAUNCH
+    GENPC_CHECK_LAUNCH();
+    return GENPC_OK;
+}

@@ -51,6 +51,44 @@ int genpc_chamfer_backward(const float *xyz1, const float *xyz2, const float *gr
                            const float *graddist2, const int *idx1, const int *idx2, float *gradxyz1,
                            float *gradxyz2, int B, int N, int M, genpc_stream_t stream);
 
+/* ---- Farthest point sampling -------------------------------------------------------------------
+ * Replaces the reference's CPU call fpsample.fps_sampling(xyz, K) (main.py:21-22, reg_xyz.py:215,
+ * DepthPrompting.py:88-90; un-vendored third-party package).  xyz [B][N][3] -> idx_out [B][K] int32,
+ * first pick = `start`, lowest index on ties; seq_out (optional, may be NULL) [B][K] receives the running
+ * distance of each pick (seq[.,0] = +inf; non-increasing afterwards).  One persistent CTA per cloud.
+ * workspace: genpc_fps_workspace_bytes (0 unless N > 32768). */
+size_t genpc_fps_workspace_bytes(int B, int N, int K);
+int genpc_fps(const float *xyz, int B, int N, int K, int start, int *idx_out, float *seq_out,
+              void *workspace, size_t workspace_bytes, genpc_stream_t stream);
+
+/* ---- DepthPrompting geometry --------------------------------------------------------------------
+ * Camera = 16 floats: [0..8] R row-major (rows right/up/backward), [9..11] t = -R*eye, [12] fx, [13] fy,
+ * [14] A, [15] Bc with ndc_z = A - Bc/depth (OpenGL projection; kaolin semantics restated).
+ *
+ * genpc_project_uv replaces DepthPrompting.getUvs (DepthPrompting.py:239-271): cams[V][16], xyz[N][3] ->
+ *   ndc[V][N][3] (the reference's `transformed_points`; ndc[..,2] is its `point_depths`), uv[V][N][2],
+ *   bounds[V][4] = (centre_x, centre_y, scale, 1-2*padding) of the per-view rescale (may be NULL).
+ * genpc_zbuffer_render replaces the pixel mapping (:179-184) + paintPixels/getRawDepth (:292-391):
+ *   pixel = trunc(uv*res) -> (row=v, col=u), clipped, (2*point_size-1)^2 splat, vertical flip; a pixel is won
+ *   by the nearest ndc_z, ties by the lowest point index (packed 64-bit atomicMin) -- where the reference's
+ *   index_put lets an arbitrary point win.  valid[V][N] (uint8, may be NULL) masks points.
+ *   Outputs (each may be NULL except zbuf): zbuf[V][res][res] packed words (empty = ~0), idx_img[V][res][res]
+ *   (-1 empty), depth_img[V][res][res] = 0.1+0.8*(1-(z-zmin)/(zmax-zmin)) (0 empty), color_img[V][3][res][res]
+ *   gathered from colors[N][3], zminmax[V][2].
+ * genpc_unproject (no reference counterpart; defined in DESIGN.md 3.4): every non-empty pixel, in raster
+ *   order, back to a 3-D point at the pixel centre: out[V][res*res][3], own[V][res*res], counts[V].
+ * workspace for the first two: genpc_depth_workspace_bytes(V). */
+size_t genpc_depth_workspace_bytes(int V);
+int genpc_project_uv(const float *cams, const float *xyz, int V, int N, int rescale, float padding, float *ndc,
+                     float *uv, float *bounds, void *workspace, size_t workspace_bytes, genpc_stream_t stream);
+int genpc_zbuffer_render(const float *uv, const float *ndc, const unsigned char *valid, const float *colors,
+                         int V, int N, int res, int point_size, unsigned long long *zbuf, int *idx_img,
+                         float *depth_img, float *color_img, float *zminmax, void *workspace,
+                         size_t workspace_bytes, genpc_stream_t stream);
+int genpc_unproject(const float *cams, const float *bounds, int rescale, const unsigned long long *zbuf,
+                    const float *ndc, int V, int N, int res, float *out, int *own, int *counts,
+                    genpc_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

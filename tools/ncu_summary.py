@@ -1,0 +1,47 @@
+#!/usr/bin/env python
+"""Summarise an .ncu-rep (ncu --set full) into a small text file for profiles/.
+   python tools/ncu_summary.py gpurun_out/prof_nn.ncu-rep profiles/r01_nn_scan_ncu.txt"""
+import csv
+import io
+import subprocess
+import sys
+
+KEYS = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+        "launch__waves_per_multiprocessor", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "sm__cycles_elapsed.max",
+        "smsp__inst_executed.sum", "sm__inst_executed.avg.per_cycle_active",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed",
+        "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+        "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_bytes.sum",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+        "smsp__warps_eligible.avg.per_cycle_active"]
+STALL = "smsp__average_warps_issue_stalled_"
+
+
+def main(rep, out):
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    lines = [f"# ncu --set full --clock-control none summary of {rep}", ""]
+    for r in data:
+        lines.append(f"== {r[hdr.index('Kernel Name')]}  (launch id {r[0]})")
+        for k in KEYS:
+            if k in hdr:
+                i = hdr.index(k)
+                lines.append(f"  {k:75s} {r[i]:>18s} {units[i]}")
+        st = [(float(r[i]), h[len(STALL):].replace("_per_issue_active.ratio", "")) for i, h in enumerate(hdr)
+              if h.startswith(STALL) and h.endswith("per_issue_active.ratio")]
+        lines.append("  warp stall reasons (warps per issue-active cycle): " +
+                     ", ".join(f"{n}={v:.2f}" for v, n in sorted(st, reverse=True)[:8]))
+        lines.append("")
+    open(out, "w").write("\n".join(lines))
+    print("\n".join(lines))
+
+
+if __name__ == "__main__":
+    main(sys.argv[1], sys.argv[2])
