@@ -12,6 +12,7 @@ _lib = None
 _vp = ctypes.c_void_p
 _int = ctypes.c_int
 _flt = ctypes.c_float
+_dbl = ctypes.c_double
 _sz = ctypes.c_size_t
 
 
@@ -31,6 +32,9 @@ _SIGNATURES = {
     "genpc_zbuffer_render": (_int, [_vp, _vp, _vp, _vp, _int, _int, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _sz,
                                     _vp]),
     "genpc_unproject": (_int, [_vp, _vp, _int, _vp, _vp, _int, _int, _int, _vp, _vp, _vp, _vp]),
+    "genpc_register_workspace_bytes": (_sz, [_int, _int, _int]),
+    "genpc_register_run": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _int, _int, _int, _int, _int,
+                                  _dbl, _dbl, _dbl, _flt, _flt, _flt, _vp, _sz, _int, _vp]),
 }
 
 

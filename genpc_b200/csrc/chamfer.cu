@@ -12,13 +12,9 @@
 //   * per-item results are merged across target splits with one packed 64-bit atomicMin per query
 //     ((dist_bits << 32) | idx: unsigned order == dist ascending, then idx ascending == the reference's
 //     lowest-index tie rule), then unpacked to dist/idx.
-#include "common.cuh"
+#include "nn_core.cuh"
 
 namespace genpc {
-
-constexpr int NN_THREADS = 256;
-constexpr int NN_SPAN = 1024;  // targets per work item (12 KB of shared memory)
-constexpr int NN_CHUNK = 16;   // index-recovery granularity
 
 struct NNDir {
     const float *q;            // queries  [B][nq][3]
@@ -33,103 +29,23 @@ struct NNParams {
 template <int QT>
 __global__ void __launch_bounds__(NN_THREADS, 2) nn_scan_kernel(const NNParams p) {
     __shared__ __align__(16) float s[3][NN_SPAN];
-    const int tid = threadIdx.x;
     int item = blockIdx.x;
     const int d = (item >= p.dir[0].items) ? 1 : 0;
     if (d) item -= p.dir[0].items;
-    NNDir D;  // field-wise select keeps the parameters in constant memory (no local copy)
-    D.q = d ? p.dir[1].q : p.dir[0].q;
-    D.t = d ? p.dir[1].t : p.dir[0].t;
-    D.out = d ? p.dir[1].out : p.dir[0].out;
-    D.nq = d ? p.dir[1].nq : p.dir[0].nq;
-    D.mt = d ? p.dir[1].mt : p.dir[0].mt;
-    D.qtiles = d ? p.dir[1].qtiles : p.dir[0].qtiles;
-    D.tsplits = d ? p.dir[1].tsplits : p.dir[0].tsplits;
-    const int ts = item % D.tsplits;
-    const int rest = item / D.tsplits;
-    const int qt = rest % D.qtiles;
-    const int b = rest / D.qtiles;
-    const int t0 = ts * NN_SPAN;
-    const int cnt = min(NN_SPAN, D.mt - t0);
-
-    // ---- stage targets: coalesced AoS read -> SoA shared, NaN padding (NaN never wins a min) ----
-    {
-        const float *tg = D.t + ((size_t)b * D.mt + t0) * 3;
-        const float qnan = __int_as_float(0x7fc00000);
-        const int lim = cnt * 3;
-        for (int i = tid; i < NN_SPAN * 3; i += NN_THREADS) {
-            const int k = i / 3, c = i - k * 3;
-            s[c][k] = (i < lim) ? __ldg(tg + i) : qnan;
-        }
-    }
-    // ---- queries into registers (negated, duplicated for the packed pipe) ----
-    float2 nqx[QT], nqy[QT], nqz[QT];
-    float best[QT];
-    int bchunk[QT];
-    const int jbase = qt * (NN_THREADS * QT) + tid;
-#pragma unroll
-    for (int q = 0; q < QT; ++q) {
-        const int j = jbase + q * NN_THREADS;
-        float x = 0.f, y = 0.f, z = 0.f;
-        if (j < D.nq) {
-            const float *qp = D.q + ((size_t)b * D.nq + j) * 3;
-            x = __ldg(qp), y = __ldg(qp + 1), z = __ldg(qp + 2);
-        }
-        nqx[q] = make_float2(-x, -x);
-        nqy[q] = make_float2(-y, -y);
-        nqz[q] = make_float2(-z, -z);
-        best[q] = __int_as_float(0x7f800000);
-        bchunk[q] = 0;
-    }
-    __syncthreads();
-
-    const int nchunks = (cnt + NN_CHUNK - 1) / NN_CHUNK;
-    const float4 *sx4 = reinterpret_cast<const float4 *>(s[0]);
-    const float4 *sy4 = reinterpret_cast<const float4 *>(s[1]);
-    const float4 *sz4 = reinterpret_cast<const float4 *>(s[2]);
-    for (int c = 0; c < nchunks; ++c) {
-        float cm[QT];
-#pragma unroll
-        for (int q = 0; q < QT; ++q) cm[q] = __int_as_float(0x7f800000);
-#pragma unroll
-        for (int kk = 0; kk < NN_CHUNK / 4; ++kk) {
-            const float4 X = sx4[c * (NN_CHUNK / 4) + kk];
-            const float4 Y = sy4[c * (NN_CHUNK / 4) + kk];
-            const float4 Z = sz4[c * (NN_CHUNK / 4) + kk];
-#pragma unroll
-            for (int q = 0; q < QT; ++q) {
-                const float2 a = sqdist_ref_x2(nqx[q], nqy[q], nqz[q], make_float2(X.x, X.y),
-                                               make_float2(Y.x, Y.y), make_float2(Z.x, Z.y));
-                const float2 e = sqdist_ref_x2(nqx[q], nqy[q], nqz[q], make_float2(X.z, X.w),
-                                               make_float2(Y.z, Y.w), make_float2(Z.z, Z.w));
-                cm[q] = fmin3(cm[q], a.x, a.y);
-                cm[q] = fmin3(cm[q], e.x, e.y);
-            }
-        }
-#pragma unroll
-        for (int q = 0; q < QT; ++q) {
-            if (cm[q] < best[q]) {  // strict: the earliest chunk keeps ties
-                best[q] = cm[q];
-                bchunk[q] = c;
-            }
-        }
-    }
-
-    // ---- recover the exact (lowest) index inside the winning chunk, merge across target splits ----
-#pragma unroll
-    for (int q = 0; q < QT; ++q) {
-        const int j = jbase + q * NN_THREADS;
-        if (j >= D.nq) continue;
-        const float qx = -nqx[q].x, qy = -nqy[q].x, qz = -nqz[q].x;
-        const int cb = bchunk[q] * NN_CHUNK;
-        int kbest = 0;
-#pragma unroll
-        for (int k = NN_CHUNK - 1; k >= 0; --k) {
-            const float dd = sqdist_ref(qx, qy, qz, s[0][cb + k], s[1][cb + k], s[2][cb + k]);
-            if (dd == best[q]) kbest = k;
-        }
-        atomicMin(D.out + (size_t)b * D.nq + j, pack_dist_idx(best[q], t0 + cb + kbest));
-    }
+    // field-wise select keeps the parameters in constant memory (no local copy)
+    const float *q = d ? p.dir[1].q : p.dir[0].q;
+    const float *t = d ? p.dir[1].t : p.dir[0].t;
+    unsigned long long *out = d ? p.dir[1].out : p.dir[0].out;
+    const int nq = d ? p.dir[1].nq : p.dir[0].nq;
+    const int mt = d ? p.dir[1].mt : p.dir[0].mt;
+    const int qtiles = d ? p.dir[1].qtiles : p.dir[0].qtiles;
+    const int tsplits = d ? p.dir[1].tsplits : p.dir[0].tsplits;
+    const int ts = item % tsplits;
+    const int rest = item / tsplits;
+    const int qt = rest % qtiles;
+    const int b = rest / qtiles;
+    nn_scan_item<QT>(s, q + (size_t)b * nq * 3, nq, qt * (NN_THREADS * QT), t + (size_t)b * mt * 3, mt, ts * NN_SPAN, 0,
+                     nullptr, nullptr, out + (size_t)b * nq);
 }
 
 __global__ void nn_unpack_kernel(const unsigned long long *__restrict__ packed, float *__restrict__ dist1,
@@ -185,13 +101,6 @@ __global__ void chamfer_grad_kernel(const float *__restrict__ xyz1, const float 
     atomicAdd(go + t * 3 + 2, -tz);
 }
 
-static int pick_qt(int nq) {
-    // queries per thread: large tiles amortise the shared-memory reads, small clouds keep lanes busy
-    if (nq >= 4 * NN_THREADS) return 4;
-    if (nq >= 2 * NN_THREADS) return 2;
-    return 1;
-}
-
 static void fill_dir(NNDir &D, const float *q, const float *t, unsigned long long *out, int B, int nq, int mt,
                      int QT) {
     D.q = q, D.t = t, D.out = out, D.nq = nq, D.mt = mt;
@@ -234,7 +143,7 @@ extern "C" int genpc_chamfer_forward(const float *xyz1, const float *xyz2, float
     cudaError_t e = cudaMemsetAsync(packed, 0xff, (n1 + n2) * 8, stream);
     if (e != cudaSuccess) return (int)e;
 
-    const int QT = pick_qt(N < M ? N : M);
+    const int QT = nn_pick_qt(N < M ? N : M);
     NNParams p;
     fill_dir(p.dir[0], xyz1, xyz2, packed, B, N, M, QT);
     fill_dir(p.dir[1], xyz2, xyz1, packed + n1, B, M, N, QT);

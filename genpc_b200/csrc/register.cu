@@ -1,0 +1,245 @@
+// register.cu -- the Geometric-Preserving-Fusion registration loop, one launch per Adam iteration.
+//
+// Replaces the Chamfer part of the reference's hot loop (diff_obj_pose.py:518-576):
+//     model(return_pts=True)                      :535  -> ObjectPoseOptim.forward :408-436 (transform :419-423)
+//     compute_loss_function(...) Chamfer term     :323-334  cd = CDp-L1(pts->ref) + 0.5*CDp-L1(ref->pts); 3.0*cd
+//     loss.backward(); optimizer.step(); .item()  :546-548  (2 ext calls = 4 NN scans + 4 grad launches + D2H sync)
+// by ONE kernel per iteration that, for every scan (and every multi-start of it):
+//   1. applies the current 7-DoF pose on the fly (queries of direction A / targets of direction B): the moving
+//      cloud is never materialised;
+//   2. runs the two NN scans that are actually needed (the reference runs four) with the shared packed-FP32
+//      work item (nn_core.cuh), merging with packed 64-bit atomicMin;
+//   3. the last CTA of a scan to finish (atomic ticket) reduces the loss and the 13 pose-gradient scalars
+//      (sum g, sum g (x) u, sum g.Ru -- SURVEY.md appendix C; no scatter atomics) in double, deterministically,
+//      back-propagates through the Gram-Schmidt 6-D rotation, applies Adam (betas .9/.999, eps 1e-8, three lr
+//      groups :524-528), stores the loss, and re-arms the packed buffers for the next launch.
+// No host synchronisation anywhere: the 500-iteration loop is 500 back-to-back launches (graph-capturable).
+#include "nn_core.cuh"
+
+namespace genpc {
+
+constexpr int REG_NPAR = 10;  // rot_6d[6], trans[3], log_scale[1]
+
+struct RegArgs {
+    const float *complete;  // [C][Nc][3] moving clouds (C = S / n_starts)
+    const float *center;    // [C][3]     centroid of each moving cloud (register_buffer('center'), :362)
+    const float *ref;       // [C][Nr][3] fixed (partial) clouds
+    float *params;          // [S][10]
+    float *adam_m;          // [S][10]
+    float *adam_v;          // [S][10]
+    unsigned long long *packedA;  // [S][Nc]
+    unsigned long long *packedB;  // [S][Nr]
+    int *counters;          // [S]
+    float *loss_hist;       // [S][T]
+    int S, n_starts, Nc, Nr, T, t_index;
+    int qtilesA, tsplitsA, itemsA, qtilesB, tsplitsB, items_per_scan;
+    float step_size[3];     // lr_g / (1 - beta1^t) for the rot / trans / log_scale groups
+    float w_fwd, w_inv, cd_weight;
+    float omb1, beta2, omb2, eps, bc2_sqrt;  // 1-beta1, beta2, 1-beta2 (rounded from double like torch's scalars)
+};
+
+__device__ __forceinline__ void load_similarity(const float *par, const float *center, Similarity &T) {
+    rot6d_to_matrix(par, T.R);
+    T.s = (float)exp((double)par[9]);  // exp in double then rounded: identical on host and device
+    T.c[0] = center[0], T.c[1] = center[1], T.c[2] = center[2];
+    T.t[0] = par[6], T.t[1] = par[7], T.t[2] = par[8];
+}
+
+__device__ __forceinline__ double block_sum(double v, double *sh) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) sh[warp] = v;
+    __syncthreads();
+    double r = 0.0;
+#pragma unroll
+    for (int w = 0; w < NN_THREADS / 32; ++w) r += sh[w];  // fixed order -> deterministic
+    return r;
+}
+
+// one gradient term: moving point index jm, fixed point index kf, squared distance d, weight coef0 = w/(count)
+__device__ __forceinline__ void accum_term(const RegArgs &a, const Similarity &T, const float *V, const float *Rf,
+                                           int jm, int kf, float d, double coef0, double *acc) {
+    const float sq = __fsqrt_rn(d);
+    acc[13] += coef0 * (double)sq;  // loss
+    if (!(d > 0.f)) return;         // the reference's sqrt backward is inf/NaN at d == 0 (loss_util.py:37); skipped
+    const float *vp = V + (size_t)jm * 3;
+    const float ux = __fmul_rn(__fsub_rn(__ldg(vp), T.c[0]), T.s);
+    const float uy = __fmul_rn(__fsub_rn(__ldg(vp + 1), T.c[1]), T.s);
+    const float uz = __fmul_rn(__fsub_rn(__ldg(vp + 2), T.c[2]), T.s);
+    const float rx = __fmaf_rn(T.R[2], uz, __fmaf_rn(T.R[1], uy, __fmul_rn(T.R[0], ux)));
+    const float ry = __fmaf_rn(T.R[5], uz, __fmaf_rn(T.R[4], uy, __fmul_rn(T.R[3], ux)));
+    const float rz = __fmaf_rn(T.R[8], uz, __fmaf_rn(T.R[7], uy, __fmul_rn(T.R[6], ux)));
+    const float px = __fadd_rn(__fadd_rn(rx, T.c[0]), T.t[0]);
+    const float py = __fadd_rn(__fadd_rn(ry, T.c[1]), T.t[1]);
+    const float pz = __fadd_rn(__fadd_rn(rz, T.c[2]), T.t[2]);
+    const float *fp = Rf + (size_t)kf * 3;
+    const double coef = coef0 / (double)sq;
+    const double gx = coef * (double)__fsub_rn(px, __ldg(fp));
+    const double gy = coef * (double)__fsub_rn(py, __ldg(fp + 1));
+    const double gz = coef * (double)__fsub_rn(pz, __ldg(fp + 2));
+    acc[0] += gx, acc[1] += gy, acc[2] += gz;                                  // dL/dt
+    acc[3] += gx * ux, acc[4] += gx * uy, acc[5] += gx * uz;                   // dL/dR (row-major)
+    acc[6] += gy * ux, acc[7] += gy * uy, acc[8] += gy * uz;
+    acc[9] += gz * ux, acc[10] += gz * uy, acc[11] += gz * uz;
+    acc[12] += gx * rx + gy * ry + gz * rz;                                    // dL/dlog_s
+}
+
+__device__ __noinline__ void finalize_scan(const RegArgs &a, int scan, const Similarity &T, double *sh) {
+    const int cloud = scan / a.n_starts;
+    const float *V = a.complete + (size_t)cloud * a.Nc * 3;
+    const float *Rf = a.ref + (size_t)cloud * a.Nr * 3;
+    unsigned long long *pA = a.packedA + (size_t)scan * a.Nc;
+    unsigned long long *pB = a.packedB + (size_t)scan * a.Nr;
+    double acc[14];
+#pragma unroll
+    for (int i = 0; i < 14; ++i) acc[i] = 0.0;
+    const double cA = (double)a.cd_weight * (double)a.w_fwd / (double)a.Nc;
+    const double cB = (double)a.cd_weight * (double)a.w_inv / (double)a.Nr;
+    for (int j = threadIdx.x; j < a.Nc; j += NN_THREADS) {  // direction A: moving point j -> its NN in ref
+        const unsigned long long w = __ldcg(pA + j);
+        pA[j] = ~0ull;  // re-arm for the next launch
+        accum_term(a, T, V, Rf, j, (int)(unsigned)(w & 0xffffffffu), __uint_as_float((unsigned)(w >> 32)), cA, acc);
+    }
+    for (int k = threadIdx.x; k < a.Nr; k += NN_THREADS) {  // direction B: ref point k -> its NN among moving pts
+        const unsigned long long w = __ldcg(pB + k);
+        pB[k] = ~0ull;
+        accum_term(a, T, V, Rf, (int)(unsigned)(w & 0xffffffffu), k, __uint_as_float((unsigned)(w >> 32)), cB, acc);
+    }
+    double tot[14];
+#pragma unroll
+    for (int i = 0; i < 14; ++i) tot[i] = block_sum(acc[i], sh);
+    if (threadIdx.x != 0) return;
+
+    float *par = a.params + (size_t)scan * REG_NPAR;
+    float *am = a.adam_m + (size_t)scan * REG_NPAR;
+    float *av = a.adam_v + (size_t)scan * REG_NPAR;
+    // ---- Gram-Schmidt backward, double ----
+    const double a1[3] = {par[0], par[1], par[2]}, a2[3] = {par[3], par[4], par[5]};
+    const double b1[3] = {T.R[0], T.R[1], T.R[2]}, b2[3] = {T.R[3], T.R[4], T.R[5]};
+    const double G1[3] = {tot[3], tot[4], tot[5]}, G2[3] = {tot[6], tot[7], tot[8]}, G3[3] = {tot[9], tot[10], tot[11]};
+    const double n1 = fmax(sqrt(a1[0] * a1[0] + a1[1] * a1[1] + a1[2] * a1[2]), 1e-12);
+    const double dp = b1[0] * a2[0] + b1[1] * a2[1] + b1[2] * a2[2];
+    const double wv[3] = {a2[0] - dp * b1[0], a2[1] - dp * b1[1], a2[2] - dp * b1[2]};
+    const double n2 = fmax(sqrt(wv[0] * wv[0] + wv[1] * wv[1] + wv[2] * wv[2]), 1e-12);
+    double H1[3] = {G1[0] + (b2[1] * G3[2] - b2[2] * G3[1]), G1[1] + (b2[2] * G3[0] - b2[0] * G3[2]),
+                    G1[2] + (b2[0] * G3[1] - b2[1] * G3[0])};
+    const double H2[3] = {G2[0] + (G3[1] * b1[2] - G3[2] * b1[1]), G2[1] + (G3[2] * b1[0] - G3[0] * b1[2]),
+                          G2[2] + (G3[0] * b1[1] - G3[1] * b1[0])};
+    const double b2H2 = b2[0] * H2[0] + b2[1] * H2[1] + b2[2] * H2[2];
+    const double dw[3] = {(H2[0] - b2[0] * b2H2) / n2, (H2[1] - b2[1] * b2H2) / n2, (H2[2] - b2[2] * b2H2) / n2};
+    const double b1dw = b1[0] * dw[0] + b1[1] * dw[1] + b1[2] * dw[2];
+    const double da2[3] = {dw[0] - b1[0] * b1dw, dw[1] - b1[1] * b1dw, dw[2] - b1[2] * b1dw};
+#pragma unroll
+    for (int i = 0; i < 3; ++i) H1[i] -= dp * dw[i] + a2[i] * b1dw;
+    const double b1H1 = b1[0] * H1[0] + b1[1] * H1[1] + b1[2] * H1[2];
+    const double da1[3] = {(H1[0] - b1[0] * b1H1) / n1, (H1[1] - b1[1] * b1H1) / n1, (H1[2] - b1[2] * b1H1) / n1};
+    float grad[REG_NPAR] = {(float)da1[0], (float)da1[1], (float)da1[2], (float)da2[0], (float)da2[1], (float)da2[2],
+                            (float)tot[0], (float)tot[1], (float)tot[2], (float)tot[12]};
+    // ---- Adam (torch.optim.Adam defaults; lr groups of diff_obj_pose.py:524-528), fp32 like torch ----
+#pragma unroll
+    for (int i = 0; i < REG_NPAR; ++i) {
+        const float step = a.step_size[i < 6 ? 0 : (i < 9 ? 1 : 2)];
+        const float g = grad[i];
+        const float m = am[i] + (g - am[i]) * a.omb1;        // exp_avg.lerp_(grad, 1-beta1)
+        const float v = a.beta2 * av[i] + a.omb2 * g * g;    // exp_avg_sq.mul_(beta2).addcmul_(g, g, 1-beta2)
+        am[i] = m, av[i] = v;
+        const float denom = sqrtf(v) / a.bc2_sqrt + a.eps;
+        par[i] = par[i] - step * (m / denom);                // param.addcdiv_(exp_avg, denom, value=-step_size)
+    }
+    if (a.loss_hist != nullptr) a.loss_hist[(size_t)scan * a.T + a.t_index] = (float)tot[13];
+    a.counters[scan] = 0;
+}
+
+template <int QT>
+__global__ void __launch_bounds__(NN_THREADS, 2) register_step_kernel(const RegArgs a) {
+    __shared__ __align__(16) float s[3][NN_SPAN];
+    __shared__ Similarity T;
+    __shared__ int is_last;
+    __shared__ double sh[NN_THREADS / 32];
+    const int scan = blockIdx.x / a.items_per_scan;
+    int item = blockIdx.x - scan * a.items_per_scan;
+    const int cloud = scan / a.n_starts;
+    if (threadIdx.x == 0) load_similarity(a.params + (size_t)scan * REG_NPAR, a.center + (size_t)cloud * 3, T);
+    __syncthreads();
+    const float *V = a.complete + (size_t)cloud * a.Nc * 3;
+    const float *Rf = a.ref + (size_t)cloud * a.Nr * 3;
+    if (item < a.itemsA) {  // A: moving queries vs fixed targets
+        const int ts = item % a.tsplitsA, qt = item / a.tsplitsA;
+        nn_scan_item<QT>(s, V, a.Nc, qt * (NN_THREADS * QT), Rf, a.Nr, ts * NN_SPAN, 0, &T, nullptr,
+                         a.packedA + (size_t)scan * a.Nc);
+    } else {                // B: fixed queries vs moving targets
+        item -= a.itemsA;
+        const int ts = item % a.tsplitsB, qt = item / a.tsplitsB;
+        nn_scan_item<QT>(s, Rf, a.Nr, qt * (NN_THREADS * QT), V, a.Nc, ts * NN_SPAN, 0, nullptr, &T,
+                         a.packedB + (size_t)scan * a.Nr);
+    }
+    // ---- ticket: the last CTA of this scan reduces loss + gradient and steps the optimiser ----
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(a.counters + scan, 1) == a.items_per_scan - 1);
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        finalize_scan(a, scan, T, sh);
+    }
+}
+
+}  // namespace genpc
+
+using namespace genpc;
+
+extern "C" size_t genpc_register_workspace_bytes(int S, int Nc, int Nr) {
+    if (S < 0 || Nc < 0 || Nr < 0) return 0;
+    return ((size_t)S * Nc + (size_t)S * Nr) * 8 + (size_t)S * sizeof(int);
+}
+
+extern "C" int genpc_register_run(const float *complete, const float *center, const float *ref, float *params,
+                                  float *adam_m, float *adam_v, float *loss_hist, int S, int n_starts, int Nc, int Nr,
+                                  int iters, int t_start, int T, double lr_rot, double lr_trans, double lr_scale,
+                                  float w_fwd, float w_inv, float cd_weight, void *workspace, size_t workspace_bytes,
+                                  int reset_workspace, genpc_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (S <= 0 || n_starts <= 0 || S % n_starts != 0 || Nc <= 0 || Nr <= 0 || iters < 0 || t_start < 0) return GENPC_ERR_SHAPE;
+    if (loss_hist != nullptr && t_start + iters > T) return GENPC_ERR_SHAPE;
+    if (workspace == nullptr || workspace_bytes < genpc_register_workspace_bytes(S, Nc, Nr)) return GENPC_ERR_WORKSPACE;
+    RegArgs a;
+    a.complete = complete, a.center = center, a.ref = ref, a.params = params, a.adam_m = adam_m, a.adam_v = adam_v;
+    a.packedA = (unsigned long long *)workspace;
+    a.packedB = a.packedA + (size_t)S * Nc;
+    a.counters = (int *)(a.packedB + (size_t)S * Nr);
+    a.loss_hist = loss_hist;
+    a.S = S, a.n_starts = n_starts, a.Nc = Nc, a.Nr = Nr, a.T = T;
+    const int QT = nn_pick_qt(Nc < Nr ? Nc : Nr);
+    a.qtilesA = (Nc + NN_THREADS * QT - 1) / (NN_THREADS * QT);
+    a.tsplitsA = (Nr + NN_SPAN - 1) / NN_SPAN;
+    a.itemsA = a.qtilesA * a.tsplitsA;
+    a.qtilesB = (Nr + NN_THREADS * QT - 1) / (NN_THREADS * QT);
+    a.tsplitsB = (Nc + NN_SPAN - 1) / NN_SPAN;
+    a.items_per_scan = a.itemsA + a.qtilesB * a.tsplitsB;
+    const long long grid = (long long)S * a.items_per_scan;
+    if (grid > 0x7fffffffLL) return GENPC_ERR_RANGE;
+    a.w_fwd = w_fwd, a.w_inv = w_inv, a.cd_weight = cd_weight;
+    a.omb1 = (float)(1.0 - 0.9), a.beta2 = (float)0.999, a.omb2 = (float)(1.0 - 0.999), a.eps = (float)1e-8;
+    if (reset_workspace) {
+        cudaError_t e = cudaMemsetAsync(a.packedA, 0xff, ((size_t)S * Nc + (size_t)S * Nr) * 8, stream);
+        if (e != cudaSuccess) return (int)e;
+        e = cudaMemsetAsync(a.counters, 0, (size_t)S * sizeof(int), stream);
+        if (e != cudaSuccess) return (int)e;
+    }
+    for (int it = 0; it < iters; ++it) {
+        const int t = t_start + it;
+        a.t_index = t;
+        const double bc1 = 1.0 - pow(0.9, (double)(t + 1));
+        a.step_size[0] = (float)(lr_rot / bc1), a.step_size[1] = (float)(lr_trans / bc1), a.step_size[2] = (float)(lr_scale / bc1);
+        a.bc2_sqrt = (float)sqrt(1.0 - pow(0.999, (double)(t + 1)));
+        switch (QT) {
+            case 4: register_step_kernel<4><<<(unsigned)grid, NN_THREADS, 0, stream>>>(a); break;
+            case 2: register_step_kernel<2><<<(unsigned)grid, NN_THREADS, 0, stream>>>(a); break;
+            default: register_step_kernel<1><<<(unsigned)grid, NN_THREADS, 0, stream>>>(a); break;
+        }
+        GENPC_CHECK_LAUNCH();
+    }
+    return GENPC_OK;
+}

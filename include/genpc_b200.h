@@ -89,6 +89,26 @@ int genpc_unproject(const float *cams, const float *bounds, int rescale, const u
                     const float *ndc, int V, int N, int res, float *out, int *own, int *counts,
                     genpc_stream_t stream);
 
+/* ---- Fused registration loop (Geometric Preserving Fusion) --------------------------------------
+ * Replaces the Chamfer part of the reference's pose/scale optimisation hot loop
+ * (optim_registration/diff_obj_pose.py:518-576: ObjectPoseOptim.forward :408-436, Chamfer term of
+ * compute_loss_function :323-334, loss.backward / Adam step / .item() :546-548) -- ONE kernel launch per
+ * Adam iteration for all scans, no host synchronisation.
+ *   complete[C][Nc][3]  moving clouds, center[C][3] their centroids, ref[C][Nr][3] fixed clouds, C = S/n_starts;
+ *   scan i (one optimisation problem: a cloud pair x one multi-start) uses cloud pair i / n_starts;
+ *   params[S][10] = rot_6d[6] | trans[3] | log_scale[1], adam_m / adam_v[S][10]: read and updated in place;
+ *   loss_hist[S][T] (may be NULL): loss of iteration t written at column t, for t in [t_start, t_start+iters);
+ *   loss = cd_weight * (w_fwd * mean sqrt NN(pts->ref) + w_inv * mean sqrt NN(ref->pts)), pts = R(s(V-c))+c+t;
+ *   Adam betas (0.9, 0.999), eps 1e-8, step sizes lr_rot / lr_trans / lr_scale (diff_obj_pose.py:524-528).
+ * workspace: genpc_register_workspace_bytes(S,Nc,Nr); pass reset_workspace=1 on the first call of a run
+ * (later calls continuing the same run pass 0 and t_start = iterations already done). */
+size_t genpc_register_workspace_bytes(int S, int Nc, int Nr);
+int genpc_register_run(const float *complete, const float *center, const float *ref, float *params,
+                       float *adam_m, float *adam_v, float *loss_hist, int S, int n_starts, int Nc, int Nr,
+                       int iters, int t_start, int T, double lr_rot, double lr_trans, double lr_scale,
+                       float w_fwd, float w_inv, float cd_weight, void *workspace, size_t workspace_bytes,
+                       int reset_workspace, genpc_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -46,6 +46,8 @@ def lib():
         L.oracle_zbuffer_resolve.argtypes = [_int, _int, _int, _u64p, _f32p, _f32p, _i32p, _f32p]
         L.oracle_unproject.argtypes = [_int, _int, _int, _f32p, _f32p, _int, _u64p, _f32p, _f32p, _i32p,
                                        _i32p]
+        L.oracle_pose_matrix.argtypes = [_f32p, _f32p]
+        L.oracle_transform.argtypes = [_int, _f32p, _f32p, _f32p, _f32p]
         _lib = L
     return _lib
 
@@ -175,6 +177,21 @@ def unproject(cams, bounds, zb, ndc, rescale=True):
     counts = np.zeros(V, np.int32)
     lib().oracle_unproject(V, N, res, cams, bounds, int(bool(rescale)), zb, ndc, out, own, counts)
     return out, own, counts
+
+
+def pose_matrix(rot6d):
+    """rotation_6d_to_matrix with explicit fp32 rounding -> R [3,3] float32."""
+    R = np.zeros(9, np.float32)
+    lib().oracle_pose_matrix(_c(rot6d, np.float32), R)
+    return R.reshape(3, 3)
+
+
+def transform(V, center, params):
+    """pts = R (s (V - c)) + c + t, params = rot6d[6] | trans[3] | log_scale[1] (diff_obj_pose.py:419-423)."""
+    V = _c(V, np.float32)
+    out = np.zeros_like(V)
+    lib().oracle_transform(V.shape[0], V, _c(center, np.float32), _c(params, np.float32), out)
+    return out
 
 
 # ----------------------------------------------------------------------------------------------------

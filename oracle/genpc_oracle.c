@@ -491,3 +491,41 @@ void oracle_unproject(int V, int N, int res, const float *cams, const float *bou
         counts[v] = cnt;
     }
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Registration geometry (ObjectPoseOptim.forward, diff_obj_pose.py:408-436).
+ * rotation_6d_to_matrix lives in un-vendored pytorch3d -> parity unpinned; restated from its published
+ * definition: b1 = normalize(a1), b2 = normalize(a2 - (b1.a2) b1), b3 = b1 x b2,
+ * rows of R; F.normalize = v / max(|v|, 1e-12).  Explicit rounding so the CUDA kernel can match bit for bit.
+ * ---------------------------------------------------------------------------------------------- */
+void oracle_pose_matrix(const float *d6, float *R) {
+    float a1x = d6[0], a1y = d6[1], a1z = d6[2], a2x = d6[3], a2y = d6[4], a2z = d6[5];
+    float n1 = fmaxf(sqrtf(fmaf(a1z, a1z, fmaf(a1y, a1y, a1x * a1x))), 1e-12f);
+    float b1x = a1x / n1, b1y = a1y / n1, b1z = a1z / n1;
+    float dp = fmaf(b1z, a2z, fmaf(b1y, a2y, b1x * a2x));
+    float wx = a2x - dp * b1x, wy = a2y - dp * b1y, wz = a2z - dp * b1z;
+    float n2 = fmaxf(sqrtf(fmaf(wz, wz, fmaf(wy, wy, wx * wx))), 1e-12f);
+    float b2x = wx / n2, b2y = wy / n2, b2z = wz / n2;
+    R[0] = b1x, R[1] = b1y, R[2] = b1z;
+    R[3] = b2x, R[4] = b2y, R[5] = b2z;
+    R[6] = b1y * b2z - b1z * b2y;
+    R[7] = b1z * b2x - b1x * b2z;
+    R[8] = b1x * b2y - b1y * b2x;
+}
+
+/* pts = R (s (V - c)) + c + t (diff_obj_pose.py:419-423), s = (float)exp((double)log_scale):
+ * l = V - c; u = l*s; r_x = fma(R02,u_z, fma(R01,u_y, R00*u_x)); p_x = (r_x + c_x) + t_x. */
+void oracle_transform(int N, const float *V, const float *c, const float *par, float *out) {
+    float R[9];
+    oracle_pose_matrix(par, R);
+    float s = (float)exp((double)par[9]);
+    for (int i = 0; i < N; i++) {
+        float ux = (V[i * 3 + 0] - c[0]) * s, uy = (V[i * 3 + 1] - c[1]) * s, uz = (V[i * 3 + 2] - c[2]) * s;
+        float rx = fmaf(R[2], uz, fmaf(R[1], uy, R[0] * ux));
+        float ry = fmaf(R[5], uz, fmaf(R[4], uy, R[3] * ux));
+        float rz = fmaf(R[8], uz, fmaf(R[7], uy, R[6] * ux));
+        out[i * 3 + 0] = (rx + c[0]) + par[6];
+        out[i * 3 + 1] = (ry + c[1]) + par[7];
+        out[i * 3 + 2] = (rz + c[2]) + par[8];
+    }
+}
