@@ -89,6 +89,26 @@ int genpc_unproject(const float *cams, const float *bounds, int rescale, const u
                     const float *ndc, int V, int N, int res, float *out, int *own, int *counts,
                     genpc_stream_t stream);
 
+/* ---- EMD (auction) ------------------------------------------------------------------------------
+ * Replaces emd.forward (emd.cpp:12-18 -> emd_cuda_forward, emd_cuda.cu:228-282; kernels clear :23,
+ * calc_unass_cnt :30, calc_unass_cnt_sum :55, calc_unass_idx :85, Bid :95, GetMax :181, Assign :196,
+ * CalcDist :217) with ONE persistent cooperative kernel.  Buffers and their required initial values are the
+ * reference's (emd_module.py:43-54): assignment = assignment_inv = -1, price = bid_increments =
+ * max_increments = 0; unass_cnt has >= B ints (the reference allocates 512).  The reference's
+ * unass_cnt_sum / cnt_tmp scratch is not needed.  Returns GENPC_ERR_SHAPE for n != m, B > 512, n % 256 != 0
+ * (emd_cuda.cu:236-249).  Outputs dist[B][n], assignment[B][n] bit-identical to the reference wherever the
+ * reference itself is deterministic (its GetMax race is resolved as "highest bidder index").
+ * workspace: genpc_emd_workspace_bytes(B). */
+size_t genpc_emd_workspace_bytes(int B);
+int genpc_emd_forward(const float *xyz1, const float *xyz2, float *dist, int *assignment, float *price,
+                      int *assignment_inv, int *bid, float *bid_increments, float *max_increments,
+                      int *unass_idx, int *unass_cnt, int *max_idx, int B, int n, int m, float eps, int iters,
+                      void *workspace, size_t workspace_bytes, genpc_stream_t stream);
+/* Replaces emd.backward (emd.cpp:20-23 -> emd_cuda_backward, emd_cuda.cu:302-316): gradient to xyz1 only,
+ * ACCUMULATED into gradxyz (must arrive zeroed, emd_module.py:83). */
+int genpc_emd_backward(const float *xyz1, const float *xyz2, float *gradxyz, const float *graddist,
+                       const int *idx, int B, int n, genpc_stream_t stream);
+
 /* ---- Fused registration loop (Geometric Preserving Fusion) --------------------------------------
  * Replaces the Chamfer part of the reference's pose/scale optimisation hot loop
  * (optim_registration/diff_obj_pose.py:518-576: ObjectPoseOptim.forward :408-436, Chamfer term of

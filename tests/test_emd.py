@@ -1,0 +1,122 @@
+"""EMD auction: the CUDA kernel bit-exact (dist + assignment) against the oracle restatement -- which itself is
+pinned on the reference's own outputs (test_oracle_golden.py) -- against the committed golden vectors, and
+against the unmodified reference extension on the same GPU; plus the reference's own `Verified EMD`
+self-consistency check (emd_module.py:112-118) and the shape errors of emd_cuda.cu:236-249."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_oracle_emd_verified_identity_and_bijection_trend():
+    rng = np.random.default_rng(0)
+    x1, x2 = rng.random((2, 512, 3), dtype=np.float32), rng.random((2, 512, 3), dtype=np.float32)
+    d, a = oracle.emd_forward(x1, x2, 0.05, 3000)           # test_emd() settings (emd_module.py:98-103)
+    assert all(len(np.unique(a[b])) == 512 for b in range(2))   # converged: a bijection
+    x2g = np.take_along_axis(x2, a[..., None].astype(np.int64), axis=1)
+    ver = ((x1.astype(np.float64) - x2g) ** 2).sum(-1)
+    assert np.allclose(d, ver, rtol=1e-5, atol=1e-9)          # "Verified EMD" (emd_module.py:112-118)
+    g = oracle.emd_backward(x1, x2, np.ones((2, 512), np.float32), a)
+    assert np.allclose(g, 2 * (x1 - x2g), rtol=1e-6, atol=1e-7)
+
+
+def test_oracle_emd_shape_errors():
+    x = np.zeros((1, 300, 3), np.float32)
+    with pytest.raises(ValueError):
+        oracle.emd_forward(x, x, 0.005, 5)                      # n % 256 != 0
+
+
+def run_ours(x1, x2, eps, iters, dev):
+    import torch
+
+    from genpc_b200.loss_functions import emdModule
+
+    d, a = emdModule()(torch.from_numpy(x1).to(dev), torch.from_numpy(x2).to(dev), eps, iters)
+    return d.cpu().numpy(), a.cpu().numpy()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,n,eps,iters", [(1, 256, 0.005, 50), (2, 512, 0.005, 50), (3, 1024, 0.002, 80),
+                                           (1, 2304, 0.005, 50), (32, 1024, 0.005, 50), (1, 8192, 0.005, 50),
+                                           (2, 2048, 0.05, 400)])
+def test_emd_gpu_bit_exact_vs_oracle(cuda, B, n, eps, iters):
+    rng = np.random.default_rng(n + B)
+    x1, x2 = rng.random((B, n, 3), dtype=np.float32), rng.random((B, n, 3), dtype=np.float32)
+    d, a = run_ours(x1, x2, eps, iters, cuda)
+    ed, ea = oracle.emd_forward(x1, x2, eps, iters)
+    assert np.array_equal(a, ea), f"{(a != ea).sum()} assignments differ"
+    assert np.array_equal(d.view(np.int32), ed.view(np.int32))
+
+
+@pytest.mark.gpu
+def test_emd_gpu_golden_and_centered_data(cuda):
+    for f in sorted(glob.glob(os.path.join(G, "emd_ref_*.npz"))):
+        z = np.load(f)
+        d, a = run_ours(z["xyz1"], z["xyz2"], float(z["eps"]), int(z["iters"]), cuda)
+        assert np.array_equal(a, z["assignment"]) and np.array_equal(d.view(np.int32), z["dist"].view(np.int32)), f
+    # the metric path feeds [-0.5, 0.5] data un-normalised (main.py:26-33)
+    rng = np.random.default_rng(3)
+    x1 = rng.random((1, 2048, 3), dtype=np.float32) - 0.5
+    x2 = rng.random((1, 2048, 3), dtype=np.float32) - 0.5
+    d, a = run_ours(x1, x2, 0.005, 50, cuda)
+    ed, ea = oracle.emd_forward(x1, x2, 0.005, 50)
+    assert np.array_equal(a, ea) and np.array_equal(d, ed)
+
+
+@pytest.mark.gpu
+def test_emd_gpu_vs_reference_extension_and_backward(cuda):
+    import torch
+
+    from genpc_b200.loss_functions import emdModule
+
+    ref = oracle.load_ref_ext("emd")
+    rng = np.random.default_rng(9)
+    B, n = 4, 4096
+    x1 = torch.from_numpy(rng.random((B, n, 3), dtype=np.float32)).to(cuda).requires_grad_(True)
+    x2 = torch.from_numpy(rng.random((B, n, 3), dtype=np.float32)).to(cuda)
+    d, a = emdModule()(x1, x2, 0.005, 50)
+    torch.sqrt(d).mean(1).mean().backward()                     # Completionloss.emd_loss reduction
+    eg = oracle.emd_backward(x1.detach().cpu().numpy(), x2.cpu().numpy(),
+                             (0.5 / torch.sqrt(d) / (B * n)).detach().cpu().numpy(), a.cpu().numpy())
+    assert np.abs(x1.grad.cpu().numpy() - eg).max() <= 1e-5 * np.abs(eg).max()
+    if ref is None:
+        pytest.skip("oracle/_ref/emd not built")
+    dev = cuda
+    dist = torch.zeros(B, n, device=dev); asg = torch.zeros(B, n, device=dev, dtype=torch.int32) - 1
+    asg_inv = torch.zeros(B, n, device=dev, dtype=torch.int32) - 1; price = torch.zeros(B, n, device=dev)
+    bid = torch.zeros(B, n, device=dev, dtype=torch.int32); binc = torch.zeros(B, n, device=dev)
+    minc = torch.zeros(B, n, device=dev); uidx = torch.zeros(B * n, device=dev, dtype=torch.int32)
+    midx = torch.zeros(B * n, device=dev, dtype=torch.int32)
+    z512 = [torch.zeros(512, dtype=torch.int32, device=dev) for _ in range(3)]
+    ref.forward(x1.detach(), x2, dist, asg, price, asg_inv, bid, binc, minc, uidx, z512[0], z512[1], z512[2], midx, 0.005, 50)
+    torch.cuda.synchronize()
+    assert torch.equal(asg, a) and torch.equal(dist, d.detach())
+
+
+@pytest.mark.gpu
+def test_emd_shape_errors_and_completionloss(cuda):
+    import torch
+
+    from genpc_b200 import _lib, emd
+    from genpc_b200.utils.loss_util import Completionloss
+
+    x = torch.rand(1, 300, 3, device=cuda)
+    z = lambda *s, dt=torch.float32: torch.zeros(*s, device=cuda, dtype=dt)
+    with pytest.raises(_lib.GenpcError):
+        emd.forward(x, x, z(1, 300), z(1, 300, dt=torch.int32), z(1, 300), z(1, 300, dt=torch.int32),
+                    z(1, 300, dt=torch.int32), z(1, 300), z(1, 300), z(300, dt=torch.int32), z(512, dt=torch.int32),
+                    z(512, dt=torch.int32), z(512, dt=torch.int32), z(300, dt=torch.int32), 0.005, 5)
+    g = torch.Generator().manual_seed(0)
+    p1, p2 = torch.rand(2, 1024, 3, generator=g).to(cuda), torch.rand(2, 1024, 3, generator=g).to(cuda)
+    for name in ("cd_l1", "cd_l2", "emd"):
+        v = Completionloss(name).get_loss(p1, p2)
+        assert v.ndim == 0 and torch.isfinite(v)
+    cl = Completionloss("cd_l1")
+    d1, d2, _, _ = cl.chamfer_dist(p1, p2)
+    assert torch.allclose(cl.chamfer_partial_l1(p1, p2), torch.sqrt(d1).mean())
+    assert torch.allclose(cl.chamfer_l1(p1, p2), (torch.sqrt(d1).mean() + torch.sqrt(d2).mean()) / 2)
