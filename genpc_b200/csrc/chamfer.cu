@@ -21,6 +21,7 @@ struct NNDir {
     const float *t;            // targets  [B][mt][3]
     unsigned long long *out;   // packed   [B][nq]
     int nq, mt, qtiles, tsplits, items;
+    int idx_base;              // added to reported target indices (shard offset; 0 for plain Chamfer)
 };
 struct NNParams {
     NNDir dir[2];
@@ -40,12 +41,13 @@ __global__ void __launch_bounds__(NN_THREADS, 2) nn_scan_kernel(const NNParams p
     const int mt = d ? p.dir[1].mt : p.dir[0].mt;
     const int qtiles = d ? p.dir[1].qtiles : p.dir[0].qtiles;
     const int tsplits = d ? p.dir[1].tsplits : p.dir[0].tsplits;
+    const int idx_base = d ? p.dir[1].idx_base : p.dir[0].idx_base;
     const int ts = item % tsplits;
     const int rest = item / tsplits;
     const int qt = rest % qtiles;
     const int b = rest / qtiles;
-    nn_scan_item<QT>(s, q + (size_t)b * nq * 3, nq, qt * (NN_THREADS * QT), t + (size_t)b * mt * 3, mt, ts * NN_SPAN, 0,
-                     nullptr, nullptr, out + (size_t)b * nq);
+    nn_scan_item<QT>(s, q + (size_t)b * nq * 3, nq, qt * (NN_THREADS * QT), t + (size_t)b * mt * 3, mt, ts * NN_SPAN,
+                     idx_base, nullptr, nullptr, out + (size_t)b * nq);
 }
 
 __global__ void nn_unpack_kernel(const unsigned long long *__restrict__ packed, float *__restrict__ dist1,
@@ -107,6 +109,14 @@ static void fill_dir(NNDir &D, const float *q, const float *t, unsigned long lon
     D.qtiles = (nq + NN_THREADS * QT - 1) / (NN_THREADS * QT);
     D.tsplits = (mt + NN_SPAN - 1) / NN_SPAN;
     D.items = B * D.qtiles * D.tsplits;
+    D.idx_base = 0;
+}
+
+template <int QT>
+static cudaError_t launch_scan(const NNParams &p, cudaStream_t stream) {
+    const long long items = (long long)p.dir[0].items + p.dir[1].items;
+    nn_scan_kernel<QT><<<(unsigned)items, NN_THREADS, 0, stream>>>(p);
+    return cudaGetLastError();
 }
 
 }  // namespace genpc
@@ -176,3 +186,39 @@ extern "C" int genpc_chamfer_backward(const float *xyz1, const float *xyz2, cons
 }
 
 extern "C" const char *genpc_version(void) { return "genpc_b200 0.1 sm_100a"; }
+
+// ---- target-sharded Chamfer (million-point clouds over several GPUs) ---------------------------------------
+// One direction, one target shard: packed[b][j] = min(packed[b][j], (dist_bits<<32 | idx_base+k)) over the
+// targets of this shard.  The caller initialises `packed` to all-ones once (init != 0 does it here), merges the
+// shards with an all-reduce-MIN over the 64-bit words (non-negative as int64 because dist >= 0), then unpacks.
+extern "C" int genpc_nn_partial_packed(const float *queries, const float *targets_shard, unsigned long long *packed,
+                                       int B, int Nq, int Mt_shard, int idx_base, int init, genpc_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (B < 0 || Nq < 0 || Mt_shard < 0 || idx_base < 0) return GENPC_ERR_SHAPE;
+    const size_t n1 = (size_t)B * Nq;
+    if (n1 == 0) return GENPC_OK;
+    if (init) {
+        cudaError_t e = cudaMemsetAsync(packed, 0xff, n1 * 8, stream);
+        if (e != cudaSuccess) return (int)e;
+    }
+    if (Mt_shard == 0) return GENPC_OK;
+    const int QT = nn_pick_qt(Nq);
+    NNParams p;
+    fill_dir(p.dir[0], queries, targets_shard, packed, B, Nq, Mt_shard, QT);
+    p.dir[0].idx_base = idx_base;
+    p.dir[1] = p.dir[0];
+    p.dir[1].items = 0;
+    if ((long long)p.dir[0].items > 0x7fffffffLL) return GENPC_ERR_RANGE;
+    cudaError_t e = QT == 4 ? launch_scan<4>(p, stream) : (QT == 2 ? launch_scan<2>(p, stream) : launch_scan<1>(p, stream));
+    if (e != cudaSuccess) return (int)e;
+    return GENPC_OK;
+}
+
+extern "C" int genpc_nn_unpack(const unsigned long long *packed, float *dist, int *idx, size_t count,
+                               genpc_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (count == 0) return GENPC_OK;
+    nn_unpack_kernel<<<(unsigned)((count + 255) / 256), 256, 0, stream>>>(packed, dist, idx, count, nullptr, nullptr, 0);
+    GENPC_CHECK_LAUNCH();
+    return GENPC_OK;
+}

@@ -1,0 +1,97 @@
+"""Multi-GPU forms of the path (one process per GPU, torch.distributed).
+
+* Independent units (batched Chamfer / EMD / FPS / views / registration scans) shard by index with NO data-path
+  collective: `shard_range` gives each rank its slice; results are gathered by the caller if it wants them.
+* Million-point Chamfer (BASELINE config C5) shards the TARGETS: every rank holds both full clouds (12 MB per
+  million points), scans all queries against its slice of the other cloud with global target indices, and the
+  partial results are merged by ONE all-reduce-MIN over packed 64-bit words (dist_bits << 32 | idx) -- NCCL over
+  NVLink (ncclInt64 / ncclMin).  dist >= 0 keeps the words non-negative as int64, and the low word makes the
+  lowest global index win ties, so the merged result is bit-identical to the single-GPU kernel.
+The host-side logic (slicing, merge, unpack) is device-agnostic and is covered on CPU with gloo (tests/).
+"""
+import torch
+import torch.distributed as dist
+
+from . import _lib
+
+EMPTY = -1  # all-ones word as int64
+
+
+def shard_range(n, rank, world):
+    """Contiguous near-even split of range(n): rank r owns [lo, hi)."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def allreduce_min_packed(packed, group=None):
+    """In-place all-reduce-MIN of packed (dist, idx) words stored as int64.  Words are non-negative, except the
+    'empty' marker -1 (all ones), which must lose against any real word: it is mapped to INT64_MAX around the
+    collective."""
+    big = torch.iinfo(torch.int64).max
+    packed.masked_fill_(packed == EMPTY, big)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(packed, op=dist.ReduceOp.MIN, group=group)
+    packed.masked_fill_(packed == big, EMPTY)
+    return packed
+
+
+def unpack_packed(packed):
+    """int64 words -> (dist float32, idx int32); pure torch so it also runs on CPU tensors (gloo tests)."""
+    hi = (packed >> 32) & 0xFFFFFFFF
+    lo = packed & 0xFFFFFFFF
+    lo32 = torch.where(lo >= 2 ** 31, lo - 2 ** 32, lo).to(torch.int32)
+    return _bits_to_float(hi), lo32
+
+
+def _bits_to_float(hi):
+    # hi holds 32-bit patterns in int64; values >= 2^31 only occur for the empty marker (NaN pattern)
+    hi32 = torch.where(hi >= 2 ** 31, hi - 2 ** 32, hi).to(torch.int32)
+    return hi32.view(torch.float32)
+
+
+def nn_partial_packed(queries, targets_shard, idx_base, packed=None):
+    """CUDA: scan all queries [B,Nq,3] against one target shard [B,Mt,3]; returns / updates packed int64 [B,Nq]."""
+    _lib.require_cuda(queries, targets_shard)
+    queries, targets_shard = queries.contiguous(), targets_shard.contiguous()
+    B, Nq, _ = queries.shape
+    Mt = targets_shard.shape[1]
+    init = packed is None
+    if init:
+        packed = torch.empty(B, Nq, dtype=torch.int64, device=queries.device)
+    with torch.cuda.device(queries.device):
+        rc = _lib.lib().genpc_nn_partial_packed(_lib.ptr(queries), _lib.ptr(targets_shard), _lib.ptr(packed), B, Nq, Mt,
+                                                int(idx_base), 1 if init else 0, _lib.current_stream(queries.device))
+    _lib.check(rc, "genpc_nn_partial_packed")
+    return packed
+
+
+def nn_unpack(packed):
+    """CUDA unpack kernel: packed int64 [..] -> (dist float32, idx int32)."""
+    _lib.require_cuda(packed)
+    d = torch.empty(packed.shape, dtype=torch.float32, device=packed.device)
+    i = torch.empty(packed.shape, dtype=torch.int32, device=packed.device)
+    with torch.cuda.device(packed.device):
+        rc = _lib.lib().genpc_nn_unpack(_lib.ptr(packed), _lib.ptr(d), _lib.ptr(i), packed.numel(),
+                                        _lib.current_stream(packed.device))
+    _lib.check(rc, "genpc_nn_unpack")
+    return d, i
+
+
+def sharded_chamfer_forward(xyz1, xyz2, group=None):
+    """Target-sharded Chamfer forward.  xyz1 [B,N,3], xyz2 [B,M,3]: the FULL clouds, identical on every rank.
+    Returns (dist1, dist2, idx1, idx2) identical on every rank and bit-identical to chamfer_3DDist."""
+    if dist.is_available() and dist.is_initialized():
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+    else:
+        rank, world = 0, 1
+    N, M = xyz1.shape[1], xyz2.shape[1]
+    lo2, hi2 = shard_range(M, rank, world)
+    lo1, hi1 = shard_range(N, rank, world)
+    p1 = nn_partial_packed(xyz1, xyz2[:, lo2:hi2], lo2)
+    p2 = nn_partial_packed(xyz2, xyz1[:, lo1:hi1], lo1)
+    packed = torch.cat([p1.reshape(-1), p2.reshape(-1)])   # one collective for both directions
+    allreduce_min_packed(packed, group)
+    d, i = nn_unpack(packed)
+    n1 = p1.numel()
+    return d[:n1].view_as(p1), d[n1:].view_as(p2), i[:n1].view_as(p1), i[n1:].view_as(p2)

@@ -51,6 +51,16 @@ int genpc_chamfer_backward(const float *xyz1, const float *xyz2, const float *gr
                            const float *graddist2, const int *idx1, const int *idx2, float *gradxyz1,
                            float *gradxyz2, int B, int N, int M, genpc_stream_t stream);
 
+/* Target-sharded Chamfer (1M x 1M clouds over 2/4/8 GPUs; no reference counterpart -- the reference is
+ * single-GPU brute force).  One direction against ONE shard of the targets: packed[b][j] =
+ * min(packed[b][j], (dist_bits << 32) | (idx_base + k)).  Shards are merged by an all-reduce-MIN over the
+ * 64-bit words (ncclInt64/ncclMin: the words are non-negative as int64 because dist >= 0; the low word makes
+ * the lowest GLOBAL index win ties), then genpc_nn_unpack splits them into dist / idx.
+ * init != 0 first fills packed with all-ones. */
+int genpc_nn_partial_packed(const float *queries, const float *targets_shard, unsigned long long *packed, int B,
+                            int Nq, int Mt_shard, int idx_base, int init, genpc_stream_t stream);
+int genpc_nn_unpack(const unsigned long long *packed, float *dist, int *idx, size_t count, genpc_stream_t stream);
+
 /* ---- Farthest point sampling -------------------------------------------------------------------
  * Replaces the reference's CPU call fpsample.fps_sampling(xyz, K) (main.py:21-22, reg_xyz.py:215,
  * DepthPrompting.py:88-90; un-vendored third-party package).  xyz [B][N][3] -> idx_out [B][K] int32,

@@ -1,0 +1,87 @@
+"""Target-sharded Chamfer: host-side logic (slicing, all-reduce-MIN of packed words, unpack) on CPU with gloo,
+world_size 2; the CUDA partial scan + merge against the oracle and the single-GPU kernel on the GPU."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import oracle
+from util import lattice_cloud, rand_cloud
+
+
+def test_shard_range_covers_everything():
+    from genpc_b200.sharded import shard_range
+
+    for n in (0, 1, 7, 1000, 1000003):
+        for w in (1, 2, 3, 8):
+            r = [shard_range(n, k, w) for k in range(w)]
+            assert r[0][0] == 0 and r[-1][1] == n
+            assert all(r[k][1] == r[k + 1][0] for k in range(w - 1))
+            assert max(b - a for a, b in r) - min(b - a for a, b in r) <= 1
+
+
+def pack_np(d, i):
+    return (d.view(np.uint32).astype(np.int64) << 32) | i.astype(np.int64)
+
+
+def _worker(rank, world, port, a, b, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from genpc_b200.sharded import allreduce_min_packed, shard_range, unpack_packed
+
+    lo, hi = shard_range(b.shape[1], rank, world)
+    if hi > lo:
+        d, i = oracle.nn_distance(a, np.ascontiguousarray(b[:, lo:hi]))   # the partial scan, done by the checker on CPU
+        packed = torch.from_numpy(pack_np(d, i + lo))
+    else:
+        packed = torch.full(a.shape[:2], -1, dtype=torch.int64)           # empty shard: all-ones words
+    allreduce_min_packed(packed)
+    dd, ii = unpack_packed(packed)
+    out[rank] = (dd.numpy().copy(), ii.numpy().copy())
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("case", ["rand", "lattice", "tiny"])
+def test_gloo_world2_merge_equals_full_scan(case):
+    if case == "rand":
+        a, b = rand_cloud(1, 2, 300), rand_cloud(2, 2, 1001)
+    elif case == "lattice":
+        a, b = lattice_cloud(3, 1, 400), lattice_cloud(4, 1, 900)     # ties must resolve to the lowest GLOBAL index
+    else:
+        a, b = rand_cloud(5, 1, 5), rand_cloud(6, 1, 1)               # rank 1 gets an empty shard
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(2, port, a, b, out), nprocs=2, join=True)
+    ed, ei = oracle.nn_distance(a, b)
+    for r in range(2):
+        d, i = out[r]
+        assert np.array_equal(d.view(np.int32), ed.view(np.int32)) and np.array_equal(i, ei)
+
+
+@pytest.mark.gpu
+def test_partial_scans_merge_to_the_single_gpu_result(cuda):
+    """Emulate 3 ranks on one GPU: per-shard partial scans + min-merge == chamfer_3DDist == oracle."""
+    from genpc_b200.loss_functions import chamfer_3DDist
+    from genpc_b200.sharded import nn_partial_packed, nn_unpack, shard_range, sharded_chamfer_forward
+
+    a, b = rand_cloud(7, 1, 50000), lattice_cloud(8, 1, 30011, side=40)
+    ta, tb = torch.from_numpy(a).to(cuda), torch.from_numpy(b).to(cuda)
+    parts = []
+    for r in range(3):
+        lo, hi = shard_range(b.shape[1], r, 3)
+        parts.append(nn_partial_packed(ta, tb[:, lo:hi], lo))
+    merged = torch.stack(parts).min(0).values            # what the all-reduce-MIN computes
+    d, i = nn_unpack(merged)
+    d1, d2, i1, i2 = chamfer_3DDist()(ta, tb)
+    assert torch.equal(d, d1) and torch.equal(i, i1)
+    ed, ei = oracle.nn_distance(a, b)
+    assert np.array_equal(d.cpu().numpy(), ed) and np.array_equal(i.cpu().numpy(), ei)
+    s = sharded_chamfer_forward(ta, tb)                    # world size 1 path
+    for x, y in zip(s, (d1, d2, i1, i2)):
+        assert torch.equal(x, y)
