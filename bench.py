@@ -151,6 +151,40 @@ def cpu_baseline(part, comp, budget_b=None):
 # The reference's stock path: dist_chamfer_3D.py:26-64 restated around the UNMODIFIED extension
 # (the file itself cannot be imported on Python 3.12: importlib.find_loader, :6)
 # ---------------------------------------------------------------------------------------------------
+def import_reference_api():
+    """The UNMODIFIED reference Python API (`loss_functions.chamfer_3DDist`) from baseline/_ref (pip-installed copy of
+    /root/reference) on top of its UNMODIFIED compiled extensions (oracle/_ref).  The only
+    shim is for the interpreter: Python 3.12 removed importlib.find_loader, which dist_chamfer_3D.py:6 calls."""
+    import importlib
+    import importlib.util
+
+    ref_pkg = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref_pkg, "loss_functions")):
+        return None
+    for name in ("chamfer_3D", "emd"):
+        d = os.path.join(ROOT, "oracle", "_ref", name)
+        if not os.path.exists(os.path.join(d, name + ".so")):
+            return None
+        if d not in sys.path:
+            sys.path.insert(0, d)
+    if not hasattr(importlib, "find_loader"):
+        importlib.find_loader = lambda name, path=None: importlib.util.find_spec(name)
+    mine = [k for k in sys.modules if k == "loss_functions" or k.startswith("loss_functions.")]
+    for k in mine:
+        del sys.modules[k]
+    sys.path.insert(0, ref_pkg)
+    try:
+        import loss_functions  # noqa: F401  (the reference's package, not genpc_b200.loss_functions)
+
+        assert os.path.realpath(loss_functions.__file__).startswith(os.path.realpath(ref_pkg))
+        return loss_functions.chamfer_3DDist()
+    except Exception as e:  # pragma: no cover
+        sys.stderr.write(f"[bench] reference API import failed: {e}\n")
+        return None
+    finally:
+        sys.path.remove(ref_pkg)
+
+
 def make_ref_function(ext):
     class RefChamfer(torch.autograd.Function):
         @staticmethod
@@ -281,6 +315,42 @@ def time_kernels_ours(dev, a, b, flush, iters=20):
     return sum(tf) / len(tf), sum(tb) / len(tb)
 
 
+def registration_metric(rank, world, dev, iters=10, total_scans=64, pts=16384):
+    """BASELINE config C3 (secondary metric): `total_scans` scans data-parallel over the ranks (strong scaling, no
+    collective), pose+scale Adam iterations on the Chamfer loss at 16384 x 16384 points, one start per scan.
+    Returns scan-iterations per second, whole job (max time over ranks)."""
+    import torch.distributed as dist
+
+    from genpc_b200.optim_registration.diff_obj_pose import RegistrationBatch
+    from genpc_b200.sharded import shard_range
+    from genpc_b200.synthetic import partial_view, rigid_perturb, superquadric
+
+    lo, hi = shard_range(total_scans, rank, world)
+    comp = np.stack([superquadric(5000 + s, pts) for s in range(lo, hi)])
+    part = np.stack([rigid_perturb(partial_view(comp[s - lo], s, pts), s)[0] for s in range(lo, hi)])
+    rb = RegistrationBatch(torch.from_numpy(comp).to(dev), torch.from_numpy(part).to(dev), n_starts=1, lr=0.01,
+                           max_iters=iters + 4)
+    rb.run(3)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    rb.run(iters)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    L = rb.losses()
+    return {"metric": "registration_scan_iters_per_sec", "value": total_scans * iters / (ms * 1e-3), "unit": "scan-iters/s",
+            "scans": total_scans, "pts": pts, "iters_timed": iters, "ms_per_iter": ms / iters, "scaling": "strong",
+            "pairs_per_s": total_scans * iters * 2.0 * pts * pts / (ms * 1e-3), "launches_per_iter": 1,
+            "loss_first_last_scan0": [float(L[0, 0]), float(L[0, rb.t - 1])],
+            "workload": "C3: pose+scale Adam steps on 3*(CDp-L1(pts->ref)+0.5*CDp-L1(ref->pts)), 1 start per scan"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -335,12 +405,18 @@ def main():
                              "note": "oracle/_ref not built: timed the CPU port"})
                 print(json.dumps(line))
             return
-        res, _ = run_gpu_arm(args, make_ref_function(ext), rank, world, dev, part, comp, "reference")
+        api = import_reference_api()
+        if api is not None:
+            fn, how = (lambda x, y: api(x, y)), ("UNMODIFIED reference API loss_functions.chamfer_3DDist (baseline/_ref) "
+                                                 "on its UNMODIFIED CUDA extension (oracle/_ref, sm_100a)")
+        else:
+            fn, how = make_ref_function(ext), ("UNMODIFIED reference chamfer_3D CUDA extension (oracle/_ref) through "
+                                               "dist_chamfer_3D.py:26-64 restated (baseline/_ref not installed)")
+        res, _ = run_gpu_arm(args, fn, rank, world, dev, part, comp, "reference")
         line.update(res)
         line.update({"impl": "reference", "gpu_launches": 4 * args.steps,
-                     "note": "UNMODIFIED reference chamfer_3D CUDA extension (oracle/_ref, built from "
-                             "/root/reference sources for sm_100a) through dist_chamfer_3D.py's stock flow "
-                             "(CPU-allocated outputs + .to(device)); the reference has no CPU implementation"})
+                     "note": how + "; stock flow = CPU-allocated outputs + .to(device) every call; the reference has "
+                                   "no CPU implementation of this path (CPU numbers in cpu_baseline)"})
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(part, comp)
         if rank == 0:
@@ -355,6 +431,11 @@ def main():
     res, (a, b, flush) = run_gpu_arm(args, lambda x, y: mod(x, y), rank, world, dev, part, comp, "ours")
     line.update(res)
     line["gpu_launches"] = 3 * args.steps  # nn_scan_kernel + nn_unpack_kernel + chamfer_grad_kernel per step
+    try:
+        reg = registration_metric(rank, world, dev)
+    except Exception as e:  # pragma: no cover
+        reg = {"error": str(e)}
+    line["registration"] = reg
     if rank == 0:
         t_fwd, t_bwd = time_kernels_ours(dev, a, b, flush)
         flops = 2.0 * B * N * M * FLOP_PER_PAIR

@@ -66,6 +66,30 @@ def build_ref(force=False):
     return out
 
 
+def install_ref_package(force=False):
+    """The base contract's one offline install: the UNMODIFIED reference Python package into baseline/_ref
+    (git-ignored, travels to the GPU box) -- from a copy under /tmp because /root/reference is read-only and the
+    build writes egg-info; --no-deps because the reference's generator dependencies are not in the wheelhouse."""
+    import shutil
+    import tempfile
+
+    root = os.path.dirname(HERE)
+    target = os.path.join(root, "baseline", "_ref")
+    if not os.path.isdir(REF):
+        return None
+    if not force and os.path.isdir(os.path.join(target, "loss_functions")):
+        return target
+    tmp = tempfile.mkdtemp(prefix="genpc_ref_")
+    src = os.path.join(tmp, "reference")
+    shutil.copytree(REF, src, ignore=shutil.ignore_patterns("data", "*.ply", ".git"))
+    os.makedirs(target, exist_ok=True)
+    subprocess.check_call([sys.executable, "-m", "pip", "install", "--quiet", "--no-index", "--no-build-isolation",
+                           "--no-deps", "--upgrade", "--find-links", "/opt/wheelhouse", "--target", target, src])
+    shutil.rmtree(tmp, ignore_errors=True)
+    return target
+
+
 if __name__ == "__main__":
     print(build_oracle(force="--force" in sys.argv))
     print(build_ref(force="--force" in sys.argv))
+    print(install_ref_package(force="--force" in sys.argv))
