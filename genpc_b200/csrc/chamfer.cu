@@ -28,7 +28,7 @@ struct NNParams {
 };
 
 template <int QT>
-__global__ void __launch_bounds__(NN_THREADS, 2) nn_scan_kernel(const NNParams p) {
+__global__ void __launch_bounds__(NN_THREADS, NN_MINBLOCKS) nn_scan_kernel(const NNParams p) {
     __shared__ __align__(16) float s[3][NN_SPAN];
     int item = blockIdx.x;
     const int d = (item >= p.dir[0].items) ? 1 : 0;

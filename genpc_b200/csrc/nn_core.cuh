@@ -15,9 +15,23 @@
 
 namespace genpc {
 
+// tunables (overridable for tools/nn_variants.sh experiments; the defaults are what ships)
+#ifndef GENPC_NN_SPAN
+#define GENPC_NN_SPAN 1024
+#endif
+#ifndef GENPC_NN_CHUNK
+#define GENPC_NN_CHUNK 16
+#endif
+#ifndef GENPC_NN_MINBLOCKS
+#define GENPC_NN_MINBLOCKS 2
+#endif
+#ifndef GENPC_NN_QT_MAX
+#define GENPC_NN_QT_MAX 4
+#endif
 constexpr int NN_THREADS = 256;
-constexpr int NN_SPAN = 1024;  // targets per work item (12 KB of shared memory)
-constexpr int NN_CHUNK = 16;   // index-recovery granularity
+constexpr int NN_SPAN = GENPC_NN_SPAN;    // targets per work item (12 B of shared memory each)
+constexpr int NN_CHUNK = GENPC_NN_CHUNK;  // index-recovery granularity
+constexpr int NN_MINBLOCKS = GENPC_NN_MINBLOCKS;
 
 // p' = R (s (p - c)) + c + t with explicit rounding (ObjectPoseOptim.forward, diff_obj_pose.py:419-423):
 //   l = p - c; u = l * s; r_x = fma(R02,u_z, fma(R01,u_y, R00*u_x)); p'_x = (r_x + c_x) + t_x
@@ -155,8 +169,8 @@ __device__ __forceinline__ void nn_scan_item(float (*s)[NN_SPAN], const float *_
 
 static inline int nn_pick_qt(int nq) {
     // queries per thread: large tiles amortise the shared-memory reads, small clouds keep lanes busy
-    if (nq >= 4 * NN_THREADS) return 4;
-    if (nq >= 2 * NN_THREADS) return 2;
+    if (GENPC_NN_QT_MAX >= 4 && nq >= 4 * NN_THREADS) return 4;
+    if (GENPC_NN_QT_MAX >= 2 && nq >= 2 * NN_THREADS) return 2;
     return 1;
 }
 

@@ -153,7 +153,7 @@ __device__ __noinline__ void finalize_scan(const RegArgs &a, int scan, const Sim
 }
 
 template <int QT>
-__global__ void __launch_bounds__(NN_THREADS, 2) register_step_kernel(const RegArgs a) {
+__global__ void __launch_bounds__(NN_THREADS, NN_MINBLOCKS) register_step_kernel(const RegArgs a) {
     __shared__ __align__(16) float s[3][NN_SPAN];
     __shared__ Similarity T;
     __shared__ int is_last;

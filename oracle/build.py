@@ -82,6 +82,13 @@ def install_ref_package(force=False):
     tmp = tempfile.mkdtemp(prefix="genpc_ref_")
     src = os.path.join(tmp, "reference")
     shutil.copytree(REF, src, ignore=shutil.ignore_patterns("data", "*.ply", ".git"))
+    # packaging only: the reference's setup.py uses find_packages(), which skips loss_functions/Chamfer3D and
+    # loss_functions/emd because they have no __init__.py (the reference imports them as namespace packages from its
+    # source tree).  Empty __init__.py files in the TEMP COPY make the wheel complete; no reference file is edited.
+    for sub in ("Chamfer3D", "emd"):
+        init = os.path.join(src, "loss_functions", sub, "__init__.py")
+        if not os.path.exists(init):
+            open(init, "w").close()
     os.makedirs(target, exist_ok=True)
     subprocess.check_call([sys.executable, "-m", "pip", "install", "--quiet", "--no-index", "--no-build-isolation",
                            "--no-deps", "--upgrade", "--find-links", "/opt/wheelhouse", "--target", target, src])

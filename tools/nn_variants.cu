@@ -1,0 +1,46 @@
+// nn_variants.cu -- times genpc_chamfer_forward for one compile-time variant of the NN work item
+// (-DGENPC_NN_SPAN=.. -DGENPC_NN_CHUNK=.. -DGENPC_NN_MINBLOCKS=.. -DGENPC_NN_QT_MAX=..) and prints a checksum.
+#include "../genpc_b200/csrc/chamfer.cu"
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+static void run(int B, int N, int M, const char *tag) {
+    size_t n1 = (size_t)B * N, n2 = (size_t)B * M;
+    std::vector<float> h1(n1 * 3), h2(n2 * 3);
+    unsigned s = 12345u;
+    auto rnd = [&]() { s = s * 1664525u + 1013904223u; return (float)(s >> 8) * (1.0f / 16777216.0f); };
+    for (auto &v : h1) v = rnd();
+    for (auto &v : h2) v = rnd();
+    float *x1, *x2, *d1, *d2; int *i1, *i2; void *ws; char *flush;
+    cudaMalloc(&x1, n1 * 12); cudaMalloc(&x2, n2 * 12); cudaMalloc(&d1, n1 * 4); cudaMalloc(&d2, n2 * 4);
+    cudaMalloc(&i1, n1 * 4); cudaMalloc(&i2, n2 * 4);
+    size_t wsb = genpc_chamfer_workspace_bytes(B, N, M); cudaMalloc(&ws, wsb); cudaMalloc(&flush, 256 << 20);
+    cudaMemcpy(x1, h1.data(), n1 * 12, cudaMemcpyHostToDevice); cudaMemcpy(x2, h2.data(), n2 * 12, cudaMemcpyHostToDevice);
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float best = 1e30f, sum = 0; int reps = 12;
+    for (int r = 0; r < reps + 3; ++r) {
+        cudaMemsetAsync(flush, r, 256 << 20);
+        cudaEventRecord(e0);
+        int rc = genpc_chamfer_forward(x1, x2, d1, d2, i1, i2, B, N, M, ws, wsb, 0);
+        cudaEventRecord(e1); cudaEventSynchronize(e1);
+        if (rc) { printf("rc=%d\n", rc); exit(1); }
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        if (r >= 3) { best = ms < best ? ms : best; sum += ms; }
+    }
+    std::vector<int> hi1(n1), hi2(n2); std::vector<float> hd1(n1);
+    cudaMemcpy(hi1.data(), i1, n1 * 4, cudaMemcpyDeviceToHost); cudaMemcpy(hi2.data(), i2, n2 * 4, cudaMemcpyDeviceToHost);
+    cudaMemcpy(hd1.data(), d1, n1 * 4, cudaMemcpyDeviceToHost);
+    unsigned long long ck = 0; for (size_t i = 0; i < n1; ++i) ck = ck * 1000003ull + (unsigned)hi1[i] + *(unsigned *)&hd1[i];
+    for (size_t i = 0; i < n2; ++i) ck = ck * 1000003ull + (unsigned)hi2[i];
+    double pairs = 2.0 * B * N * M;
+    printf("{\"variant\": \"span%d_chunk%d_minb%d_qt%d\", \"shape\": \"%s\", \"best_ms\": %.4f, \"avg_ms\": %.4f, \"pairs_per_s\": %.4g, \"tflops\": %.2f, \"checksum\": \"%llx\"}\n",
+           GENPC_NN_SPAN, GENPC_NN_CHUNK, GENPC_NN_MINBLOCKS, GENPC_NN_QT_MAX, tag, best, sum / reps, pairs / (best * 1e-3), pairs * 8 / (best * 1e-3) / 1e12, ck);
+    cudaFree(x1); cudaFree(x2); cudaFree(d1); cudaFree(d2); cudaFree(i1); cudaFree(i2); cudaFree(ws); cudaFree(flush);
+}
+int main() {
+    run(32, 2048, 16384, "C2_B32_2048x16384");
+    run(1, 16384, 16384, "B1_16384x16384");
+    run(8, 16384, 16384, "B8_16384x16384");
+    return 0;
+}
