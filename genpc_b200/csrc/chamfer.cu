@@ -12,7 +12,15 @@
 //   * per-item results are merged across target splits with one packed 64-bit atomicMin per query
 //     ((dist_bits << 32) | idx: unsigned order == dist ascending, then idx ascending == the reference's
 //     lowest-index tie rule), then unpacked to dist/idx.
+#include <cstdlib>
+#include <cstring>
+
 #include "nn_core.cuh"
+#include "nn_sym.cuh"
+
+#ifndef GENPC_DEFAULT_SYM
+#define GENPC_DEFAULT_SYM true
+#endif
 
 namespace genpc {
 
@@ -119,6 +127,47 @@ static cudaError_t launch_scan(const NNParams &p, cudaStream_t stream) {
     return cudaGetLastError();
 }
 
+// Symmetric path: rows = the larger cloud (registers), cols = the smaller one (shared-memory sweep).
+static int chamfer_forward_sym(const float *xyz1, const float *xyz2, float *dist1, float *dist2, int *idx1, int *idx2,
+                               int B, int N, int M, unsigned long long *packed, cudaStream_t stream) {
+    const bool swap = M > N;
+    SymParams p;
+    p.rows = swap ? xyz2 : xyz1, p.cols = swap ? xyz1 : xyz2;
+    p.nr = swap ? M : N, p.nc = swap ? N : M;
+    float *dist_r = swap ? dist2 : dist1, *dist_c = swap ? dist1 : dist2;
+    int *idx_r = swap ? idx2 : idx1, *idx_c = swap ? idx1 : idx2;
+    p.prow = packed, p.pcol = packed + (size_t)B * p.nr;
+    // measured on B200 (profiles/r01c_sym_variants.txt): QT=4 at 3 CTAs/SM is within 1 % of QT=8 at 2 CTAs/SM on
+    // large clouds and clearly better when the grid is small
+    int QT = p.nr >= 1024 ? 4 : 2;
+    const char *fq = getenv("GENPC_SYM_QT");  // experiments only
+    if (fq != nullptr && (atoi(fq) == 8 || atoi(fq) == 4 || atoi(fq) == 2)) QT = atoi(fq);
+    p.rtiles = (p.nr + SYM_THREADS * QT - 1) / (SYM_THREADS * QT);
+    // column span: the largest that still gives >= 2 waves of work items (3 CTAs x 148 SMs), at least 256 columns
+    int span = SYM_SPAN_MAX;
+    const long long want = 2LL * 3 * GENPC_NUM_SMS;
+    while (span > 256 && (long long)B * p.rtiles * ((p.nc + span - 1) / span) < want) span >>= 1;
+    const char *fs = getenv("GENPC_SYM_SPAN");
+    if (fs != nullptr && atoi(fs) >= 32 && atoi(fs) <= SYM_SPAN_MAX && atoi(fs) % 32 == 0) span = atoi(fs);
+    p.span = span;
+    p.cspans = (p.nc + span - 1) / span;
+    const long long items = (long long)B * p.rtiles * p.cspans;
+    if (items > 0x7fffffffLL) return GENPC_ERR_RANGE;
+    switch (QT) {
+        case 8: nn_sym_kernel<8><<<(unsigned)items, SYM_THREADS, 0, stream>>>(p); break;
+        case 4: nn_sym_kernel<4><<<(unsigned)items, SYM_THREADS, 0, stream>>>(p); break;
+        default: nn_sym_kernel<2><<<(unsigned)items, SYM_THREADS, 0, stream>>>(p); break;
+    }
+    GENPC_CHECK_LAUNCH();
+    const size_t nrw = (size_t)B * p.nr, ncw = (size_t)B * p.nc;
+    nn_unpack_kernel<<<(unsigned)((nrw + 255) / 256), 256, 0, stream>>>(p.prow, dist_r, idx_r, nrw, nullptr, nullptr, 0);
+    GENPC_CHECK_LAUNCH();
+    nn_sym_fixup_kernel<<<(unsigned)((ncw * 32 + 255) / 256), 256, 0, stream>>>(p.rows, p.cols, p.pcol, B, p.nr, p.nc,
+                                                                                32 * QT, dist_c, idx_c);
+    GENPC_CHECK_LAUNCH();
+    return GENPC_OK;
+}
+
 }  // namespace genpc
 
 using namespace genpc;
@@ -152,6 +201,11 @@ extern "C" int genpc_chamfer_forward(const float *xyz1, const float *xyz2, float
     unsigned long long *packed = (unsigned long long *)workspace;
     cudaError_t e = cudaMemsetAsync(packed, 0xff, (n1 + n2) * 8, stream);
     if (e != cudaSuccess) return (int)e;
+
+    // "sym": one evaluation of every distance feeds both directions (nn_sym.cuh); "scan": one scan per direction
+    const char *mode = getenv("GENPC_CHAMFER_MODE");
+    const bool want_sym = (mode == nullptr) ? GENPC_DEFAULT_SYM : (strcmp(mode, "sym") == 0);
+    if (want_sym && (N > M ? N : M) >= 512) return chamfer_forward_sym(xyz1, xyz2, dist1, dist2, idx1, idx2, B, N, M, packed, stream);
 
     const int QT = nn_pick_qt(N < M ? N : M);
     NNParams p;

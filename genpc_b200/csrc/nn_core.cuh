@@ -20,7 +20,7 @@ namespace genpc {
 #define GENPC_NN_SPAN 1024
 #endif
 #ifndef GENPC_NN_CHUNK
-#define GENPC_NN_CHUNK 16
+#define GENPC_NN_CHUNK 8
 #endif
 #ifndef GENPC_NN_MINBLOCKS
 #define GENPC_NN_MINBLOCKS 2

@@ -1,0 +1,205 @@
+// nn_sym.cuh -- symmetric Chamfer scan: every distance is evaluated ONCE and feeds both directions.
+//
+// d(j,k) = fma(dz,dz,fma(dx,dx,dy*dy)) is bit-identical whichever cloud plays "query" (the differences only
+// change sign and every product is a square), so the N x M matrix the reference evaluates twice
+// (chamfer3D.cu:142-143) is evaluated once here: the FMA pipe -- the unit that bounds this kernel (2 packed
+// instructions/clk/SM, 3 per point pair) -- does half the work per directed pair.
+//
+//   rows  = the cloud held in registers (QT points per thread, a warp owns 32*QT CONSECUTIVE rows),
+//   cols  = the cloud swept through shared memory in spans (SoA, NaN padded), 32 columns per block.
+//   row side: running minimum by FMNMX3, winning 8-column chunk id tracked, exact lowest index recovered by a
+//             re-scan of that chunk, merged across column spans by a packed 64-bit atomicMin (as nn_core.cuh);
+//   col side: per 32-column block every lane folds its QT rows into 32 accumulators (FMNMX3 over row pairs),
+//             a 31-step butterfly (SHFL + FMNMX) leaves lane l with the warp-wide minimum of column l, and ONE
+//             coalesced 64-bit atomicMin per lane publishes (dist_bits << 32 | row_block_id).  The exact lowest
+//             row index is recovered afterwards by nn_sym_fixup_kernel, which re-scans only the winning
+//             32*QT-row block of each column (lowest block wins ties, first match inside it => lowest index).
+#pragma once
+#include "common.cuh"
+
+namespace genpc {
+
+constexpr int SYM_THREADS = 256;
+constexpr int SYM_SPAN_MAX = 1024;  // columns staged per item (<= 12 KB shared memory)
+constexpr int SYM_CHUNK = 8;        // row-side index-recovery granularity (columns)
+
+struct SymParams {
+    const float *rows;             // [B][nr][3]
+    const float *cols;             // [B][nc][3]
+    unsigned long long *prow;      // [B][nr]  (dist, col index)
+    unsigned long long *pcol;      // [B][nc]  (dist, row block id)
+    int nr, nc, rtiles, cspans, span;
+};
+
+// v[e] (e = 0..31) per lane -> returns min over all lanes of v[lane]   (element index == lane id)
+__device__ __forceinline__ float butterfly_min32(float (&v)[32], int lane) {
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        const bool up = (lane & o) != 0;
+#pragma unroll
+        for (int i = 0; i < o; ++i) {
+            const float keep = up ? v[i + o] : v[i];
+            const float send = up ? v[i] : v[i + o];
+            v[i] = fminf(keep, __shfl_xor_sync(0xffffffffu, send, o));
+        }
+    }
+    return v[0];
+}
+
+#ifndef GENPC_SYM_MINB8
+#define GENPC_SYM_MINB8 2
+#endif
+#ifndef GENPC_SYM_MINB4
+#define GENPC_SYM_MINB4 3
+#endif
+template <int QT>
+__global__ void __launch_bounds__(SYM_THREADS, (QT >= 8 ? GENPC_SYM_MINB8 : GENPC_SYM_MINB4)) nn_sym_kernel(const SymParams p) {
+    static_assert(QT % 2 == 0, "rows are folded in pairs");
+    __shared__ __align__(16) float s[3][SYM_SPAN_MAX];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int item = blockIdx.x;
+    const int cs = item % p.cspans;
+    item /= p.cspans;
+    const int rt = item % p.rtiles;
+    const int b = item / p.rtiles;
+    const int c0 = cs * p.span;
+    const int cnt = min(p.span, p.nc - c0);
+    const int cnt32 = (cnt + 31) & ~31;
+    const float qnan = __int_as_float(0x7fc00000);
+    // ---- stage the column span ----
+    {
+        const float *cp = p.cols + ((size_t)b * p.nc + c0) * 3;
+        for (int k = tid; k < cnt32; k += SYM_THREADS) {
+            float x = qnan, y = qnan, z = qnan;
+            if (k < cnt) x = __ldg(cp + k * 3), y = __ldg(cp + k * 3 + 1), z = __ldg(cp + k * 3 + 2);
+            s[0][k] = x, s[1][k] = y, s[2][k] = z;
+        }
+    }
+    // ---- rows into registers (negated; NaN for out-of-range rows: they never win a min on either side) ----
+    float2 nqx[QT], nqy[QT], nqz[QT];
+    float best[QT];
+    int bchunk[QT];
+    const int rblock = rt * (SYM_THREADS / 32) + warp;          // global id of this warp's 32*QT-row block
+    const int jbase = rblock * (32 * QT) + lane;
+    const float *rp = p.rows + (size_t)b * p.nr * 3;
+#pragma unroll
+    for (int qi = 0; qi < QT; ++qi) {
+        const int j = jbase + qi * 32;
+        float x = qnan, y = qnan, z = qnan;
+        if (j < p.nr) x = __ldg(rp + (size_t)j * 3), y = __ldg(rp + (size_t)j * 3 + 1), z = __ldg(rp + (size_t)j * 3 + 2);
+        nqx[qi] = make_float2(-x, -x);
+        nqy[qi] = make_float2(-y, -y);
+        nqz[qi] = make_float2(-z, -z);
+        best[qi] = __int_as_float(0x7f800000);
+        bchunk[qi] = 0;
+    }
+    __syncthreads();
+
+    const float4 *sx4 = reinterpret_cast<const float4 *>(s[0]);
+    const float4 *sy4 = reinterpret_cast<const float4 *>(s[1]);
+    const float4 *sz4 = reinterpret_cast<const float4 *>(s[2]);
+    unsigned long long *pcol = p.pcol + (size_t)b * p.nc + c0;
+    const float inf = __int_as_float(0x7f800000);
+    for (int blk = 0; blk < cnt32 / 32; ++blk) {
+        float cacc[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) cacc[i] = inf;
+#pragma unroll
+        for (int sub = 0; sub < 32 / SYM_CHUNK; ++sub) {
+            float cm[QT];
+#pragma unroll
+            for (int qi = 0; qi < QT; ++qi) cm[qi] = inf;
+#pragma unroll
+            for (int kk = 0; kk < SYM_CHUNK / 4; ++kk) {
+                const int g = blk * 8 + sub * (SYM_CHUNK / 4) + kk;  // float4 group index
+                const float4 X = sx4[g], Y = sy4[g], Z = sz4[g];
+                const int t = sub * SYM_CHUNK + kk * 4;               // column offset inside the block
+#pragma unroll
+                for (int qi = 0; qi < QT; qi += 2) {
+                    const float2 a0 = sqdist_ref_x2(nqx[qi], nqy[qi], nqz[qi], make_float2(X.x, X.y),
+                                                    make_float2(Y.x, Y.y), make_float2(Z.x, Z.y));
+                    const float2 e0 = sqdist_ref_x2(nqx[qi], nqy[qi], nqz[qi], make_float2(X.z, X.w),
+                                                    make_float2(Y.z, Y.w), make_float2(Z.z, Z.w));
+                    const float2 a1 = sqdist_ref_x2(nqx[qi + 1], nqy[qi + 1], nqz[qi + 1], make_float2(X.x, X.y),
+                                                    make_float2(Y.x, Y.y), make_float2(Z.x, Z.y));
+                    const float2 e1 = sqdist_ref_x2(nqx[qi + 1], nqy[qi + 1], nqz[qi + 1], make_float2(X.z, X.w),
+                                                    make_float2(Y.z, Y.w), make_float2(Z.z, Z.w));
+                    cm[qi] = fmin3(cm[qi], a0.x, a0.y);
+                    cm[qi] = fmin3(cm[qi], e0.x, e0.y);
+                    cm[qi + 1] = fmin3(cm[qi + 1], a1.x, a1.y);
+                    cm[qi + 1] = fmin3(cm[qi + 1], e1.x, e1.y);
+                    cacc[t + 0] = fmin3(cacc[t + 0], a0.x, a1.x);
+                    cacc[t + 1] = fmin3(cacc[t + 1], a0.y, a1.y);
+                    cacc[t + 2] = fmin3(cacc[t + 2], e0.x, e1.x);
+                    cacc[t + 3] = fmin3(cacc[t + 3], e0.y, e1.y);
+                }
+            }
+#pragma unroll
+            for (int qi = 0; qi < QT; ++qi) {
+                if (cm[qi] < best[qi]) {  // strict: the earliest chunk keeps ties
+                    best[qi] = cm[qi];
+                    bchunk[qi] = blk * (32 / SYM_CHUNK) + sub;
+                }
+            }
+        }
+        // ---- column side: warp-wide minimum of column (blk*32 + lane), published with the row-block id ----
+        const float cmin = butterfly_min32(cacc, lane);
+        const int col = blk * 32 + lane;
+        if (col < cnt && cmin < inf) atomicMin(pcol + col, pack_dist_idx(cmin, rblock));
+    }
+
+    // ---- row side: exact lowest column index inside the winning chunk, merged across column spans ----
+    unsigned long long *prow = p.prow + (size_t)b * p.nr;
+#pragma unroll
+    for (int qi = 0; qi < QT; ++qi) {
+        const int j = jbase + qi * 32;
+        if (j >= p.nr || !(best[qi] < inf)) continue;
+        const float qx = -nqx[qi].x, qy = -nqy[qi].x, qz = -nqz[qi].x;
+        const int cb = bchunk[qi] * SYM_CHUNK;
+        int kbest = 0;
+#pragma unroll
+        for (int k = SYM_CHUNK - 1; k >= 0; --k) {
+            const float dd = sqdist_ref(qx, qy, qz, s[0][cb + k], s[1][cb + k], s[2][cb + k]);
+            if (dd == best[qi]) kbest = k;
+        }
+        atomicMin(prow + j, pack_dist_idx(best[qi], c0 + cb + kbest));
+    }
+}
+
+// Column fix-up: one warp per column; re-scan the winning row block (32*QT consecutive rows) for the first row
+// whose distance equals the published minimum; writes the final dist / idx of the column cloud.
+__global__ void __launch_bounds__(256) nn_sym_fixup_kernel(const float *__restrict__ rows, const float *__restrict__ cols,
+                                                           const unsigned long long *__restrict__ pcol, int B, int nr,
+                                                           int nc, int rows_per_block, float *__restrict__ dist_out,
+                                                           int *__restrict__ idx_out) {
+    const size_t w = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= (size_t)B * nc) return;
+    const size_t b = w / nc;
+    const unsigned long long word = __ldg(pcol + w);
+    const float d = __uint_as_float((unsigned)(word >> 32));
+    const int blk = (int)(unsigned)(word & 0xffffffffu);
+    const float cx = __ldg(cols + w * 3), cy = __ldg(cols + w * 3 + 1), cz = __ldg(cols + w * 3 + 2);
+    const float *rp = rows + b * (size_t)nr * 3;
+    int found = 0;
+    for (int r0 = blk * rows_per_block; r0 < (blk + 1) * rows_per_block; r0 += 32) {
+        const int j = r0 + lane;
+        bool hit = false;
+        if (j < nr) {
+            const float dd = sqdist_ref(cx, cy, cz, __ldg(rp + (size_t)j * 3), __ldg(rp + (size_t)j * 3 + 1),
+                                        __ldg(rp + (size_t)j * 3 + 2));
+            hit = (dd == d);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (m) {
+            found = r0 + __ffs(m) - 1;
+            break;
+        }
+    }
+    if (lane == 0) {
+        dist_out[w] = d;
+        idx_out[w] = found;
+    }
+}
+
+}  // namespace genpc

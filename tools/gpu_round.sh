@@ -21,7 +21,7 @@ ref)
 ncu)
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
       python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:"${NCU_KERNEL:-nn_scan}" -s 3 -c 2 -f -o gpurun_out/prof_nn \
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:"${NCU_KERNEL:-nn_sym_kernel}" -s 3 -c 2 -f -o gpurun_out/prof_nn \
       python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1 ;;
 smoke)
   timeout 600 python __graft_entry__.py --smoke > gpurun_out/smoke.log 2>&1 ;;

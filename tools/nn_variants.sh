@@ -2,7 +2,7 @@
 # build (here, no GPU needed) or run (on the GPU box) the NN work-item variants
 set -e
 cd "$(dirname "$0")/.."
-VARIANTS="1024:16:2:4 1024:16:3:4 1024:16:3:2 2048:16:2:4 1024:32:2:4 2048:32:3:2 512:16:2:4 1024:8:2:4"
+VARIANTS="2048:8:2:4 2048:8:3:2 2048:4:2:4 4096:8:2:4 1024:4:2:4 2048:8:3:4 4096:8:3:2 4096:4:2:4"
 mkdir -p tools/variants gpurun_out
 if [ "$1" = "build" ]; then
   for v in $VARIANTS; do IFS=: read sp ch mb qt <<< "$v"
