@@ -15,7 +15,7 @@
 //             row index is recovered afterwards by nn_sym_fixup_kernel, which re-scans only the winning
 //             32*QT-row block of each column (lowest block wins ties, first match inside it => lowest index).
 #pragma once
-#include "common.cuh"
+#include "nn_core.cuh"
 
 namespace genpc {
 
@@ -52,26 +52,30 @@ __device__ __forceinline__ float butterfly_min32(float (&v)[32], int lane) {
 #ifndef GENPC_SYM_MINB4
 #define GENPC_SYM_MINB4 3
 #endif
+#define GENPC_SYM_MINB(QT) ((QT) >= 8 ? GENPC_SYM_MINB8 : GENPC_SYM_MINB4)
+
+// One work item: row tile `rt` (SYM_THREADS*QT rows) x column span [c0, c0+span) of ONE cloud pair.
+// rows/cols/prow/pcol point at the first element of the pair's clouds / packed words.  colT: optional similarity
+// applied to the columns while they are staged (registration: the moving cloud), nullptr = identity.
 template <int QT>
-__global__ void __launch_bounds__(SYM_THREADS, (QT >= 8 ? GENPC_SYM_MINB8 : GENPC_SYM_MINB4)) nn_sym_kernel(const SymParams p) {
+__device__ __forceinline__ void nn_sym_item(float (*s)[SYM_SPAN_MAX], const float *__restrict__ rows, int nr, int rt,
+                                            const float *__restrict__ cols, int nc, int c0, int span,
+                                            const Similarity *colT, unsigned long long *__restrict__ prow_,
+                                            unsigned long long *__restrict__ pcol_) {
     static_assert(QT % 2 == 0, "rows are folded in pairs");
-    __shared__ __align__(16) float s[3][SYM_SPAN_MAX];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    int item = blockIdx.x;
-    const int cs = item % p.cspans;
-    item /= p.cspans;
-    const int rt = item % p.rtiles;
-    const int b = item / p.rtiles;
-    const int c0 = cs * p.span;
-    const int cnt = min(p.span, p.nc - c0);
+    const int cnt = min(span, nc - c0);
     const int cnt32 = (cnt + 31) & ~31;
     const float qnan = __int_as_float(0x7fc00000);
     // ---- stage the column span ----
     {
-        const float *cp = p.cols + ((size_t)b * p.nc + c0) * 3;
+        const float *cp = cols + (size_t)c0 * 3;
         for (int k = tid; k < cnt32; k += SYM_THREADS) {
             float x = qnan, y = qnan, z = qnan;
-            if (k < cnt) x = __ldg(cp + k * 3), y = __ldg(cp + k * 3 + 1), z = __ldg(cp + k * 3 + 2);
+            if (k < cnt) {
+                x = __ldg(cp + k * 3), y = __ldg(cp + k * 3 + 1), z = __ldg(cp + k * 3 + 2);
+                if (colT != nullptr) apply_similarity(*colT, x, y, z);
+            }
             s[0][k] = x, s[1][k] = y, s[2][k] = z;
         }
     }
@@ -81,12 +85,12 @@ __global__ void __launch_bounds__(SYM_THREADS, (QT >= 8 ? GENPC_SYM_MINB8 : GENP
     int bchunk[QT];
     const int rblock = rt * (SYM_THREADS / 32) + warp;          // global id of this warp's 32*QT-row block
     const int jbase = rblock * (32 * QT) + lane;
-    const float *rp = p.rows + (size_t)b * p.nr * 3;
+    const float *rp = rows;
 #pragma unroll
     for (int qi = 0; qi < QT; ++qi) {
         const int j = jbase + qi * 32;
         float x = qnan, y = qnan, z = qnan;
-        if (j < p.nr) x = __ldg(rp + (size_t)j * 3), y = __ldg(rp + (size_t)j * 3 + 1), z = __ldg(rp + (size_t)j * 3 + 2);
+        if (j < nr) x = __ldg(rp + (size_t)j * 3), y = __ldg(rp + (size_t)j * 3 + 1), z = __ldg(rp + (size_t)j * 3 + 2);
         nqx[qi] = make_float2(-x, -x);
         nqy[qi] = make_float2(-y, -y);
         nqz[qi] = make_float2(-z, -z);
@@ -98,7 +102,7 @@ __global__ void __launch_bounds__(SYM_THREADS, (QT >= 8 ? GENPC_SYM_MINB8 : GENP
     const float4 *sx4 = reinterpret_cast<const float4 *>(s[0]);
     const float4 *sy4 = reinterpret_cast<const float4 *>(s[1]);
     const float4 *sz4 = reinterpret_cast<const float4 *>(s[2]);
-    unsigned long long *pcol = p.pcol + (size_t)b * p.nc + c0;
+    unsigned long long *pcol = pcol_ + c0;
     const float inf = __int_as_float(0x7f800000);
     for (int blk = 0; blk < cnt32 / 32; ++blk) {
         float cacc[32];
@@ -149,11 +153,11 @@ __global__ void __launch_bounds__(SYM_THREADS, (QT >= 8 ? GENPC_SYM_MINB8 : GENP
     }
 
     // ---- row side: exact lowest column index inside the winning chunk, merged across column spans ----
-    unsigned long long *prow = p.prow + (size_t)b * p.nr;
+    unsigned long long *prow = prow_;
 #pragma unroll
     for (int qi = 0; qi < QT; ++qi) {
         const int j = jbase + qi * 32;
-        if (j >= p.nr || !(best[qi] < inf)) continue;
+        if (j >= nr || !(best[qi] < inf)) continue;
         const float qx = -nqx[qi].x, qy = -nqy[qi].x, qz = -nqz[qi].x;
         const int cb = bchunk[qi] * SYM_CHUNK;
         int kbest = 0;
@@ -166,21 +170,22 @@ __global__ void __launch_bounds__(SYM_THREADS, (QT >= 8 ? GENPC_SYM_MINB8 : GENP
     }
 }
 
-// Column fix-up: one warp per column; re-scan the winning row block (32*QT consecutive rows) for the first row
-// whose distance equals the published minimum; writes the final dist / idx of the column cloud.
-__global__ void __launch_bounds__(256) nn_sym_fixup_kernel(const float *__restrict__ rows, const float *__restrict__ cols,
-                                                           const unsigned long long *__restrict__ pcol, int B, int nr,
-                                                           int nc, int rows_per_block, float *__restrict__ dist_out,
-                                                           int *__restrict__ idx_out) {
-    const size_t w = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (w >= (size_t)B * nc) return;
-    const size_t b = w / nc;
-    const unsigned long long word = __ldg(pcol + w);
-    const float d = __uint_as_float((unsigned)(word >> 32));
-    const int blk = (int)(unsigned)(word & 0xffffffffu);
-    const float cx = __ldg(cols + w * 3), cy = __ldg(cols + w * 3 + 1), cz = __ldg(cols + w * 3 + 2);
-    const float *rp = rows + b * (size_t)nr * 3;
+template <int QT>
+__global__ void __launch_bounds__(SYM_THREADS, GENPC_SYM_MINB(QT)) nn_sym_kernel(const SymParams p) {
+    __shared__ __align__(16) float s[3][SYM_SPAN_MAX];
+    int item = blockIdx.x;
+    const int cs = item % p.cspans;
+    item /= p.cspans;
+    const int rt = item % p.rtiles;
+    const int b = item / p.rtiles;
+    nn_sym_item<QT>(s, p.rows + (size_t)b * p.nr * 3, p.nr, rt, p.cols + (size_t)b * p.nc * 3, p.nc, cs * p.span, p.span,
+                    nullptr, p.prow + (size_t)b * p.nr, p.pcol + (size_t)b * p.nc);
+}
+
+// Exact lowest row index of one column from its published (dist, row block) word: the calling WARP re-scans the
+// winning block (rows_per_block consecutive rows, 32 per step) for the first row whose distance equals dist.
+__device__ __forceinline__ int sym_fix_column(const float *__restrict__ rp, int nr, int rows_per_block, float cx, float cy,
+                                              float cz, float d, int blk, int lane) {
     int found = 0;
     for (int r0 = blk * rows_per_block; r0 < (blk + 1) * rows_per_block; r0 += 32) {
         const int j = r0 + lane;
@@ -196,6 +201,23 @@ __global__ void __launch_bounds__(256) nn_sym_fixup_kernel(const float *__restri
             break;
         }
     }
+    return found;
+}
+
+// Column fix-up: one warp per column; writes the final dist / idx of the column cloud.
+__global__ void __launch_bounds__(256) nn_sym_fixup_kernel(const float *__restrict__ rows, const float *__restrict__ cols,
+                                                           const unsigned long long *__restrict__ pcol, int B, int nr,
+                                                           int nc, int rows_per_block, float *__restrict__ dist_out,
+                                                           int *__restrict__ idx_out) {
+    const size_t w = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= (size_t)B * nc) return;
+    const size_t b = w / nc;
+    const unsigned long long word = __ldg(pcol + w);
+    const float d = __uint_as_float((unsigned)(word >> 32));
+    const int blk = (int)(unsigned)(word & 0xffffffffu);
+    const float cx = __ldg(cols + w * 3), cy = __ldg(cols + w * 3 + 1), cz = __ldg(cols + w * 3 + 2);
+    const int found = sym_fix_column(rows + b * (size_t)nr * 3, nr, rows_per_block, cx, cy, cz, d, blk, lane);
     if (lane == 0) {
         dist_out[w] = d;
         idx_out[w] = found;
