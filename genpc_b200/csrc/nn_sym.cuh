@@ -205,7 +205,7 @@ __device__ __forceinline__ int sym_fix_column(const float *__restrict__ rp, int 
 }
 
 // Column fix-up: one warp per column; writes the final dist / idx of the column cloud.
-__global__ void __launch_bounds__(256) nn_sym_fixup_kernel(const float *__restrict__ rows, const float *__restrict__ cols,
+static __global__ void __launch_bounds__(256) nn_sym_fixup_kernel(const float *__restrict__ rows, const float *__restrict__ cols,
                                                            const unsigned long long *__restrict__ pcol, int B, int nr,
                                                            int nc, int rows_per_block, float *__restrict__ dist_out,
                                                            int *__restrict__ idx_out) {
