@@ -10,6 +10,11 @@
 // point, two REDUX warp reductions (max of the value bits, then min index among the lanes that hold it),
 // ONE __syncthreads (double-buffered 32-entry exchange), and the same two REDUX again.
 // Clouds larger than 1024*PPT_MAX points fall back to a global-memory loop with the same arithmetic.
+#include <cooperative_groups.h>
+
+#include <cstdlib>
+#include <cstring>
+
 #include "common.cuh"
 
 namespace genpc {
@@ -143,6 +148,130 @@ __global__ void __launch_bounds__(FPS_THREADS, 1) fps_gmem_kernel(const float *_
     }
 }
 
+// ---- thread-block-cluster version: the cloud lives in the REGISTERS of CS CTAs (CS SMs) ----------------------
+// Large single clouds are bound by one SM's L1/LSU when a lone CTA re-reads 12 B/point every pick (16384 points:
+// 3.6 ms for 2048 picks).  A cluster of CS CTAs keeps PPT <= 4 points per thread entirely in registers; per pick
+// each CTA finds its own candidate (REDUX + one __syncthreads), the owning thread posts (value, index, x, y, z) into
+// slot [parity][rank] of EVERY CTA of the cluster through distributed shared memory, one cluster barrier, and every
+// thread reads the CS candidates locally -- the winner's coordinates travel with it, so the loop has no global
+// loads at all.  Same arithmetic and tie rule as fps_reg_kernel (bit-identical results).
+namespace cg = cooperative_groups;
+
+struct FpsCand {
+    unsigned val;  // running distance bits + 1 (0 = padding)
+    int idx;
+    float x, y, z;
+    int pad[3];
+};
+
+template <int PPT, int CS>
+__global__ void __launch_bounds__(FPS_THREADS, 1) fps_cluster_kernel(const float *__restrict__ xyz, int N, int K, int start,
+                                                                      int *__restrict__ idx_out, float *__restrict__ seq_out) {
+    __shared__ unsigned sval[2][FPS_WARPS];
+    __shared__ int sidx[2][FPS_WARPS];
+    __shared__ __align__(16) FpsCand cand[2][CS];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int b = blockIdx.x / CS, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float *p = xyz + (size_t)b * N * 3;
+    // point i of the cloud lives in CTA (i / 1024) % CS ... interleaved so that every CTA holds a similar share:
+    // global index of (rank, k, tid) = (k * CS + rank) * 1024 + tid
+    float px[PPT], py[PPT], pz[PPT], run[PPT];
+#pragma unroll
+    for (int k = 0; k < PPT; ++k) {
+        const int i = (k * CS + rank) * FPS_THREADS + tid;
+        px[k] = py[k] = pz[k] = 0.f;
+        if (i < N) {
+            px[k] = __ldg(p + (size_t)i * 3), py[k] = __ldg(p + (size_t)i * 3 + 1), pz[k] = __ldg(p + (size_t)i * 3 + 2);
+            run[k] = __int_as_float(0x7f800000);
+        } else {
+            run[k] = -1.f;
+        }
+    }
+    float lx = __ldg(p + (size_t)start * 3), ly = __ldg(p + (size_t)start * 3 + 1), lz = __ldg(p + (size_t)start * 3 + 2);
+    int cur = start;
+    cluster.sync();
+    for (int s = 0; s < K; ++s) {
+        if (rank == 0 && tid == 0) idx_out[(size_t)b * K + s] = cur;
+        float best = -2.f;
+        int best_i = 0x7fffffff, best_k = 0;
+#pragma unroll
+        for (int k = 0; k < PPT; ++k) {
+            const float dx = __fsub_rn(px[k], lx), dy = __fsub_rn(py[k], ly), dz = __fsub_rn(pz[k], lz);
+            const float d = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+            const float r = (run[k] < d) ? run[k] : d;
+            run[k] = r;
+            if (r > best) {  // k ascending == index ascending inside a thread
+                best = r;
+                best_i = (k * CS + rank) * FPS_THREADS + tid;
+                best_k = k;
+            }
+        }
+        const int par = s & 1;
+        int winner;
+        fps_block_argmax(best, best_i, sval, sidx, par, lane, warp, winner);
+        if (winner == best_i && best_i != 0x7fffffff) {  // exactly one thread of the CTA owns the candidate
+            unsigned m = 0;
+#pragma unroll
+            for (int w = 0; w < FPS_WARPS; ++w) m = max(m, sval[par][w]);
+            FpsCand c;
+            c.val = m, c.idx = best_i;
+            c.x = px[0], c.y = py[0], c.z = pz[0];
+#pragma unroll
+            for (int k = 1; k < PPT; ++k)
+                if (best_k == k) c.x = px[k], c.y = py[k], c.z = pz[k];
+            c.pad[0] = c.pad[1] = c.pad[2] = 0;
+#pragma unroll
+            for (int r = 0; r < CS; ++r) {
+                FpsCand *dst = cluster.map_shared_rank(&cand[par][rank], r);
+                *reinterpret_cast<int4 *>(dst) = *reinterpret_cast<int4 *>(&c);
+                *(reinterpret_cast<int4 *>(dst) + 1) = *(reinterpret_cast<int4 *>(&c) + 1);
+            }
+        } else if (tid == 0 && winner == 0x7fffffff) {   // CTA holds only padding: post an empty candidate
+            FpsCand c;
+            c.val = 0, c.idx = 0x7fffffff, c.x = c.y = c.z = 0.f, c.pad[0] = c.pad[1] = c.pad[2] = 0;
+#pragma unroll
+            for (int r = 0; r < CS; ++r) {
+                FpsCand *dst = cluster.map_shared_rank(&cand[par][rank], r);
+                *reinterpret_cast<int4 *>(dst) = *reinterpret_cast<int4 *>(&c);
+                *(reinterpret_cast<int4 *>(dst) + 1) = *(reinterpret_cast<int4 *>(&c) + 1);
+            }
+        }
+        cluster.sync();
+        unsigned bv = 0;
+        int bi = 0x7fffffff;
+#pragma unroll
+        for (int r = 0; r < CS; ++r) {
+            const FpsCand c = cand[par][r];
+            if (c.val > bv || (c.val == bv && c.idx < bi)) {
+                bv = c.val, bi = c.idx;
+                lx = c.x, ly = c.y, lz = c.z;
+            }
+        }
+        if (seq_out != nullptr && rank == 0 && tid == 0) {
+            if (s == 0) seq_out[(size_t)b * K] = __int_as_float(0x7f800000);
+            if (s + 1 < K) seq_out[(size_t)b * K + s + 1] = __uint_as_float(bv - 1u);
+        }
+        cur = bi;
+    }
+    cluster.sync();  // no CTA may exit while a sibling can still write into its shared memory
+}
+
+template <int PPT, int CS>
+static cudaError_t launch_fps_cluster(const float *xyz, int B, int N, int K, int start, int *idx_out, float *seq_out,
+                                      cudaStream_t stream) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(B * CS));
+    cfg.blockDim = dim3(FPS_THREADS);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CS, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr, cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, fps_cluster_kernel<PPT, CS>, xyz, N, K, start, idx_out, seq_out);
+}
+
 }  // namespace genpc
 
 using namespace genpc;
@@ -158,6 +287,17 @@ extern "C" int genpc_fps(const float *xyz, int B, int N, int K, int start, int *
     if (B < 0 || N <= 0 || K < 0 || K > N || start < 0 || start >= N) return GENPC_ERR_SHAPE;
     if (B == 0 || K == 0) return GENPC_OK;
     const int ppt = (N + FPS_THREADS - 1) / FPS_THREADS;
+    // clusters of 8 CTAs when the batch alone cannot fill the chip and the cloud is big enough to be LSU/L1 bound
+    const char *fm = getenv("GENPC_FPS_MODE");
+    const bool want_cluster = (fm == nullptr) ? (ppt > 4 && ppt <= 32 && B * 8 <= GENPC_NUM_SMS) : (strcmp(fm, "cluster") == 0 && ppt <= 32);
+    if (want_cluster) {
+        cudaError_t e;
+        if (ppt <= 8) e = launch_fps_cluster<1, 8>(xyz, B, N, K, start, idx_out, seq_out, stream);
+        else if (ppt <= 16) e = launch_fps_cluster<2, 8>(xyz, B, N, K, start, idx_out, seq_out, stream);
+        else e = launch_fps_cluster<4, 8>(xyz, B, N, K, start, idx_out, seq_out, stream);
+        if (e != cudaSuccess) return (int)e;
+        return GENPC_OK;
+    }
 #define FPS_LAUNCH(P) fps_reg_kernel<P, (P <= 4)><<<B, FPS_THREADS, 0, stream>>>(xyz, N, K, start, idx_out, seq_out)
     if (ppt <= 1) FPS_LAUNCH(1);
     else if (ppt <= 2) FPS_LAUNCH(2);

@@ -21,7 +21,13 @@ namespace genpc {
 
 constexpr int SYM_THREADS = 256;
 constexpr int SYM_SPAN_MAX = 1024;  // columns staged per item (<= 12 KB shared memory)
-constexpr int SYM_CHUNK = 8;        // row-side index-recovery granularity (columns)
+#ifndef GENPC_SYM_CHUNK
+#define GENPC_SYM_CHUNK 8
+#endif
+#ifndef GENPC_SYM_REDUX
+#define GENPC_SYM_REDUX 1
+#endif
+constexpr int SYM_CHUNK = GENPC_SYM_CHUNK;  // row-side index-recovery granularity (columns)
 
 struct SymParams {
     const float *rows;             // [B][nr][3]
@@ -50,7 +56,7 @@ __device__ __forceinline__ float butterfly_min32(float (&v)[32], int lane) {
 #define GENPC_SYM_MINB8 2
 #endif
 #ifndef GENPC_SYM_MINB4
-#define GENPC_SYM_MINB4 3
+#define GENPC_SYM_MINB4 2
 #endif
 #define GENPC_SYM_MINB(QT) ((QT) >= 8 ? GENPC_SYM_MINB8 : GENPC_SYM_MINB4)
 
@@ -147,7 +153,17 @@ __device__ __forceinline__ void nn_sym_item(float (*s)[SYM_SPAN_MAX], const floa
             }
         }
         // ---- column side: warp-wide minimum of column (blk*32 + lane), published with the row-block id ----
+#if GENPC_SYM_REDUX
+        unsigned mine = 0x7f800000u;  // distances are >= 0: their bit patterns order like the floats
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+            const unsigned r = __reduce_min_sync(0xffffffffu, __float_as_uint(cacc[c]));
+            if (lane == c) mine = r;
+        }
+        const float cmin = __uint_as_float(mine);
+#else
         const float cmin = butterfly_min32(cacc, lane);
+#endif
         const int col = blk * 32 + lane;
         if (col < cnt && cmin < inf) atomicMin(pcol + col, pack_dist_idx(cmin, rblock));
     }

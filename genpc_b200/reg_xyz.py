@@ -1,0 +1,197 @@
+"""Scale / ICP search of the Geometric-Preserving-Fusion stage on the GPU (reference: reg_xyz.py).
+
+The reference scores 11 isotropic + 1000 anisotropic scale candidates one at a time: deepcopy -> Open3D ICP on the
+CPU -> H2D -> two Chamfer extension calls (4 NN scans) -> `cd < best_loss` D2H sync (reg_xyz.py:60-96, 146-173).
+Here the candidates ARE the batch dimension: one batched point-to-point ICP (NN from the Chamfer kernel + a
+batched 3x3 Kabsch/SVD) and one Chamfer call score all of them, everything stays on the device.
+
+Open3D is not vendored: `registration_icp` (point-to-point, default criteria: 30 iterations, relative fitness /
+RMSE 1e-6), voxel down-sampling and `remove_statistical_outlier` are restated from their documented behaviour
+(parity unpinned).  Function names and argument meaning follow the reference.
+"""
+import numpy as np
+import torch
+
+from .fps import furthest_point_sample
+from .loss_functions import chamfer_3DDist
+from .optim_registration.diff_obj_pose import object_pose_optimization_points
+from .utils.dataUtils import normalize_numpy, voxel_down_sample  # noqa: F401
+
+_cd = chamfer_3DDist()
+
+
+def _apply(T, pts):
+    """T [K,4,4], pts [K,N,3] -> transformed points."""
+    return pts @ T[:, :3, :3].transpose(1, 2) + T[:, None, :3, 3]
+
+
+def chamfer_partial_l1_batched(src, tgt, cd_inv_weight=0.0):
+    """Per-candidate score of the reference's sweep (reg_xyz.py:81-84, 167-170):
+    CDp-L1(src->tgt) + cd_inv_weight * CDp-L1(tgt->src), src [K,Ns,3], tgt [K,Nt,3] -> [K]."""
+    d1, d2, _, _ = _cd(src.contiguous(), tgt.contiguous())
+    return torch.sqrt(d1).mean(1) + cd_inv_weight * torch.sqrt(d2).mean(1)
+
+
+def icp_point_to_point(source, target, max_correspondence_distance=0.05, init_transform=None, max_iteration=30,
+                       relative_fitness=1e-6, relative_rmse=1e-6):
+    """Batched Open3D-style registration_icp (TransformationEstimationPointToPoint, no scaling).
+    source [K,Ns,3], target [K,Nt,3] (or [1,Nt,3]) -> (T [K,4,4], fitness [K], inlier_rmse [K])."""
+    K, Ns, _ = source.shape
+    dev = source.device
+    if target.shape[0] == 1 and K > 1:
+        target = target.expand(K, -1, -1)
+    target = target.contiguous()
+    T = torch.eye(4, device=dev).repeat(K, 1, 1) if init_transform is None else \
+        torch.as_tensor(init_transform, dtype=torch.float32, device=dev).expand(K, 4, 4).clone()
+    thr2 = float(max_correspondence_distance) ** 2
+    active = torch.ones(K, dtype=torch.bool, device=dev)
+    fit_prev = torch.zeros(K, device=dev)
+    rmse_prev = torch.zeros(K, device=dev)
+    fitness = torch.zeros(K, device=dev)
+    rmse = torch.zeros(K, device=dev)
+    for it in range(max_iteration + 1):
+        cur = _apply(T, source)
+        d1, _, i1, _ = _cd(cur.contiguous(), target)
+        inl = d1 < thr2
+        cnt = inl.sum(1).clamp(min=1).float()
+        fitness = inl.sum(1).float() / Ns
+        rmse = torch.sqrt((d1 * inl).sum(1) / cnt)
+        if it > 0:
+            conv = ((fitness - fit_prev).abs() < relative_fitness) & ((rmse - rmse_prev).abs() < relative_rmse)
+            active = active & ~conv
+        if it == max_iteration or not bool(active.any()):
+            break
+        fit_prev, rmse_prev = fitness, rmse
+        # Kabsch on the inlier correspondences (cur -> target[nn])
+        nn = torch.gather(target, 1, i1.long()[..., None].expand(-1, -1, 3))
+        w = inl.float()[..., None]
+        mu_s = (cur * w).sum(1) / cnt[:, None]
+        mu_t = (nn * w).sum(1) / cnt[:, None]
+        H = ((cur - mu_s[:, None]) * w).transpose(1, 2) @ (nn - mu_t[:, None])
+        U, _, Vh = torch.linalg.svd(H.double())
+        V, Ut = Vh.transpose(1, 2), U.transpose(1, 2)
+        D = torch.eye(3, dtype=torch.float64, device=dev).repeat(K, 1, 1)
+        D[:, 2, 2] = torch.sign(torch.linalg.det(V @ Ut))
+        R = (V @ D @ Ut).float()
+        t = mu_t - (R @ mu_s[..., None])[..., 0]
+        upd = torch.eye(4, device=dev).repeat(K, 1, 1)
+        upd[:, :3, :3], upd[:, :3, 3] = R, t
+        ok = (active & (inl.sum(1) >= 3))[:, None, None]
+        T = torch.where(ok, upd @ T, T)
+    return T, fitness, rmse
+
+
+def icp_with_scaling_xyz(source, target, scales, max_correspondence_distance=0.05, init_transform=None):
+    """reg_xyz.py:9-21 batched: scale the source per axis (scales [K,3]) then ICP.  Returns (scaled source, T, fitness, rmse)."""
+    scales = torch.as_tensor(scales, dtype=torch.float32, device=source.device)
+    src = source[None] * scales[:, None, :] if source.dim() == 2 else source * scales[:, None, :]
+    T, f, r = icp_point_to_point(src, target if target.dim() == 3 else target[None], max_correspondence_distance,
+                                 init_transform)
+    return src, T, f, r
+
+
+def icp_with_scaling(source, target, scale, max_correspondence_distance=0.05, init_transform=None):
+    """reg_xyz.py:24-38 batched over `scale` [K]: ICP, then ICP again from result @ diag(scale)."""
+    scale = torch.as_tensor(scale, dtype=torch.float32, device=source.device).reshape(-1)
+    K = scale.shape[0]
+    src = source[None].expand(K, -1, -1).contiguous()
+    tgt = target[None].contiguous()
+    T0, _, _ = icp_point_to_point(src, tgt, max_correspondence_distance, init_transform)
+    S = torch.eye(4, device=source.device).repeat(K, 1, 1)
+    S[:, 0, 0] = S[:, 1, 1] = S[:, 2, 2] = scale
+    return icp_point_to_point(src, tgt, max_correspondence_distance, T0 @ S)
+
+
+def iterative_scale_search(source_xyz, target_xyz, scale_ranges, scale_steps, init_transform=None, cd_inv_weight=0.0,
+                           chunk=250):
+    """reg_xyz.py:60-96: scale_steps^3 anisotropic candidates (z outer, x, y inner -- the reference's loop order, so
+    `cd < best_loss` ties resolve identically: first candidate wins), each ICP-refined and scored by partial CD-L1.
+    Returns (best_scales_transformation 4x4 np, best_loss float, best_transformation 4x4 np)."""
+    dev = source_xyz.device
+    xs = np.linspace(scale_ranges[0][0], scale_ranges[0][1], scale_steps)
+    ys = np.linspace(scale_ranges[1][0], scale_ranges[1][1], scale_steps)
+    zs = np.linspace(scale_ranges[2][0], scale_ranges[2][1], scale_steps)
+    cand = np.array([[x, y, z] for z in zs for x in xs for y in ys], dtype=np.float32)
+    losses, Ts = [], []
+    for c0 in range(0, len(cand), chunk):
+        sc = torch.from_numpy(cand[c0:c0 + chunk]).to(dev)
+        src, T, _, _ = icp_with_scaling_xyz(source_xyz, target_xyz, sc, 0.075, init_transform)
+        tgt = target_xyz[None].expand(src.shape[0], -1, -1)
+        # the reference scores the SCALED (not ICP-transformed) source copy against the target (:79-84)
+        losses.append(chamfer_partial_l1_batched(src, tgt, cd_inv_weight))
+        Ts.append(T)
+    losses, Ts = torch.cat(losses), torch.cat(Ts)
+    k = int(torch.argmin(losses))  # argmin returns the first minimum == the reference's strict `<` update
+    best = np.eye(4)
+    best[0, 0], best[1, 1], best[2, 2] = cand[k]
+    return best, float(losses[k]), Ts[k].double().cpu().numpy()
+
+
+def remove_close_points(source_xyz, target_xyz, distance_threshold=0.0001):
+    """reg_xyz.py:41-57: keep the target points whose nearest source point is at squared distance >= threshold
+    (Open3D's KD-tree returns squared distances).  One NN launch instead of a Python loop of KD-tree queries."""
+    d1, _, _, _ = _cd(target_xyz[None].contiguous(), source_xyz[None].contiguous())
+    return d1[0] >= distance_threshold
+
+
+def remove_statistical_outlier(xyz, nb_neighbors=20, std_ratio=2.5, chunk=4096):
+    """Open3D remove_statistical_outlier restated: mean distance to the nb_neighbors nearest neighbours, keep points
+    below mean + std_ratio * std.  (utils/dataUtils.py:652-666; adjacent helper, torch.cdist in chunks.)"""
+    n = xyz.shape[0]
+    md = torch.empty(n, device=xyz.device)
+    for c0 in range(0, n, chunk):
+        d = torch.cdist(xyz[c0:c0 + chunk], xyz)
+        md[c0:c0 + chunk] = d.topk(nb_neighbors + 1, largest=False).values[:, 1:].mean(1)
+    return md <= md.mean() + std_ratio * md.std(unbiased=False)
+
+
+def reg_points(partial_xyz, complete_xyz, cd_inv_weight=0.5, diff_init=True, reg_fine_xyz=False, dataset="redwood",
+               n_fused=20000, lr=0.01, iters=200):
+    """In-memory form of reg() (reg_xyz.py:99-223): differentiable init -> 11-scale coarse ICP sweep -> optional
+    per-axis scale grid -> fuse (drop generated points that coincide with scan points, FPS to n_fused, outlier filter).
+    partial_xyz = the scan (`color_point.ply`), complete_xyz = the generated shape.  Returns dict of device tensors."""
+    dev = partial_xyz.device
+    source, target = partial_xyz.float(), complete_xyz.float()
+    diff_T = np.eye(4)
+    if diff_init:
+        T = object_pose_optimization_points(voxel_down_sample(target, 0.02), voxel_down_sample(source, 0.02), lr=lr,
+                                            iters=iters, device=dev)
+        diff_T = np.linalg.inv(T)                                   # reg_xyz.py:122
+    dT = torch.as_tensor(diff_T, dtype=torch.float32, device=dev)
+    source = source @ dT[:3, :3].T + dT[:3, 3]                      # partial into the generated shape's frame (:126)
+    tn, _, _ = normalize_numpy(target.cpu().numpy(), range=0.5)     # :131
+    target = torch.as_tensor(tn, dtype=torch.float32, device=dev)
+    # coarse sweep (:146-173), all 11 scales at once
+    scales = np.linspace(1.5, 0.8, 11)
+    s_down, t_down = voxel_down_sample(source, 0.03), voxel_down_sample(target, 0.03)
+    Ts, _, _ = icp_with_scaling(s_down, t_down, scales, 0.075)
+    inv = torch.linalg.inv(Ts.double()).float()
+    t_moved = _apply(inv, t_down[None].expand(len(scales), -1, -1))
+    cd = chamfer_partial_l1_batched(s_down[None].expand(len(scales), -1, -1), t_moved, cd_inv_weight)
+    k = int(torch.argmin(cd))
+    coarse = Ts[k]
+    out = {"best_scale": float(scales[k]), "coarse_loss": float(cd[k]), "coarse_transformation": coarse}
+    tgt_full = target
+    if reg_fine_xyz:
+        source = source @ coarse[:3, :3].T + coarse[:3, 3]          # :176
+        s_in = source if dataset in ("pcn", "kitti") else voxel_down_sample(source, 0.03)
+        t_in = voxel_down_sample(target, 0.04 if dataset in ("pcn", "kitti") else 0.03)
+        Sx, loss_xyz, Txyz = iterative_scale_search(s_in, t_in, [(0.8, 1.2)] * 3, 10, None, cd_inv_weight)
+        for Mx in (np.linalg.inv(Sx), np.linalg.inv(Txyz)):         # :194-197
+            Mt = torch.as_tensor(Mx, dtype=torch.float32, device=dev)
+            tgt_full = tgt_full @ Mt[:3, :3].T + Mt[:3, 3]
+        ci = torch.linalg.inv(coarse.double()).float()
+        source = source @ ci[:3, :3].T + ci[:3, 3]                  # :199-200
+        out.update(best_scales=np.diag(Sx)[:3].copy(), fine_loss=loss_xyz)
+    for Mt in (torch.linalg.inv(coarse.double()).float(), torch.as_tensor(np.linalg.inv(diff_T), dtype=torch.float32, device=dev)):
+        tgt_full = tgt_full @ Mt[:3, :3].T + Mt[:3, 3]              # :202-205
+    di = torch.as_tensor(np.linalg.inv(diff_T), dtype=torch.float32, device=dev)
+    source = source @ di[:3, :3].T + di[:3, 3]                      # :206
+    keep = remove_close_points(source, tgt_full, 0.0001)            # :210
+    fused = torch.cat([source, tgt_full[keep]])
+    if fused.shape[0] > n_fused:
+        idx = furthest_point_sample(fused[None].contiguous(), n_fused, 0)[0].long()   # :215
+        fused = fused[idx]
+    fused = fused[remove_statistical_outlier(fused, std_ratio=2.5)]                   # :219
+    out.update(fused=fused, source=source, target=tgt_full)
+    return out

@@ -60,3 +60,26 @@ def test_fps_gpu_ties_and_api(cuda):
     assert np.array_equal(idx.cpu().numpy(), oracle.fps(a, 100, 0))
     out = fps_sampling(a[0], 50)           # fpsample-shaped call: numpy in, numpy out
     assert isinstance(out, np.ndarray) and np.array_equal(out.astype(np.int32), oracle.fps(a[:1], 50, 0)[0])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,N,K,start", [(1, 16384, 2048, 0), (2, 5000, 300, 4999), (1, 9000, 500, 3), (3, 20000, 64, 1),
+                                         (1, 32768, 100, 0), (1, 1500, 200, 7)])
+def test_fps_cluster_kernel_bit_exact(cuda, B, N, K, start):
+    """The thread-block-cluster / DSMEM kernel (forced through GENPC_FPS_MODE) against the oracle."""
+    import os
+
+    import torch
+
+    from genpc_b200.fps import furthest_point_sample
+
+    a = shape_cloud(N + 1, B, N)
+    os.environ["GENPC_FPS_MODE"] = "cluster"
+    try:
+        idx, seq = furthest_point_sample(torch.from_numpy(a).to(cuda), K, start, return_seq=True)
+        torch.cuda.synchronize()
+    finally:
+        del os.environ["GENPC_FPS_MODE"]
+    eidx, eseq = oracle.fps(a, K, start, True)
+    assert np.array_equal(idx.cpu().numpy(), eidx)
+    assert np.array_equal(seq.cpu().numpy().view(np.int32), eseq.view(np.int32))

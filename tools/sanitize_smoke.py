@@ -1,0 +1,27 @@
+"""Small invocation of every kernel family, meant to run under compute-sanitizer (memcheck / racecheck)."""
+import os, sys
+import numpy as np
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from genpc_b200 import depth as D
+from genpc_b200.fps import furthest_point_sample
+from genpc_b200.loss_functions import chamfer_3DDist, emdModule
+from genpc_b200.optim_registration.diff_obj_pose import RegistrationBatch
+from genpc_b200.sharded import nn_partial_packed, nn_unpack
+dev = torch.device("cuda:0")
+g = torch.Generator().manual_seed(0)
+for (B, N, M) in [(2, 700, 1300), (1, 3000, 999), (2, 100, 37)]:   # sym path, sym with tails, scan path
+    a = torch.rand(B, N, 3, generator=g).to(dev).requires_grad_(True); b = torch.rand(B, M, 3, generator=g).to(dev).requires_grad_(True)
+    d1, d2, i1, i2 = chamfer_3DDist()(a, b); (d1.mean() + d2.mean()).backward()
+x = torch.rand(2, 512, 3, generator=g).to(dev); y = torch.rand(2, 512, 3, generator=g).to(dev)
+emdModule()(x, y, 0.005, 10)
+furthest_point_sample(torch.rand(2, 5000, 3, generator=g).to(dev), 64, 0)
+furthest_point_sample(torch.rand(1, 40000, 3, generator=g).to(dev), 8, 0)
+pts = torch.rand(3000, 3, generator=g).to(dev) - 0.5
+cams, _ = D.create_cameras(3, 1.6, 49.1, 64, dev)
+ndc, uv, bnd = D.project_uv(cams, pts); r = D.zbuffer_render(uv, ndc, 64, 2); D.unproject(cams, bnd, r["zbuf"], ndc)
+for (nc, nr) in [(1500, 900), (20000, 12000)]:                      # single-launch path and symmetric two-launch path
+    rb = RegistrationBatch(torch.rand(1, nc, 3, generator=g).to(dev) - 0.5, torch.rand(1, nr, 3, generator=g).to(dev) - 0.5, n_starts=2)
+    rb.run(2)
+p = nn_partial_packed(torch.rand(1, 2000, 3, generator=g).to(dev), torch.rand(1, 700, 3, generator=g).to(dev), 100); nn_unpack(p)
+torch.cuda.synchronize(); print("sanitize smoke done")
