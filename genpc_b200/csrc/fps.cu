@@ -24,7 +24,7 @@ constexpr int FPS_WARPS = FPS_THREADS / 32;
 
 __device__ __forceinline__ void fps_block_argmax(float best, int best_i, unsigned (*sval)[FPS_WARPS],
                                                  int (*sidx)[FPS_WARPS], int parity, int lane, int warp,
-                                                 int &winner) {
+                                                 int &winner, unsigned *bmax_out = nullptr) {
     // running distances are >= 0 (or -1 for padding, mapped to 0 bits below) -> bit pattern orders like the float
     unsigned vb = best < 0.f ? 0u : __float_as_uint(best) + 1u;  // +1 keeps real 0.0 above the padding
     unsigned wmax = __reduce_max_sync(0xffffffffu, vb);
@@ -40,6 +40,7 @@ __device__ __forceinline__ void fps_block_argmax(float best, int best_i, unsigne
     unsigned bmax = __reduce_max_sync(0xffffffffu, v2);
     int c2 = (v2 == bmax) ? i2 : 0x7fffffff;
     winner = __reduce_min_sync(0xffffffffu, c2);
+    if (bmax_out != nullptr) *bmax_out = bmax;
 }
 
 template <int PPT, bool CREG>
@@ -152,10 +153,61 @@ __global__ void __launch_bounds__(FPS_THREADS, 1) fps_gmem_kernel(const float *_
 // Large single clouds are bound by one SM's L1/LSU when a lone CTA re-reads 12 B/point every pick (16384 points:
 // 3.6 ms for 2048 picks).  A cluster of CS CTAs keeps PPT <= 4 points per thread entirely in registers; per pick
 // each CTA finds its own candidate (REDUX + one __syncthreads), the owning thread posts (value, index, x, y, z) into
-// slot [parity][rank] of EVERY CTA of the cluster through distributed shared memory, one cluster barrier, and every
-// thread reads the CS candidates locally -- the winner's coordinates travel with it, so the loop has no global
+// slot [parity][rank] of EVERY CTA of the cluster with asynchronous distributed-shared-memory stores that complete
+// transaction bytes on the receiver's mbarrier (st.async ... mbarrier::complete_tx::bytes); one thread per CTA waits
+// on the local mbarrier.  (Measured per pick: barrier.cluster 1.41 us, st.shared::cluster + release/acquire arrive
+// 1.45 us, st.async + complete_tx: see profiles/.)  Every thread then reads the CS candidates locally -- the winner's coordinates travel with it, so the loop has no global
 // loads at all.  Same arithmetic and tie rule as fps_reg_kernel (bit-identical results).
 namespace cg = cooperative_groups;
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ unsigned mapa_u32(unsigned addr, unsigned rank) {
+    unsigned r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_cluster_v4(unsigned addr, int4 v) {
+    asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void mbar_init(unsigned addr, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(addr), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(unsigned cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// asynchronous DSMEM store that signals the receiver's mbarrier by transaction bytes (no release fence on the sender,
+// no cluster-scope acquire on the receiver: visibility comes with the phase completion)
+__device__ __forceinline__ void st_async_v4(unsigned cluster_addr, int4 v, unsigned cluster_mbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(cluster_addr),
+                 "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(cluster_mbar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arm(unsigned addr, unsigned tx_bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(addr), "r"(tx_bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned addr, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(addr), "r"(parity) : "memory");
+}
+// post one 32-byte candidate into slot [par][rank] of every CTA of the cluster, then release-arrive on each receiver
+template <int CS>
+__device__ __forceinline__ void fps_post(const void *cand_slot, const void *bar, const int4 lo, const int4 hi) {
+    const unsigned slot = smem_u32(cand_slot), b = smem_u32(bar);
+#pragma unroll
+    for (int r = 0; r < CS; ++r) {
+        const unsigned dst = mapa_u32(slot, r);
+        st_cluster_v4(dst, lo);
+        st_cluster_v4(dst + 16, hi);
+        mbar_arrive_remote(mapa_u32(b, r));
+    }
+}
 
 struct FpsCand {
     unsigned val;  // running distance bits + 1 (0 = padding)
@@ -170,6 +222,7 @@ __global__ void __launch_bounds__(FPS_THREADS, 1) fps_cluster_kernel(const float
     __shared__ unsigned sval[2][FPS_WARPS];
     __shared__ int sidx[2][FPS_WARPS];
     __shared__ __align__(16) FpsCand cand[2][CS];
+    __shared__ __align__(8) unsigned long long mbar[2];  // one mbarrier per parity, CS remote arrivals per pick
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
     const int b = blockIdx.x / CS, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -190,6 +243,13 @@ __global__ void __launch_bounds__(FPS_THREADS, 1) fps_cluster_kernel(const float
     }
     float lx = __ldg(p + (size_t)start * 3), ly = __ldg(p + (size_t)start * 3 + 1), lz = __ldg(p + (size_t)start * 3 + 2);
     int cur = start;
+    if (tid == 0) {
+        mbar_init(smem_u32(&mbar[0]), 1);
+        mbar_init(smem_u32(&mbar[1]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_arm(smem_u32(&mbar[0]), CS * 32);  // each pick delivers CS candidates of 32 bytes into this CTA
+        mbar_arm(smem_u32(&mbar[1]), CS * 32);
+    }
     cluster.sync();
     for (int s = 0; s < K; ++s) {
         if (rank == 0 && tid == 0) idx_out[(size_t)b * K + s] = cur;
@@ -209,35 +269,33 @@ __global__ void __launch_bounds__(FPS_THREADS, 1) fps_cluster_kernel(const float
         }
         const int par = s & 1;
         int winner;
-        fps_block_argmax(best, best_i, sval, sidx, par, lane, warp, winner);
-        if (winner == best_i && best_i != 0x7fffffff) {  // exactly one thread of the CTA owns the candidate
-            unsigned m = 0;
-#pragma unroll
-            for (int w = 0; w < FPS_WARPS; ++w) m = max(m, sval[par][w]);
-            FpsCand c;
-            c.val = m, c.idx = best_i;
-            c.x = px[0], c.y = py[0], c.z = pz[0];
+        unsigned bmax;
+        fps_block_argmax(best, best_i, sval, sidx, par, lane, warp, winner, &bmax);
+        // the warp that owns the CTA's candidate posts it: the owner lane's coordinates are shuffled to lanes 0..CS-1,
+        // which write to one destination CTA each (a single thread posting to all CS CTAs serialises CS release-arrives,
+        // each waiting for its own DSMEM stores: measured 2.5 us per pick)
+        const int wtid = (winner == 0x7fffffff) ? 0 : (winner & (FPS_THREADS - 1));
+        if (warp == (wtid >> 5)) {
+            float cx = px[0], cy = py[0], cz = pz[0];
 #pragma unroll
             for (int k = 1; k < PPT; ++k)
-                if (best_k == k) c.x = px[k], c.y = py[k], c.z = pz[k];
-            c.pad[0] = c.pad[1] = c.pad[2] = 0;
-#pragma unroll
-            for (int r = 0; r < CS; ++r) {
-                FpsCand *dst = cluster.map_shared_rank(&cand[par][rank], r);
-                *reinterpret_cast<int4 *>(dst) = *reinterpret_cast<int4 *>(&c);
-                *(reinterpret_cast<int4 *>(dst) + 1) = *(reinterpret_cast<int4 *>(&c) + 1);
-            }
-        } else if (tid == 0 && winner == 0x7fffffff) {   // CTA holds only padding: post an empty candidate
-            FpsCand c;
-            c.val = 0, c.idx = 0x7fffffff, c.x = c.y = c.z = 0.f, c.pad[0] = c.pad[1] = c.pad[2] = 0;
-#pragma unroll
-            for (int r = 0; r < CS; ++r) {
-                FpsCand *dst = cluster.map_shared_rank(&cand[par][rank], r);
-                *reinterpret_cast<int4 *>(dst) = *reinterpret_cast<int4 *>(&c);
-                *(reinterpret_cast<int4 *>(dst) + 1) = *(reinterpret_cast<int4 *>(&c) + 1);
+                if (best_k == k) cx = px[k], cy = py[k], cz = pz[k];
+            const int src = wtid & 31;
+            cx = __shfl_sync(0xffffffffu, cx, src), cy = __shfl_sync(0xffffffffu, cy, src), cz = __shfl_sync(0xffffffffu, cz, src);
+            if (lane < CS) {
+                const int4 lo = make_int4((int)bmax, winner, __float_as_int(cx), __float_as_int(cy));
+                const int4 hi = make_int4(__float_as_int(cz), 0, 0, 0);
+                const unsigned dst = mapa_u32(smem_u32(&cand[par][rank]), lane);
+                const unsigned bar = mapa_u32(smem_u32(&mbar[par]), lane);
+                st_async_v4(dst, lo, bar);
+                st_async_v4(dst + 16, hi, bar);
             }
         }
-        cluster.sync();
+        if (tid == 0) {
+            mbar_wait(smem_u32(&mbar[par]), (unsigned)((s >> 1) & 1));  // all CS candidates of this pick have landed
+            mbar_arm(smem_u32(&mbar[par]), CS * 32);                      // re-arm for pick s+2 (nobody can post it yet)
+        }
+        __syncthreads();
         unsigned bv = 0;
         int bi = 0x7fffffff;
 #pragma unroll
@@ -287,9 +345,11 @@ extern "C" int genpc_fps(const float *xyz, int B, int N, int K, int start, int *
     if (B < 0 || N <= 0 || K < 0 || K > N || start < 0 || start >= N) return GENPC_ERR_SHAPE;
     if (B == 0 || K == 0) return GENPC_OK;
     const int ppt = (N + FPS_THREADS - 1) / FPS_THREADS;
-    // clusters of 8 CTAs when the batch alone cannot fill the chip and the cloud is big enough to be LSU/L1 bound
+    // clusters of 8 CTAs when the batch alone cannot fill the chip and the cloud is big enough to be LSU/L1 bound.
+    // Measured on B200 (profiles/r01d_fps.txt): a pick costs 1.15 us through the cluster exchange whatever N is, and
+    // 0.35 / 0.51 / 1.02 / 1.78 / 4.23 us in the single CTA at N = 1024 / 4096 / 8192 / 16384 / 32768.
     const char *fm = getenv("GENPC_FPS_MODE");
-    const bool want_cluster = (fm == nullptr) ? (ppt > 4 && ppt <= 32 && B * 8 <= GENPC_NUM_SMS) : (strcmp(fm, "cluster") == 0 && ppt <= 32);
+    const bool want_cluster = (fm == nullptr) ? (ppt > 8 && ppt <= 32 && B * 8 <= GENPC_NUM_SMS) : (strcmp(fm, "cluster") == 0 && ppt <= 32);
     if (want_cluster) {
         cudaError_t e;
         if (ppt <= 8) e = launch_fps_cluster<1, 8>(xyz, B, N, K, start, idx_out, seq_out, stream);
