@@ -102,7 +102,8 @@ __device__ int compact_unassigned(const int *__restrict__ asg, int *__restrict__
 }
 
 __global__ void __launch_bounds__(EMD_THREADS) emd_auction_kernel(const EmdArgs a) {
-    __shared__ float4 stg[EMD_CHUNK];  // x, y, z, price
+    __shared__ float4 stg[EMD_CHUNK];  // x, y, z, c = fl(3 - price) (pre-filter operand)
+    __shared__ float sprice[EMD_CHUNK];
     __shared__ BidState smerge[EMD_THREADS];
     __shared__ int sscan[EMD_THREADS / 32];
     __shared__ int s_last;
@@ -163,19 +164,28 @@ __global__ void __launch_bounds__(EMD_THREADS) emd_auction_kernel(const EmdArgs 
                     }
                     BidState st;
                     st.best = -1e9f, st.better = -1e9f, st.bi = -1;
+                    float bm = -2e9f;  // better - margin (pre-filter threshold)
                     for (int k2 = 0; k2 < n; k2 += EMD_CHUNK) {
                         const int end_k = min(EMD_CHUNK, n - k2);
                         __syncthreads();
                         for (int k = tid; k < end_k; k += EMD_THREADS) {
                             const float *tp = p2 + (size_t)(k2 + k) * 3;
-                            stg[k] = make_float4(__ldg(tp), __ldg(tp + 1), __ldg(tp + 2), __ldcg(pr + k2 + k));
+                            const float pk = __ldcg(pr + k2 + k);
+                            stg[k] = make_float4(__ldg(tp), __ldg(tp + 1), __ldg(tp + 2), __fsub_rn(3.0f, pk));
+                            sprice[k] = pk;
                         }
                         __syncthreads();
                         if (active) {
                             for (int kl = tpt; kl < end_k; kl += T) {
                                 const float4 t = stg[kl];
                                 const float s = sqdist_ref(x1, y1, z1, t.x, t.y, t.z);
-                                const float d = (float)((3.0 - (double)__fsqrt_rn(s)) - (double)t.w);
+                                // conservative pre-filter (no sqrt, no FP64): a candidate can only matter if its value
+                                // d >= better, i.e. sqrt(s) <= 3 - price - better up to a few ulps; bm = better - margin
+                                // with margin = 1e-4*max(1,|better|) (hundreds of ulps) makes "tq > 0 && s <= tq^2" a
+                                // superset of those candidates.  Everything that passes takes the exact path below.
+                                const float tq = __fsub_rn(t.w, bm);
+                                if (!(tq > 0.f && s <= __fmul_rn(tq, tq))) continue;
+                                const float d = (float)((3.0 - (double)__fsqrt_rn(s)) - (double)sprice[kl]);
                                 if (d > st.best) {
                                     st.better = st.best;
                                     st.best = d;
@@ -186,6 +196,7 @@ __global__ void __launch_bounds__(EMD_THREADS) emd_auction_kernel(const EmdArgs 
                                         ref_visit_key(k2 + kl, n, tpu_ref) < ref_visit_key(st.bi, n, tpu_ref))
                                         st.bi = k2 + kl;
                                 }
+                                bm = __fsub_rn(st.better, __fmul_rn(1e-4f, fmaxf(1.f, fabsf(st.better))));
                             }
                         }
                     }
