@@ -137,6 +137,7 @@ static int chamfer_forward_sym(const float *xyz1, const float *xyz2, float *dist
     float *dist_r = swap ? dist2 : dist1, *dist_c = swap ? dist1 : dist2;
     int *idx_r = swap ? idx2 : idx1, *idx_c = swap ? idx1 : idx2;
     p.prow = packed, p.pcol = packed + (size_t)B * p.nr;
+    p.rblock_base = 0;
     // measured on B200 (profiles/r01c_sym_variants.txt): QT=4 at 3 CTAs/SM is within 1 % of QT=8 at 2 CTAs/SM on
     // large clouds and clearly better when the grid is small
     int QT = p.nr >= 1024 ? 4 : 2;
@@ -273,6 +274,53 @@ extern "C" int genpc_nn_unpack(const unsigned long long *packed, float *dist, in
     cudaStream_t stream = (cudaStream_t)stream_;
     if (count == 0) return GENPC_OK;
     nn_unpack_kernel<<<(unsigned)((count + 255) / 256), 256, 0, stream>>>(packed, dist, idx, count, nullptr, nullptr, 0);
+    GENPC_CHECK_LAUNCH();
+    return GENPC_OK;
+}
+
+// ---- row-sharded symmetric Chamfer (multi-GPU, every pair evaluated once across the whole job) ----------------
+// Rank r owns rows [row_base, row_base + nr_shard) of cloud 1 (row_base a multiple of 128) and scans them against
+// ALL of cloud 2: prow_shard gets the final (dist, idx2) words of its rows, pcol gets (dist, GLOBAL row block)
+// partial minima for every point of cloud 2.  pcol is merged across ranks by all-reduce-MIN, then
+// genpc_chamfer_sym_fixup resolves the row blocks to exact lowest indices against the FULL cloud 1.
+extern "C" int genpc_chamfer_sym_partial(const float *rows_shard, const float *cols, unsigned long long *prow_shard,
+                                         unsigned long long *pcol, int B, int nr_shard, int nc, int row_base,
+                                         int init_cols, genpc_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (B < 0 || nr_shard < 0 || nc < 0 || row_base < 0 || row_base % 128 != 0) return GENPC_ERR_SHAPE;
+    if (B > 1 && row_base != 0) return GENPC_ERR_SHAPE;  // a shard of a batched cloud is not contiguous: B == 1 only
+    cudaError_t e;
+    if (init_cols && (size_t)B * nc) {
+        e = cudaMemsetAsync(pcol, 0xff, (size_t)B * nc * 8, stream);
+        if (e != cudaSuccess) return (int)e;
+    }
+    if ((size_t)B * nr_shard == 0) return GENPC_OK;
+    e = cudaMemsetAsync(prow_shard, 0xff, (size_t)B * nr_shard * 8, stream);
+    if (e != cudaSuccess) return (int)e;
+    if (nc == 0) return GENPC_OK;
+    SymParams p;
+    p.rows = rows_shard, p.cols = cols, p.prow = prow_shard, p.pcol = pcol;
+    p.nr = nr_shard, p.nc = nc, p.rblock_base = row_base / 128;
+    p.rtiles = (nr_shard + SYM_THREADS * 4 - 1) / (SYM_THREADS * 4);
+    int span = SYM_SPAN_MAX;
+    const long long want = 2LL * 3 * GENPC_NUM_SMS;
+    while (span > 256 && (long long)B * p.rtiles * ((nc + span - 1) / span) < want) span >>= 1;
+    p.span = span, p.cspans = (nc + span - 1) / span;
+    const long long items = (long long)B * p.rtiles * p.cspans;
+    if (items > 0x7fffffffLL) return GENPC_ERR_RANGE;
+    nn_sym_kernel<4><<<(unsigned)items, SYM_THREADS, 0, stream>>>(p);
+    GENPC_CHECK_LAUNCH();
+    return GENPC_OK;
+}
+
+extern "C" int genpc_chamfer_sym_fixup(const float *rows_full, const float *cols, const unsigned long long *pcol, int B,
+                                       int nr_full, int nc, float *dist_cols, int *idx_cols, genpc_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (B < 0 || nr_full < 0 || nc < 0) return GENPC_ERR_SHAPE;
+    const size_t ncw = (size_t)B * nc;
+    if (ncw == 0) return GENPC_OK;
+    nn_sym_fixup_kernel<<<(unsigned)((ncw * 32 + 255) / 256), 256, 0, stream>>>(rows_full, cols, pcol, B, nr_full, nc, 128,
+                                                                                dist_cols, idx_cols);
     GENPC_CHECK_LAUNCH();
     return GENPC_OK;
 }

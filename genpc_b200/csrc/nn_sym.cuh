@@ -35,6 +35,7 @@ struct SymParams {
     unsigned long long *prow;      // [B][nr]  (dist, col index)
     unsigned long long *pcol;      // [B][nc]  (dist, row block id)
     int nr, nc, rtiles, cspans, span;
+    int rblock_base;               // added to published row-block ids (row shard offset / rows_per_block)
 };
 
 // v[e] (e = 0..31) per lane -> returns min over all lanes of v[lane]   (element index == lane id)
@@ -67,7 +68,7 @@ template <int QT>
 __device__ __forceinline__ void nn_sym_item(float (*s)[SYM_SPAN_MAX], const float *__restrict__ rows, int nr, int rt,
                                             const float *__restrict__ cols, int nc, int c0, int span,
                                             const Similarity *colT, unsigned long long *__restrict__ prow_,
-                                            unsigned long long *__restrict__ pcol_) {
+                                            unsigned long long *__restrict__ pcol_, int rblock_base = 0) {
     static_assert(QT % 2 == 0, "rows are folded in pairs");
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int cnt = min(span, nc - c0);
@@ -165,7 +166,7 @@ __device__ __forceinline__ void nn_sym_item(float (*s)[SYM_SPAN_MAX], const floa
         const float cmin = butterfly_min32(cacc, lane);
 #endif
         const int col = blk * 32 + lane;
-        if (col < cnt && cmin < inf) atomicMin(pcol + col, pack_dist_idx(cmin, rblock));
+        if (col < cnt && cmin < inf) atomicMin(pcol + col, pack_dist_idx(cmin, rblock_base + rblock));
     }
 
     // ---- row side: exact lowest column index inside the winning chunk, merged across column spans ----
@@ -195,7 +196,7 @@ __global__ void __launch_bounds__(SYM_THREADS, GENPC_SYM_MINB(QT)) nn_sym_kernel
     const int rt = item % p.rtiles;
     const int b = item / p.rtiles;
     nn_sym_item<QT>(s, p.rows + (size_t)b * p.nr * 3, p.nr, rt, p.cols + (size_t)b * p.nc * 3, p.nc, cs * p.span, p.span,
-                    nullptr, p.prow + (size_t)b * p.nr, p.pcol + (size_t)b * p.nc);
+                    nullptr, p.prow + (size_t)b * p.nr, p.pcol + (size_t)b * p.nc, p.rblock_base);
 }
 
 // Exact lowest row index of one column from its published (dist, row block) word: the calling WARP re-scans the

@@ -9,6 +9,8 @@
   lowest global index win ties, so the merged result is bit-identical to the single-GPU kernel.
 The host-side logic (slicing, merge, unpack) is device-agnostic and is covered on CPU with gloo (tests/).
 """
+import ctypes
+
 import torch
 import torch.distributed as dist
 
@@ -78,9 +80,52 @@ def nn_unpack(packed):
     return d, i
 
 
+def shard_range_aligned(n, rank, world, align=128):
+    """Like shard_range but every boundary except the last is a multiple of `align` (row blocks of the symmetric scan)."""
+    blocks = (n + align - 1) // align
+    lo, hi = shard_range(blocks, rank, world)
+    return min(lo * align, n), min(hi * align, n)
+
+
 def sharded_chamfer_forward(xyz1, xyz2, group=None):
-    """Target-sharded Chamfer forward.  xyz1 [B,N,3], xyz2 [B,M,3]: the FULL clouds, identical on every rank.
-    Returns (dist1, dist2, idx1, idx2) identical on every rank and bit-identical to chamfer_3DDist."""
+    """Sharded Chamfer forward, every point pair evaluated ONCE across the job.  xyz1 [1,N,3], xyz2 [1,M,3]: the FULL
+    clouds, identical on every rank.  Rank r scans its 128-aligned row slice of xyz1 against all of xyz2 with the
+    symmetric kernel: exact (dist1, idx1) for its rows, partial (dist, row block) minima for every point of xyz2.
+    ONE all-reduce-MIN over [packed rows | packed cols] (16 MB for 1M + 1M points) completes both, a local fix-up
+    resolves idx2.  Returns (dist1, dist2, idx1, idx2) identical on every rank and bit-identical to chamfer_3DDist.
+    Batched inputs (B > 1) fall back to the target-sharded scan (sharded_chamfer_forward_targets)."""
+    if xyz1.shape[0] != 1:
+        return sharded_chamfer_forward_targets(xyz1, xyz2, group)
+    _lib.require_cuda(xyz1, xyz2)
+    xyz1, xyz2 = xyz1.contiguous().float(), xyz2.contiguous().float()
+    if dist.is_available() and dist.is_initialized():
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+    else:
+        rank, world = 0, 1
+    N, M = xyz1.shape[1], xyz2.shape[1]
+    dev = xyz1.device
+    lo, hi = shard_range_aligned(N, rank, world)
+    packed = torch.full((N + M,), EMPTY, dtype=torch.int64, device=dev)   # [rows of cloud 1 | cols = cloud 2]
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        rows = xyz1[0, lo:hi]
+        rc = L.genpc_chamfer_sym_partial(_lib.ptr(rows) if hi > lo else None, _lib.ptr(xyz2),
+                                         ctypes.c_void_p(packed.data_ptr() + lo * 8), ctypes.c_void_p(packed.data_ptr() + N * 8),
+                                         1, hi - lo, M, lo, 0, _lib.current_stream(dev))
+        _lib.check(rc, "genpc_chamfer_sym_partial")
+        allreduce_min_packed(packed, group)
+        d1, i1 = nn_unpack(packed[:N])
+        d2 = torch.empty(M, dtype=torch.float32, device=dev)
+        i2 = torch.empty(M, dtype=torch.int32, device=dev)
+        rc = L.genpc_chamfer_sym_fixup(_lib.ptr(xyz1), _lib.ptr(xyz2), ctypes.c_void_p(packed.data_ptr() + N * 8), 1, N, M,
+                                       _lib.ptr(d2), _lib.ptr(i2), _lib.current_stream(dev))
+        _lib.check(rc, "genpc_chamfer_sym_fixup")
+    return d1[None], d2[None], i1[None], i2[None]
+
+
+def sharded_chamfer_forward_targets(xyz1, xyz2, group=None):
+    """Target-sharded Chamfer forward (one scan per direction and shard).  xyz1 [B,N,3], xyz2 [B,M,3]: the FULL clouds,
+    identical on every rank.  Returns (dist1, dist2, idx1, idx2) identical on every rank, bit-identical to chamfer_3DDist."""
     if dist.is_available() and dist.is_initialized():
         rank, world = dist.get_rank(group), dist.get_world_size(group)
     else:

@@ -61,6 +61,17 @@ int genpc_nn_partial_packed(const float *queries, const float *targets_shard, un
                             int Nq, int Mt_shard, int idx_base, int init, genpc_stream_t stream);
 int genpc_nn_unpack(const unsigned long long *packed, float *dist, int *idx, size_t count, genpc_stream_t stream);
 
+/* Row-sharded SYMMETRIC Chamfer: every point pair of the job is evaluated once.  Rank r scans its rows
+ * [row_base, row_base+nr_shard) of cloud 1 (row_base % 128 == 0; B == 1 when row_base != 0) against ALL of cloud 2:
+ * prow_shard[b][j] = final (dist, idx into cloud 2) of its rows, pcol[b][k] = min over its rows of
+ * (dist, GLOBAL 128-row block id).  pcol is merged across ranks by all-reduce-MIN, then genpc_chamfer_sym_fixup
+ * resolves each block id to the exact lowest row index against the FULL cloud 1 and writes dist/idx of cloud 2. */
+int genpc_chamfer_sym_partial(const float *rows_shard, const float *cols, unsigned long long *prow_shard,
+                              unsigned long long *pcol, int B, int nr_shard, int nc, int row_base, int init_cols,
+                              genpc_stream_t stream);
+int genpc_chamfer_sym_fixup(const float *rows_full, const float *cols, const unsigned long long *pcol, int B,
+                            int nr_full, int nc, float *dist_cols, int *idx_cols, genpc_stream_t stream);
+
 /* ---- Farthest point sampling -------------------------------------------------------------------
  * Replaces the reference's CPU call fpsample.fps_sampling(xyz, K) (main.py:21-22, reg_xyz.py:215,
  * DepthPrompting.py:88-90; un-vendored third-party package).  xyz [B][N][3] -> idx_out [B][K] int32,

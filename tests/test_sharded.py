@@ -82,6 +82,41 @@ def test_partial_scans_merge_to_the_single_gpu_result(cuda):
     assert torch.equal(d, d1) and torch.equal(i, i1)
     ed, ei = oracle.nn_distance(a, b)
     assert np.array_equal(d.cpu().numpy(), ed) and np.array_equal(i.cpu().numpy(), ei)
-    s = sharded_chamfer_forward(ta, tb)                    # world size 1 path
+    s = sharded_chamfer_forward(ta, tb)                    # world size 1 path (row-sharded symmetric scan)
     for x, y in zip(s, (d1, d2, i1, i2)):
         assert torch.equal(x, y)
+
+
+@pytest.mark.gpu
+def test_row_sharded_symmetric_partials_merge_exactly(cuda):
+    """Emulate 3 ranks of the row-sharded symmetric scheme on one GPU (min-merge == all-reduce-MIN)."""
+    import ctypes
+
+    from genpc_b200 import _lib
+    from genpc_b200.loss_functions import chamfer_3DDist
+    from genpc_b200.sharded import EMPTY, nn_unpack, shard_range_aligned
+
+    a, b = lattice_cloud(9, 1, 20011, side=30), rand_cloud(10, 1, 33333) * 30
+    ta, tb = torch.from_numpy(a).to(cuda), torch.from_numpy(b).to(cuda)
+    N, M = a.shape[1], b.shape[1]
+    L = _lib.lib()
+    parts = []
+    for r in range(3):
+        lo, hi = shard_range_aligned(N, r, 3)
+        assert lo % 128 == 0
+        packed = torch.full((N + M,), EMPTY, dtype=torch.int64, device=cuda)
+        rc = L.genpc_chamfer_sym_partial(_lib.ptr(ta[0, lo:hi]), _lib.ptr(tb), ctypes.c_void_p(packed.data_ptr() + lo * 8),
+                                         ctypes.c_void_p(packed.data_ptr() + N * 8), 1, hi - lo, M, lo, 0,
+                                         _lib.current_stream(cuda))
+        assert rc == 0
+        parts.append(torch.where(packed == EMPTY, torch.iinfo(torch.int64).max, packed))
+    merged = torch.stack(parts).min(0).values
+    d1, i1 = nn_unpack(merged[:N].contiguous())
+    d2 = torch.empty(M, device=cuda); i2 = torch.empty(M, dtype=torch.int32, device=cuda)
+    rc = L.genpc_chamfer_sym_fixup(_lib.ptr(ta), _lib.ptr(tb), ctypes.c_void_p(merged.data_ptr() + N * 8), 1, N, M,
+                                   _lib.ptr(d2), _lib.ptr(i2), _lib.current_stream(cuda))
+    assert rc == 0
+    e = chamfer_3DDist()(ta, tb)
+    assert torch.equal(d1, e[0][0]) and torch.equal(i1, e[2][0]) and torch.equal(d2, e[1][0]) and torch.equal(i2, e[3][0])
+    ed, ei = oracle.nn_distance(b, a)
+    assert np.array_equal(i2.cpu().numpy(), ei[0]) and np.array_equal(d2.cpu().numpy(), ed[0])
