@@ -142,7 +142,7 @@ static int chamfer_forward_sym(const float *xyz1, const float *xyz2, float *dist
     // large clouds and clearly better when the grid is small
     int QT = p.nr >= 1024 ? 4 : 2;
     const char *fq = getenv("GENPC_SYM_QT");  // experiments only
-    if (fq != nullptr && (atoi(fq) == 8 || atoi(fq) == 4 || atoi(fq) == 2)) QT = atoi(fq);
+    if (fq != nullptr && (atoi(fq) == 8 || atoi(fq) == 6 || atoi(fq) == 4 || atoi(fq) == 2)) QT = atoi(fq);
     p.rtiles = (p.nr + SYM_THREADS * QT - 1) / (SYM_THREADS * QT);
     // column span: the largest that still gives >= 2 waves of work items (3 CTAs x 148 SMs), at least 256 columns
     int span = SYM_SPAN_MAX;
@@ -156,6 +156,7 @@ static int chamfer_forward_sym(const float *xyz1, const float *xyz2, float *dist
     if (items > 0x7fffffffLL) return GENPC_ERR_RANGE;
     switch (QT) {
         case 8: nn_sym_kernel<8><<<(unsigned)items, SYM_THREADS, 0, stream>>>(p); break;
+        case 6: nn_sym_kernel<6><<<(unsigned)items, SYM_THREADS, 0, stream>>>(p); break;
         case 4: nn_sym_kernel<4><<<(unsigned)items, SYM_THREADS, 0, stream>>>(p); break;
         default: nn_sym_kernel<2><<<(unsigned)items, SYM_THREADS, 0, stream>>>(p); break;
     }
