@@ -33,6 +33,7 @@ B, N, M = 32, 2048, 16384
 FLOP_PER_PAIR = 8            # 3 sub, 3 mul, 2 add
 FP32_NOMINAL_TFLOPS = 74.4   # 148 SM x 128 lanes x 2 x 1.965 GHz (not in MEASURED_PEAKS.json)
 L2_FLUSH_BYTES = 256 << 20
+NCU_DRAM_BYTES_NN_SYM = 11821312 + 2048  # measured once under ncu (read + write), C2 shape
 
 
 def env_int(k, d):
@@ -450,7 +451,10 @@ def main():
                             "peak": FP32_NOMINAL_TFLOPS, "unit": "TFLOP/s", "frac": ach / FP32_NOMINAL_TFLOPS,
                             "peak_source": "nominal FFMA peak 148x128x2x1.965 GHz (MEASURED_PEAKS.json has no FP32 "
                                            "figure; measured issue rates in profiles/fp32_peak_b200.json)",
-                            "ms": t_fwd, "pairs_per_s": 2.0 * B * N * M / (t_fwd * 1e-3), "traffic": None}
+                            "ms": t_fwd, "pairs_per_s": 2.0 * B * N * M / (t_fwd * 1e-3),
+                            "algorithmic_bytes_per_launch": 20.0 * B * (N + M),
+                            "traffic": NCU_DRAM_BYTES_NN_SYM, "traffic_source": "ncu --set full, dram__bytes_read.sum + "
+                            "dram__bytes_write.sum per launch of nn_sym_kernel (profiles/r01c_nn_sym_ncu.txt)"}
         if m and "nn_mix_packed" in m:
             line["roofline"]["measured_mix_peak_tflops"] = m["nn_mix_packed"].get("tflops")
         bwd_bytes = 44.0 * B * (N + M)

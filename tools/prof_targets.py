@@ -1,0 +1,34 @@
+"""One small workload per kernel family, for ncu:  python tools/prof_targets.py {register|emd|fps|depth|sharded}"""
+import os, sys
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+dev = torch.device("cuda:0")
+what = sys.argv[1]
+g = torch.Generator().manual_seed(0)
+if what == "register":
+    from genpc_b200.optim_registration.diff_obj_pose import RegistrationBatch
+    from genpc_b200.synthetic import partial_view, rigid_perturb, superquadric
+    import numpy as np
+    comp = np.stack([superquadric(s, 16384) for s in range(16)])
+    part = np.stack([rigid_perturb(partial_view(comp[s], s, 16384), s)[0] for s in range(16)])
+    rb = RegistrationBatch(torch.from_numpy(comp).to(dev), torch.from_numpy(part).to(dev), n_starts=1, max_iters=8)
+    rb.run(4)
+elif what == "emd":
+    from genpc_b200.loss_functions import emdModule
+    x, y = torch.rand(8, 8192, 3, generator=g).to(dev), torch.rand(8, 8192, 3, generator=g).to(dev)
+    emdModule()(x, y, 0.005, 50); emdModule()(x, y, 0.005, 50)
+elif what == "fps":
+    from genpc_b200.fps import furthest_point_sample
+    x = torch.rand(1, 16384, 3, generator=g).to(dev)
+    furthest_point_sample(x, 2048, 0); furthest_point_sample(x, 2048, 0)
+    os.environ["GENPC_FPS_MODE"] = "cta"
+    furthest_point_sample(x, 2048, 0)
+elif what == "depth":
+    from genpc_b200 import depth as D
+    from genpc_b200.synthetic import superquadric
+    pts = torch.from_numpy(superquadric(0, 71372)).to(dev)
+    cams, _ = D.create_cameras(8, 1.6, 49.1, 512, dev)
+    for _ in range(2):
+        ndc, uv, b = D.project_uv(cams, pts, True, 0.15); r = D.zbuffer_render(uv, ndc, 512, 2); D.unproject(cams, b, r["zbuf"], ndc, True)
+torch.cuda.synchronize()
+print("done", what)
