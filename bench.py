@@ -174,8 +174,11 @@ def import_reference_api():
     for k in mine:
         del sys.modules[k]
     sys.path.insert(0, ref_pkg)
+    import contextlib
+
     try:
-        import loss_functions  # noqa: F401  (the reference's package, not genpc_b200.loss_functions)
+        with contextlib.redirect_stdout(sys.stderr):  # the reference prints at import; stdout carries ONE JSON line
+            import loss_functions  # noqa: F401  (the reference's package, not genpc_b200.loss_functions)
 
         assert os.path.realpath(loss_functions.__file__).startswith(os.path.realpath(ref_pkg))
         return loss_functions.chamfer_3DDist()

@@ -83,32 +83,54 @@ __global__ void chamfer_grad_kernel(const float *__restrict__ xyz1, const float 
                                     float *gx1, float *gx2, int B, int N, int M) {
     const size_t n1 = (size_t)B * N, n2 = (size_t)B * M;
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n1 + n2) return;
-    const float *a, *o, *gd;
-    const int *idx;
-    float *ga, *go;
-    int na, no;
-    if (i < n1) {
-        a = xyz1, o = xyz2, gd = gd1, idx = idx1, ga = gx1, go = gx2, na = N, no = M;
-    } else {
-        i -= n1;
-        a = xyz2, o = xyz1, gd = gd2, idx = idx2, ga = gx2, go = gx1, na = M, no = N;
+    const int lane = threadIdx.x & 31;
+    const bool valid = i < n1 + n2;
+    const int dir = (valid && i >= n1) ? 1 : 0;
+    if (dir) i -= n1;
+    const float *a = dir ? xyz2 : xyz1, *o = dir ? xyz1 : xyz2, *gd = dir ? gd2 : gd1;
+    const int *idx = dir ? idx2 : idx1;
+    float *ga = dir ? gx2 : gx1, *go = dir ? gx1 : gx2;
+    const int na = dir ? M : N, no = dir ? N : M;
+    size_t t = 0;
+    float tx = 0.f, ty = 0.f, tz = 0.f;
+    if (valid) {
+        const size_t b = i / na;
+        const float x1 = __ldg(a + i * 3), y1 = __ldg(a + i * 3 + 1), z1 = __ldg(a + i * 3 + 2);
+        t = b * no + __ldg(idx + i);
+        const float x2 = __ldg(o + t * 3), y2 = __ldg(o + t * 3 + 1), z2 = __ldg(o + t * 3 + 2);
+        const float g = __fmul_rn(__ldg(gd + i), 2.f);
+        tx = __fmul_rn(g, __fsub_rn(x1, x2));
+        ty = __fmul_rn(g, __fsub_rn(y1, y2));
+        tz = __fmul_rn(g, __fsub_rn(z1, z2));
+        atomicAdd(ga + i * 3 + 0, tx);  // own term: one writer per element here, but the other direction scatters
+        atomicAdd(ga + i * 3 + 1, ty);  // into the same array concurrently -> atomic
+        atomicAdd(ga + i * 3 + 2, tz);
     }
-    const size_t b = i / na;
-    const float x1 = __ldg(a + i * 3), y1 = __ldg(a + i * 3 + 1), z1 = __ldg(a + i * 3 + 2);
-    const int j2 = __ldg(idx + i);
-    const size_t t = b * no + j2;
-    const float x2 = __ldg(o + t * 3), y2 = __ldg(o + t * 3 + 1), z2 = __ldg(o + t * 3 + 2);
-    const float g = __fmul_rn(__ldg(gd + i), 2.f);
-    const float tx = __fmul_rn(g, __fsub_rn(x1, x2));
-    const float ty = __fmul_rn(g, __fsub_rn(y1, y2));
-    const float tz = __fmul_rn(g, __fsub_rn(z1, z2));
-    atomicAdd(ga + i * 3 + 0, tx);
-    atomicAdd(ga + i * 3 + 1, ty);
-    atomicAdd(ga + i * 3 + 2, tz);
-    atomicAdd(go + t * 3 + 0, -tx);
-    atomicAdd(go + t * 3 + 1, -ty);
-    atomicAdd(go + t * 3 + 2, -tz);
+    // scatter term, warp-aggregated: lanes that hit the same neighbour (common when many points of a dense cloud share
+    // one nearest neighbour in a sparse one and the cloud is stored with spatial locality) are summed by shuffles
+    // and issue ONE set of atomics.
+    const unsigned long long key = valid ? ((unsigned long long)t * 2ull + (unsigned)dir) : (~0ull - (unsigned)lane);
+    const unsigned peers = __match_any_sync(0xffffffffu, key);
+    if (peers == (1u << lane)) {
+        if (valid) {
+            atomicAdd(go + t * 3 + 0, -tx);
+            atomicAdd(go + t * 3 + 1, -ty);
+            atomicAdd(go + t * 3 + 2, -tz);
+        }
+        return;
+    }
+    const int leader = __ffs(peers) - 1;
+    float sx = -tx, sy = -ty, sz = -tz;
+    for (unsigned m = peers & (peers - 1u); m; m &= m - 1u) {  // every lane of the group runs the same trip count
+        const int src = __ffs(m) - 1;
+        const float ox = __shfl_sync(peers, -tx, src), oy = __shfl_sync(peers, -ty, src), oz = __shfl_sync(peers, -tz, src);
+        sx += ox, sy += oy, sz += oz;
+    }
+    if (lane == leader) {  // groups only form among valid lanes (invalid lanes carry unique keys)
+        atomicAdd(go + t * 3 + 0, sx);
+        atomicAdd(go + t * 3 + 1, sy);
+        atomicAdd(go + t * 3 + 2, sz);
+    }
 }
 
 static void fill_dir(NNDir &D, const float *q, const float *t, unsigned long long *out, int B, int nq, int mt,

@@ -200,10 +200,38 @@ __global__ void __launch_bounds__(SYM_THREADS, GENPC_SYM_MINB(QT)) nn_sym_kernel
 }
 
 // Exact lowest row index of one column from its published (dist, row block) word: the calling WARP re-scans the
-// winning block (rows_per_block consecutive rows, 32 per step) for the first row whose distance equals dist.
+// winning block (32*NS consecutive rows) for the first row whose distance equals dist.  All NS strips are loaded
+// up front (one exposed memory latency instead of one per strip; the scan is latency bound, not bandwidth bound).
+template <int NS>
+__device__ __forceinline__ int sym_fix_column_t(const float *__restrict__ rp, int nr, float cx, float cy, float cz, float d,
+                                                int blk, int lane) {
+    float rx[NS], ry[NS], rz[NS];
+    const int r0 = blk * (32 * NS);
+#pragma unroll
+    for (int q = 0; q < NS; ++q) {
+        const int j = min(r0 + q * 32 + lane, nr - 1);
+        rx[q] = __ldg(rp + (size_t)j * 3), ry[q] = __ldg(rp + (size_t)j * 3 + 1), rz[q] = __ldg(rp + (size_t)j * 3 + 2);
+    }
+    int found = 0;
+    bool done = false;
+#pragma unroll
+    for (int q = 0; q < NS; ++q) {
+        const int j = r0 + q * 32 + lane;
+        const bool hit = (j < nr) && (sqdist_ref(cx, cy, cz, rx[q], ry[q], rz[q]) == d);
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (!done && m) {
+            found = r0 + q * 32 + __ffs(m) - 1;
+            done = true;
+        }
+    }
+    return found;
+}
+
 __device__ __forceinline__ int sym_fix_column(const float *__restrict__ rp, int nr, int rows_per_block, float cx, float cy,
                                               float cz, float d, int blk, int lane) {
-    int found = 0;
+    if (rows_per_block == 128) return sym_fix_column_t<4>(rp, nr, cx, cy, cz, d, blk, lane);
+    if (rows_per_block == 64) return sym_fix_column_t<2>(rp, nr, cx, cy, cz, d, blk, lane);
+    int found = 0;  // generic (QT = 6 / 8 experiments)
     for (int r0 = blk * rows_per_block; r0 < (blk + 1) * rows_per_block; r0 += 32) {
         const int j = r0 + lane;
         bool hit = false;

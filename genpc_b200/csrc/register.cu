@@ -62,8 +62,8 @@ __device__ __forceinline__ double block_sum(double v, double *sh) {
     if (lane == 0) sh[warp] = v;
     __syncthreads();
     double r = 0.0;
-#pragma unroll
-    for (int w = 0; w < NN_THREADS / 32; ++w) r += sh[w];  // fixed order -> deterministic
+    const int nw = blockDim.x >> 5;
+    for (int w = 0; w < nw; ++w) r += sh[w];  // fixed order -> deterministic
     return r;
 }
 
@@ -106,16 +106,20 @@ __device__ __noinline__ void finalize_scan(const RegArgs &a, int scan, const Sim
     for (int i = 0; i < 14; ++i) acc[i] = 0.0;
     const double cA = (double)a.cd_weight * (double)a.w_fwd / (double)a.Nc;
     const double cB = (double)a.cd_weight * (double)a.w_inv / (double)a.Nr;
-    for (int j = threadIdx.x; j < a.Nc; j += NN_THREADS) {  // direction A: moving point j -> its NN in ref
+    const int nthr = blockDim.x;
+#pragma unroll 4
+    for (int j = threadIdx.x; j < a.Nc; j += nthr) {  // direction A: moving point j -> its NN in ref
         const unsigned long long w = __ldcg(pA + j);
-        pA[j] = ~0ull;  // re-arm for the next launch
         accum_term(a, T, V, Rf, j, (int)(unsigned)(w & 0xffffffffu), __uint_as_float((unsigned)(w >> 32)), cA, acc);
     }
-    for (int k = threadIdx.x; k < a.Nr; k += NN_THREADS) {  // direction B: ref point k -> its NN among moving pts
+#pragma unroll 4
+    for (int k = threadIdx.x; k < a.Nr; k += nthr) {  // direction B: ref point k -> its NN among moving pts
         const unsigned long long w = __ldcg(pB + k);
-        pB[k] = ~0ull;
         accum_term(a, T, V, Rf, (int)(unsigned)(w & 0xffffffffu), k, __uint_as_float((unsigned)(w >> 32)), cB, acc);
     }
+    __syncthreads();
+    for (int j = threadIdx.x; j < a.Nc; j += nthr) pA[j] = ~0ull;  // re-arm for the next launch
+    for (int k = threadIdx.x; k < a.Nr; k += nthr) pB[k] = ~0ull;
     double tot[14];
 #pragma unroll
     for (int i = 0; i < 14; ++i) tot[i] = block_sum(acc[i], sh);
@@ -166,7 +170,7 @@ __global__ void __launch_bounds__(NN_THREADS, NN_MINBLOCKS) register_step_kernel
     __shared__ __align__(16) float s[3][NN_SPAN];
     __shared__ Similarity T;
     __shared__ int is_last;
-    __shared__ double sh[NN_THREADS / 32];
+    __shared__ double sh[32];
     const int scan = blockIdx.x / a.items_per_scan;
     int item = blockIdx.x - scan * a.items_per_scan;
     const int cloud = scan / a.n_starts;
@@ -215,11 +219,12 @@ __global__ void __launch_bounds__(SYM_THREADS, GENPC_SYM_MINB(QT)) register_sym_
 
 // launch 2: one warp per moving point resolves its (dist, row block) word to the exact lowest index of the fixed
 //           cloud; the last CTA of a scan (ticket) then reduces loss + gradient and steps Adam (finalize_scan).
-constexpr int FIX_COLS_PER_CTA = 64;
-__global__ void __launch_bounds__(NN_THREADS) register_finish_kernel(const RegArgs a) {
+constexpr int FIX_THREADS = 512;
+constexpr int FIX_COLS_PER_CTA = 128;
+__global__ void __launch_bounds__(FIX_THREADS) register_finish_kernel(const RegArgs a) {
     __shared__ Similarity T;
     __shared__ int is_last;
-    __shared__ double sh[NN_THREADS / 32];
+    __shared__ double sh[FIX_THREADS / 32];
     const int scan = blockIdx.x / a.fix_ctas;
     const int part = blockIdx.x - scan * a.fix_ctas;
     const int cloud = scan / a.n_starts;
@@ -229,7 +234,7 @@ __global__ void __launch_bounds__(NN_THREADS) register_finish_kernel(const RegAr
     const float *V = a.complete + (size_t)cloud * a.Nc * 3;
     const float *Rf = a.ref + (size_t)cloud * a.Nr * 3;
     unsigned long long *pA = a.packedA + (size_t)scan * a.Nc;
-    for (int c = part * FIX_COLS_PER_CTA + warp; c < min(a.Nc, (part + 1) * FIX_COLS_PER_CTA); c += NN_THREADS / 32) {
+    for (int c = part * FIX_COLS_PER_CTA + warp; c < min(a.Nc, (part + 1) * FIX_COLS_PER_CTA); c += FIX_THREADS / 32) {
         const unsigned long long w = __ldcg(pA + c);
         const float d = __uint_as_float((unsigned)(w >> 32));
         float x = __ldg(V + (size_t)c * 3), y = __ldg(V + (size_t)c * 3 + 1), z = __ldg(V + (size_t)c * 3 + 2);
@@ -323,7 +328,7 @@ extern "C" int genpc_register_run(const float *complete, const float *center, co
             if (SQT == 4) register_sym_scan_kernel<4><<<(unsigned)sgrid, SYM_THREADS, 0, stream>>>(a);
             else register_sym_scan_kernel<2><<<(unsigned)sgrid, SYM_THREADS, 0, stream>>>(a);
             GENPC_CHECK_LAUNCH();
-            register_finish_kernel<<<(unsigned)fgrid, NN_THREADS, 0, stream>>>(a);
+            register_finish_kernel<<<(unsigned)fgrid, FIX_THREADS, 0, stream>>>(a);
             GENPC_CHECK_LAUNCH();
             continue;
         }

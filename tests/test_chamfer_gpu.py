@@ -152,3 +152,21 @@ def test_golden_vectors(cuda):
         got = run_ours(z["xyz1"], z["xyz2"], cuda)
         for g, name in zip(got, ("dist1", "dist2", "idx1", "idx2")):
             assert np.array_equal(g, z[name]), f"{os.path.basename(f)}:{name}"
+
+
+def test_backward_warp_aggregated_scatter(cuda):
+    """Many points share one nearest neighbour (8 targets for 5000 queries): the scatter term takes the
+    warp-aggregated path (lanes with equal neighbour summed by shuffles, one set of atomics per group)."""
+    from genpc_b200.loss_functions import chamfer_3DDist
+
+    a, b = rand_cloud(31, 2, 5000), rand_cloud(32, 2, 8)
+    rng = np.random.default_rng(1)
+    g1 = rng.standard_normal((2, 5000)).astype(np.float32)
+    g2 = rng.standard_normal((2, 8)).astype(np.float32)
+    ta = torch.from_numpy(a).to(cuda).requires_grad_(True)
+    tb = torch.from_numpy(b).to(cuda).requires_grad_(True)
+    d1, d2, i1, i2 = chamfer_3DDist()(ta, tb)
+    ((d1 * torch.from_numpy(g1).to(cuda)).sum() + (d2 * torch.from_numpy(g2).to(cuda)).sum()).backward()
+    e1, e2 = oracle.chamfer_backward(a, b, g1, g2, i1.cpu().numpy(), i2.cpu().numpy())
+    for got, exp in ((ta.grad.cpu().numpy(), e1), (tb.grad.cpu().numpy(), e2)):
+        assert np.abs(got - exp).max() <= 1e-5 * np.abs(exp).max() + 1e-12
