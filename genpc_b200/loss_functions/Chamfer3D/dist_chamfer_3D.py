@@ -1,8 +1,14 @@
-"""Drop-in for the reference's loss_functions/Chamfer3D/dist_chamfer_3D.py (:26-74).
+"""Chamfer distance module -- drop-in for the reference's loss_functions/Chamfer3D/dist_chamfer_3D.py (:26-74).
 
-Same classes, same call signature and return tuple; the differences are the two the reference gets wrong
-for a device-resident pipeline: outputs are allocated on the device instead of on
-the CPU followed by .to(device) (:33-42, :56-60), and kernels go to the current stream.
+    dist1, dist2, idx1, idx2 = chamfer_3DDist()(input1, input2)        # [B,N,3], [B,M,3] CUDA tensors
+
+dist1[b,j] = min_k |input1[b,j] - input2[b,k]|^2 with idx1 the arg-min (lowest index on ties), dist2/idx2 the other
+direction; differentiable w.r.t. both inputs.  GPU tensors only, exactly like the reference (:25) -- a CPU tensor
+raises instead of silently falling back.
+
+What differs from the reference is only where memory lives: outputs and gradients are created on the inputs' device
+(the reference allocates them on the CPU and copies them over on every call, :33-42 and :56-60), the kernels write
+every output element so no zero-fill is needed, and launches go to the current stream.
 """
 import torch
 from torch import nn
@@ -11,19 +17,17 @@ from torch.autograd import Function
 from ... import chamfer_3D
 
 
-# Chamfer's distance module -- GPU tensors only (as the reference, :25)
+def _outputs(like, count):
+    shape = (like.shape[0], count)
+    return (torch.empty(shape, dtype=torch.float32, device=like.device),
+            torch.empty(shape, dtype=torch.int32, device=like.device))
+
+
 class chamfer_3DFunction(Function):
     @staticmethod
     def forward(ctx, xyz1, xyz2):
-        batchsize, n, _ = xyz1.size()
-        _, m, _ = xyz2.size()
-        device = xyz1.device
-        # the kernels write every element (and zero-fill the degenerate N == 0 / M == 0 cases), so the reference's
-        # zero-initialisation (:33-37) would only add four fill launches
-        dist1 = torch.empty(batchsize, n, device=device)
-        dist2 = torch.empty(batchsize, m, device=device)
-        idx1 = torch.empty(batchsize, n, dtype=torch.int32, device=device)
-        idx2 = torch.empty(batchsize, m, dtype=torch.int32, device=device)
+        dist1, idx1 = _outputs(xyz1, xyz1.shape[1])
+        dist2, idx2 = _outputs(xyz2, xyz2.shape[1])
         chamfer_3D.forward(xyz1, xyz2, dist1, dist2, idx1, idx2)
         ctx.save_for_backward(xyz1, xyz2, idx1, idx2)
         ctx.mark_non_differentiable(idx1, idx2)
@@ -32,19 +36,12 @@ class chamfer_3DFunction(Function):
     @staticmethod
     def backward(ctx, graddist1, graddist2, gradidx1, gradidx2):
         xyz1, xyz2, idx1, idx2 = ctx.saved_tensors
-        graddist1 = graddist1.contiguous()
-        graddist2 = graddist2.contiguous()
-        gradxyz1 = torch.zeros_like(xyz1)
-        gradxyz2 = torch.zeros_like(xyz2)
-        chamfer_3D.backward(xyz1, xyz2, gradxyz1, gradxyz2, graddist1, graddist2, idx1, idx2)
-        return gradxyz1, gradxyz2
+        # the native backward ACCUMULATES (atomics), so the gradients start from zero as in the reference (:56-57)
+        grads = torch.zeros_like(xyz1), torch.zeros_like(xyz2)
+        chamfer_3D.backward(xyz1, xyz2, grads[0], grads[1], graddist1.contiguous(), graddist2.contiguous(), idx1, idx2)
+        return grads
 
 
 class chamfer_3DDist(nn.Module):
-    def __init__(self):
-        super(chamfer_3DDist, self).__init__()
-
     def forward(self, input1, input2):
-        input1 = input1.contiguous()
-        input2 = input2.contiguous()
-        return chamfer_3DFunction.apply(input1, input2)
+        return chamfer_3DFunction.apply(input1.contiguous(), input2.contiguous())

@@ -1,11 +1,14 @@
-"""Drop-in for the reference's loss_functions/emd/emd_module.py (:29-95): EMD approximation (auction algorithm).
+"""EMD approximation (auction algorithm) -- drop-in for the reference's loss_functions/emd/emd_module.py (:29-95).
 
-Input  xyz1, xyz2: [#batch, #points, 3] (xyz1 predicted, xyz2 ground truth), same size, #points % 256 == 0,
-       #batch <= 512; eps balances error rate and convergence speed; iters = number of auction iterations.
-Output dist [#batch, #points] (sqrt(dist) -> L2 distance), assignment [#batch, #points] (index of the matched
-       ground-truth point; an approximation, not guaranteed to be a bijection).  Gradient for xyz1 only.
-Differences from the reference: tensors stay on the device they arrive on (the reference hard-codes
-device="cuda", :41-54, which breaks under DataParallel on any GPU but 0) and work goes to the current stream.
+    dist, assignment = emdModule()(xyz1, xyz2, eps, iters)
+
+xyz1 (prediction) and xyz2 (ground truth) are [batch, points, 3] with equal point counts, points % 256 == 0 and
+batch <= 512 (checked with the reference's asserts, :36-39).  `dist` [batch, points] holds squared matched
+distances (sqrt -> L2), `assignment` [batch, points] the matched ground-truth index (an approximation, not
+necessarily a bijection).  Only xyz1 receives a gradient (:83-87).
+
+Unlike the reference, which hard-codes device="cuda" for every scratch tensor (:41-54), everything lives on the
+device the inputs arrive on, and the single persistent kernel runs on the current stream.
 """
 import torch
 from torch import nn
@@ -13,54 +16,53 @@ from torch.autograd import Function
 
 from ... import emd
 
+_COUNTERS = 512  # length of the reference's three counter tensors (:52-54)
+
+
+def _scratch(batch, n, device):
+    """The caller-allocated state of emd.forward with the reference's initial values (:43-54)."""
+    f = dict(device=device, dtype=torch.float32)
+    i = dict(device=device, dtype=torch.int32)
+    return {
+        "dist": torch.zeros(batch, n, **f),
+        "assignment": torch.full((batch, n), -1, **i),
+        "price": torch.zeros(batch, n, **f),
+        "assignment_inv": torch.full((batch, n), -1, **i),
+        "bid": torch.zeros(batch, n, **i),
+        "bid_increments": torch.zeros(batch, n, **f),
+        "max_increments": torch.zeros(batch, n, **f),
+        "unass_idx": torch.zeros(batch * n, **i),
+        "unass_cnt": torch.zeros(_COUNTERS, **i),
+        "unass_cnt_sum": torch.zeros(_COUNTERS, **i),
+        "cnt_tmp": torch.zeros(_COUNTERS, **i),
+        "max_idx": torch.zeros(batch * n, **i),
+    }
+
 
 class emdFunction(Function):
     @staticmethod
     def forward(ctx, xyz1, xyz2, eps, iters):
-        batchsize, n, _ = xyz1.size()
-        _, m, _ = xyz2.size()
-
-        assert n == m
-        assert xyz1.size()[0] == xyz2.size()[0]
+        batch, n, _ = xyz1.size()
+        assert n == xyz2.size()[1]
+        assert batch == xyz2.size()[0]
         assert n % 256 == 0
-        assert batchsize <= 512
-
-        xyz1 = xyz1.contiguous().float()
-        xyz2 = xyz2.contiguous().float()
-        dev = xyz1.device
-        dist = torch.zeros(batchsize, n, device=dev)
-        assignment = torch.full((batchsize, n), -1, device=dev, dtype=torch.int32)
-        assignment_inv = torch.full((batchsize, m), -1, device=dev, dtype=torch.int32)
-        price = torch.zeros(batchsize, m, device=dev)
-        bid = torch.zeros(batchsize, n, device=dev, dtype=torch.int32)
-        bid_increments = torch.zeros(batchsize, n, device=dev)
-        max_increments = torch.zeros(batchsize, m, device=dev)
-        unass_idx = torch.zeros(batchsize * n, device=dev, dtype=torch.int32)
-        max_idx = torch.zeros(batchsize * m, device=dev, dtype=torch.int32)
-        unass_cnt = torch.zeros(512, dtype=torch.int32, device=dev)
-        unass_cnt_sum = torch.zeros(512, dtype=torch.int32, device=dev)
-        cnt_tmp = torch.zeros(512, dtype=torch.int32, device=dev)
-
-        emd.forward(xyz1, xyz2, dist, assignment, price, assignment_inv, bid, bid_increments, max_increments,
-                    unass_idx, unass_cnt, unass_cnt_sum, cnt_tmp, max_idx, eps, iters)
-
-        ctx.save_for_backward(xyz1, xyz2, assignment)
-        ctx.mark_non_differentiable(assignment)
-        return dist, assignment
+        assert batch <= 512
+        pred = xyz1.contiguous().float()
+        truth = xyz2.contiguous().float()
+        st = _scratch(batch, n, pred.device)
+        emd.forward(pred, truth, *st.values(), eps, iters)
+        ctx.save_for_backward(pred, truth, st["assignment"])
+        ctx.mark_non_differentiable(st["assignment"])
+        return st["dist"], st["assignment"]
 
     @staticmethod
     def backward(ctx, graddist, gradidx):
-        xyz1, xyz2, assignment = ctx.saved_tensors
-        graddist = graddist.contiguous()
-        gradxyz1 = torch.zeros_like(xyz1)
-        gradxyz2 = torch.zeros_like(xyz2)
-        emd.backward(xyz1, xyz2, gradxyz1, graddist, assignment)
-        return gradxyz1, gradxyz2, None, None
+        pred, truth, assignment = ctx.saved_tensors
+        grad_pred = torch.zeros_like(pred)
+        emd.backward(pred, truth, grad_pred, graddist.contiguous(), assignment)
+        return grad_pred, torch.zeros_like(truth), None, None
 
 
 class emdModule(nn.Module):
-    def __init__(self):
-        super(emdModule, self).__init__()
-
     def forward(self, input1, input2, eps, iters):
         return emdFunction.apply(input1, input2, eps, iters)

@@ -1,56 +1,62 @@
-"""Drop-in for the reference's utils/loss_util.py (:8-53): Completionloss with the same methods and reductions.
+"""Completion losses on the B200 kernels: the drop-in for the reference's `Completionloss` (utils/loss_util.py:8-53).
 
-The reference wraps emdModule in nn.DataParallel (:12), which only scatters the batch over the visible GPUs of
-ONE process; here the EMD module is called directly (one process per GPU is the multi-GPU model of this build,
-see genpc_b200.sharded), results are identical.
+Same constructor argument (`'cd_l1' | 'cd_l2' | 'emd'`), same public methods and reductions:
+
+    chamfer_l1          (mean sqrt d1 + mean sqrt d2) / 2          reference :25-29
+    chamfer_l2           mean d1 + mean d2                          :31-33
+    chamfer_partial_l1   mean sqrt d1                               :35-38
+    chamfer_partial_l2   mean d1                                    :40-43
+    emd_loss             mean_b mean_n sqrt(dist), eps .005, 50 it  :45-49
+    get_loss             the metric selected by `loss_func`         :51-53
+
+The reference wraps emdModule in nn.DataParallel (:12), i.e. one process scattering the batch over its visible
+GPUs; this build's multi-GPU model is one process per GPU (genpc_b200.sharded), so the module is called directly.
 """
 import torch
 
 from ..loss_functions import chamfer_3DDist, emdModule
 
+_EMD_EPS, _EMD_ITERS = 0.005, 50
+_KNOWN = ("cd_l1", "cd_l2", "emd")
+
+
+def _l1(d):
+    return torch.sqrt(d).mean()
+
 
 class Completionloss:
-    def __init__(self, loss_func='cd_l1'):
+    def __init__(self, loss_func="cd_l1"):
+        if loss_func not in _KNOWN:
+            raise Exception("loss function {} not supported yet!".format(loss_func))
         self.loss_func = loss_func
         self.chamfer_dist = chamfer_3DDist()
         self.EMD = emdModule()
+        self.metric = {"cd_l1": self.chamfer_l1, "cd_l2": self.chamfer_l2, "emd": self.emd_loss}[loss_func]
+        if loss_func != "emd":
+            self.partial_matching = self.chamfer_partial_l1 if loss_func == "cd_l1" else self.chamfer_partial_l2
 
-        if loss_func == 'cd_l1':
-            self.metric = self.chamfer_l1
-            self.partial_matching = self.chamfer_partial_l1
-        elif loss_func == 'cd_l2':
-            self.metric = self.chamfer_l2
-            self.partial_matching = self.chamfer_partial_l2
-        elif loss_func == 'emd':
-            self.metric = self.emd_loss
-        else:
-            raise Exception('loss function {} not supported yet!'.format(loss_func))
+    # one extension call serves both directions; partial variants keep only the first cloud's distances
+    def _nn(self, first, second):
+        dist_first, dist_second, _, _ = self.chamfer_dist(first, second)
+        return dist_first, dist_second
 
     def chamfer_l1(self, p1, p2):
-        d1, d2, _, _ = self.chamfer_dist(p1, p2)
-        d1 = torch.mean(torch.sqrt(d1))
-        d2 = torch.mean(torch.sqrt(d2))
-        return (d1 + d2) / 2
+        a, b = self._nn(p1, p2)
+        return (_l1(a) + _l1(b)) / 2
 
     def chamfer_l2(self, p1, p2):
-        d1, d2, _, _ = self.chamfer_dist(p1, p2)
-        return torch.mean(d1) + torch.mean(d2)
+        a, b = self._nn(p1, p2)
+        return a.mean() + b.mean()
 
     def chamfer_partial_l1(self, pcd1, pcd2):
-        d1, d2, _, _ = self.chamfer_dist(pcd1, pcd2)
-        d1 = torch.mean(torch.sqrt(d1))
-        return d1
+        return _l1(self._nn(pcd1, pcd2)[0])
 
     def chamfer_partial_l2(self, pcd1, pcd2):
-        d1, d2, _, _ = self.chamfer_dist(pcd1, pcd2)
-        d1 = torch.mean(d1)
-        return d1
+        return self._nn(pcd1, pcd2)[0].mean()
 
     def emd_loss(self, p1, p2):
-        d1, _ = self.EMD(p1, p2, eps=0.005, iters=50)
-        d = torch.sqrt(d1).mean(1).mean()
-        return d
+        sq, _ = self.EMD(p1, p2, eps=_EMD_EPS, iters=_EMD_ITERS)
+        return torch.sqrt(sq).mean(1).mean()
 
     def get_loss(self, gen, gt):
-        loss = self.metric(gen, gt)
-        return loss
+        return self.metric(gen, gt)
