@@ -216,9 +216,14 @@ struct FpsCand {
     int pad[3];
 };
 
-template <int PPT, int CS>
+// SMEMC = false: coordinates in registers (PPT <= 4, N <= 32768).  SMEMC = true: coordinates in the CTA's dynamic
+// shared memory as SoA (3 * PPT * 1024 floats, up to 221 KB at PPT = 18 -> clouds of up to 147 456 points, the sizes
+// the reference feeds to fpsample: 45 K - 170 K), running distances still in registers.
+template <int PPT, int CS, bool SMEMC>
 __global__ void __launch_bounds__(FPS_THREADS, 1) fps_cluster_kernel(const float *__restrict__ xyz, int N, int K, int start,
                                                                       int *__restrict__ idx_out, float *__restrict__ seq_out) {
+    extern __shared__ __align__(16) float dyn_xyz[];
+    float *sx = dyn_xyz, *sy = dyn_xyz + PPT * FPS_THREADS, *sz = dyn_xyz + 2 * PPT * FPS_THREADS;
     __shared__ unsigned sval[2][FPS_WARPS];
     __shared__ int sidx[2][FPS_WARPS];
     __shared__ __align__(16) FpsCand cand[2][CS];
@@ -229,17 +234,20 @@ __global__ void __launch_bounds__(FPS_THREADS, 1) fps_cluster_kernel(const float
     const float *p = xyz + (size_t)b * N * 3;
     // point i of the cloud lives in CTA (i / 1024) % CS ... interleaved so that every CTA holds a similar share:
     // global index of (rank, k, tid) = (k * CS + rank) * 1024 + tid
-    float px[PPT], py[PPT], pz[PPT], run[PPT];
+    constexpr int RP = SMEMC ? 1 : PPT;
+    float px[RP], py[RP], pz[RP], run[PPT];
 #pragma unroll
     for (int k = 0; k < PPT; ++k) {
         const int i = (k * CS + rank) * FPS_THREADS + tid;
-        px[k] = py[k] = pz[k] = 0.f;
+        float x = 0.f, y = 0.f, z = 0.f;
         if (i < N) {
-            px[k] = __ldg(p + (size_t)i * 3), py[k] = __ldg(p + (size_t)i * 3 + 1), pz[k] = __ldg(p + (size_t)i * 3 + 2);
+            x = __ldg(p + (size_t)i * 3), y = __ldg(p + (size_t)i * 3 + 1), z = __ldg(p + (size_t)i * 3 + 2);
             run[k] = __int_as_float(0x7f800000);
         } else {
             run[k] = -1.f;
         }
+        if (SMEMC) sx[k * FPS_THREADS + tid] = x, sy[k * FPS_THREADS + tid] = y, sz[k * FPS_THREADS + tid] = z;
+        else px[k % RP] = x, py[k % RP] = y, pz[k % RP] = z;
     }
     float lx = __ldg(p + (size_t)start * 3), ly = __ldg(p + (size_t)start * 3 + 1), lz = __ldg(p + (size_t)start * 3 + 2);
     int cur = start;
@@ -257,7 +265,10 @@ __global__ void __launch_bounds__(FPS_THREADS, 1) fps_cluster_kernel(const float
         int best_i = 0x7fffffff, best_k = 0;
 #pragma unroll
         for (int k = 0; k < PPT; ++k) {
-            const float dx = __fsub_rn(px[k], lx), dy = __fsub_rn(py[k], ly), dz = __fsub_rn(pz[k], lz);
+            const float qx = SMEMC ? sx[k * FPS_THREADS + tid] : px[k % RP];
+            const float qy = SMEMC ? sy[k * FPS_THREADS + tid] : py[k % RP];
+            const float qz = SMEMC ? sz[k * FPS_THREADS + tid] : pz[k % RP];
+            const float dx = __fsub_rn(qx, lx), dy = __fsub_rn(qy, ly), dz = __fsub_rn(qz, lz);
             const float d = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
             const float r = (run[k] < d) ? run[k] : d;
             run[k] = r;
@@ -276,10 +287,15 @@ __global__ void __launch_bounds__(FPS_THREADS, 1) fps_cluster_kernel(const float
         // each waiting for its own DSMEM stores: measured 2.5 us per pick)
         const int wtid = (winner == 0x7fffffff) ? 0 : (winner & (FPS_THREADS - 1));
         if (warp == (wtid >> 5)) {
-            float cx = px[0], cy = py[0], cz = pz[0];
+            float cx, cy, cz;
+            if (SMEMC) {
+                cx = sx[best_k * FPS_THREADS + tid], cy = sy[best_k * FPS_THREADS + tid], cz = sz[best_k * FPS_THREADS + tid];
+            } else {
+                cx = px[0], cy = py[0], cz = pz[0];
 #pragma unroll
-            for (int k = 1; k < PPT; ++k)
-                if (best_k == k) cx = px[k], cy = py[k], cz = pz[k];
+                for (int k = 1; k < RP; ++k)
+                    if (best_k == k) cx = px[k], cy = py[k], cz = pz[k];
+            }
             const int src = wtid & 31;
             cx = __shfl_sync(0xffffffffu, cx, src), cy = __shfl_sync(0xffffffffu, cy, src), cz = __shfl_sync(0xffffffffu, cz, src);
             if (lane < CS) {
@@ -315,19 +331,24 @@ __global__ void __launch_bounds__(FPS_THREADS, 1) fps_cluster_kernel(const float
     cluster.sync();  // no CTA may exit while a sibling can still write into its shared memory
 }
 
-template <int PPT, int CS>
+template <int PPT, int CS, bool SMEMC>
 static cudaError_t launch_fps_cluster(const float *xyz, int B, int N, int K, int start, int *idx_out, float *seq_out,
                                       cudaStream_t stream) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(B * CS));
     cfg.blockDim = dim3(FPS_THREADS);
-    cfg.dynamicSmemBytes = 0;
+    cfg.dynamicSmemBytes = SMEMC ? (size_t)3 * PPT * FPS_THREADS * sizeof(float) : 0;
+    if (SMEMC) {
+        cudaError_t e = cudaFuncSetAttribute(fps_cluster_kernel<PPT, CS, SMEMC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)cfg.dynamicSmemBytes);
+        if (e != cudaSuccess) return e;
+    }
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CS, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr, cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, fps_cluster_kernel<PPT, CS>, xyz, N, K, start, idx_out, seq_out);
+    return cudaLaunchKernelEx(&cfg, fps_cluster_kernel<PPT, CS, SMEMC>, xyz, N, K, start, idx_out, seq_out);
 }
 
 }  // namespace genpc
@@ -349,12 +370,15 @@ extern "C" int genpc_fps(const float *xyz, int B, int N, int K, int start, int *
     // Measured on B200 (profiles/r01d_fps.txt): a pick costs 1.15 us through the cluster exchange whatever N is, and
     // 0.35 / 0.51 / 1.02 / 1.78 / 4.23 us in the single CTA at N = 1024 / 4096 / 8192 / 16384 / 32768.
     const char *fm = getenv("GENPC_FPS_MODE");
-    const bool want_cluster = (fm == nullptr) ? (ppt > 8 && ppt <= 32 && B * 8 <= GENPC_NUM_SMS) : (strcmp(fm, "cluster") == 0 && ppt <= 32);
+    const bool want_cluster = (fm == nullptr) ? (ppt > 8 && ppt <= 144 && B * 8 <= GENPC_NUM_SMS) : (strcmp(fm, "cluster") == 0 && ppt <= 144);
     if (want_cluster) {
         cudaError_t e;
-        if (ppt <= 8) e = launch_fps_cluster<1, 8>(xyz, B, N, K, start, idx_out, seq_out, stream);
-        else if (ppt <= 16) e = launch_fps_cluster<2, 8>(xyz, B, N, K, start, idx_out, seq_out, stream);
-        else e = launch_fps_cluster<4, 8>(xyz, B, N, K, start, idx_out, seq_out, stream);
+        if (ppt <= 8) e = launch_fps_cluster<1, 8, false>(xyz, B, N, K, start, idx_out, seq_out, stream);
+        else if (ppt <= 16) e = launch_fps_cluster<2, 8, false>(xyz, B, N, K, start, idx_out, seq_out, stream);
+        else if (ppt <= 32) e = launch_fps_cluster<4, 8, false>(xyz, B, N, K, start, idx_out, seq_out, stream);
+        else if (ppt <= 64) e = launch_fps_cluster<8, 8, true>(xyz, B, N, K, start, idx_out, seq_out, stream);
+        else if (ppt <= 96) e = launch_fps_cluster<12, 8, true>(xyz, B, N, K, start, idx_out, seq_out, stream);
+        else e = launch_fps_cluster<18, 8, true>(xyz, B, N, K, start, idx_out, seq_out, stream);
         if (e != cudaSuccess) return (int)e;
         return GENPC_OK;
     }

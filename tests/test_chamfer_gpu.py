@@ -170,3 +170,28 @@ def test_backward_warp_aggregated_scatter(cuda):
     e1, e2 = oracle.chamfer_backward(a, b, g1, g2, i1.cpu().numpy(), i2.cpu().numpy())
     for got, exp in ((ta.grad.cpu().numpy(), e1), (tb.grad.cpu().numpy(), e2)):
         assert np.abs(got - exp).max() <= 1e-5 * np.abs(exp).max() + 1e-12
+
+
+def test_forward_fuzz_shapes_and_distributions(cuda):
+    """Seeded sweep over awkward shapes (unaligned sizes, tiny / huge aspect ratios, both kernel paths) and point
+    distributions (uniform, clustered, duplicated points, lattice ties): bit-exact against the oracle every time."""
+    rng = np.random.default_rng(2026)
+    for trial in range(40):
+        B = int(rng.integers(1, 5))
+        N = int(rng.choice([1, 2, 31, 33, 127, 129, 511, 513, 1000, 1023, 1025, 2049, 4099, 7001]))
+        M = int(rng.choice([1, 3, 32, 100, 255, 257, 512, 777, 1024, 1300, 2047, 3001, 9973]))
+        kind = trial % 4
+        if kind == 0:
+            a, b = rand_cloud(trial, B, N), rand_cloud(trial + 1000, B, M)
+        elif kind == 1:   # clustered, far from the origin (large magnitudes, small differences)
+            a, b = rand_cloud(trial, B, N, 0.01, 37.5), rand_cloud(trial + 1000, B, M, 0.01, 37.5)
+        elif kind == 2:   # duplicated points: exact ties on both sides
+            a, b = rand_cloud(trial, B, N), rand_cloud(trial + 1000, B, M)
+            a[:, N // 2:] = a[:, :N - N // 2]
+            b[:, M // 2:] = b[:, :M - M // 2]
+        else:
+            a, b = lattice_cloud(trial, B, N, side=5), lattice_cloud(trial + 1000, B, M, side=5)
+        got = run_ours(a, b, cuda)
+        exp = oracle.chamfer_forward(a, b)
+        for g, e, name in zip(got, exp, ("dist1", "dist2", "idx1", "idx2")):
+            assert np.array_equal(g.view(np.int32), e.view(np.int32)), (trial, B, N, M, kind, name)

@@ -64,7 +64,8 @@ def test_fps_gpu_ties_and_api(cuda):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("B,N,K,start", [(1, 16384, 2048, 0), (2, 5000, 300, 4999), (1, 9000, 500, 3), (3, 20000, 64, 1),
-                                         (1, 32768, 100, 0), (1, 1500, 200, 7)])
+                                         (1, 32768, 100, 0), (1, 1500, 200, 7), (1, 71372, 300, 11), (2, 100000, 40, 0),
+                                         (1, 147000, 24, 146999)])
 def test_fps_cluster_kernel_bit_exact(cuda, B, N, K, start):
     """The thread-block-cluster / DSMEM kernel (forced through GENPC_FPS_MODE) against the oracle."""
     import os
