@@ -180,8 +180,11 @@ def import_reference_api():
         with contextlib.redirect_stdout(sys.stderr):  # the reference prints at import; stdout carries ONE JSON line
             import loss_functions  # noqa: F401  (the reference's package, not genpc_b200.loss_functions)
 
+            from utils.loss_util import Completionloss as RefCompletionloss  # the reference's own loss facade
+
         assert os.path.realpath(loss_functions.__file__).startswith(os.path.realpath(ref_pkg))
-        return loss_functions.chamfer_3DDist()
+        ref_loss = RefCompletionloss("cd_l2")          # utils/loss_util.py:8-23 (also builds DataParallel(emdModule))
+        return ref_loss.get_loss                        # == chamfer_l2: mean(d1) + mean(d2)
     except Exception as e:  # pragma: no cover
         sys.stderr.write(f"[bench] reference API import failed: {e}\n")
         return None
@@ -225,8 +228,9 @@ def chamfer_l2_loss(fn, a, b):
     return torch.mean(d1) + torch.mean(d2)
 
 
-def run_gpu_arm(args, fn, rank, world, dev, part, comp, tag):
-    """Times K steps device-resident (`value`) and K steps end-to-end from pinned host buffers (`e2e`)."""
+def run_gpu_arm(args, loss_fn, rank, world, dev, part, comp, tag):
+    """Times K steps device-resident (`value`) and K steps end-to-end from pinned host buffers (`e2e`).
+    loss_fn(a, b) -> scalar loss is the public API call: Completionloss('cd_l2').get_loss of either implementation."""
     import torch.distributed as dist
 
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
@@ -238,14 +242,14 @@ def run_gpu_arm(args, fn, rank, world, dev, part, comp, tag):
     def step_resident():
         a.grad = None
         b.grad = None
-        loss = chamfer_l2_loss(fn, a, b)
+        loss = loss_fn(a, b)
         loss.backward()
         return loss
 
     def step_e2e():
         da = ha.to(dev, non_blocking=True).requires_grad_(True)
         db = hb.to(dev, non_blocking=True).requires_grad_(True)
-        loss = chamfer_l2_loss(fn, da, db)
+        loss = loss_fn(da, db)
         loss.backward()
         hloss.copy_(loss.detach(), non_blocking=True)
         return loss
@@ -411,11 +415,13 @@ def main():
             return
         api = import_reference_api()
         if api is not None:
-            fn, how = (lambda x, y: api(x, y)), ("UNMODIFIED reference API loss_functions.chamfer_3DDist (baseline/_ref) "
-                                                 "on its UNMODIFIED CUDA extension (oracle/_ref, sm_100a)")
+            fn, how = api, ("UNMODIFIED reference API utils.loss_util.Completionloss('cd_l2').get_loss (baseline/_ref) "
+                            "on its UNMODIFIED CUDA extension (oracle/_ref, sm_100a)")
         else:
-            fn, how = make_ref_function(ext), ("UNMODIFIED reference chamfer_3D CUDA extension (oracle/_ref) through "
-                                               "dist_chamfer_3D.py:26-64 restated (baseline/_ref not installed)")
+            raw = make_ref_function(ext)
+            fn, how = (lambda x, y: chamfer_l2_loss(raw, x, y)), ("UNMODIFIED reference chamfer_3D CUDA extension "
+                                                                  "(oracle/_ref) through dist_chamfer_3D.py:26-64 and "
+                                                                  "loss_util.py:31-33 restated (baseline/_ref not installed)")
         res, _ = run_gpu_arm(args, fn, rank, world, dev, part, comp, "reference")
         line.update(res)
         line.update({"impl": "reference", "gpu_launches": 4 * args.steps,
@@ -429,12 +435,14 @@ def main():
             torch.distributed.destroy_process_group()
         return
 
-    from genpc_b200.loss_functions import chamfer_3DDist
+    from genpc_b200.utils.loss_util import Completionloss
 
-    mod = chamfer_3DDist()
-    res, (a, b, flush) = run_gpu_arm(args, lambda x, y: mod(x, y), rank, world, dev, part, comp, "ours")
+    ours_loss = Completionloss("cd_l2")   # the reference's facade name and call: get_loss == chamfer_l2
+    res, (a, b, flush) = run_gpu_arm(args, ours_loss.get_loss, rank, world, dev, part, comp, "ours")
     line.update(res)
-    line["gpu_launches"] = 4 * args.steps  # nn_sym_kernel + nn_unpack_kernel + nn_sym_fixup_kernel + chamfer_grad_kernel
+    # per step: nn_sym_kernel, nn_unpack_kernel, nn_sym_fixup_kernel, chamfer_loss_kernel, chamfer_loss_grad_kernel
+    line["gpu_launches"] = 5 * args.steps
+    line["config"]["api"] = "genpc_b200.utils.loss_util.Completionloss('cd_l2').get_loss(gen, gt); loss.backward()"
     try:
         reg = registration_metric(rank, world, dev)
     except Exception as e:  # pragma: no cover

@@ -25,6 +25,10 @@ _SIGNATURES = {
     "genpc_chamfer_workspace_bytes": (_sz, [_int, _int, _int]),
     "genpc_chamfer_forward": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _int, _vp, _sz, _vp]),
     "genpc_chamfer_backward": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _int, _vp]),
+    "genpc_chamfer_loss_workspace_bytes": (_sz, []),
+    "genpc_chamfer_loss": (_int, [_vp, _vp, _sz, _sz, _int, _flt, _flt, _vp, _vp, _sz, _vp]),
+    "genpc_chamfer_loss_backward": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _int, _flt, _flt, _vp, _vp, _int, _int,
+                                           _int, _vp]),
     "genpc_nn_partial_packed": (_int, [_vp, _vp, _vp, _int, _int, _int, _int, _int, _vp]),
     "genpc_nn_unpack": (_int, [_vp, _vp, _vp, _sz, _vp]),
     "genpc_chamfer_sym_partial": (_int, [_vp, _vp, _vp, _vp, _int, _int, _int, _int, _int, _vp]),

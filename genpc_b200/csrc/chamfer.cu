@@ -347,3 +347,132 @@ extern "C" int genpc_chamfer_sym_fixup(const float *rows_full, const float *cols
     GENPC_CHECK_LAUNCH();
     return GENPC_OK;
 }
+
+// ---- fused loss reductions (Completionloss hot calls: utils/loss_util.py:25-43) ----------------------------------
+// loss = w1 * mean f(dist1) + w2 * mean f(dist2), f = sqrt (chamfer_l1 / chamfer_partial_l1) or identity (l2 forms).
+// One launch, deterministic: fixed-size grid, per-CTA partial sums in double, the last CTA (ticket) adds the partials
+// in index order.  Replaces the ~8 tiny torch launches (sqrt, mean, add, div and their backward) per call.
+namespace genpc {
+constexpr int LOSS_CTAS = 2 * GENPC_NUM_SMS;
+
+__global__ void __launch_bounds__(256) chamfer_loss_kernel(const float *__restrict__ d1, const float *__restrict__ d2,
+                                                           size_t n1, size_t n2, int use_sqrt, float w1, float w2,
+                                                           double *partial, unsigned *ticket, float *out) {
+    __shared__ double sh[2][8];
+    __shared__ int is_last;
+    double s1 = 0.0, s2 = 0.0;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n1; i += stride)
+        s1 += (double)(use_sqrt ? __fsqrt_rn(__ldg(d1 + i)) : __ldg(d1 + i));
+    if (w2 != 0.f)
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride)
+            s2 += (double)(use_sqrt ? __fsqrt_rn(__ldg(d2 + i)) : __ldg(d2 + i));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s1 += __shfl_xor_sync(0xffffffffu, s1, o), s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) sh[0][warp] = s1, sh[1][warp] = s2;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0, b = 0.0;
+        for (int w = 0; w < 8; ++w) a += sh[0][w], b += sh[1][w];
+        partial[2 * blockIdx.x] = a, partial[2 * blockIdx.x + 1] = b;
+        __threadfence();
+        is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last && threadIdx.x == 0) {
+        __threadfence();
+        double a = 0.0, b = 0.0;
+        for (unsigned c = 0; c < gridDim.x; ++c) a += __ldcg(partial + 2 * c), b += __ldcg(partial + 2 * c + 1);
+        const double m1 = n1 ? a / (double)n1 : 0.0, m2 = (n2 && w2 != 0.f) ? b / (double)n2 : 0.0;
+        out[0] = (float)((double)w1 * m1 + (double)w2 * m2);
+        *ticket = 0;
+    }
+}
+
+// Backward of the fused loss: graddist = upstream * w / n (* 0.5 / sqrt(d) for the L1 forms, inf at d == 0 exactly as
+// torch's sqrt backward, loss_util.py:37) folded into the gradient kernel: same six terms as NmDistanceGradKernel.
+__global__ void chamfer_loss_grad_kernel(const float *__restrict__ xyz1, const float *__restrict__ xyz2,
+                                         const float *__restrict__ d1, const float *__restrict__ d2,
+                                         const int *__restrict__ idx1, const int *__restrict__ idx2,
+                                         const float *__restrict__ upstream, int use_sqrt, float w1, float w2, float *gx1,
+                                         float *gx2, int B, int N, int M) {
+    const size_t n1 = (size_t)B * N, n2 = (w2 != 0.f) ? (size_t)B * M : 0;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const bool valid = i < n1 + n2;
+    const int dir = (valid && i >= n1) ? 1 : 0;
+    if (dir) i -= n1;
+    const float *a = dir ? xyz2 : xyz1, *o = dir ? xyz1 : xyz2, *dd = dir ? d2 : d1;
+    const int *idx = dir ? idx2 : idx1;
+    float *ga = dir ? gx2 : gx1, *go = dir ? gx1 : gx2;
+    const int na = dir ? M : N, no = dir ? N : M;
+    size_t t = 0;
+    float tx = 0.f, ty = 0.f, tz = 0.f;
+    if (valid) {
+        const size_t b = i / na;
+        const float x1 = __ldg(a + i * 3), y1 = __ldg(a + i * 3 + 1), z1 = __ldg(a + i * 3 + 2);
+        t = b * no + __ldg(idx + i);
+        const float x2 = __ldg(o + t * 3), y2 = __ldg(o + t * 3 + 1), z2 = __ldg(o + t * 3 + 2);
+        float gd = __fmul_rn(__ldg(upstream), __fdiv_rn(dir ? w2 : w1, (float)(dir ? (size_t)B * M : n1)));
+        if (use_sqrt) gd = __fmul_rn(gd, __fdiv_rn(0.5f, __fsqrt_rn(__ldg(dd + i))));
+        const float g = __fmul_rn(gd, 2.f);
+        tx = __fmul_rn(g, __fsub_rn(x1, x2));
+        ty = __fmul_rn(g, __fsub_rn(y1, y2));
+        tz = __fmul_rn(g, __fsub_rn(z1, z2));
+        atomicAdd(ga + i * 3 + 0, tx);
+        atomicAdd(ga + i * 3 + 1, ty);
+        atomicAdd(ga + i * 3 + 2, tz);
+    }
+    const unsigned long long key = valid ? ((unsigned long long)t * 2ull + (unsigned)dir) : (~0ull - (unsigned)lane);
+    const unsigned peers = __match_any_sync(0xffffffffu, key);
+    if (peers == (1u << lane)) {
+        if (valid) {
+            atomicAdd(go + t * 3 + 0, -tx);
+            atomicAdd(go + t * 3 + 1, -ty);
+            atomicAdd(go + t * 3 + 2, -tz);
+        }
+        return;
+    }
+    const int leader = __ffs(peers) - 1;
+    float sx = -tx, sy = -ty, sz = -tz;
+    for (unsigned m = peers & (peers - 1u); m; m &= m - 1u) {
+        const int src = __ffs(m) - 1;
+        const float ox = __shfl_sync(peers, -tx, src), oy = __shfl_sync(peers, -ty, src), oz = __shfl_sync(peers, -tz, src);
+        sx += ox, sy += oy, sz += oz;
+    }
+    if (lane == leader) {
+        atomicAdd(go + t * 3 + 0, sx);
+        atomicAdd(go + t * 3 + 1, sy);
+        atomicAdd(go + t * 3 + 2, sz);
+    }
+}
+}  // namespace genpc
+
+extern "C" size_t genpc_chamfer_loss_workspace_bytes(void) { return (size_t)LOSS_CTAS * 2 * sizeof(double) + 16; }
+
+// workspace must be zero-initialised ONCE by the caller (the ticket word is re-armed by the kernel itself).
+extern "C" int genpc_chamfer_loss(const float *dist1, const float *dist2, size_t n1, size_t n2, int use_sqrt, float w1,
+                                  float w2, float *out, void *workspace, size_t workspace_bytes, genpc_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (workspace == nullptr || workspace_bytes < genpc_chamfer_loss_workspace_bytes()) return GENPC_ERR_WORKSPACE;
+    double *partial = (double *)workspace;
+    unsigned *ticket = (unsigned *)(partial + (size_t)LOSS_CTAS * 2);
+    chamfer_loss_kernel<<<LOSS_CTAS, 256, 0, stream>>>(dist1, dist2, n1, n2, use_sqrt, w1, w2, partial, ticket, out);
+    GENPC_CHECK_LAUNCH();
+    return GENPC_OK;
+}
+
+extern "C" int genpc_chamfer_loss_backward(const float *xyz1, const float *xyz2, const float *dist1, const float *dist2,
+                                           const int *idx1, const int *idx2, const float *upstream, int use_sqrt,
+                                           float w1, float w2, float *gradxyz1, float *gradxyz2, int B, int N, int M,
+                                           genpc_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (B < 0 || N < 0 || M < 0) return GENPC_ERR_SHAPE;
+    if (N == 0 || M == 0 || B == 0) return GENPC_OK;
+    const size_t tot = (size_t)B * N + ((w2 != 0.f) ? (size_t)B * M : 0);
+    chamfer_loss_grad_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(xyz1, xyz2, dist1, dist2, idx1, idx2, upstream,
+                                                                                 use_sqrt, w1, w2, gradxyz1, gradxyz2, B, N, M);
+    GENPC_CHECK_LAUNCH();
+    return GENPC_OK;
+}

@@ -70,6 +70,9 @@ __device__ __forceinline__ void nn_sym_item(float (*s)[SYM_SPAN_MAX], const floa
                                             const Similarity *colT, unsigned long long *__restrict__ prow_,
                                             unsigned long long *__restrict__ pcol_, int rblock_base = 0) {
     static_assert(QT % 2 == 0, "rows are folded in pairs");
+#if GENPC_SYM_REDUX == 2
+    __shared__ unsigned scol[SYM_THREADS / 32][32];
+#endif
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int cnt = min(span, nc - c0);
     const int cnt32 = (cnt + 31) & ~31;
@@ -154,7 +157,18 @@ __device__ __forceinline__ void nn_sym_item(float (*s)[SYM_SPAN_MAX], const floa
             }
         }
         // ---- column side: warp-wide minimum of column (blk*32 + lane), published with the row-block id ----
-#if GENPC_SYM_REDUX
+#if GENPC_SYM_REDUX == 2
+        // warp minimum of every column by REDUX, parked in shared memory by lane 0 (LSU pipe) and picked up with one
+        // LDS per lane -- keeps the per-column select (ISETP + SEL) off the ALU pipe, which bounds this kernel
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+            const unsigned r = __reduce_min_sync(0xffffffffu, __float_as_uint(cacc[c]));
+            if (lane == 0) scol[warp][c] = r;
+        }
+        __syncwarp();
+        const float cmin = __uint_as_float(scol[warp][lane]);
+        __syncwarp();
+#elif GENPC_SYM_REDUX
         unsigned mine = 0x7f800000u;  // distances are >= 0: their bit patterns order like the floats
 #pragma unroll
         for (int c = 0; c < 32; ++c) {

@@ -51,6 +51,20 @@ int genpc_chamfer_backward(const float *xyz1, const float *xyz2, const float *gr
                            const float *graddist2, const int *idx1, const int *idx2, float *gradxyz1,
                            float *gradxyz2, int B, int N, int M, genpc_stream_t stream);
 
+/* Fused loss reductions over the forward outputs (the reference's Completionloss methods, utils/loss_util.py:25-43,
+ * evaluate them with ~8 tiny torch launches per call and as many again in backward):
+ *   out[0] = w1 * mean f(dist1) + w2 * mean f(dist2),  f = sqrt when use_sqrt (chamfer_l1: w1=w2=.5, chamfer_partial_l1:
+ *   w1=1,w2=0) else identity (chamfer_l2: w1=w2=1, chamfer_partial_l2: w1=1,w2=0).  Deterministic single launch.
+ * workspace: genpc_chamfer_loss_workspace_bytes() bytes, zeroed ONCE by the caller, reusable on the same stream.
+ * genpc_chamfer_loss_backward accumulates d(loss)/d(xyz) * upstream[0] into gradxyz1/2 (zeroed by the caller), with the
+ * per-point factor w/n (* 0.5/sqrt(dist)) folded into the six terms of NmDistanceGradKernel (chamfer3D.cu:155-174). */
+size_t genpc_chamfer_loss_workspace_bytes(void);
+int genpc_chamfer_loss(const float *dist1, const float *dist2, size_t n1, size_t n2, int use_sqrt, float w1, float w2,
+                       float *out, void *workspace, size_t workspace_bytes, genpc_stream_t stream);
+int genpc_chamfer_loss_backward(const float *xyz1, const float *xyz2, const float *dist1, const float *dist2,
+                                const int *idx1, const int *idx2, const float *upstream, int use_sqrt, float w1, float w2,
+                                float *gradxyz1, float *gradxyz2, int B, int N, int M, genpc_stream_t stream);
+
 /* Target-sharded Chamfer (1M x 1M clouds over 2/4/8 GPUs; no reference counterpart -- the reference is
  * single-GPU brute force).  One direction against ONE shard of the targets: packed[b][j] =
  * min(packed[b][j], (dist_bits << 32) | (idx_base + k)).  Shards are merged by an all-reduce-MIN over the

@@ -195,3 +195,25 @@ def test_forward_fuzz_shapes_and_distributions(cuda):
         exp = oracle.chamfer_forward(a, b)
         for g, e, name in zip(got, exp, ("dist1", "dist2", "idx1", "idx2")):
             assert np.array_equal(g.view(np.int32), e.view(np.int32)), (trial, B, N, M, kind, name)
+
+
+@pytest.mark.parametrize("name", ["chamfer_l1", "chamfer_l2", "chamfer_partial_l1", "chamfer_partial_l2"])
+def test_completionloss_fused_equals_torch_expression(cuda, name):
+    """Completionloss' fused reduction / backward kernels against the reference's literal torch expressions
+    (utils/loss_util.py:25-43): value and gradients within 1e-5 relative."""
+    from genpc_b200.utils.loss_util import Completionloss
+
+    a, b = shape_cloud(41, 3, 1500), shape_cloud(42, 3, 4000)
+    res = {}
+    for fused in (True, False):
+        cl = Completionloss("cd_l1")
+        cl.fused = fused
+        ta = torch.from_numpy(a).to(cuda).requires_grad_(True)
+        tb = torch.from_numpy(b).to(cuda).requires_grad_(True)
+        loss = getattr(cl, name)(ta, tb)
+        (loss * 3.0).backward()
+        res[fused] = (float(loss), ta.grad.cpu().numpy(), tb.grad.cpu().numpy())
+    assert abs(res[True][0] - res[False][0]) <= 1e-5 * abs(res[False][0])
+    for k in (1, 2):
+        scale = np.abs(res[False][k]).max()
+        assert np.abs(res[True][k] - res[False][k]).max() <= 1e-5 * scale + 1e-12
