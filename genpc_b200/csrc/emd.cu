@@ -102,7 +102,8 @@ __device__ int compact_unassigned(const int *__restrict__ asg, int *__restrict__
 }
 
 __global__ void __launch_bounds__(EMD_THREADS) emd_auction_kernel(const EmdArgs a) {
-    __shared__ float4 stg[EMD_CHUNK];  // x, y, z, c = fl(3 - price) (pre-filter operand)
+    __shared__ __align__(16) float sx[EMD_CHUNK], sy[EMD_CHUNK], sz[EMD_CHUNK];  // targets, SoA (pairs feed FADD2/FFMA2)
+    __shared__ __align__(16) float sc[EMD_CHUNK];                                 // c = fl(3 - price): pre-filter operand
     __shared__ float sprice[EMD_CHUNK];
     __shared__ BidState smerge[EMD_THREADS];
     __shared__ int sscan[EMD_THREADS / 32];
@@ -148,6 +149,8 @@ __global__ void __launch_bounds__(EMD_THREADS) emd_auction_kernel(const EmdArgs 
             if (U > 0) {
                 const int upb_ref = (U + block_cnt - 1) / block_cnt;
                 const int tpu_ref = 256 / upb_ref;
+                // points per item: spread the U bidders over the group; every item re-stages the whole target cloud, so
+                // fewer, fuller items win (a rounds*P balance model measured 3x slower at B=32: staging dominated)
                 int P = (U + a.group - 1) / a.group;
                 P = max(1, min(P, EMD_THREADS));
                 const int T = EMD_THREADS / P;
@@ -171,20 +174,14 @@ __global__ void __launch_bounds__(EMD_THREADS) emd_auction_kernel(const EmdArgs 
                         for (int k = tid; k < end_k; k += EMD_THREADS) {
                             const float *tp = p2 + (size_t)(k2 + k) * 3;
                             const float pk = __ldcg(pr + k2 + k);
-                            stg[k] = make_float4(__ldg(tp), __ldg(tp + 1), __ldg(tp + 2), __fsub_rn(3.0f, pk));
+                            sx[k] = __ldg(tp), sy[k] = __ldg(tp + 1), sz[k] = __ldg(tp + 2);
+                            sc[k] = __fsub_rn(3.0f, pk);
                             sprice[k] = pk;
                         }
                         __syncthreads();
                         if (active) {
-                            for (int kl = tpt; kl < end_k; kl += T) {
-                                const float4 t = stg[kl];
-                                const float s = sqdist_ref(x1, y1, z1, t.x, t.y, t.z);
-                                // conservative pre-filter (no sqrt, no FP64): a candidate can only matter if its value
-                                // d >= better, i.e. sqrt(s) <= 3 - price - better up to a few ulps; bm = better - margin
-                                // with margin = 1e-4*max(1,|better|) (hundreds of ulps) makes "tq > 0 && s <= tq^2" a
-                                // superset of those candidates.  Everything that passes takes the exact path below.
-                                const float tq = __fsub_rn(t.w, bm);
-                                if (!(tq > 0.f && s <= __fmul_rn(tq, tq))) continue;
+                            // exact evaluation of one candidate (the reference's arithmetic and tie rule)
+                            auto consider = [&](int kl, float s) {
                                 const float d = (float)((3.0 - (double)__fsqrt_rn(s)) - (double)sprice[kl]);
                                 if (d > st.best) {
                                     st.better = st.best;
@@ -197,6 +194,29 @@ __global__ void __launch_bounds__(EMD_THREADS) emd_auction_kernel(const EmdArgs 
                                         st.bi = k2 + kl;
                                 }
                                 bm = __fsub_rn(st.better, __fmul_rn(1e-4f, fmaxf(1.f, fabsf(st.better))));
+                            };
+                            // two targets per step on the packed FP32 pipe.  Conservative pre-filter (no sqrt, no FP64):
+                            // a candidate can only matter if its value d >= better, i.e. sqrt(s) <= 3 - price - better up
+                            // to a few ulps; bm = better - margin with margin = 1e-4*max(1,|better|) (hundreds of ulps)
+                            // makes "tq > 0 && s <= tq^2" a superset of those candidates; whatever passes takes the exact
+                            // path above, so the result is bit-identical to evaluating every candidate exactly.
+                            const float2 nx = make_float2(-x1, -x1), ny = make_float2(-y1, -y1), nz = make_float2(-z1, -z1);
+                            for (int kp = tpt; kp < (end_k >> 1); kp += T) {   // end_k is even (n % 256 == 0)
+                                const float2 tx = reinterpret_cast<const float2 *>(sx)[kp];
+                                const float2 ty = reinterpret_cast<const float2 *>(sy)[kp];
+                                const float2 tz = reinterpret_cast<const float2 *>(sz)[kp];
+                                const float2 tc = reinterpret_cast<const float2 *>(sc)[kp];
+                                const float2 s2 = sqdist_ref_x2(nx, ny, nz, tx, ty, tz);
+                                const float2 tq = __fadd2_rn(tc, make_float2(-bm, -bm));
+                                const float2 tq2 = __fmul2_rn(tq, tq);
+                                const bool c0 = tq.x > 0.f && s2.x <= tq2.x;
+                                const bool c1 = tq.y > 0.f && s2.y <= tq2.y;
+                                if (c0) consider(2 * kp, s2.x);
+                                if (c1) {
+                                    // bm may have risen while handling the first candidate; the filter stays conservative
+                                    // because it was evaluated against the OLDER (lower) threshold
+                                    consider(2 * kp + 1, s2.y);
+                                }
                             }
                         }
                     }
