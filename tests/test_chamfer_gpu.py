@@ -13,7 +13,8 @@ from util import lattice_cloud, rand_cloud, shape_cloud
 pytestmark = pytest.mark.gpu
 
 SHAPES = [(1, 1, 1), (1, 5, 3), (2, 37, 513), (3, 600, 64), (1, 1025, 1023), (2, 2048, 16384),
-          (1, 255, 4097), (4, 1000, 1000), (1, 16384, 16384), (1, 3, 70000)]
+          (1, 255, 4097), (4, 1000, 1000), (1, 16384, 16384), (1, 3, 70000),
+          (1, 71372, 16384)]  # the last one is BASELINE config C1's shape (data/01184.ply has 71 372 points)
 
 
 def run_ours(a, b, dev):

@@ -29,6 +29,14 @@ def ev_time(fn, reps=5, warm=2):
     return min(ts), sum(ts) / len(ts)
 
 
+# ---- C1: B=1, 71372 x 16384 Chamfer forward (the reference's own CPU-runnable case, here on the GPU) ----
+from genpc_b200.loss_functions import chamfer_3DDist  # noqa: E402
+a1 = torch.from_numpy(superquadric(1, 71372)[None]).to(dev)
+b1 = torch.from_numpy(superquadric(2, 16384)[None]).to(dev)
+mn, av = ev_time(lambda: chamfer_3DDist()(a1, b1))
+out["c1_chamfer_fwd_71372x16384_ms"] = mn
+out["c1_pairs_per_s"] = 2.0 * 71372 * 16384 / (mn * 1e-3)
+
 # ---- C4: FPS 16384 -> 2048 (B=1 and B=32) ----
 for B in (1, 32, 148):
     x = torch.rand(B, 16384, 3, device=dev)
