@@ -62,6 +62,14 @@ def views1k():
     D.zbuffer_render(uv, ndc, 256, 1)
 out["visibility_1024views_256_10000pts_ms"] = ev_time(views1k)[0]
 
+# ---- the reference's default stage-1 geometry: 1024 views, res 256, 71 372 points (DepthPrompting.getDepth) ----
+from genpc_b200.DepthPrompting import DepthPrompting  # noqa: E402
+dp = DepthPrompting(dict(view_num=1024, res=256, cam_res=256, downsample_num=10000))
+rgb = torch.rand(71372, 3, device=dev)
+dp.getDepth(pts, rgb); torch.cuda.synchronize()
+t0 = time.perf_counter(); dp.getDepth(pts, rgb); torch.cuda.synchronize()
+out["depthprompting_getDepth_1024views_res256_71372pts_ms"] = (time.perf_counter() - t0) * 1e3
+
 # ---- C3: registration, 64 scans x 16384 pts, 1 start each (scan-iters/s) ----
 S = int(os.environ.get("REG_SCANS", 64))
 comp = np.stack([superquadric(s, 16384) for s in range(S)])
