@@ -21,6 +21,9 @@
 #ifndef GENPC_DEFAULT_SYM
 #define GENPC_DEFAULT_SYM true
 #endif
+#ifndef GENPC_DEFAULT_PERSIST
+#define GENPC_DEFAULT_PERSIST false
+#endif
 
 namespace genpc {
 
@@ -151,7 +154,7 @@ static cudaError_t launch_scan(const NNParams &p, cudaStream_t stream) {
 
 // Symmetric path: rows = the larger cloud (registers), cols = the smaller one (shared-memory sweep).
 static int chamfer_forward_sym(const float *xyz1, const float *xyz2, float *dist1, float *dist2, int *idx1, int *idx2,
-                               int B, int N, int M, unsigned long long *packed, cudaStream_t stream) {
+                               int B, int N, int M, unsigned long long *packed, int *counter, cudaStream_t stream) {
     const bool swap = M > N;
     SymParams p;
     p.rows = swap ? xyz2 : xyz1, p.cols = swap ? xyz1 : xyz2;
@@ -176,6 +179,14 @@ static int chamfer_forward_sym(const float *xyz1, const float *xyz2, float *dist
     p.cspans = (p.nc + span - 1) / span;
     const long long items = (long long)B * p.rtiles * p.cspans;
     if (items > 0x7fffffffLL) return GENPC_ERR_RANGE;
+    const char *pm = getenv("GENPC_SYM_PERSIST");
+    const bool persist = (pm == nullptr) ? GENPC_DEFAULT_PERSIST : (atoi(pm) != 0);
+    if (persist && (QT == 4 || QT == 2) && counter != nullptr) {
+        // persistent grid: 2 CTAs per SM, items handed out by an atomic counter, next span prefetched with cp.async
+        const int grid = (int)(items < 2LL * GENPC_NUM_SMS ? items : 2LL * GENPC_NUM_SMS);
+        if (QT == 4) nn_sym_persistent_kernel<4><<<grid, SYM_THREADS, 0, stream>>>(p, (int)items, counter);
+        else nn_sym_persistent_kernel<2><<<grid, SYM_THREADS, 0, stream>>>(p, (int)items, counter);
+    } else
     switch (QT) {
         case 8: nn_sym_kernel<8><<<(unsigned)items, SYM_THREADS, 0, stream>>>(p); break;
         case 6: nn_sym_kernel<6><<<(unsigned)items, SYM_THREADS, 0, stream>>>(p); break;
@@ -198,7 +209,7 @@ using namespace genpc;
 
 extern "C" size_t genpc_chamfer_workspace_bytes(int B, int N, int M) {
     if (B < 0 || N < 0 || M < 0) return 0;
-    return ((size_t)B * N + (size_t)B * M) * sizeof(unsigned long long);
+    return ((size_t)B * N + (size_t)B * M) * sizeof(unsigned long long) + 16;  // packed words + work-item counter
 }
 
 extern "C" int genpc_chamfer_forward(const float *xyz1, const float *xyz2, float *dist1, float *dist2,
@@ -229,7 +240,12 @@ extern "C" int genpc_chamfer_forward(const float *xyz1, const float *xyz2, float
     // "sym": one evaluation of every distance feeds both directions (nn_sym.cuh); "scan": one scan per direction
     const char *mode = getenv("GENPC_CHAMFER_MODE");
     const bool want_sym = (mode == nullptr) ? GENPC_DEFAULT_SYM : (strcmp(mode, "sym") == 0);
-    if (want_sym && (N > M ? N : M) >= 512) return chamfer_forward_sym(xyz1, xyz2, dist1, dist2, idx1, idx2, B, N, M, packed, stream);
+    if (want_sym && (N > M ? N : M) >= 512) {
+        int *counter = (int *)(packed + n1 + n2);  // work-item counter of the persistent kernel (after the packed words)
+        e = cudaMemsetAsync(counter, 0, 16, stream);
+        if (e != cudaSuccess) return (int)e;
+        return chamfer_forward_sym(xyz1, xyz2, dist1, dist2, idx1, idx2, B, N, M, packed, counter, stream);
+    }
 
     const int QT = nn_pick_qt(N < M ? N : M);
     NNParams p;

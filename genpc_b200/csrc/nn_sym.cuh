@@ -64,7 +64,8 @@ __device__ __forceinline__ float butterfly_min32(float (&v)[32], int lane) {
 // One work item: row tile `rt` (SYM_THREADS*QT rows) x column span [c0, c0+span) of ONE cloud pair.
 // rows/cols/prow/pcol point at the first element of the pair's clouds / packed words.  colT: optional similarity
 // applied to the columns while they are staged (registration: the moving cloud), nullptr = identity.
-template <int QT>
+// PRESTAGED: the caller already holds the (NaN padded) span in `s` and has synchronised (persistent kernel).
+template <int QT, bool PRESTAGED = false>
 __device__ __forceinline__ void nn_sym_item(float (*s)[SYM_SPAN_MAX], const float *__restrict__ rows, int nr, int rt,
                                             const float *__restrict__ cols, int nc, int c0, int span,
                                             const Similarity *colT, unsigned long long *__restrict__ prow_,
@@ -78,7 +79,7 @@ __device__ __forceinline__ void nn_sym_item(float (*s)[SYM_SPAN_MAX], const floa
     const int cnt32 = (cnt + 31) & ~31;
     const float qnan = __int_as_float(0x7fc00000);
     // ---- stage the column span ----
-    {
+    if (!PRESTAGED) {
         const float *cp = cols + (size_t)c0 * 3;
         for (int k = tid; k < cnt32; k += SYM_THREADS) {
             float x = qnan, y = qnan, z = qnan;
@@ -107,7 +108,7 @@ __device__ __forceinline__ void nn_sym_item(float (*s)[SYM_SPAN_MAX], const floa
         best[qi] = __int_as_float(0x7f800000);
         bchunk[qi] = 0;
     }
-    __syncthreads();
+    if (!PRESTAGED) __syncthreads();
 
     const float4 *sx4 = reinterpret_cast<const float4 *>(s[0]);
     const float4 *sy4 = reinterpret_cast<const float4 *>(s[1]);
@@ -211,6 +212,60 @@ __global__ void __launch_bounds__(SYM_THREADS, GENPC_SYM_MINB(QT)) nn_sym_kernel
     const int b = item / p.rtiles;
     nn_sym_item<QT>(s, p.rows + (size_t)b * p.nr * 3, p.nr, rt, p.cols + (size_t)b * p.nc * 3, p.nc, cs * p.span, p.span,
                     nullptr, p.prow + (size_t)b * p.nr, p.pcol + (size_t)b * p.nc, p.rblock_base);
+}
+
+// Persistent form: one CTA pair per SM loops over work items handed out by an atomic counter; the NEXT item's column
+// span is copied global -> shared with cp.async (LDGSTS, 4-byte granules so the AoS -> SoA transposition happens in the
+// copy itself) into the other half of a double buffer while the current item is being scanned.
+__device__ __forceinline__ void cp_async_f32(float *smem_dst, const float *gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+
+template <int QT>
+__global__ void __launch_bounds__(SYM_THREADS, GENPC_SYM_MINB(QT)) nn_sym_persistent_kernel(const SymParams p, int total, int *counter) {
+    __shared__ __align__(16) float s[2][3][SYM_SPAN_MAX];
+    __shared__ int s_next;
+    const int tid = threadIdx.x;
+    const float qnan = __int_as_float(0x7fc00000);
+    auto stage = [&](int item, int buf) {
+        if (item >= total) return;
+        const int cs = item % p.cspans;
+        const int b = (item / p.cspans) / p.rtiles;
+        const int c0 = cs * p.span;
+        const int cnt = min(p.span, p.nc - c0);
+        const int cnt32 = (cnt + 31) & ~31;
+        const float *cp = p.cols + ((size_t)b * p.nc + c0) * 3;
+        for (int k = tid; k < cnt32; k += SYM_THREADS) {
+            if (k < cnt) {
+                cp_async_f32(&s[buf][0][k], cp + k * 3);
+                cp_async_f32(&s[buf][1][k], cp + k * 3 + 1);
+                cp_async_f32(&s[buf][2][k], cp + k * 3 + 2);
+            } else {
+                s[buf][0][k] = qnan, s[buf][1][k] = qnan, s[buf][2][k] = qnan;
+            }
+        }
+    };
+    int item = blockIdx.x, buf = 0;
+    stage(item, 0);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    while (item < total) {
+        if (tid == 0) s_next = atomicAdd(counter, 1) + (int)gridDim.x;
+        __syncthreads();  // s_next visible; everybody is done with the buffer about to be refilled
+        const int next = s_next;
+        stage(next, buf ^ 1);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        __syncthreads();  // the current span has landed for every thread
+        const int cs = item % p.cspans;
+        const int rest = item / p.cspans;
+        const int rt = rest % p.rtiles;
+        const int b = rest / p.rtiles;
+        nn_sym_item<QT, true>(s[buf], p.rows + (size_t)b * p.nr * 3, p.nr, rt, p.cols + (size_t)b * p.nc * 3, p.nc, cs * p.span,
+                              p.span, nullptr, p.prow + (size_t)b * p.nr, p.pcol + (size_t)b * p.nc, p.rblock_base);
+        item = next;
+        buf ^= 1;
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 // Exact lowest row index of one column from its published (dist, row block) word: the calling WARP re-scans the

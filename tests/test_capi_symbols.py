@@ -34,7 +34,7 @@ def test_python_binding_table_matches_header():
     assert sorted(_lib._SIGNATURES) == declared_symbols()
     L = _lib.lib()
     assert L.genpc_version().decode().startswith("genpc_b200")
-    assert L.genpc_chamfer_workspace_bytes(2, 3, 5) == (2 * 3 + 2 * 5) * 8
+    assert L.genpc_chamfer_workspace_bytes(2, 3, 5) == (2 * 3 + 2 * 5) * 8 + 16
 
 
 def test_no_cpu_fallback():
