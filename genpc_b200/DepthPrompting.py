@@ -46,10 +46,13 @@ class DepthPrompting:
         ndc, uv, _ = D.project_uv(cams, points, self.cfg.rescale, self.cfg.padding)
         r = D.zbuffer_render(uv, ndc, res, 1)
         V, N = uv.shape[0], uv.shape[1]
-        vis = torch.zeros(V, N + 1, dtype=torch.bool, device=points.device)
-        idx = r["idx"].reshape(V, -1).long()
-        vis.scatter_(1, torch.where(idx < 0, torch.full_like(idx, N), idx), True)
-        return vis[:, :N]
+        # a point is visible in a view iff it owns at least one pixel of that view's z-buffer
+        idx = r["idx"].reshape(V, -1)
+        flat = (idx.to(torch.int64) + torch.arange(V, device=idx.device, dtype=torch.int64)[:, None] * (N + 1))
+        flat = flat[idx >= 0]
+        vis = torch.zeros(V * (N + 1), dtype=torch.bool, device=points.device)
+        vis[flat] = True
+        return vis.view(V, N + 1)[:, :N]
 
     # DepthPrompting.py:87-98
     def viewpoint_select(self, xyz):
@@ -87,11 +90,14 @@ class DepthPrompting:
     # DepthPrompting.py:100-237 geometry only: best view, uv/depth of that view, sparse depth + masks
     def getDepth(self, xyz, rgb=None):
         with torch.no_grad():
-            point_uvs, point_depths, ndc = self.getUvs(self.cameras, xyz, self.cfg.rescale, self.cfg.padding)
+            # the reference projects ALL points through ALL view_num cameras first (877 MB at 1024 views x 71 372
+            # points, :102) and then uses one view; the result is identical when the view is chosen first
             best = int(self.viewpoint_select(xyz))
-            vis = self.getVisiblePoints(xyz, self.cameras[best:best + 1])[0]
-            out = self.getRawDepth(point_uvs[best], ndc[best], rgb, valid=vis)
-            self.point_uv = point_uvs[best]
+            cam = self.cameras[best:best + 1]
+            point_uvs, point_depths, ndc = self.getUvs(cam, xyz, self.cfg.rescale, self.cfg.padding)
+            vis = self.getVisiblePoints(xyz, cam)[0]
+            out = self.getRawDepth(point_uvs[0], ndc[0], rgb, valid=vis)
+            self.point_uv = point_uvs[0]
             self.view = self.viewpoints[best]
             self.cam = self.cameras[best]
             return (best,) + tuple(out)
