@@ -131,3 +131,67 @@ def test_multistart_and_pose_recovery_16k(cuda):
     T = rb.transforms()[0].cpu().numpy()
     T2 = object_pose_optimization_points(comp, part, lr=0.01, iters=200)
     assert np.array_equal(T, T2)                                   # deterministic, identical through the mirror API
+
+
+@pytest.mark.gpu
+def test_trajectory_vs_reference_machinery_on_gpu(cuda):
+    """The reference's own machinery on the same GPU: its UNMODIFIED Chamfer extension (oracle/_ref) inside torch
+    autograd, the forward expression of ObjectPoseOptim.forward (diff_obj_pose.py:419-423), the Chamfer term of
+    compute_loss_function (:326-327, weight 3.0 :334) and torch.optim.Adam with the three lr groups (:524-528), all
+    fp32 -- against the fused kernels.  The reference's backward accumulates with unordered float atomics, so it is
+    not bit-reproducible itself; tolerance: 1e-5 relative on every loss of the trajectory, 1e-4 absolute on parameters
+    after 30 steps."""
+    import torch
+
+    from genpc_b200.optim_registration.diff_obj_pose import RegistrationBatch, rotation_6d_to_matrix
+
+    ext = oracle.load_ref_ext("chamfer_3D")
+    if ext is None:
+        pytest.skip("oracle/_ref/chamfer_3D not built")
+
+    class RefChamfer(torch.autograd.Function):          # dist_chamfer_3D.py:26-64 around the unmodified extension
+        @staticmethod
+        def forward(ctx, a, b):
+            B, n, _ = a.shape
+            m = b.shape[1]
+            d1 = torch.zeros(B, n, device=a.device); d2 = torch.zeros(B, m, device=a.device)
+            i1 = torch.zeros(B, n, dtype=torch.int32, device=a.device); i2 = torch.zeros(B, m, dtype=torch.int32, device=a.device)
+            ext.forward(a, b, d1, d2, i1, i2)
+            ctx.save_for_backward(a, b, i1, i2)
+            return d1, d2, i1, i2
+
+        @staticmethod
+        def backward(ctx, g1, g2, _a, _b):
+            a, b, i1, i2 = ctx.saved_tensors
+            ga, gb = torch.zeros_like(a), torch.zeros_like(b)
+            ext.backward(a, b, ga, gb, g1.contiguous(), g2.contiguous(), i1, i2)
+            return ga, gb
+
+    def partial_l1(p, q):                                # Completionloss.chamfer_partial_l1 (loss_util.py:35-38)
+        d1, _, _, _ = RefChamfer.apply(p.contiguous(), q.contiguous())
+        return torch.sqrt(d1).mean()
+
+    comp, part, _ = make_pair(11, 4096, 3000)
+    V, Rf = torch.from_numpy(comp).to(cuda), torch.from_numpy(part).to(cuda)
+    iters, lr = 30, 0.01
+    rb = RegistrationBatch(V[None], Rf[None], n_starts=1, lr=lr)
+    center = rb.center[0].clone()
+    p0 = rb.params[0].clone()
+    rot = p0[:6].clone().requires_grad_(True); trans = p0[6:9].clone().requires_grad_(True); ls = p0[9:].clone().requires_grad_(True)
+    opt = torch.optim.Adam([{"params": [rot], "lr": lr}, {"params": [trans], "lr": lr * 0.2}, {"params": [ls], "lr": lr * 0.1}])
+    ref_losses = []
+    for _ in range(iters):
+        opt.zero_grad()
+        R = rotation_6d_to_matrix(rot[None])[0]
+        local = (V - center) * torch.exp(ls)[0]
+        pts = (R @ local.T).T + center + trans
+        loss = 3.0 * (partial_l1(pts[None], Rf[None]) + 0.5 * partial_l1(Rf[None], pts[None]))
+        loss.backward()
+        opt.step()
+        ref_losses.append(float(loss.detach()))
+    rb.run(iters)
+    ours = rb.losses()[0].cpu().numpy()
+    ref_losses = np.array(ref_losses)
+    assert np.abs(ours - ref_losses).max() <= 1e-5 * np.abs(ref_losses).max() * 3, np.abs(ours - ref_losses).max()
+    ref_p = torch.cat([rot, trans, ls]).detach().cpu().numpy()
+    assert np.abs(rb.params[0].cpu().numpy() - ref_p).max() <= 1e-4, np.abs(rb.params[0].cpu().numpy() - ref_p).max()
