@@ -396,13 +396,22 @@ __global__ void __launch_bounds__(256) chamfer_loss_kernel(const float *__restri
         is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
     }
     __syncthreads();
-    if (is_last && threadIdx.x == 0) {
+    if (is_last) {  // the last CTA adds the per-CTA partials: fixed assignment + fixed tree => deterministic
         __threadfence();
         double a = 0.0, b = 0.0;
-        for (unsigned c = 0; c < gridDim.x; ++c) a += __ldcg(partial + 2 * c), b += __ldcg(partial + 2 * c + 1);
-        const double m1 = n1 ? a / (double)n1 : 0.0, m2 = (n2 && w2 != 0.f) ? b / (double)n2 : 0.0;
-        out[0] = (float)((double)w1 * m1 + (double)w2 * m2);
-        *ticket = 0;
+        for (unsigned c = threadIdx.x; c < gridDim.x; c += blockDim.x) a += __ldcg(partial + 2 * c), b += __ldcg(partial + 2 * c + 1);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o), b += __shfl_xor_sync(0xffffffffu, b, o);
+        __syncthreads();
+        if (lane == 0) sh[0][warp] = a, sh[1][warp] = b;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            a = 0.0, b = 0.0;
+            for (int w = 0; w < 8; ++w) a += sh[0][w], b += sh[1][w];
+            const double m1 = n1 ? a / (double)n1 : 0.0, m2 = (n2 && w2 != 0.f) ? b / (double)n2 : 0.0;
+            out[0] = (float)((double)w1 * m1 + (double)w2 * m2);
+            *ticket = 0;
+        }
     }
 }
 

@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(SYM_THREADS, GENPC_SYM_MINB(QT)) register_sym_
 //           cloud; the last CTA of a scan (ticket) then reduces loss + gradient and steps Adam (finalize_scan).
 constexpr int FIX_THREADS = 512;
 constexpr int FIX_COLS_PER_CTA = 128;
-__global__ void __launch_bounds__(FIX_THREADS) register_finish_kernel(const RegArgs a) {
+__global__ void __launch_bounds__(FIX_THREADS, 2) register_finish_kernel(const RegArgs a) {
     __shared__ Similarity T;
     __shared__ int is_last;
     __shared__ double sh[FIX_THREADS / 32];
