@@ -195,10 +195,9 @@ static int chamfer_forward_sym(const float *xyz1, const float *xyz2, float *dist
     }
     GENPC_CHECK_LAUNCH();
     const size_t nrw = (size_t)B * p.nr, ncw = (size_t)B * p.nc;
-    nn_unpack_kernel<<<(unsigned)((nrw + 255) / 256), 256, 0, stream>>>(p.prow, dist_r, idx_r, nrw, nullptr, nullptr, 0);
-    GENPC_CHECK_LAUNCH();
-    nn_sym_fixup_kernel<<<(unsigned)((ncw * 32 + 255) / 256), 256, 0, stream>>>(p.rows, p.cols, p.pcol, B, p.nr, p.nc,
-                                                                                32 * QT, dist_c, idx_c);
+    const unsigned fix_blocks = (unsigned)((ncw * 32 + 255) / 256), unpack_blocks = (unsigned)((nrw + 255) / 256);
+    nn_sym_epilogue_kernel<<<fix_blocks + unpack_blocks, 256, 0, stream>>>(p.rows, p.cols, p.prow, p.pcol, B, p.nr, p.nc, 32 * QT,
+                                                                           fix_blocks, dist_r, idx_r, dist_c, idx_c);
     GENPC_CHECK_LAUNCH();
     return GENPC_OK;
 }
@@ -242,8 +241,11 @@ extern "C" int genpc_chamfer_forward(const float *xyz1, const float *xyz2, float
     const bool want_sym = (mode == nullptr) ? GENPC_DEFAULT_SYM : (strcmp(mode, "sym") == 0);
     if (want_sym && (N > M ? N : M) >= 512) {
         int *counter = (int *)(packed + n1 + n2);  // work-item counter of the persistent kernel (after the packed words)
-        e = cudaMemsetAsync(counter, 0, 16, stream);
-        if (e != cudaSuccess) return (int)e;
+        const char *pm = getenv("GENPC_SYM_PERSIST");
+        if ((pm == nullptr) ? GENPC_DEFAULT_PERSIST : (atoi(pm) != 0)) {
+            e = cudaMemsetAsync(counter, 0, 16, stream);
+            if (e != cudaSuccess) return (int)e;
+        }
         return chamfer_forward_sym(xyz1, xyz2, dist1, dist2, idx1, idx2, B, N, M, packed, counter, stream);
     }
 

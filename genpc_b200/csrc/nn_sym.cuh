@@ -318,7 +318,40 @@ __device__ __forceinline__ int sym_fix_column(const float *__restrict__ rp, int 
     return found;
 }
 
-// Column fix-up: one warp per column; writes the final dist / idx of the column cloud.
+// Forward epilogue in ONE launch: blocks [0, fix_blocks) resolve the column words (one warp per column, exact lowest
+// row index from the winning row block) and write dist/idx of the column cloud; the remaining blocks unpack the row
+// words into dist/idx of the row cloud.
+static __global__ void __launch_bounds__(256) nn_sym_epilogue_kernel(const float *__restrict__ rows, const float *__restrict__ cols,
+                                                                     const unsigned long long *__restrict__ prow,
+                                                                     const unsigned long long *__restrict__ pcol, int B, int nr,
+                                                                     int nc, int rows_per_block, unsigned fix_blocks,
+                                                                     float *__restrict__ dist_r, int *__restrict__ idx_r,
+                                                                     float *__restrict__ dist_c, int *__restrict__ idx_c) {
+    if (blockIdx.x >= fix_blocks) {
+        const size_t i = (size_t)(blockIdx.x - fix_blocks) * blockDim.x + threadIdx.x;
+        if (i < (size_t)B * nr) {
+            const unsigned long long w = __ldg(prow + i);
+            dist_r[i] = __uint_as_float((unsigned)(w >> 32));
+            idx_r[i] = (int)(unsigned)(w & 0xffffffffu);
+        }
+        return;
+    }
+    const size_t w = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= (size_t)B * nc) return;
+    const size_t b = w / nc;
+    const unsigned long long word = __ldg(pcol + w);
+    const float d = __uint_as_float((unsigned)(word >> 32));
+    const int blk = (int)(unsigned)(word & 0xffffffffu);
+    const float cx = __ldg(cols + w * 3), cy = __ldg(cols + w * 3 + 1), cz = __ldg(cols + w * 3 + 2);
+    const int found = sym_fix_column(rows + b * (size_t)nr * 3, nr, rows_per_block, cx, cy, cz, d, blk, lane);
+    if (lane == 0) {
+        dist_c[w] = d;
+        idx_c[w] = found;
+    }
+}
+
+// Column fix-up alone (row-sharded multi-GPU path): one warp per column; writes the final dist / idx of the column cloud.
 static __global__ void __launch_bounds__(256) nn_sym_fixup_kernel(const float *__restrict__ rows, const float *__restrict__ cols,
                                                            const unsigned long long *__restrict__ pcol, int B, int nr,
                                                            int nc, int rows_per_block, float *__restrict__ dist_out,
