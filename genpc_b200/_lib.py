@@ -24,6 +24,11 @@ _SIGNATURES = {
     "genpc_version": (ctypes.c_char_p, []),
     "genpc_chamfer_workspace_bytes": (_sz, [_int, _int, _int]),
     "genpc_chamfer_forward": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _int, _vp, _sz, _vp]),
+    "genpc_host_feed_create": (_int, [ctypes.POINTER(_vp)]),
+    "genpc_host_feed_destroy": (_int, [_vp]),
+    "genpc_host_feed_error": (_int, [_vp, _vp]),
+    "genpc_chamfer_forward_host": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _int, _int, _vp, _sz,
+                                          _vp]),
     "genpc_chamfer_backward": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _int, _vp]),
     "genpc_chamfer_loss_workspace_bytes": (_sz, []),
     "genpc_chamfer_loss": (_int, [_vp, _vp, _sz, _sz, _int, _flt, _flt, _vp, _vp, _sz, _vp]),

@@ -24,6 +24,9 @@
 #ifndef GENPC_DEFAULT_PERSIST
 #define GENPC_DEFAULT_PERSIST false
 #endif
+#ifndef GENPC_DEFAULT_BALANCED
+#define GENPC_DEFAULT_BALANCED true
+#endif
 
 namespace genpc {
 
@@ -153,8 +156,10 @@ static cudaError_t launch_scan(const NNParams &p, cudaStream_t stream) {
 }
 
 // Symmetric path: rows = the larger cloud (registers), cols = the smaller one (shared-memory sweep).
+// gate != nullptr: host-fed launch (nn_sym_gated_kernel), see genpc_chamfer_forward_host.
 static int chamfer_forward_sym(const float *xyz1, const float *xyz2, float *dist1, float *dist2, int *idx1, int *idx2,
-                               int B, int N, int M, unsigned long long *packed, int *counter, cudaStream_t stream) {
+                               int B, int N, int M, unsigned long long *packed, int *counter, cudaStream_t stream,
+                               const unsigned *gate = nullptr, unsigned gate_gen = 0, int gate_pairs = 1) {
     const bool swap = M > N;
     SymParams p;
     p.rows = swap ? xyz2 : xyz1, p.cols = swap ? xyz1 : xyz2;
@@ -163,11 +168,12 @@ static int chamfer_forward_sym(const float *xyz1, const float *xyz2, float *dist
     int *idx_r = swap ? idx2 : idx1, *idx_c = swap ? idx1 : idx2;
     p.prow = packed, p.pcol = packed + (size_t)B * p.nr;
     p.rblock_base = 0;
+    p.gate = gate, p.gate_gen = gate_gen, p.gate_pairs = gate_pairs;
     // measured on B200 (profiles/r01c_sym_variants.txt): QT=4 at 3 CTAs/SM is within 1 % of QT=8 at 2 CTAs/SM on
     // large clouds and clearly better when the grid is small
     int QT = p.nr >= 1024 ? 4 : 2;
     const char *fq = getenv("GENPC_SYM_QT");  // experiments only
-    if (fq != nullptr && (atoi(fq) == 8 || atoi(fq) == 6 || atoi(fq) == 4 || atoi(fq) == 2)) QT = atoi(fq);
+    if (gate == nullptr && fq != nullptr && (atoi(fq) == 8 || atoi(fq) == 6 || atoi(fq) == 4 || atoi(fq) == 2)) QT = atoi(fq);
     p.rtiles = (p.nr + SYM_THREADS * QT - 1) / (SYM_THREADS * QT);
     // column span: the largest that still gives >= 2 waves of work items (3 CTAs x 148 SMs), at least 256 columns
     int span = SYM_SPAN_MAX;
@@ -181,11 +187,30 @@ static int chamfer_forward_sym(const float *xyz1, const float *xyz2, float *dist
     if (items > 0x7fffffffLL) return GENPC_ERR_RANGE;
     const char *pm = getenv("GENPC_SYM_PERSIST");
     const bool persist = (pm == nullptr) ? GENPC_DEFAULT_PERSIST : (atoi(pm) != 0);
-    if (persist && (QT == 4 || QT == 2) && counter != nullptr) {
+    // measured on B200 (profiles/r01h_sym_balanced_vs_grid.txt): with fewer than two waves of full-span work items the
+    // balanced form wins (B=1 16384^2 +5 %, 3 x 5000 x 3333 +12 %); with more, one CTA per item is 4-5 % faster (resident
+    // CTAs drift out of phase, so staging / publishing of one overlaps the scan of the other)
+    const char *bm = getenv("GENPC_SYM_BALANCED");
+    const bool few_items = (long long)B * p.rtiles * ((p.nc + SYM_SPAN_MAX - 1) / SYM_SPAN_MAX) < 4LL * GENPC_NUM_SMS;
+    const bool balanced = (bm == nullptr) ? (GENPC_DEFAULT_BALANCED && few_items) : (atoi(bm) != 0);
+    if (gate != nullptr) {
+        if (QT >= 4) nn_sym_gated_kernel<4><<<(unsigned)items, SYM_THREADS, 0, stream>>>(p);
+        else nn_sym_gated_kernel<2><<<(unsigned)items, SYM_THREADS, 0, stream>>>(p);
+    } else if (balanced && !persist && (QT == 4 || QT == 2)) {
+        // balanced grid: 2 resident CTAs per SM, each walks an equal share of the (row tile x 32-column block) units
+        const int upj = (p.nc + 31) / 32;
+        const long long units = (long long)B * p.rtiles * upj;
+        if (units > 0x7fffffffLL) return GENPC_ERR_RANGE;
+        const int grid = (int)(units < 2LL * GENPC_NUM_SMS ? units : 2LL * GENPC_NUM_SMS);
+        if (QT == 4) nn_sym_balanced_kernel<4><<<grid, SYM_THREADS, 0, stream>>>(p, (int)units, upj);
+        else nn_sym_balanced_kernel<2><<<grid, SYM_THREADS, 0, stream>>>(p, (int)units, upj);
+#if GENPC_SYM_SPAN_MAX <= 1024
+    } else if (persist && (QT == 4 || QT == 2) && counter != nullptr) {
         // persistent grid: 2 CTAs per SM, items handed out by an atomic counter, next span prefetched with cp.async
         const int grid = (int)(items < 2LL * GENPC_NUM_SMS ? items : 2LL * GENPC_NUM_SMS);
         if (QT == 4) nn_sym_persistent_kernel<4><<<grid, SYM_THREADS, 0, stream>>>(p, (int)items, counter);
         else nn_sym_persistent_kernel<2><<<grid, SYM_THREADS, 0, stream>>>(p, (int)items, counter);
+#endif
     } else
     switch (QT) {
         case 8: nn_sym_kernel<8><<<(unsigned)items, SYM_THREADS, 0, stream>>>(p); break;
@@ -283,6 +308,114 @@ extern "C" int genpc_chamfer_backward(const float *xyz1, const float *xyz2, cons
 
 extern "C" const char *genpc_version(void) { return "genpc_b200 0.1 sm_100a"; }
 
+// ---- host-fed Chamfer forward: the H2D copy of the clouds overlaps the scan ------------------------------------------
+// The e2e form of the hot call (BASELINE metric measured from HOST buffers): the clouds are cut into `chunks` groups of
+// cloud pairs; a private copy stream moves chunk after chunk from (pinned) host memory into the caller's device
+// buffers and, behind every chunk, DMA-writes the call's generation number into that chunk's gate word.  ONE full-size
+// nn_sym_gated_kernel is launched right after the first chunk has been queued: its CTAs run in batch order and only
+// wait when they get ahead of the copy engine (PCIe: 7 MB = 0.13 ms for C2, the scan: 0.27 ms), so the transfer costs
+// one chunk of latency instead of the whole copy.  Flags are written by the copy engine, never by a kernel or memset
+// (those need SM resources the resident scan CTAs hold).
+struct genpc_host_feed {
+    cudaStream_t copy_stream;
+    cudaEvent_t ready, copied;
+    unsigned *gate;    // device: GATE_MAX_CHUNKS generation words + the error word
+    unsigned *h_ring;  // pinned: source words of the gate writes
+    unsigned gen;
+    int device;
+};
+static constexpr int FEED_RING = 256;
+
+extern "C" int genpc_host_feed_create(genpc_host_feed_t **out) {
+    if (out == nullptr) return GENPC_ERR_SHAPE;
+    genpc_host_feed *f = (genpc_host_feed *)calloc(1, sizeof(genpc_host_feed));
+    if (f == nullptr) return (int)cudaErrorMemoryAllocation;
+    cudaError_t e = cudaGetDevice(&f->device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&f->copy_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&f->ready, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&f->copied, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&f->gate, (GATE_MAX_CHUNKS + 1) * sizeof(unsigned));
+    if (e == cudaSuccess) e = cudaMemset(f->gate, 0, (GATE_MAX_CHUNKS + 1) * sizeof(unsigned));
+    if (e == cudaSuccess) e = cudaHostAlloc((void **)&f->h_ring, FEED_RING * sizeof(unsigned), cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+        genpc_host_feed_destroy(f);
+        return (int)e;
+    }
+    *out = f;
+    return GENPC_OK;
+}
+
+extern "C" int genpc_host_feed_destroy(genpc_host_feed_t *f) {
+    if (f == nullptr) return GENPC_OK;
+    if (f->copy_stream) cudaStreamSynchronize(f->copy_stream), cudaStreamDestroy(f->copy_stream);
+    if (f->ready) cudaEventDestroy(f->ready);
+    if (f->copied) cudaEventDestroy(f->copied);
+    if (f->gate) cudaFree(f->gate);
+    if (f->h_ring) cudaFreeHost(f->h_ring);
+    free(f);
+    return GENPC_OK;
+}
+
+extern "C" int genpc_chamfer_forward_host(genpc_host_feed_t *f, const float *h_xyz1, const float *h_xyz2, float *xyz1,
+                                          float *xyz2, float *dist1, float *dist2, int *idx1, int *idx2, int B, int N,
+                                          int M, int chunks, void *workspace, size_t workspace_bytes,
+                                          genpc_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (f == nullptr || B < 0 || N < 0 || M < 0) return GENPC_ERR_SHAPE;
+    const size_t n1 = (size_t)B * N, n2 = (size_t)B * M;
+    if (n1 + n2 == 0) return GENPC_OK;
+    cudaError_t e;
+#define FEED_CHECK(x) do { e = (x); if (e != cudaSuccess) return (int)e; } while (0)
+    const bool sym = (N > M ? N : M) >= 512 && N > 0 && M > 0;
+    if (!sym || B < 2 || chunks < 2) {
+        // tiny clouds / a single pair: nothing worth overlapping -- copy on the caller's stream, then the plain entry
+        if (n1) FEED_CHECK(cudaMemcpyAsync(xyz1, h_xyz1, n1 * 12, cudaMemcpyHostToDevice, stream));
+        if (n2) FEED_CHECK(cudaMemcpyAsync(xyz2, h_xyz2, n2 * 12, cudaMemcpyHostToDevice, stream));
+        return genpc_chamfer_forward(xyz1, xyz2, dist1, dist2, idx1, idx2, B, N, M, workspace, workspace_bytes, stream_);
+    }
+    if (workspace == nullptr || workspace_bytes < genpc_chamfer_workspace_bytes(B, N, M)) return GENPC_ERR_WORKSPACE;
+    if (chunks > GATE_MAX_CHUNKS) chunks = GATE_MAX_CHUNKS;
+    if (chunks > B) chunks = B;
+    const int pairs = (B + chunks - 1) / chunks;  // cloud pairs per chunk
+    chunks = (B + pairs - 1) / pairs;
+    const unsigned gen = ++f->gen;
+    if (gen % FEED_RING == 0) FEED_CHECK(cudaEventSynchronize(f->copied));  // the ring slot about to be reused has been read
+    unsigned *src = f->h_ring + gen % FEED_RING;
+    *src = gen;
+    // the device buffers may still be read by earlier work on the caller's stream
+    FEED_CHECK(cudaEventRecord(f->ready, stream));
+    FEED_CHECK(cudaStreamWaitEvent(f->copy_stream, f->ready, 0));
+    // ALL copies are queued before the scan is launched: once the kernel is resident and waiting, nothing it needs may
+    // depend on further progress of this host thread (a lazily loaded module, a profiler serialising launches or
+    // CUDA_LAUNCH_BLOCKING would otherwise turn the wait into a deadlock that only the kernel's timeout breaks)
+    for (int c = 0; c < chunks; ++c) {
+        const int b0 = c * pairs, nb = (B - b0 < pairs) ? B - b0 : pairs;
+        FEED_CHECK(cudaMemcpyAsync(xyz1 + (size_t)b0 * N * 3, h_xyz1 + (size_t)b0 * N * 3, (size_t)nb * N * 12,
+                                   cudaMemcpyHostToDevice, f->copy_stream));
+        FEED_CHECK(cudaMemcpyAsync(xyz2 + (size_t)b0 * M * 3, h_xyz2 + (size_t)b0 * M * 3, (size_t)nb * M * 12,
+                                   cudaMemcpyHostToDevice, f->copy_stream));
+        FEED_CHECK(cudaMemcpyAsync(f->gate + c, src, sizeof(unsigned), cudaMemcpyHostToDevice, f->copy_stream));
+    }
+    unsigned long long *packed = (unsigned long long *)workspace;
+    FEED_CHECK(cudaMemsetAsync(packed, 0xff, (n1 + n2) * 8, stream));
+    const int rc = chamfer_forward_sym(xyz1, xyz2, dist1, dist2, idx1, idx2, B, N, M, packed, nullptr, stream, f->gate, gen, pairs);
+    if (rc != GENPC_OK) return rc;
+    FEED_CHECK(cudaEventRecord(f->copied, f->copy_stream));
+    FEED_CHECK(cudaStreamWaitEvent(stream, f->copied, 0));  // later work on the caller's stream sees complete clouds
+#undef FEED_CHECK
+    return GENPC_OK;
+}
+
+// 1 if a gated launch of this feed ever timed out waiting for its data (results of that call are invalid).
+extern "C" int genpc_host_feed_error(genpc_host_feed_t *f, genpc_stream_t stream_) {
+    if (f == nullptr) return GENPC_ERR_SHAPE;
+    unsigned v = 0;
+    cudaError_t e = cudaMemcpyAsync(&v, f->gate + GATE_ERR_SLOT, sizeof(unsigned), cudaMemcpyDeviceToHost, (cudaStream_t)stream_);
+    if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream_);
+    if (e != cudaSuccess) return (int)e;
+    return v ? 1 : 0;
+}
+
 // ---- target-sharded Chamfer (million-point clouds over several GPUs) ---------------------------------------
 // One direction, one target shard: packed[b][j] = min(packed[b][j], (dist_bits<<32 | idx_base+k)) over the
 // targets of this shard.  The caller initialises `packed` to all-ones once (init != 0 does it here), merges the
@@ -342,6 +475,7 @@ extern "C" int genpc_chamfer_sym_partial(const float *rows_shard, const float *c
     SymParams p;
     p.rows = rows_shard, p.cols = cols, p.prow = prow_shard, p.pcol = pcol;
     p.nr = nr_shard, p.nc = nc, p.rblock_base = row_base / 128;
+    p.gate = nullptr, p.gate_gen = 0, p.gate_pairs = 1;
     p.rtiles = (nr_shard + SYM_THREADS * 4 - 1) / (SYM_THREADS * 4);
     int span = SYM_SPAN_MAX;
     const long long want = 2LL * 3 * GENPC_NUM_SMS;

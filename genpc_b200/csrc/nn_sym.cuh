@@ -20,7 +20,10 @@
 namespace genpc {
 
 constexpr int SYM_THREADS = 256;
-constexpr int SYM_SPAN_MAX = 1024;  // columns staged per item (<= 12 KB shared memory)
+#ifndef GENPC_SYM_SPAN_MAX
+#define GENPC_SYM_SPAN_MAX 1024
+#endif
+constexpr int SYM_SPAN_MAX = GENPC_SYM_SPAN_MAX;  // columns staged per item (12 B of shared memory each)
 #ifndef GENPC_SYM_CHUNK
 #define GENPC_SYM_CHUNK 8
 #endif
@@ -36,7 +39,19 @@ struct SymParams {
     unsigned long long *pcol;      // [B][nc]  (dist, row block id)
     int nr, nc, rtiles, cspans, span;
     int rblock_base;               // added to published row-block ids (row shard offset / rows_per_block)
+    // host-fed launches (genpc_chamfer_forward_host): cloud pair b may be read once gate[b / gate_pairs] has reached
+    // gate_gen -- the H2D copy of its chunk has landed (written by a 4-byte DMA queued behind the chunk's copies)
+    const unsigned *gate;
+    unsigned gate_gen;
+    int gate_pairs;
 };
+
+// Coordinates arriving by DMA while the kernel is resident must not go through the non-coherent path (ld.global.nc
+// assumes data that is read-only for the whole launch): gated launches read them with ld.global.cg instead.
+template <bool COHERENT>
+__device__ __forceinline__ float ld_coord(const float *p) {
+    return COHERENT ? __ldcg(p) : __ldg(p);
+}
 
 // v[e] (e = 0..31) per lane -> returns min over all lanes of v[lane]   (element index == lane id)
 __device__ __forceinline__ float butterfly_min32(float (&v)[32], int lane) {
@@ -65,7 +80,7 @@ __device__ __forceinline__ float butterfly_min32(float (&v)[32], int lane) {
 // rows/cols/prow/pcol point at the first element of the pair's clouds / packed words.  colT: optional similarity
 // applied to the columns while they are staged (registration: the moving cloud), nullptr = identity.
 // PRESTAGED: the caller already holds the (NaN padded) span in `s` and has synchronised (persistent kernel).
-template <int QT, bool PRESTAGED = false>
+template <int QT, bool PRESTAGED = false, bool COHERENT = false>
 __device__ __forceinline__ void nn_sym_item(float (*s)[SYM_SPAN_MAX], const float *__restrict__ rows, int nr, int rt,
                                             const float *__restrict__ cols, int nc, int c0, int span,
                                             const Similarity *colT, unsigned long long *__restrict__ prow_,
@@ -84,7 +99,7 @@ __device__ __forceinline__ void nn_sym_item(float (*s)[SYM_SPAN_MAX], const floa
         for (int k = tid; k < cnt32; k += SYM_THREADS) {
             float x = qnan, y = qnan, z = qnan;
             if (k < cnt) {
-                x = __ldg(cp + k * 3), y = __ldg(cp + k * 3 + 1), z = __ldg(cp + k * 3 + 2);
+                x = ld_coord<COHERENT>(cp + k * 3), y = ld_coord<COHERENT>(cp + k * 3 + 1), z = ld_coord<COHERENT>(cp + k * 3 + 2);
                 if (colT != nullptr) apply_similarity(*colT, x, y, z);
             }
             s[0][k] = x, s[1][k] = y, s[2][k] = z;
@@ -101,7 +116,9 @@ __device__ __forceinline__ void nn_sym_item(float (*s)[SYM_SPAN_MAX], const floa
     for (int qi = 0; qi < QT; ++qi) {
         const int j = jbase + qi * 32;
         float x = qnan, y = qnan, z = qnan;
-        if (j < nr) x = __ldg(rp + (size_t)j * 3), y = __ldg(rp + (size_t)j * 3 + 1), z = __ldg(rp + (size_t)j * 3 + 2);
+        if (j < nr)
+            x = ld_coord<COHERENT>(rp + (size_t)j * 3), y = ld_coord<COHERENT>(rp + (size_t)j * 3 + 1),
+            z = ld_coord<COHERENT>(rp + (size_t)j * 3 + 2);
         nqx[qi] = make_float2(-x, -x);
         nqy[qi] = make_float2(-y, -y);
         nqz[qi] = make_float2(-z, -z);
@@ -214,6 +231,69 @@ __global__ void __launch_bounds__(SYM_THREADS, GENPC_SYM_MINB(QT)) nn_sym_kernel
                     nullptr, p.prow + (size_t)b * p.nr, p.pcol + (size_t)b * p.nc, p.rblock_base);
 }
 
+// Host-fed form: same work items, but the clouds are still arriving from pinned host memory while the kernel runs.
+// Thread 0 of every CTA waits (acquire, system scope) until the generation word of its cloud pair's chunk has been
+// written by the copy stream, then the CTA proceeds exactly like nn_sym_kernel.  CTAs are dispatched in blockIdx
+// order == batch order == copy order, so waiting CTAs only ever wait for the chunk the copy engine is working on.
+// A spin that outlives GATE_TIMEOUT_CLK raises gate[GATE_ERR_SLOT] and goes on (garbage out, reported by the host call
+// of the NEXT step) rather than hanging the GPU.
+constexpr int GATE_MAX_CHUNKS = 64;
+constexpr int GATE_ERR_SLOT = GATE_MAX_CHUNKS;
+constexpr long long GATE_TIMEOUT_CLK = 4000000000LL;  // ~2 s at 1.965 GHz
+
+template <int QT>
+__global__ void __launch_bounds__(SYM_THREADS, GENPC_SYM_MINB(QT)) nn_sym_gated_kernel(const SymParams p) {
+    __shared__ __align__(16) float s[3][SYM_SPAN_MAX];
+    int item = blockIdx.x;
+    const int cs = item % p.cspans;
+    item /= p.cspans;
+    const int rt = item % p.rtiles;
+    const int b = item / p.rtiles;
+    if (threadIdx.x == 0) {
+        const unsigned *g = p.gate + b / p.gate_pairs;
+        const long long t0 = clock64();
+        for (;;) {
+            unsigned v;
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(g) : "memory");
+            if ((int)(v - p.gate_gen) >= 0) break;
+            if (clock64() - t0 > GATE_TIMEOUT_CLK) {
+                atomicExch(const_cast<unsigned *>(p.gate) + GATE_ERR_SLOT, 1u);
+                break;
+            }
+            __nanosleep(128);
+        }
+    }
+    __syncthreads();
+    nn_sym_item<QT, false, true>(s, p.rows + (size_t)b * p.nr * 3, p.nr, rt, p.cols + (size_t)b * p.nc * 3, p.nc, cs * p.span,
+                                 p.span, nullptr, p.prow + (size_t)b * p.nr, p.pcol + (size_t)b * p.nc, p.rblock_base);
+}
+
+// Balanced form ("stream-K" over the distance matrix): the work of the whole launch is counted in UNITS of one row
+// tile x one 32-column block, linearised as (cloud pair, row tile, column block), and cut into gridDim.x equal
+// contiguous ranges -- one per resident CTA (2 per SM).  A CTA walks its range as a sequence of ordinary work items
+// (same row tile, up to SYM_SPAN_MAX consecutive columns), so every CTA executes the same number of column blocks
+// +-1 whatever the problem shape: no partial last wave (C2: 1024 items over 296 slots = 3.46 waves before) and
+// B = 1 problems fill the machine.  Results are merged by the same packed atomicMin words, hence bit-identical.
+template <int QT>
+__global__ void __launch_bounds__(SYM_THREADS, GENPC_SYM_MINB(QT)) nn_sym_balanced_kernel(const SymParams p, int total_units,
+                                                                                         int units_per_job) {
+    __shared__ __align__(16) float s[3][SYM_SPAN_MAX];
+    int u = (int)((long long)total_units * blockIdx.x / gridDim.x);
+    const int u_end = (int)((long long)total_units * (blockIdx.x + 1) / gridDim.x);
+    int job = u / units_per_job;
+    int blk = u - job * units_per_job;
+    while (u < u_end) {
+        int nblk = min(min(units_per_job - blk, SYM_SPAN_MAX / 32), u_end - u);  // row tile end / one smem span / range end
+        const int rt = job % p.rtiles, b = job / p.rtiles;
+        nn_sym_item<QT>(s, p.rows + (size_t)b * p.nr * 3, p.nr, rt, p.cols + (size_t)b * p.nc * 3, p.nc, blk * 32, nblk * 32,
+                        nullptr, p.prow + (size_t)b * p.nr, p.pcol + (size_t)b * p.nc, p.rblock_base);
+        u += nblk, blk += nblk;
+        if (blk == units_per_job) blk = 0, ++job;
+        __syncthreads();  // every warp is done with the span before the next item overwrites it
+    }
+}
+
+#if GENPC_SYM_SPAN_MAX <= 1024  // the double buffer must fit the 48 KB static shared-memory limit
 // Persistent form: one CTA pair per SM loops over work items handed out by an atomic counter; the NEXT item's column
 // span is copied global -> shared with cp.async (LDGSTS, 4-byte granules so the AoS -> SoA transposition happens in the
 // copy itself) into the other half of a double buffer while the current item is being scanned.
@@ -267,6 +347,7 @@ __global__ void __launch_bounds__(SYM_THREADS, GENPC_SYM_MINB(QT)) nn_sym_persis
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
+#endif
 
 // Exact lowest row index of one column from its published (dist, row block) word: the calling WARP re-scans the
 // winning block (32*NS consecutive rows) for the first row whose distance equals dist.  All NS strips are loaded

@@ -38,6 +38,7 @@ struct RegArgs {
     unsigned long long *packedA;  // [S][Nc]
     unsigned long long *packedB;  // [S][Nr]
     int *counters;          // [S]
+    double *partials;       // [S][fix_ctas][14] per-CTA loss / gradient partial sums (symmetric path)
     float *loss_hist;       // [S][T]
     int S, n_starts, Nc, Nr, T, t_index;
     int qtilesA, tsplitsA, itemsA, qtilesB, tsplitsB, items_per_scan;
@@ -95,36 +96,9 @@ __device__ __forceinline__ void accum_term(const RegArgs &a, const Similarity &T
     acc[12] += gx * rx + gy * ry + gz * rz;                                    // dL/dlog_s
 }
 
-__device__ __noinline__ void finalize_scan(const RegArgs &a, int scan, const Similarity &T, double *sh) {
-    const int cloud = scan / a.n_starts;
-    const float *V = a.complete + (size_t)cloud * a.Nc * 3;
-    const float *Rf = a.ref + (size_t)cloud * a.Nr * 3;
-    unsigned long long *pA = a.packedA + (size_t)scan * a.Nc;
-    unsigned long long *pB = a.packedB + (size_t)scan * a.Nr;
-    double acc[14];
-#pragma unroll
-    for (int i = 0; i < 14; ++i) acc[i] = 0.0;
-    const double cA = (double)a.cd_weight * (double)a.w_fwd / (double)a.Nc;
-    const double cB = (double)a.cd_weight * (double)a.w_inv / (double)a.Nr;
-    const int nthr = blockDim.x;
-#pragma unroll 4
-    for (int j = threadIdx.x; j < a.Nc; j += nthr) {  // direction A: moving point j -> its NN in ref
-        const unsigned long long w = __ldcg(pA + j);
-        accum_term(a, T, V, Rf, j, (int)(unsigned)(w & 0xffffffffu), __uint_as_float((unsigned)(w >> 32)), cA, acc);
-    }
-#pragma unroll 4
-    for (int k = threadIdx.x; k < a.Nr; k += nthr) {  // direction B: ref point k -> its NN among moving pts
-        const unsigned long long w = __ldcg(pB + k);
-        accum_term(a, T, V, Rf, (int)(unsigned)(w & 0xffffffffu), k, __uint_as_float((unsigned)(w >> 32)), cB, acc);
-    }
-    __syncthreads();
-    for (int j = threadIdx.x; j < a.Nc; j += nthr) pA[j] = ~0ull;  // re-arm for the next launch
-    for (int k = threadIdx.x; k < a.Nr; k += nthr) pB[k] = ~0ull;
-    double tot[14];
-#pragma unroll
-    for (int i = 0; i < 14; ++i) tot[i] = block_sum(acc[i], sh);
-    if (threadIdx.x != 0) return;
-
+// Single thread: Gram-Schmidt backward on the 13 reduced gradient scalars, Adam step, loss record,
+// ticket re-armed.  tot = {dL/dt[3], dL/dR[9] row-major, dL/dlog_s, loss}.
+__device__ __noinline__ void pose_update(const RegArgs &a, int scan, const Similarity &T, const double *tot) {
     float *par = a.params + (size_t)scan * REG_NPAR;
     float *am = a.adam_m + (size_t)scan * REG_NPAR;
     float *av = a.adam_v + (size_t)scan * REG_NPAR;
@@ -163,6 +137,39 @@ __device__ __noinline__ void finalize_scan(const RegArgs &a, int scan, const Sim
     }
     if (a.loss_hist != nullptr) a.loss_hist[(size_t)scan * a.T + a.t_index] = (float)tot[13];
     a.counters[scan] = 0;
+}
+
+__device__ __noinline__ void finalize_scan(const RegArgs &a, int scan, const Similarity &T, double *sh) {
+    const int cloud = scan / a.n_starts;
+    const float *V = a.complete + (size_t)cloud * a.Nc * 3;
+    const float *Rf = a.ref + (size_t)cloud * a.Nr * 3;
+    unsigned long long *pA = a.packedA + (size_t)scan * a.Nc;
+    unsigned long long *pB = a.packedB + (size_t)scan * a.Nr;
+    double acc[14];
+#pragma unroll
+    for (int i = 0; i < 14; ++i) acc[i] = 0.0;
+    const double cA = (double)a.cd_weight * (double)a.w_fwd / (double)a.Nc;
+    const double cB = (double)a.cd_weight * (double)a.w_inv / (double)a.Nr;
+    const int nthr = blockDim.x;
+#pragma unroll 4
+    for (int j = threadIdx.x; j < a.Nc; j += nthr) {  // direction A: moving point j -> its NN in ref
+        const unsigned long long w = __ldcg(pA + j);
+        accum_term(a, T, V, Rf, j, (int)(unsigned)(w & 0xffffffffu), __uint_as_float((unsigned)(w >> 32)), cA, acc);
+    }
+#pragma unroll 4
+    for (int k = threadIdx.x; k < a.Nr; k += nthr) {  // direction B: ref point k -> its NN among moving pts
+        const unsigned long long w = __ldcg(pB + k);
+        accum_term(a, T, V, Rf, (int)(unsigned)(w & 0xffffffffu), k, __uint_as_float((unsigned)(w >> 32)), cB, acc);
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < a.Nc; j += nthr) pA[j] = ~0ull;  // re-arm for the next launch
+    for (int k = threadIdx.x; k < a.Nr; k += nthr) pB[k] = ~0ull;
+    double tot[14];
+#pragma unroll
+    for (int i = 0; i < 14; ++i) tot[i] = block_sum(acc[i], sh);
+    if (threadIdx.x != 0) return;
+
+    pose_update(a, scan, T, tot);
 }
 
 template <int QT>
@@ -218,13 +225,18 @@ __global__ void __launch_bounds__(SYM_THREADS, GENPC_SYM_MINB(QT)) register_sym_
 }
 
 // launch 2: one warp per moving point resolves its (dist, row block) word to the exact lowest index of the fixed
-//           cloud; the last CTA of a scan (ticket) then reduces loss + gradient and steps Adam (finalize_scan).
+//           cloud; then EVERY CTA reduces the loss / gradient terms of its own 128 moving points (direction A) and of its
+//           slice of the fixed cloud (direction B) to 14 doubles (fixed thread assignment, fixed tree), re-arms the packed
+//           words it consumed and stores the partial; the last CTA of a scan (ticket) adds the per-CTA partials in index
+//           order -- deterministic -- and steps Adam (pose_update).  (The single-CTA finalize_scan of the small path
+//           serialised 32 K gather + double-precision terms per scan: 64 CTAs busy, the rest of the GPU idle.)
 constexpr int FIX_THREADS = 512;
 constexpr int FIX_COLS_PER_CTA = 128;
 __global__ void __launch_bounds__(FIX_THREADS, 2) register_finish_kernel(const RegArgs a) {
     __shared__ Similarity T;
     __shared__ int is_last;
-    __shared__ double sh[FIX_THREADS / 32];
+    __shared__ double sh[FIX_THREADS / 32][14];
+    __shared__ double tot[14];
     const int scan = blockIdx.x / a.fix_ctas;
     const int part = blockIdx.x - scan * a.fix_ctas;
     const int cloud = scan / a.n_starts;
@@ -234,7 +246,9 @@ __global__ void __launch_bounds__(FIX_THREADS, 2) register_finish_kernel(const R
     const float *V = a.complete + (size_t)cloud * a.Nc * 3;
     const float *Rf = a.ref + (size_t)cloud * a.Nr * 3;
     unsigned long long *pA = a.packedA + (size_t)scan * a.Nc;
-    for (int c = part * FIX_COLS_PER_CTA + warp; c < min(a.Nc, (part + 1) * FIX_COLS_PER_CTA); c += FIX_THREADS / 32) {
+    unsigned long long *pB = a.packedB + (size_t)scan * a.Nr;
+    const int c_lo = part * FIX_COLS_PER_CTA, c_hi = min(a.Nc, c_lo + FIX_COLS_PER_CTA);
+    for (int c = c_lo + warp; c < c_hi; c += FIX_THREADS / 32) {
         const unsigned long long w = __ldcg(pA + c);
         const float d = __uint_as_float((unsigned)(w >> 32));
         float x = __ldg(V + (size_t)c * 3), y = __ldg(V + (size_t)c * 3 + 1), z = __ldg(V + (size_t)c * 3 + 2);
@@ -242,14 +256,60 @@ __global__ void __launch_bounds__(FIX_THREADS, 2) register_finish_kernel(const R
         const int found = sym_fix_column(Rf, a.Nr, a.rows_per_block, x, y, z, d, (int)(unsigned)(w & 0xffffffffu), lane);
         if (lane == 0) pA[c] = pack_dist_idx(d, found);
     }
-    __threadfence();
+    __syncthreads();  // the fixed-up words of this CTA's columns are visible to the whole CTA
+    // ---- this CTA's share of the loss / gradient terms ----
+    double acc[14];
+#pragma unroll
+    for (int i = 0; i < 14; ++i) acc[i] = 0.0;
+    const double cA = (double)a.cd_weight * (double)a.w_fwd / (double)a.Nc;
+    const double cB = (double)a.cd_weight * (double)a.w_inv / (double)a.Nr;
+    for (int c = c_lo + (int)threadIdx.x; c < c_hi; c += FIX_THREADS) {  // direction A: moving point c -> its NN in ref
+        const unsigned long long w = pA[c];
+        pA[c] = ~0ull;                                                   // re-arm for the next iteration
+        accum_term(a, T, V, Rf, c, (int)(unsigned)(w & 0xffffffffu), __uint_as_float((unsigned)(w >> 32)), cA, acc);
+    }
+    const int rows_per_cta = (a.Nr + a.fix_ctas - 1) / a.fix_ctas;
+    const int k_lo = part * rows_per_cta, k_hi = min(a.Nr, k_lo + rows_per_cta);
+    // direction B: fixed point k -> its NN among the moving points; upper threads first so that both directions overlap
+    for (int k = k_lo + (FIX_THREADS - 1 - (int)threadIdx.x); k < k_hi; k += FIX_THREADS) {
+        const unsigned long long w = __ldcg(pB + k);
+        pB[k] = ~0ull;
+        accum_term(a, T, V, Rf, (int)(unsigned)(w & 0xffffffffu), k, __uint_as_float((unsigned)(w >> 32)), cB, acc);
+    }
+#pragma unroll
+    for (int i = 0; i < 14; ++i) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+        if (lane == 0) sh[warp][i] = acc[i];
+    }
+    __syncthreads();
+    double *partial = a.partials + ((size_t)scan * a.fix_ctas + part) * 14;
+    if (threadIdx.x < 14) {
+        double r = 0.0;
+#pragma unroll
+        for (int w = 0; w < FIX_THREADS / 32; ++w) r += sh[w][threadIdx.x];  // fixed order
+        partial[threadIdx.x] = r;
+        __threadfence();
+    }
     __syncthreads();
     if (threadIdx.x == 0) is_last = (atomicAdd(a.counters + scan, 1) == a.ticket_total - 1);
     __syncthreads();
-    if (is_last) {
-        __threadfence();
-        finalize_scan(a, scan, T, sh);
+    if (!is_last) return;
+    __threadfence();
+    // ---- last CTA of the scan: partials of all CTAs, in index order ----
+    if (warp < 14) {
+        const double *pp = a.partials + (size_t)scan * a.fix_ctas * 14 + warp;
+        double r = 0.0;
+        for (int q0 = 0; q0 < a.fix_ctas; q0 += 32) {  // 32 partials per step: lane tree, then chunks in order
+            double v = (q0 + lane < a.fix_ctas) ? __ldcg(pp + (size_t)(q0 + lane) * 14) : 0.0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            r += v;
+        }
+        if (lane == 0) tot[warp] = r;
     }
+    __syncthreads();
+    if (threadIdx.x == 0) pose_update(a, scan, T, tot);
 }
 
 }  // namespace genpc
@@ -258,7 +318,8 @@ using namespace genpc;
 
 extern "C" size_t genpc_register_workspace_bytes(int S, int Nc, int Nr) {
     if (S < 0 || Nc < 0 || Nr < 0) return 0;
-    return ((size_t)S * Nc + (size_t)S * Nr) * 8 + (size_t)S * sizeof(int);
+    const size_t fix_ctas = ((size_t)Nc + FIX_COLS_PER_CTA - 1) / FIX_COLS_PER_CTA;
+    return ((size_t)S * Nc + (size_t)S * Nr) * 8 + (size_t)S * fix_ctas * 14 * sizeof(double) + (size_t)S * sizeof(int);
 }
 
 extern "C" int genpc_register_run(const float *complete, const float *center, const float *ref, float *params,
@@ -274,7 +335,8 @@ extern "C" int genpc_register_run(const float *complete, const float *center, co
     a.complete = complete, a.center = center, a.ref = ref, a.params = params, a.adam_m = adam_m, a.adam_v = adam_v;
     a.packedA = (unsigned long long *)workspace;
     a.packedB = a.packedA + (size_t)S * Nc;
-    a.counters = (int *)(a.packedB + (size_t)S * Nr);
+    a.partials = (double *)(a.packedB + (size_t)S * Nr);
+    a.counters = (int *)(a.partials + (size_t)S * ((Nc + FIX_COLS_PER_CTA - 1) / FIX_COLS_PER_CTA) * 14);
     a.loss_hist = loss_hist;
     a.S = S, a.n_starts = n_starts, a.Nc = Nc, a.Nr = Nr, a.T = T;
     const int QT = nn_pick_qt(Nc < Nr ? Nc : Nr);

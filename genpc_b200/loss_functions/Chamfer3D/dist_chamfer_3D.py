@@ -42,6 +42,39 @@ class chamfer_3DFunction(Function):
         return grads
 
 
+class chamfer_3DHostFunction(Function):
+    """chamfer_3DFunction whose inputs start on the host: xyz1 / xyz2 are uninitialised CUDA leaves that the call fills
+    from the CPU tensors h1 / h2 while the scan is already running on the chunks that have arrived."""
+
+    @staticmethod
+    def forward(ctx, xyz1, xyz2, h1, h2, chunks):
+        dist1, idx1 = _outputs(xyz1, xyz1.shape[1])
+        dist2, idx2 = _outputs(xyz2, xyz2.shape[1])
+        chamfer_3D.forward_host(h1, h2, xyz1, xyz2, dist1, dist2, idx1, idx2, chunks)
+        ctx.save_for_backward(xyz1, xyz2, idx1, idx2)
+        ctx.mark_non_differentiable(idx1, idx2)
+        return dist1, dist2, idx1, idx2
+
+    @staticmethod
+    def backward(ctx, graddist1, graddist2, gradidx1, gradidx2):
+        return chamfer_3DFunction.backward(ctx, graddist1, graddist2, gradidx1, gradidx2) + (None, None, None)
+
+
+def host_leaves(h1, h2, device=None):
+    """Uninitialised CUDA leaf tensors shaped like the CPU clouds h1 / h2 (they receive the data and the gradients)."""
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    return (torch.empty(h1.shape, dtype=torch.float32, device=device).requires_grad_(True),
+            torch.empty(h2.shape, dtype=torch.float32, device=device).requires_grad_(True))
+
+
 class chamfer_3DDist(nn.Module):
     def forward(self, input1, input2):
         return chamfer_3DFunction.apply(input1.contiguous(), input2.contiguous())
+
+    def forward_from_host(self, input1, input2, device=None, chunks=6):
+        """`forward` for CPU (pinned) inputs -- the reference's `chamfer(x.cuda(), y.cuda())` with the host-to-device
+        copy overlapped with the scan.  Returns (dist1, dist2, idx1, idx2, xyz1, xyz2): xyz1 / xyz2 are the CUDA copies
+        of the inputs, leaves of the autograd graph (their .grad receives d/d input1, d/d input2)."""
+        xyz1, xyz2 = host_leaves(input1, input2, device)
+        out = chamfer_3DHostFunction.apply(xyz1, xyz2, input1.contiguous().float(), input2.contiguous().float(), chunks)
+        return out + (xyz1, xyz2)

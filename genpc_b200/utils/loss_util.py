@@ -42,7 +42,7 @@ class _FusedChamferLoss(Function):
     the scan plus ~16 elementwise / reduction launches of the torch expression.  Same value up to summation order."""
 
     @staticmethod
-    def forward(ctx, xyz1, xyz2, use_sqrt, w1, w2):
+    def forward(ctx, xyz1, xyz2, use_sqrt, w1, w2, h1=None, h2=None, chunks=6):
         _lib.require_cuda(xyz1, xyz2)
         a, b = xyz1.contiguous().float(), xyz2.contiguous().float()
         B, N, _ = a.shape
@@ -52,7 +52,10 @@ class _FusedChamferLoss(Function):
         d2 = torch.empty(B, M, device=dev)
         i1 = torch.empty(B, N, dtype=torch.int32, device=dev)
         i2 = torch.empty(B, M, dtype=torch.int32, device=dev)
-        chamfer_3D.forward(a, b, d1, d2, i1, i2)
+        if h1 is None:
+            chamfer_3D.forward(a, b, d1, d2, i1, i2)
+        else:  # host-fed: xyz1 / xyz2 are uninitialised leaves, filled from h1 / h2 while the scan runs
+            chamfer_3D.forward_host(h1, h2, a, b, d1, d2, i1, i2, chunks)
         out = torch.empty((), device=dev)
         ws = _workspace(dev)
         with torch.cuda.device(dev):
@@ -76,7 +79,7 @@ class _FusedChamferLoss(Function):
                                                         _lib.ptr(i2), _lib.ptr(up), use_sqrt, w1, w2, _lib.ptr(ga),
                                                         _lib.ptr(gb), B, N, M, _lib.current_stream(a.device))
         _lib.check(rc, "genpc_chamfer_loss_backward")
-        return ga, gb, None, None, None
+        return ga, gb, None, None, None, None, None, None
 
 
 class Completionloss:
@@ -127,3 +130,18 @@ class Completionloss:
 
     def get_loss(self, gen, gt):
         return self.metric(gen, gt)
+
+    _HOST_CFG = {"cd_l1": (True, 0.5, 0.5), "cd_l2": (False, 1.0, 1.0)}
+
+    def get_loss_from_host(self, gen, gt, device=None, chunks=6):
+        """`get_loss(gen.cuda(), gt.cuda())` for CPU (pinned) clouds, with the host-to-device copy overlapped with the
+        scan (genpc_chamfer_forward_host): returns (loss, gen_cuda, gt_cuda); after `loss.backward()` the gradients are
+        in gen_cuda.grad / gt_cuda.grad.  Chamfer metrics only (the EMD auction needs every point before it starts)."""
+        if self.loss_func not in self._HOST_CFG:
+            raise Exception("get_loss_from_host supports cd_l1 / cd_l2")
+        from ..loss_functions.Chamfer3D.dist_chamfer_3D import host_leaves
+
+        a, b = host_leaves(gen, gt, device)
+        use_sqrt, w1, w2 = self._HOST_CFG[self.loss_func]
+        loss = _FusedChamferLoss.apply(a, b, use_sqrt, w1, w2, gen.contiguous().float(), gt.contiguous().float(), chunks)
+        return loss, a, b

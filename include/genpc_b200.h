@@ -2,9 +2,10 @@
  * genpc_b200.h -- C ABI of libgenpc_b200.so, the B200 (sm_100a) drop-in for GenPC's geometric hot path.
  *
  * Conventions (mirroring the reference's pybind surface):
- *   - every pointer is a DEVICE pointer unless the name ends in `_host`;
+ *   - every pointer is a DEVICE pointer unless the name starts with `h_` (host memory, pinned for full speed);
  *   - the caller owns every buffer, including outputs and workspaces; nothing is allocated or freed here
- *     (reference: dist_chamfer_3D.py:33-42, emd_module.py:43-54);
+ *     (reference: dist_chamfer_3D.py:33-42, emd_module.py:43-54) -- the one exception is the genpc_host_feed_t
+ *     handle, which owns a copy stream, two events and 260 B of flags;
  *   - clouds are contiguous AoS float[B][N][3] (chamfer3D.cu:19,23-25), indices are int32;
  *   - all work is enqueued on `stream` (a cudaStream_t; pass 0 for the legacy default stream the
  *     reference uses, chamfer3D.cu:142) and the call returns without synchronising;
@@ -43,6 +44,24 @@ size_t genpc_chamfer_workspace_bytes(int B, int N, int M);
 int genpc_chamfer_forward(const float *xyz1, const float *xyz2, float *dist1, float *dist2, int *idx1,
                           int *idx2, int B, int N, int M, void *workspace, size_t workspace_bytes,
                           genpc_stream_t stream);
+
+/* Host-fed forward: the same result as genpc_chamfer_forward, but the clouds start in HOST memory
+ * (h_xyz1 [B][N][3], h_xyz2 [B][M][3]; pinned memory for an asynchronous full-speed copy) and their transfer into the
+ * caller's device buffers xyz1 / xyz2 is overlapped with the scan: the call cuts the batch into `chunks` groups of
+ * cloud pairs (6 is a good value for a PCN batch: every chunk costs three copy-engine commands; clamped to [1, min(B, 64)]), copies them on the handle's private stream, and the ONE
+ * scan launch on `stream` consumes each group as soon as its copy has landed.  This is the reference's stock flow
+ * `xyz.cuda()` + chamfer_3D.forward (dist_chamfer_3D.py:33-47) with the 7 MB PCIe transfer of a PCN batch hidden
+ * behind 0.27 ms of compute.  On return, all work is queued; `stream` is ordered after the copies, so xyz1 / xyz2 can
+ * be used by later work on `stream` (e.g. genpc_chamfer_backward).  A handle serves one call at a time per device;
+ * genpc_host_feed_error reports (and synchronises `stream`) whether a launch ever timed out waiting for its data.
+ * Every 256th call waits on the host for the previous call's copies (recycling of the pinned flag source ring). */
+typedef struct genpc_host_feed genpc_host_feed_t;
+int genpc_host_feed_create(genpc_host_feed_t **feed);
+int genpc_host_feed_destroy(genpc_host_feed_t *feed);
+int genpc_host_feed_error(genpc_host_feed_t *feed, genpc_stream_t stream);
+int genpc_chamfer_forward_host(genpc_host_feed_t *feed, const float *h_xyz1, const float *h_xyz2, float *xyz1,
+                               float *xyz2, float *dist1, float *dist2, int *idx1, int *idx2, int B, int N, int M,
+                               int chunks, void *workspace, size_t workspace_bytes, genpc_stream_t stream);
 
 /* Replaces chamfer_3D.backward (chamfer_cuda.cpp:22-27 -> chamfer_cuda_backward, chamfer3D.cu:176-195,
  * kernel NmDistanceGradKernel :155-174).  ACCUMULATES into gradxyz1/gradxyz2, which must arrive zeroed

@@ -42,5 +42,7 @@ int main() {
     run(32, 2048, 16384, "C2_B32_2048x16384");
     run(1, 16384, 16384, "B1_16384x16384");
     run(8, 16384, 16384, "B8_16384x16384");
+    run(1, 71372, 16384, "C1_71372x16384");
+    run(3, 5000, 3333, "B3_5000x3333");
     return 0;
 }
