@@ -377,9 +377,32 @@ __device__ __forceinline__ int sym_fix_column_t(const float *__restrict__ rp, in
     return found;
 }
 
+// 128-row block, vector form: the block is 1536 contiguous bytes, every lane takes 48 of them (rows r0 + 4*lane .. +3)
+// with three LDG.128 instead of twelve LDG.32 -- the fix-up is bound by load instructions and their latency, not by
+// bytes.  Needs the block entirely inside the cloud and a 16-byte aligned block start; the caller checks both.
+__device__ __forceinline__ int sym_fix_column_v4(const float *__restrict__ rp, float cx, float cy, float cz, float d, int blk,
+                                                 int lane) {
+    const int r0 = blk * 128;
+    const float4 *bp = reinterpret_cast<const float4 *>(rp + (size_t)r0 * 3) + lane * 3;
+    const float4 v0 = __ldg(bp), v1 = __ldg(bp + 1), v2 = __ldg(bp + 2);
+    int first = 4;  // lowest matching row of this lane's four, 4 = none (tested last to first)
+    if (sqdist_ref(cx, cy, cz, v2.y, v2.z, v2.w) == d) first = 3;
+    if (sqdist_ref(cx, cy, cz, v1.z, v1.w, v2.x) == d) first = 2;
+    if (sqdist_ref(cx, cy, cz, v0.w, v1.x, v1.y) == d) first = 1;
+    if (sqdist_ref(cx, cy, cz, v0.x, v0.y, v0.z) == d) first = 0;
+    const unsigned m = __ballot_sync(0xffffffffu, first < 4);
+    if (m == 0) return 0;
+    const int src = __ffs(m) - 1;  // lanes hold ascending rows: the lowest lane with a match holds the lowest index
+    return r0 + 4 * src + __shfl_sync(0xffffffffu, first, src);
+}
+
 __device__ __forceinline__ int sym_fix_column(const float *__restrict__ rp, int nr, int rows_per_block, float cx, float cy,
                                               float cz, float d, int blk, int lane) {
-    if (rows_per_block == 128) return sym_fix_column_t<4>(rp, nr, cx, cy, cz, d, blk, lane);
+    if (rows_per_block == 128) {
+        if ((blk + 1) * 128 <= nr && (reinterpret_cast<size_t>(rp) & 15) == 0)  // warp-uniform
+            return sym_fix_column_v4(rp, cx, cy, cz, d, blk, lane);
+        return sym_fix_column_t<4>(rp, nr, cx, cy, cz, d, blk, lane);
+    }
     if (rows_per_block == 64) return sym_fix_column_t<2>(rp, nr, cx, cy, cz, d, blk, lane);
     int found = 0;  // generic (QT = 6 / 8 experiments)
     for (int r0 = blk * rows_per_block; r0 < (blk + 1) * rows_per_block; r0 += 32) {
