@@ -20,6 +20,12 @@ class GenpcError(RuntimeError):
     pass
 
 
+class ChamferFuse(ctypes.Structure):
+    """genpc_chamfer_fuse_t (include/genpc_b200.h)."""
+    _fields_ = [("workspace_armed", _int), ("use_sqrt", _int), ("w1", _flt), ("w2", _flt), ("loss_out", _vp),
+                ("loss_workspace", _vp), ("loss_workspace_bytes", _sz), ("zero1", _vp), ("zero2", _vp)]
+
+
 _SIGNATURES = {
     "genpc_version": (ctypes.c_char_p, []),
     "genpc_chamfer_workspace_bytes": (_sz, [_int, _int, _int]),
@@ -29,6 +35,11 @@ _SIGNATURES = {
     "genpc_host_feed_error": (_int, [_vp, _vp]),
     "genpc_chamfer_forward_host": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _int, _int, _vp, _sz,
                                           _vp]),
+    "genpc_chamfer_fuse_workspace_bytes": (_sz, [_int, _int, _int]),
+    "genpc_chamfer_forward_fused": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _int, _vp, _sz,
+                                           ctypes.POINTER(ChamferFuse), _vp]),
+    "genpc_chamfer_forward_host_fused": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _int, _int, _vp,
+                                                _sz, ctypes.POINTER(ChamferFuse), _vp]),
     "genpc_chamfer_backward": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _int, _vp]),
     "genpc_chamfer_loss_workspace_bytes": (_sz, []),
     "genpc_chamfer_loss": (_int, [_vp, _vp, _sz, _sz, _int, _flt, _flt, _vp, _vp, _sz, _vp]),

@@ -159,7 +159,9 @@ static cudaError_t launch_scan(const NNParams &p, cudaStream_t stream) {
 // gate != nullptr: host-fed launch (nn_sym_gated_kernel), see genpc_chamfer_forward_host.
 static int chamfer_forward_sym(const float *xyz1, const float *xyz2, float *dist1, float *dist2, int *idx1, int *idx2,
                                int B, int N, int M, unsigned long long *packed, int *counter, cudaStream_t stream,
-                               const unsigned *gate = nullptr, unsigned gate_gen = 0, int gate_pairs = 1) {
+                               const unsigned *gate = nullptr, unsigned gate_gen = 0, int gate_pairs = 1,
+                               const genpc_chamfer_fuse_t *fuse = nullptr, double *fuse_partial = nullptr,
+                               unsigned *fuse_ticket = nullptr) {
     const bool swap = M > N;
     SymParams p;
     p.rows = swap ? xyz2 : xyz1, p.cols = swap ? xyz1 : xyz2;
@@ -220,11 +222,33 @@ static int chamfer_forward_sym(const float *xyz1, const float *xyz2, float *dist
     }
     GENPC_CHECK_LAUNCH();
     const size_t nrw = (size_t)B * p.nr, ncw = (size_t)B * p.nc;
-    const unsigned fix_blocks = (unsigned)((ncw * 32 + 255) / 256), unpack_blocks = (unsigned)((nrw + 255) / 256);
-    nn_sym_epilogue_kernel<<<fix_blocks + unpack_blocks, 256, 0, stream>>>(p.rows, p.cols, p.prow, p.pcol, B, p.nr, p.nc, 32 * QT,
-                                                                           fix_blocks, dist_r, idx_r, dist_c, idx_c);
+    const unsigned fix_blocks = (unsigned)((ncw + EPI_COLS_PER_CTA - 1) / EPI_COLS_PER_CTA);
+    const unsigned unpack_blocks = (unsigned)((nrw + EPI_ROWS_PER_CTA - 1) / EPI_ROWS_PER_CTA);
+    EpiFuse f;
+    memset(&f, 0, sizeof(f));
+    if (fuse == nullptr) {
+        nn_sym_epilogue_kernel<false><<<fix_blocks + unpack_blocks, 256, 0, stream>>>(
+            p.rows, p.cols, p.prow, p.pcol, B, p.nr, p.nc, 32 * QT, fix_blocks, dist_r, idx_r, dist_c, idx_c, f);
+    } else {
+        // dist1 belongs to xyz1: the row cloud unless the clouds were swapped
+        const double f1 = (fuse->w1 != 0.f) ? (double)fuse->w1 / (double)((size_t)B * N) : 0.0;
+        const double f2 = (fuse->w2 != 0.f) ? (double)fuse->w2 / (double)((size_t)B * M) : 0.0;
+        f.frow = swap ? f2 : f1, f.fcol = swap ? f1 : f2;
+        f.use_sqrt = fuse->use_sqrt, f.rearm = 1;
+        if (fuse->loss_out != nullptr) f.partial = fuse_partial, f.ticket = fuse_ticket, f.loss_out = fuse->loss_out;
+        f.zero[0] = fuse->zero1, f.nzero[0] = (size_t)B * N * 3;
+        f.zero[1] = fuse->zero2, f.nzero[1] = (size_t)B * M * 3;
+        nn_sym_epilogue_kernel<true><<<fix_blocks + unpack_blocks, 256, 0, stream>>>(
+            p.rows, p.cols, p.prow, p.pcol, B, p.nr, p.nc, 32 * QT, fix_blocks, dist_r, idx_r, dist_c, idx_c, f);
+    }
     GENPC_CHECK_LAUNCH();
     return GENPC_OK;
+}
+
+// Number of epilogue CTAs of the symmetric path (one loss partial each), whichever cloud ends up as rows.
+static size_t sym_epilogue_ctas(int B, int N, int M) {
+    const size_t nr = (size_t)B * (N > M ? N : M), nc = (size_t)B * (N > M ? M : N);
+    return (nc + EPI_COLS_PER_CTA - 1) / EPI_COLS_PER_CTA + (nr + EPI_ROWS_PER_CTA - 1) / EPI_ROWS_PER_CTA;
 }
 
 }  // namespace genpc
@@ -236,13 +260,55 @@ extern "C" size_t genpc_chamfer_workspace_bytes(int B, int N, int M) {
     return ((size_t)B * N + (size_t)B * M) * sizeof(unsigned long long) + 16;  // packed words + work-item counter
 }
 
-extern "C" int genpc_chamfer_forward(const float *xyz1, const float *xyz2, float *dist1, float *dist2,
-                                     int *idx1, int *idx2, int B, int N, int M, void *workspace,
-                                     size_t workspace_bytes, genpc_stream_t stream_) {
+static bool takes_sym_path(int N, int M) {
+    // "sym": one evaluation of every distance feeds both directions (nn_sym.cuh); "scan": one scan per direction
+    const char *mode = getenv("GENPC_CHAMFER_MODE");
+    const bool want_sym = (mode == nullptr) ? GENPC_DEFAULT_SYM : (strcmp(mode, "sym") == 0);
+    return want_sym && N > 0 && M > 0 && (N > M ? N : M) >= 512;
+}
+
+extern "C" size_t genpc_chamfer_fuse_workspace_bytes(int B, int N, int M) {
+    if (B < 0 || N < 0 || M < 0) return 0;
+    const size_t a = sym_epilogue_ctas(B, N, M) * sizeof(double) + 16;  // one partial per epilogue CTA + the ticket
+    const size_t b = genpc_chamfer_loss_workspace_bytes();              // non-symmetric path: the plain loss kernel
+    return a > b ? a : b;
+}
+
+// The unfused tail of a fused call, for the shapes that do not take the symmetric path (tiny or empty clouds).
+static int fuse_tail_unfused(const genpc_chamfer_fuse_t *fuse, const float *dist1, const float *dist2, int B, int N, int M,
+                             cudaStream_t stream) {
+    cudaError_t e;
+    const size_t n1 = (size_t)B * N, n2 = (size_t)B * M;
+    if (fuse->zero1 != nullptr && n1) {
+        e = cudaMemsetAsync(fuse->zero1, 0, n1 * 12, stream);
+        if (e != cudaSuccess) return (int)e;
+    }
+    if (fuse->zero2 != nullptr && n2) {
+        e = cudaMemsetAsync(fuse->zero2, 0, n2 * 12, stream);
+        if (e != cudaSuccess) return (int)e;
+    }
+    if (fuse->loss_out == nullptr) return GENPC_OK;
+    return genpc_chamfer_loss(dist1, dist2, n1, n2, fuse->use_sqrt, fuse->w1, fuse->w2, fuse->loss_out, fuse->loss_workspace,
+                              fuse->loss_workspace_bytes, (genpc_stream_t)stream);
+}
+
+static int fuse_check(const genpc_chamfer_fuse_t *fuse, int B, int N, int M) {
+    if (fuse == nullptr || fuse->loss_out == nullptr) return GENPC_OK;
+    if (fuse->loss_workspace == nullptr || fuse->loss_workspace_bytes < genpc_chamfer_fuse_workspace_bytes(B, N, M))
+        return GENPC_ERR_WORKSPACE;
+    return GENPC_OK;
+}
+
+extern "C" int genpc_chamfer_forward_fused(const float *xyz1, const float *xyz2, float *dist1, float *dist2,
+                                           int *idx1, int *idx2, int B, int N, int M, void *workspace,
+                                           size_t workspace_bytes, const genpc_chamfer_fuse_t *fuse,
+                                           genpc_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (B < 0 || N < 0 || M < 0) return GENPC_ERR_SHAPE;
+    int rc = fuse_check(fuse, B, N, M);
+    if (rc != GENPC_OK) return rc;
     const size_t n1 = (size_t)B * N, n2 = (size_t)B * M;
-    if (n1 + n2 == 0) return GENPC_OK;
+    if (n1 + n2 == 0) return fuse ? fuse_tail_unfused(fuse, dist1, dist2, B, N, M, stream) : GENPC_OK;
     if (N == 0 || M == 0) {
         // the reference's kernels write nothing in this case; outputs keep the zeros they were allocated with
         if (n1) {
@@ -254,24 +320,27 @@ extern "C" int genpc_chamfer_forward(const float *xyz1, const float *xyz2, float
             cudaMemsetAsync(idx2, 0, n2 * 4, stream);
         }
         GENPC_CHECK_LAUNCH();
-        return GENPC_OK;
+        return fuse ? fuse_tail_unfused(fuse, dist1, dist2, B, N, M, stream) : GENPC_OK;
     }
     if (workspace == nullptr || workspace_bytes < genpc_chamfer_workspace_bytes(B, N, M)) return GENPC_ERR_WORKSPACE;
     unsigned long long *packed = (unsigned long long *)workspace;
-    cudaError_t e = cudaMemsetAsync(packed, 0xff, (n1 + n2) * 8, stream);
-    if (e != cudaSuccess) return (int)e;
-
-    // "sym": one evaluation of every distance feeds both directions (nn_sym.cuh); "scan": one scan per direction
-    const char *mode = getenv("GENPC_CHAMFER_MODE");
-    const bool want_sym = (mode == nullptr) ? GENPC_DEFAULT_SYM : (strcmp(mode, "sym") == 0);
-    if (want_sym && (N > M ? N : M) >= 512) {
+    cudaError_t e;
+    const bool sym = takes_sym_path(N, M);
+    if (!(sym && fuse != nullptr && fuse->workspace_armed)) {  // an armed workspace already holds all-ones words
+        e = cudaMemsetAsync(packed, 0xff, (n1 + n2) * 8, stream);
+        if (e != cudaSuccess) return (int)e;
+    }
+    if (sym) {
         int *counter = (int *)(packed + n1 + n2);  // work-item counter of the persistent kernel (after the packed words)
         const char *pm = getenv("GENPC_SYM_PERSIST");
         if ((pm == nullptr) ? GENPC_DEFAULT_PERSIST : (atoi(pm) != 0)) {
             e = cudaMemsetAsync(counter, 0, 16, stream);
             if (e != cudaSuccess) return (int)e;
         }
-        return chamfer_forward_sym(xyz1, xyz2, dist1, dist2, idx1, idx2, B, N, M, packed, counter, stream);
+        double *partial = fuse ? (double *)fuse->loss_workspace : nullptr;
+        unsigned *ticket = partial ? (unsigned *)(partial + sym_epilogue_ctas(B, N, M)) : nullptr;
+        return chamfer_forward_sym(xyz1, xyz2, dist1, dist2, idx1, idx2, B, N, M, packed, counter, stream, nullptr, 0, 1, fuse,
+                                   partial, ticket);
     }
 
     const int QT = nn_pick_qt(N < M ? N : M);
@@ -289,7 +358,14 @@ extern "C" int genpc_chamfer_forward(const float *xyz1, const float *xyz2, float
     const size_t tot = n1 + n2;
     nn_unpack_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(packed, dist1, idx1, n1, dist2, idx2, n2);
     GENPC_CHECK_LAUNCH();
-    return GENPC_OK;
+    return fuse ? fuse_tail_unfused(fuse, dist1, dist2, B, N, M, stream) : GENPC_OK;
+}
+
+extern "C" int genpc_chamfer_forward(const float *xyz1, const float *xyz2, float *dist1, float *dist2,
+                                     int *idx1, int *idx2, int B, int N, int M, void *workspace,
+                                     size_t workspace_bytes, genpc_stream_t stream_) {
+    return genpc_chamfer_forward_fused(xyz1, xyz2, dist1, dist2, idx1, idx2, B, N, M, workspace, workspace_bytes, nullptr,
+                                       stream_);
 }
 
 extern "C" int genpc_chamfer_backward(const float *xyz1, const float *xyz2, const float *graddist1,
@@ -360,18 +436,29 @@ extern "C" int genpc_chamfer_forward_host(genpc_host_feed_t *f, const float *h_x
                                           float *xyz2, float *dist1, float *dist2, int *idx1, int *idx2, int B, int N,
                                           int M, int chunks, void *workspace, size_t workspace_bytes,
                                           genpc_stream_t stream_) {
+    return genpc_chamfer_forward_host_fused(f, h_xyz1, h_xyz2, xyz1, xyz2, dist1, dist2, idx1, idx2, B, N, M, chunks, workspace,
+                                            workspace_bytes, nullptr, stream_);
+}
+
+extern "C" int genpc_chamfer_forward_host_fused(genpc_host_feed_t *f, const float *h_xyz1, const float *h_xyz2, float *xyz1,
+                                                float *xyz2, float *dist1, float *dist2, int *idx1, int *idx2, int B,
+                                                int N, int M, int chunks, void *workspace, size_t workspace_bytes,
+                                                const genpc_chamfer_fuse_t *fuse, genpc_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (f == nullptr || B < 0 || N < 0 || M < 0) return GENPC_ERR_SHAPE;
     const size_t n1 = (size_t)B * N, n2 = (size_t)B * M;
-    if (n1 + n2 == 0) return GENPC_OK;
+    if (n1 + n2 == 0)
+        return genpc_chamfer_forward_fused(xyz1, xyz2, dist1, dist2, idx1, idx2, B, N, M, workspace, workspace_bytes, fuse, stream_);
+    const int frc = fuse_check(fuse, B, N, M);
+    if (frc != GENPC_OK) return frc;
     cudaError_t e;
 #define FEED_CHECK(x) do { e = (x); if (e != cudaSuccess) return (int)e; } while (0)
-    const bool sym = (N > M ? N : M) >= 512 && N > 0 && M > 0;
+    const bool sym = takes_sym_path(N, M);
     if (!sym || B < 2 || chunks < 2) {
         // tiny clouds / a single pair: nothing worth overlapping -- copy on the caller's stream, then the plain entry
         if (n1) FEED_CHECK(cudaMemcpyAsync(xyz1, h_xyz1, n1 * 12, cudaMemcpyHostToDevice, stream));
         if (n2) FEED_CHECK(cudaMemcpyAsync(xyz2, h_xyz2, n2 * 12, cudaMemcpyHostToDevice, stream));
-        return genpc_chamfer_forward(xyz1, xyz2, dist1, dist2, idx1, idx2, B, N, M, workspace, workspace_bytes, stream_);
+        return genpc_chamfer_forward_fused(xyz1, xyz2, dist1, dist2, idx1, idx2, B, N, M, workspace, workspace_bytes, fuse, stream_);
     }
     if (workspace == nullptr || workspace_bytes < genpc_chamfer_workspace_bytes(B, N, M)) return GENPC_ERR_WORKSPACE;
     if (chunks > GATE_MAX_CHUNKS) chunks = GATE_MAX_CHUNKS;
@@ -397,8 +484,11 @@ extern "C" int genpc_chamfer_forward_host(genpc_host_feed_t *f, const float *h_x
         FEED_CHECK(cudaMemcpyAsync(f->gate + c, src, sizeof(unsigned), cudaMemcpyHostToDevice, f->copy_stream));
     }
     unsigned long long *packed = (unsigned long long *)workspace;
-    FEED_CHECK(cudaMemsetAsync(packed, 0xff, (n1 + n2) * 8, stream));
-    const int rc = chamfer_forward_sym(xyz1, xyz2, dist1, dist2, idx1, idx2, B, N, M, packed, nullptr, stream, f->gate, gen, pairs);
+    if (!(fuse != nullptr && fuse->workspace_armed)) FEED_CHECK(cudaMemsetAsync(packed, 0xff, (n1 + n2) * 8, stream));
+    double *partial = fuse ? (double *)fuse->loss_workspace : nullptr;
+    unsigned *ticket = partial ? (unsigned *)(partial + sym_epilogue_ctas(B, N, M)) : nullptr;
+    const int rc = chamfer_forward_sym(xyz1, xyz2, dist1, dist2, idx1, idx2, B, N, M, packed, nullptr, stream, f->gate, gen, pairs,
+                                       fuse, partial, ticket);
     if (rc != GENPC_OK) return rc;
     FEED_CHECK(cudaEventRecord(f->copied, f->copy_stream));
     FEED_CHECK(cudaStreamWaitEvent(stream, f->copied, 0));  // later work on the caller's stream sees complete clouds
@@ -494,8 +584,13 @@ extern "C" int genpc_chamfer_sym_fixup(const float *rows_full, const float *cols
     if (B < 0 || nr_full < 0 || nc < 0) return GENPC_ERR_SHAPE;
     const size_t ncw = (size_t)B * nc;
     if (ncw == 0) return GENPC_OK;
-    nn_sym_fixup_kernel<<<(unsigned)((ncw * 32 + 255) / 256), 256, 0, stream>>>(rows_full, cols, pcol, B, nr_full, nc, 128,
-                                                                                dist_cols, idx_cols);
+    // the column half of the forward epilogue alone (no row blocks, nothing fused: pcol is only read)
+    EpiFuse f;
+    memset(&f, 0, sizeof(f));
+    const unsigned fix_blocks = (unsigned)((ncw + EPI_COLS_PER_CTA - 1) / EPI_COLS_PER_CTA);
+    nn_sym_epilogue_kernel<false><<<fix_blocks, 256, 0, stream>>>(rows_full, cols, nullptr, const_cast<unsigned long long *>(pcol), B,
+                                                                  nr_full, nc, 128, fix_blocks, nullptr, nullptr, dist_cols,
+                                                                  idx_cols, f);
     GENPC_CHECK_LAUNCH();
     return GENPC_OK;
 }

@@ -12,7 +12,7 @@
 //   col side: per 32-column block every lane folds its QT rows into 32 accumulators (FMNMX3 over row pairs),
 //             a 31-step butterfly (SHFL + FMNMX) leaves lane l with the warp-wide minimum of column l, and ONE
 //             coalesced 64-bit atomicMin per lane publishes (dist_bits << 32 | row_block_id).  The exact lowest
-//             row index is recovered afterwards by nn_sym_fixup_kernel, which re-scans only the winning
+//             row index is recovered afterwards by nn_sym_epilogue_kernel, which re-scans only the winning
 //             32*QT-row block of each column (lowest block wins ties, first match inside it => lowest index).
 #pragma once
 #include "nn_core.cuh"
@@ -422,56 +422,149 @@ __device__ __forceinline__ int sym_fix_column(const float *__restrict__ rp, int 
     return found;
 }
 
-// Forward epilogue in ONE launch: blocks [0, fix_blocks) resolve the column words (one warp per column, exact lowest
-// row index from the winning row block) and write dist/idx of the column cloud; the remaining blocks unpack the row
-// words into dist/idx of the row cloud.
-static __global__ void __launch_bounds__(256) nn_sym_epilogue_kernel(const float *__restrict__ rows, const float *__restrict__ cols,
-                                                                     const unsigned long long *__restrict__ prow,
-                                                                     const unsigned long long *__restrict__ pcol, int B, int nr,
-                                                                     int nc, int rows_per_block, unsigned fix_blocks,
-                                                                     float *__restrict__ dist_r, int *__restrict__ idx_r,
-                                                                     float *__restrict__ dist_c, int *__restrict__ idx_c) {
-    if (blockIdx.x >= fix_blocks) {
-        const size_t i = (size_t)(blockIdx.x - fix_blocks) * blockDim.x + threadIdx.x;
-        if (i < (size_t)B * nr) {
-            const unsigned long long w = __ldg(prow + i);
-            dist_r[i] = __uint_as_float((unsigned)(w >> 32));
-            idx_r[i] = (int)(unsigned)(w & 0xffffffffu);
-        }
-        return;
-    }
-    const size_t w = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (w >= (size_t)B * nc) return;
-    const size_t b = w / nc;
-    const unsigned long long word = __ldg(pcol + w);
-    const float d = __uint_as_float((unsigned)(word >> 32));
-    const int blk = (int)(unsigned)(word & 0xffffffffu);
-    const float cx = __ldg(cols + w * 3), cy = __ldg(cols + w * 3 + 1), cz = __ldg(cols + w * 3 + 2);
-    const int found = sym_fix_column(rows + b * (size_t)nr * 3, nr, rows_per_block, cx, cy, cz, d, blk, lane);
-    if (lane == 0) {
-        dist_c[w] = d;
-        idx_c[w] = found;
+// Optional extra duties of the forward epilogue (genpc_chamfer_forward_fused): everything that used to be separate tiny
+// launches around the scan in a loss step -- the loss reduction, the zero-fill of the gradient accumulators that the
+// backward kernel adds into, and re-arming the packed words so that the next call on the same workspace needs no memset.
+struct EpiFuse {
+    double *partial;        // one slot per epilogue CTA; nullptr: no loss
+    unsigned *ticket;       // zero between launches (re-armed by the last CTA)
+    float *loss_out;        // device scalar
+    double fcol, frow;      // loss = fcol * sum_cols f(d) + frow * sum_rows f(d)   (w / count; 0 drops the side)
+    int use_sqrt;           // f = sqrt or identity
+    int rearm;              // store all-ones back into every packed word after reading it
+    float *zero[2];         // buffers to zero-fill, or nullptr
+    size_t nzero[2];        // their sizes in floats
+};
+
+__device__ __forceinline__ void epi_zero_fill(float *z, size_t n, size_t g, size_t total_threads) {
+    if (z == nullptr) return;
+    if ((reinterpret_cast<size_t>(z) & 15) == 0) {
+        float4 *z4 = reinterpret_cast<float4 *>(z);
+        const size_t n4 = n >> 2;
+        for (size_t i = g; i < n4; i += total_threads) z4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (g < (n & 3)) z[(n4 << 2) + g] = 0.f;
+    } else {
+        for (size_t i = g; i < n; i += total_threads) z[i] = 0.f;
     }
 }
 
-// Column fix-up alone (row-sharded multi-GPU path): one warp per column; writes the final dist / idx of the column cloud.
-static __global__ void __launch_bounds__(256) nn_sym_fixup_kernel(const float *__restrict__ rows, const float *__restrict__ cols,
-                                                           const unsigned long long *__restrict__ pcol, int B, int nr,
-                                                           int nc, int rows_per_block, float *__restrict__ dist_out,
-                                                           int *__restrict__ idx_out) {
-    const size_t w = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (w >= (size_t)B * nc) return;
-    const size_t b = w / nc;
-    const unsigned long long word = __ldg(pcol + w);
-    const float d = __uint_as_float((unsigned)(word >> 32));
-    const int blk = (int)(unsigned)(word & 0xffffffffu);
-    const float cx = __ldg(cols + w * 3), cy = __ldg(cols + w * 3 + 1), cz = __ldg(cols + w * 3 + 2);
-    const int found = sym_fix_column(rows + b * (size_t)nr * 3, nr, rows_per_block, cx, cy, cz, d, blk, lane);
-    if (lane == 0) {
-        dist_out[w] = d;
-        idx_out[w] = found;
+// Forward epilogue in ONE launch: blocks [0, fix_blocks) resolve the column words (exact lowest row index from the
+// winning row block) and write dist/idx of the column cloud; the remaining blocks unpack the row words into dist/idx of
+// the row cloud.  CTAs are FAT -- a warp resolves EPI_CPW consecutive columns (lane k fetches word + point of column k up
+// front, the columns are handed round by shuffles and their row-block loads are independent), a thread unpacks EPI_RPT
+// rows -- because the thin form (one column per warp, one row per thread: 10 240 CTAs on C2) is bound by the dependent
+// L2 latencies of every CTA, not by bytes.  FUSED: additionally the duties of EpiFuse; the loss is deterministic (one
+// double partial per CTA from a fixed tree, the last CTA -- ticket -- adds the partials of each side in index order).
+constexpr int EPI_CPW = 8;                        // columns per warp
+constexpr int EPI_COLS_PER_CTA = 8 * EPI_CPW;     // 256 threads
+constexpr int EPI_RPT = 8;                        // rows per thread
+constexpr int EPI_ROWS_PER_CTA = 256 * EPI_RPT;
+
+template <bool FUSED>
+static __global__ void __launch_bounds__(256) nn_sym_epilogue_kernel(const float *__restrict__ rows, const float *__restrict__ cols,
+                                                                     unsigned long long *__restrict__ prow,
+                                                                     unsigned long long *__restrict__ pcol, int B, int nr,
+                                                                     int nc, int rows_per_block, unsigned fix_blocks,
+                                                                     float *__restrict__ dist_r, int *__restrict__ idx_r,
+                                                                     float *__restrict__ dist_c, int *__restrict__ idx_c,
+                                                                     const EpiFuse f) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double term = 0.0;  // sum of f(d) over the output elements this thread owns
+    if (blockIdx.x >= fix_blocks) {
+        const size_t n = (size_t)B * nr;
+        const size_t i0 = (size_t)(blockIdx.x - fix_blocks) * EPI_ROWS_PER_CTA + threadIdx.x;
+        unsigned long long w[EPI_RPT];
+#pragma unroll
+        for (int k = 0; k < EPI_RPT; ++k) {
+            const size_t i = i0 + (size_t)k * 256;
+            w[k] = (i < n) ? __ldcg(prow + i) : 0ull;
+        }
+#pragma unroll
+        for (int k = 0; k < EPI_RPT; ++k) {
+            const size_t i = i0 + (size_t)k * 256;
+            if (i < n) {
+                const float d = __uint_as_float((unsigned)(w[k] >> 32));
+                dist_r[i] = d;
+                idx_r[i] = (int)(unsigned)(w[k] & 0xffffffffu);
+                if (FUSED) {
+                    if (f.rearm) prow[i] = ~0ull;
+                    term += (double)(f.use_sqrt ? __fsqrt_rn(d) : d);
+                }
+            }
+        }
+    } else {
+        const size_t n = (size_t)B * nc;
+        const size_t w0 = ((size_t)blockIdx.x * 8 + warp) * EPI_CPW;  // first column of this warp
+        const size_t mine = w0 + (lane % EPI_CPW);
+        unsigned long long my_w = 0ull;
+        float mx = 0.f, my = 0.f, mz = 0.f;
+        size_t my_base = 0;
+        if (mine < n) {
+            my_w = __ldcg(pcol + mine);
+            mx = __ldg(cols + mine * 3), my = __ldg(cols + mine * 3 + 1), mz = __ldg(cols + mine * 3 + 2);
+            my_base = (mine / nc) * (size_t)nr * 3;
+        }
+        int my_found = 0;
+#pragma unroll
+        for (int k = 0; k < EPI_CPW; ++k) {
+            if (w0 + k >= n) break;  // warp-uniform
+            const unsigned long long word = __shfl_sync(0xffffffffu, my_w, k);
+            const float cx = __shfl_sync(0xffffffffu, mx, k), cy = __shfl_sync(0xffffffffu, my, k), cz = __shfl_sync(0xffffffffu, mz, k);
+            const size_t base = __shfl_sync(0xffffffffu, my_base, k);
+            const int found = sym_fix_column(rows + base, nr, rows_per_block, cx, cy, cz, __uint_as_float((unsigned)(word >> 32)),
+                                             (int)(unsigned)(word & 0xffffffffu), lane);
+            if (lane == k) my_found = found;
+        }
+        if (lane < EPI_CPW && mine < n) {
+            const float d = __uint_as_float((unsigned)(my_w >> 32));
+            dist_c[mine] = d;
+            idx_c[mine] = my_found;
+            if (FUSED) {
+                if (f.rearm) pcol[mine] = ~0ull;
+                term = (double)(f.use_sqrt ? __fsqrt_rn(d) : d);
+            }
+        }
+    }
+    if (FUSED) {
+        const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x, total_threads = (size_t)gridDim.x * blockDim.x;
+        epi_zero_fill(f.zero[0], f.nzero[0], g, total_threads);
+        epi_zero_fill(f.zero[1], f.nzero[1], g, total_threads);
+        if (f.partial == nullptr) return;
+        __shared__ double sh[8];
+        __shared__ double sh2[2][8];
+        __shared__ int is_last;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) term += __shfl_xor_sync(0xffffffffu, term, o);
+        if (lane == 0) sh[warp] = term;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double a = 0.0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) a += sh[w];
+            f.partial[blockIdx.x] = a;
+            __threadfence();
+            is_last = (atomicAdd(f.ticket, 1u) == gridDim.x - 1);
+        }
+        __syncthreads();
+        if (!is_last) return;
+        __threadfence();
+        double sc = 0.0, sr = 0.0;  // fixed assignment + fixed tree => deterministic
+        for (unsigned c = threadIdx.x; c < fix_blocks; c += blockDim.x) sc += __ldcg(f.partial + c);
+        for (unsigned c = fix_blocks + threadIdx.x; c < gridDim.x; c += blockDim.x) sr += __ldcg(f.partial + c);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sc += __shfl_xor_sync(0xffffffffu, sc, o), sr += __shfl_xor_sync(0xffffffffu, sr, o);
+        if (lane == 0) sh2[0][warp] = sc, sh2[1][warp] = sr;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            sc = 0.0, sr = 0.0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) sc += sh2[0][w], sr += sh2[1][w];
+            double loss = 0.0;
+            if (f.fcol != 0.0) loss += f.fcol * sc;
+            if (f.frow != 0.0) loss += f.frow * sr;
+            f.loss_out[0] = (float)loss;
+            *f.ticket = 0;
+        }
     }
 }
 

@@ -248,13 +248,30 @@ __global__ void __launch_bounds__(FIX_THREADS, 2) register_finish_kernel(const R
     unsigned long long *pA = a.packedA + (size_t)scan * a.Nc;
     unsigned long long *pB = a.packedB + (size_t)scan * a.Nr;
     const int c_lo = part * FIX_COLS_PER_CTA, c_hi = min(a.Nc, c_lo + FIX_COLS_PER_CTA);
-    for (int c = c_lo + warp; c < c_hi; c += FIX_THREADS / 32) {
-        const unsigned long long w = __ldcg(pA + c);
-        const float d = __uint_as_float((unsigned)(w >> 32));
-        float x = __ldg(V + (size_t)c * 3), y = __ldg(V + (size_t)c * 3 + 1), z = __ldg(V + (size_t)c * 3 + 2);
-        apply_similarity(T, x, y, z);
-        const int found = sym_fix_column(Rf, a.Nr, a.rows_per_block, x, y, z, d, (int)(unsigned)(w & 0xffffffffu), lane);
-        if (lane == 0) pA[c] = pack_dist_idx(d, found);
+    {
+        // a warp resolves FIX_COLS_PER_WARP columns (c_lo + warp + k * warps): lane k fetches the word and the transformed
+        // point of column k up front (ONE exposed L2 latency for all of them instead of one per column), the columns
+        // are then handed round by shuffles and their row-block loads are independent, so they overlap as well
+        constexpr int FIX_WARPS = FIX_THREADS / 32, FIX_COLS_PER_WARP = FIX_COLS_PER_CTA / FIX_WARPS;
+        static_assert(FIX_COLS_PER_WARP <= 32, "one lane per column");
+        const int my_c = c_lo + warp + FIX_WARPS * (lane % FIX_COLS_PER_WARP);
+        unsigned long long my_w = 0ull;
+        float mx = 0.f, my = 0.f, mz = 0.f;
+        if (my_c < c_hi) {
+            my_w = __ldcg(pA + my_c);
+            mx = __ldg(V + (size_t)my_c * 3), my = __ldg(V + (size_t)my_c * 3 + 1), mz = __ldg(V + (size_t)my_c * 3 + 2);
+            apply_similarity(T, mx, my, mz);
+        }
+#pragma unroll
+        for (int k = 0; k < FIX_COLS_PER_WARP; ++k) {
+            const int c = c_lo + warp + FIX_WARPS * k;
+            if (c >= c_hi) break;  // warp-uniform
+            const unsigned long long w = __shfl_sync(0xffffffffu, my_w, k);
+            const float x = __shfl_sync(0xffffffffu, mx, k), y = __shfl_sync(0xffffffffu, my, k), z = __shfl_sync(0xffffffffu, mz, k);
+            const float d = __uint_as_float((unsigned)(w >> 32));
+            const int found = sym_fix_column(Rf, a.Nr, a.rows_per_block, x, y, z, d, (int)(unsigned)(w & 0xffffffffu), lane);
+            if (lane == 0) pA[c] = pack_dist_idx(d, found);
+        }
     }
     __syncthreads();  // the fixed-up words of this CTA's columns are visible to the whole CTA
     // ---- this CTA's share of the loss / gradient terms ----

@@ -63,6 +63,36 @@ int genpc_chamfer_forward_host(genpc_host_feed_t *feed, const float *h_xyz1, con
                                float *xyz2, float *dist1, float *dist2, int *idx1, int *idx2, int B, int N, int M,
                                int chunks, void *workspace, size_t workspace_bytes, genpc_stream_t stream);
 
+/* Fused forms of the two forward entries for a loss step (Completionloss.get_loss + backward, utils/loss_util.py:25-43
+ * over dist_chamfer_3D.py:26-64): the ONE epilogue launch that follows the scan also
+ *   - reduces the loss  loss_out[0] = w1 * mean f(dist1) + w2 * mean f(dist2)  (f = sqrt when use_sqrt; deterministic:
+ *     one double partial per CTA, added in index order by the last CTA) -- what genpc_chamfer_loss does in its own launch;
+ *   - zero-fills zero1 [B][N][3] / zero2 [B][M][3] (either may be NULL): the gradient accumulators that
+ *     genpc_chamfer_backward / genpc_chamfer_loss_backward add into (dist_chamfer_3D.py:56-57 does it with two fills);
+ *   - stores all-ones back into every packed word it consumed, so the NEXT fused call with the same B, N, M on the same
+ *     `workspace` may pass workspace_armed = 1 and skip the memset.  (workspace_armed = 0 is always correct.)
+ * A loss step is then 3 launches (scan, epilogue, gradient) instead of 7.  dist/idx outputs are unchanged, bit for bit.
+ * loss_workspace: genpc_chamfer_fuse_workspace_bytes(B,N,M) bytes, zeroed ONCE by the caller (only read when loss_out
+ * is not NULL).  fuse == NULL makes both calls identical to the plain entries.  Shapes that do not take the symmetric
+ * path (tiny or empty clouds) run the same duties as separate launches. */
+typedef struct genpc_chamfer_fuse {
+    int workspace_armed;         /* in: the packed words of `workspace` are all-ones (left so by a previous fused call) */
+    int use_sqrt;                /* loss: f = sqrt (chamfer_l1 forms) or identity (chamfer_l2 forms) */
+    float w1, w2;                /* loss weights; a side with weight 0 is left out */
+    float *loss_out;             /* device scalar, NULL: no loss */
+    void *loss_workspace;
+    size_t loss_workspace_bytes;
+    float *zero1, *zero2;        /* device buffers to zero-fill, NULL: none */
+} genpc_chamfer_fuse_t;
+size_t genpc_chamfer_fuse_workspace_bytes(int B, int N, int M);
+int genpc_chamfer_forward_fused(const float *xyz1, const float *xyz2, float *dist1, float *dist2, int *idx1, int *idx2,
+                                int B, int N, int M, void *workspace, size_t workspace_bytes,
+                                const genpc_chamfer_fuse_t *fuse, genpc_stream_t stream);
+int genpc_chamfer_forward_host_fused(genpc_host_feed_t *feed, const float *h_xyz1, const float *h_xyz2, float *xyz1,
+                                     float *xyz2, float *dist1, float *dist2, int *idx1, int *idx2, int B, int N, int M,
+                                     int chunks, void *workspace, size_t workspace_bytes,
+                                     const genpc_chamfer_fuse_t *fuse, genpc_stream_t stream);
+
 /* Replaces chamfer_3D.backward (chamfer_cuda.cpp:22-27 -> chamfer_cuda_backward, chamfer3D.cu:176-195,
  * kernel NmDistanceGradKernel :155-174).  ACCUMULATES into gradxyz1/gradxyz2, which must arrive zeroed
  * exactly as in the reference (dist_chamfer_3D.py:56-57). */

@@ -218,3 +218,65 @@ def test_completionloss_fused_equals_torch_expression(cuda, name):
     for k in (1, 2):
         scale = np.abs(res[False][k]).max()
         assert np.abs(res[True][k] - res[False][k]).max() <= 1e-5 * scale + 1e-12
+
+
+@pytest.mark.parametrize("B,N,M,use_sqrt,w1,w2", [(3, 1500, 4000, 1, 0.5, 0.5), (2, 5000, 700, 0, 1.0, 1.0),
+                                                  (4, 2048, 16384, 1, 1.0, 0.0), (2, 100, 300, 0, 1.0, 1.0)])
+def test_fused_forward_c_abi(cuda, B, N, M, use_sqrt, w1, w2):
+    """genpc_chamfer_forward_fused straight through the C ABI, three calls on ONE workspace (the 2nd and 3rd with
+    workspace_armed = 1, i.e. without a memset): dist/idx bit-identical to the plain entry, the loss equal to the
+    reference expression (loss_util.py:25-43) within 1e-6 relative, the two accumulators zero-filled.  The last
+    shape does not take the symmetric path (same duties as separate launches)."""
+    from genpc_b200 import _lib
+    from genpc_b200.loss_functions import chamfer_3DDist
+
+    L = _lib.lib()
+    packed_bytes = L.genpc_chamfer_workspace_bytes(B, N, M)
+    packed = torch.empty(packed_bytes, dtype=torch.uint8, device=cuda)
+    loss_ws = torch.zeros(L.genpc_chamfer_fuse_workspace_bytes(B, N, M), dtype=torch.uint8, device=cuda)
+    armed = 0
+    for call in range(3):
+        a, b = shape_cloud(100 + call, B, N), rand_cloud(200 + call, B, M, 0.8, -0.4)
+        ta, tb = torch.from_numpy(a).to(cuda), torch.from_numpy(b).to(cuda)
+        d1 = torch.empty(B, N, device=cuda); d2 = torch.empty(B, M, device=cuda)
+        i1 = torch.empty(B, N, dtype=torch.int32, device=cuda); i2 = torch.empty(B, M, dtype=torch.int32, device=cuda)
+        z1 = torch.full((B, N, 3), 7.0, device=cuda); z2 = torch.full((B, M, 3), -3.0, device=cuda)
+        out = torch.full((), float("nan"), device=cuda)
+        fuse = _lib.ChamferFuse(armed, use_sqrt, w1, w2, out.data_ptr(), loss_ws.data_ptr(), loss_ws.numel(), z1.data_ptr(),
+                                z2.data_ptr())
+        rc = L.genpc_chamfer_forward_fused(_lib.ptr(ta), _lib.ptr(tb), _lib.ptr(d1), _lib.ptr(d2), _lib.ptr(i1), _lib.ptr(i2),
+                                           B, N, M, _lib.ptr(packed), packed_bytes, fuse, _lib.current_stream(cuda))
+        assert rc == 0
+        armed = 1
+        e1, e2, j1, j2 = chamfer_3DDist()(ta, tb)
+        assert torch.equal(d1, e1) and torch.equal(d2, e2) and torch.equal(i1, j1) and torch.equal(i2, j2), call
+        f = torch.sqrt if use_sqrt else (lambda t: t)
+        exp = w1 * f(e1.double()).mean() + (w2 * f(e2.double()).mean() if w2 else 0.0)
+        assert abs(float(out) - float(exp)) <= 1e-6 * abs(float(exp)), call
+        assert not z1.any() and not z2.any()
+
+
+def test_fused_loss_steps_reuse_workspace(cuda):
+    """Completionloss on the fused step, several steps at one shape (re-armed workspace) and interleaved shapes, each
+    against the literal torch expression; a second backward through a retained graph gets fresh accumulators."""
+    from genpc_b200.utils.loss_util import Completionloss
+
+    fused, plain = Completionloss("cd_l1"), Completionloss("cd_l1")
+    plain.fused = False
+    for step, (B, N, M) in enumerate([(2, 3000, 1200), (2, 3000, 1200), (1, 600, 9000), (2, 3000, 1200), (1, 40, 50)]):
+        a, b = shape_cloud(300 + step, B, N), shape_cloud(400 + step, B, M)
+        res = []
+        for cl in (fused, plain):
+            ta = torch.from_numpy(a).to(cuda).requires_grad_(True)
+            tb = torch.from_numpy(b).to(cuda).requires_grad_(True)
+            loss = cl.get_loss(ta, tb)
+            loss.backward(retain_graph=True)
+            g_first = ta.grad.clone()
+            ta.grad = None
+            loss.backward()
+            assert torch.allclose(ta.grad, g_first, rtol=1e-5, atol=1e-9)
+            res.append((float(loss), ta.grad.cpu().numpy(), tb.grad.cpu().numpy()))
+        assert abs(res[0][0] - res[1][0]) <= 1e-5 * abs(res[1][0])
+        for k in (1, 2):
+            scale = np.abs(res[1][k]).max()
+            assert np.abs(res[0][k] - res[1][k]).max() <= 1e-5 * scale + 1e-12

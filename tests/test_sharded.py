@@ -120,3 +120,29 @@ def test_row_sharded_symmetric_partials_merge_exactly(cuda):
     assert torch.equal(d1, e[0][0]) and torch.equal(i1, e[2][0]) and torch.equal(d2, e[1][0]) and torch.equal(i2, e[3][0])
     ed, ei = oracle.nn_distance(b, a)
     assert np.array_equal(i2.cpu().numpy(), ei[0]) and np.array_equal(d2.cpu().numpy(), ed[0])
+
+
+@pytest.mark.gpu
+def test_sharded_module_is_differentiable_like_chamfer_3DDist(cuda):
+    """sharded_chamfer_3DDist (world size 1 here): same outputs as chamfer_3DDist, gradients within the atomics'
+    summation-order tolerance (1e-5 relative, both backward passes accumulate with float atomics)."""
+    from genpc_b200.loss_functions import chamfer_3DDist
+    from genpc_b200.sharded import sharded_chamfer_3DDist
+
+    a, b = rand_cloud(11, 1, 40000), rand_cloud(12, 1, 25000)
+    res = []
+    for mod in (chamfer_3DDist(), sharded_chamfer_3DDist()):
+        ta = torch.from_numpy(a).to(cuda).requires_grad_(True)
+        tb = torch.from_numpy(b).to(cuda).requires_grad_(True)
+        d1, d2, i1, i2 = mod(ta, tb)
+        (d1.sqrt().mean() + 0.5 * d2.mean()).backward()
+        res.append((d1.detach(), d2.detach(), i1, i2, ta.grad, tb.grad))
+    for x, y in zip(res[0][:4], res[1][:4]):
+        assert torch.equal(x, y)
+    g1 = (0.5 / np.sqrt(res[0][0].cpu().numpy()) / d1.numel()).astype(np.float32)      # d loss / d dist1
+    g2 = np.full(b.shape[:2], 0.5 / d2.numel(), np.float32)
+    e1, e2 = oracle.chamfer_backward(a, b, g1, g2, res[0][2].cpu().numpy(), res[0][3].cpu().numpy())
+    for k, exp in ((4, e1), (5, e2)):           # both modules against the double-accumulated oracle, 1e-5 of the scale
+        scale = np.abs(exp).max()
+        for r in res:
+            assert np.abs(r[k].cpu().numpy() - exp).max() <= 1e-5 * scale + 1e-12
