@@ -482,8 +482,8 @@ def main():
                             "algorithmic_bytes_per_launch": 20.0 * B * (N + M),
                             "traffic": NCU_DRAM_BYTES_NN_SYM, "traffic_source": "ncu --set full, dram__bytes_read.sum + "
                             "dram__bytes_write.sum per launch of nn_sym_kernel (profiles/r01c_nn_sym_ncu.txt)"}
-        if m and "nn_mix_packed" in m:
-            line["roofline"]["measured_mix_peak_tflops"] = m["nn_mix_packed"].get("tflops")
+        if m and "ffma2" in m:
+            line["roofline"]["measured_ffma2_tflops"] = m["ffma2"].get("tflops")
         bwd_bytes = 44.0 * B * (N + M)
         gbs = bwd_bytes / (t_bwd * 1e-3) / 1e9
         line["roofline_bwd"] = {"bound": "hbm", "kernel": "chamfer_grad_kernel", "achieved": gbs, "peak": hbm_peak,

@@ -75,30 +75,46 @@ __device__ __forceinline__ void st_release(int *p, int v) {
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// ascending compaction of {j : assignment[j] == -1} into uidx; returns the count (valid in every thread)
+// ascending compaction of {j : assignment[j] == -1} into uidx; returns the count (valid in every thread).
+// Warp w owns the contiguous slice [w * n/8, (w+1) * n/8): pass 1 counts it with coalesced loads + ballots (no block
+// barrier inside, loads independent), one barrier publishes the eight warp totals, pass 2 re-reads the slice (L1) and
+// writes the indices.  (The first form walked the array 256 elements at a time with two block barriers per step:
+// 64 barriers at n = 8192, most of an iteration's serial tail.)
 __device__ int compact_unassigned(const int *__restrict__ asg, int *__restrict__ uidx, int *__restrict__ midx, int n,
                                   int *sscan) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    int base = 0;
-    for (int t0 = 0; t0 < n; t0 += EMD_THREADS) {
-        const int j = t0 + tid;
-        const int f = (j < n) ? (__ldcg(asg + j) == -1) : 0;
-        if (j < n) midx[j] = -1;  // re-arm GetMax for the next iteration
-        const unsigned bal = __ballot_sync(0xffffffffu, f);
-        if (lane == 0) sscan[warp] = __popc(bal);
-        __syncthreads();
-        int woff = 0, tot = 0;
-#pragma unroll
-        for (int w = 0; w < EMD_THREADS / 32; ++w) {
-            const int c = sscan[w];
-            woff += (w < warp) ? c : 0;
-            tot += c;
-        }
-        if (f) uidx[base + woff + __popc(bal & ((1u << lane) - 1u))] = j;
-        base += tot;
-        __syncthreads();
+    constexpr int WARPS = EMD_THREADS / 32;
+    const int per_warp = n / WARPS;  // n % 256 == 0
+    const int j0 = warp * per_warp;
+    int cnt = 0;
+#pragma unroll 4
+    for (int r = 0; r < per_warp; r += 32) {
+        const int j = j0 + r + lane;
+        const int f = (__ldcg(asg + j) == -1);
+        midx[j] = -1;  // re-arm GetMax for the next iteration
+        cnt += __popc(__ballot_sync(0xffffffffu, f));
     }
-    return base;
+    if (lane == 0) sscan[warp] = cnt;
+    __syncthreads();
+    int base = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < WARPS; ++w) {
+        const int c = sscan[w];
+        base += (w < warp) ? c : 0;
+        tot += c;
+    }
+    if (cnt > 0) {
+#pragma unroll 4
+        for (int r = 0; r < per_warp; r += 32) {
+            const int j = j0 + r + lane;
+            const int f = (__ldcg(asg + j) == -1);
+            const unsigned bal = __ballot_sync(0xffffffffu, f);
+            if (f) uidx[base + __popc(bal & ((1u << lane) - 1u))] = j;
+            base += __popc(bal);
+        }
+    }
+    __syncthreads();  // sscan may be reused
+    return tot;
 }
 
 __global__ void __launch_bounds__(EMD_THREADS) emd_auction_kernel(const EmdArgs a) {
@@ -138,6 +154,7 @@ __global__ void __launch_bounds__(EMD_THREADS) emd_auction_kernel(const EmdArgs 
             }
         }
 
+        bool complete = false;  // every point assigned: the remaining iterations change nothing (reference: empty launches)
         for (int it = 0; it < a.iters; ++it) {
             const bool last = (it == a.iters - 1);
             if (tid == 0) {
@@ -145,6 +162,10 @@ __global__ void __launch_bounds__(EMD_THREADS) emd_auction_kernel(const EmdArgs 
             }
             __syncthreads();
             const int U = __ldcg(a.unass_cnt + b);
+            if (U == 0) {  // same value in every CTA of the group (read behind the same flag generation)
+                complete = true;
+                break;
+            }
             // ---- Bid (emd_cuda.cu:95-179) ----
             if (U > 0) {
                 const int upb_ref = (U + block_cnt - 1) / block_cnt;
@@ -288,7 +309,7 @@ __global__ void __launch_bounds__(EMD_THREADS) emd_auction_kernel(const EmdArgs 
             }
         }
         // ---- CalcDist (:217-226), split over the group ----
-        if (tid == 0) {
+        if (tid == 0 && !complete) {
             while (ld_acquire(flag) < a.iters + 1) __nanosleep(64);
         }
         __syncthreads();

@@ -1,7 +1,7 @@
 // fp32_peak.cu -- FP32 CUDA-core issue-rate microbenchmark for B200 (sm_100a).
 // MEASURED_PEAKS.json has no FP32 figure; the Chamfer NN scan is FP32-pipe bound, so its roofline
-// denominator is measured here: scalar FFMA/FADD/FMUL, packed FFMA2/FADD2/FMUL2, FMNMX3 and the exact
-// instruction mix of the NN inner loop.  Prints one JSON object.  Build:
+// denominator is measured here: scalar FFMA/FADD, packed FFMA2/FADD2/FMUL2 and FMNMX3 issue rates (instruction MIXES are
+// measured by tools/issue_mix.cu).  Prints one JSON object.  Build:
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/fp32_peak tools/fp32_peak.cu
 #include <cuda_runtime.h>
 #include <cstdio>
@@ -11,12 +11,12 @@
 #define CHAINS 16
 #define INNER 64
 
-enum Mode { FFMA = 0, FFMA2, FADD, FADD2, FMUL2, FMNMX3, MIX_SCALAR, MIX_PACKED, MIX_PACKED_NOMIN, NMODES };
-static const char *names[NMODES] = {"ffma", "ffma2", "fadd", "fadd2", "fmul2", "fmnmx3", "nn_mix_scalar",
-                                    "nn_mix_packed", "nn_mix_packed_nomin"};
-// lane-flops per asm statement group (per thread per inner step per chain)
-static const double flops_per_step[NMODES] = {2, 4, 1, 2, 2, 0, 8, 16, 16};
-static const double instr_per_step[NMODES] = {1, 1, 1, 1, 1, 1, 7, 7, 6};
+enum Mode { FFMA = 0, FFMA2, FADD, FADD2, FMUL2, FMNMX3, NMODES };
+static const char *names[NMODES] = {"ffma", "ffma2", "fadd", "fadd2", "fmul2", "fmnmx3"};
+// lane-flops and instructions per asm statement group (per thread per inner step per chain pair): the scalar modes and
+// FMNMX3 issue TWO instructions per group (one per chain), the packed modes one.
+static const double flops_per_step[NMODES] = {4, 4, 2, 2, 2, 0};
+static const double instr_per_step[NMODES] = {2, 1, 2, 1, 1, 2};
 
 template <int MODE>
 __global__ void __launch_bounds__(256) peak_kernel(float *out, int iters, float seed, long long *cycles) {
@@ -61,34 +61,6 @@ __global__ void __launch_bounds__(256) peak_kernel(float *out, int iters, float 
                 } else if (MODE == FMNMX3) {
                     asm volatile("min.f32 %0, %0, %1, %2;" : "+f"(a[i]) : "f"(b[i]), "f"(b[i + 1]));
                     asm volatile("min.f32 %0, %0, %1, %2;" : "+f"(a[i + 1]) : "f"(b[i]), "f"(b[i + 1]));
-                } else if (MODE == MIX_SCALAR) {
-                    // one pair: 3 FADD, FMUL, 2 FFMA, FMNMX (x2 for the two chains)
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        float dx, dy, dz, s;
-                        asm volatile("add.rn.f32 %0, %1, %2;" : "=f"(dx) : "f"(a[i + h]), "f"(c0));
-                        asm volatile("add.rn.f32 %0, %1, %2;" : "=f"(dy) : "f"(b[i + h]), "f"(c1));
-                        asm volatile("add.rn.f32 %0, %1, %2;" : "=f"(dz) : "f"(a[i + h]), "f"(c2));
-                        asm volatile("mul.rn.f32 %0, %1, %1;" : "=f"(s) : "f"(dy));
-                        asm volatile("fma.rn.f32 %0, %1, %1, %0;" : "+f"(s) : "f"(dx));
-                        asm volatile("fma.rn.f32 %0, %1, %1, %0;" : "+f"(s) : "f"(dz));
-                        asm volatile("min.f32 %0, %0, %1;" : "+f"(m) : "f"(s));
-                    }
-                } else if (MODE == MIX_PACKED || MODE == MIX_PACKED_NOMIN) {
-                    // two pairs: 3 FADD2, FMUL2, 2 FFMA2, FMNMX3
-                    float s0, s1;
-                    asm volatile(
-                        "{.reg .b64 x, y, z, q, dx, dy, dz, s;\n"
-                        "mov.b64 x, {%2, %3}; mov.b64 y, {%4, %5}; mov.b64 z, {%3, %2}; mov.b64 q, {%6, %6};\n"
-                        "add.rn.f32x2 dx, x, q; add.rn.f32x2 dy, y, q; add.rn.f32x2 dz, z, q;\n"
-                        "mul.rn.f32x2 s, dy, dy; fma.rn.f32x2 s, dx, dx, s; fma.rn.f32x2 s, dz, dz, s;\n"
-                        "mov.b64 {%0, %1}, s;}"
-                        : "=f"(s0), "=f"(s1)
-                        : "f"(a[i]), "f"(a[i + 1]), "f"(b[i]), "f"(b[i + 1]), "f"(c0));
-                    if (MODE == MIX_PACKED)
-                        asm volatile("min.f32 %0, %0, %1, %2;" : "+f"(m) : "f"(s0), "f"(s1));
-                    else
-                        asm volatile("" ::"f"(s0), "f"(s1));
                 }
             }
         }
@@ -158,10 +130,7 @@ int main(int argc, char **argv) {
     run<FADD2>(sms, cps, iters, dout, dcyc, &tf, &ipc);
     run<FMUL2>(sms, cps, iters, dout, dcyc, &tf, &ipc);
     run<FMNMX3>(sms, cps, iters, dout, dcyc, &tf, &ipc);
-    run<MIX_SCALAR>(sms, cps, iters, dout, dcyc, &tf, &ipc);
-    run<MIX_PACKED>(sms, cps, iters, dout, dcyc, &tf, &ipc);
-    run<MIX_PACKED_NOMIN>(sms, cps, iters, dout, dcyc, &tf, &ipc);
-    printf("  \"note\": \"tflops counts FMA=2; nn_mix_* count 8 flop per point pair\"\n}\n");
+    printf("  \"note\": \"tflops counts FMA=2; instruction mixes: tools/issue_mix.cu\"\n}\n");
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         fprintf(stderr, "CUDA error: %s\n", cudaGetErrorString(e));
