@@ -231,7 +231,17 @@ __global__ void __launch_bounds__(SYM_THREADS, GENPC_SYM_MINB(QT)) register_sym_
 //           order -- deterministic -- and steps Adam (pose_update).  (The single-CTA finalize_scan of the small path
 //           serialised 32 K gather + double-precision terms per scan: 64 CTAs busy, the rest of the GPU idle.)
 constexpr int FIX_THREADS = 512;
-constexpr int FIX_COLS_PER_CTA = 128;
+// moving points per finish CTA: measured on B200, 64 scans x 16384^2 (profiles/r01i_registration_finish.txt):
+// 128 -> 4.41, 256 -> 4.32, 512 -> 4.28 ms per iteration (fewer tickets / partial reductions per point); the largest
+// size that still gives every resident-CTA slot (2 per SM) one CTA is used.
+static int fix_cols_per_cta(int S, int Nc) {
+    const char *e = getenv("GENPC_FIX_COLS");  // experiments only
+    if (e != nullptr && (atoi(e) == 128 || atoi(e) == 256 || atoi(e) == 512)) return atoi(e);
+    for (int cols = 512; cols > 128; cols >>= 1)
+        if ((long long)S * ((Nc + cols - 1) / cols) >= 2LL * GENPC_NUM_SMS) return cols;
+    return 128;
+}
+template <int FIX_COLS_PER_CTA>
 __global__ void __launch_bounds__(FIX_THREADS, 2) register_finish_kernel(const RegArgs a) {
     __shared__ Similarity T;
     __shared__ int is_last;
@@ -335,7 +345,7 @@ using namespace genpc;
 
 extern "C" size_t genpc_register_workspace_bytes(int S, int Nc, int Nr) {
     if (S < 0 || Nc < 0 || Nr < 0) return 0;
-    const size_t fix_ctas = ((size_t)Nc + FIX_COLS_PER_CTA - 1) / FIX_COLS_PER_CTA;
+    const size_t fix_ctas = ((size_t)Nc + 128 - 1) / 128;  // sized for the finest CTA granularity
     return ((size_t)S * Nc + (size_t)S * Nr) * 8 + (size_t)S * fix_ctas * 14 * sizeof(double) + (size_t)S * sizeof(int);
 }
 
@@ -353,7 +363,7 @@ extern "C" int genpc_register_run(const float *complete, const float *center, co
     a.packedA = (unsigned long long *)workspace;
     a.packedB = a.packedA + (size_t)S * Nc;
     a.partials = (double *)(a.packedB + (size_t)S * Nr);
-    a.counters = (int *)(a.partials + (size_t)S * ((Nc + FIX_COLS_PER_CTA - 1) / FIX_COLS_PER_CTA) * 14);
+    a.counters = (int *)(a.partials + (size_t)S * ((Nc + 128 - 1) / 128) * 14);
     a.loss_hist = loss_hist;
     a.S = S, a.n_starts = n_starts, a.Nc = Nc, a.Nr = Nr, a.T = T;
     const int QT = nn_pick_qt(Nc < Nr ? Nc : Nr);
@@ -375,6 +385,7 @@ extern "C" int genpc_register_run(const float *complete, const float *center, co
     const bool sym = (mode == nullptr ? big : strcmp(mode, "sym") == 0) && Nr >= 512;
     const int SQT = Nr >= 1024 ? 4 : 2;
     long long sgrid = 0, fgrid = 0;
+    const int fix_cols = fix_cols_per_cta(S, Nc);
     if (sym) {
         a.rtiles = (Nr + SYM_THREADS * SQT - 1) / (SYM_THREADS * SQT);
         int span = SYM_SPAN_MAX;
@@ -383,7 +394,7 @@ extern "C" int genpc_register_run(const float *complete, const float *center, co
         a.span = span;
         a.cspans = (Nc + span - 1) / span;
         a.rows_per_block = 32 * SQT;
-        a.fix_ctas = (Nc + FIX_COLS_PER_CTA - 1) / FIX_COLS_PER_CTA;
+        a.fix_ctas = (Nc + fix_cols - 1) / fix_cols;
         a.ticket_total = a.fix_ctas;
         sgrid = (long long)S * a.rtiles * a.cspans;
         fgrid = (long long)S * a.fix_ctas;
@@ -407,7 +418,9 @@ extern "C" int genpc_register_run(const float *complete, const float *center, co
             if (SQT == 4) register_sym_scan_kernel<4><<<(unsigned)sgrid, SYM_THREADS, 0, stream>>>(a);
             else register_sym_scan_kernel<2><<<(unsigned)sgrid, SYM_THREADS, 0, stream>>>(a);
             GENPC_CHECK_LAUNCH();
-            register_finish_kernel<<<(unsigned)fgrid, FIX_THREADS, 0, stream>>>(a);
+            if (fix_cols == 512) register_finish_kernel<512><<<(unsigned)fgrid, FIX_THREADS, 0, stream>>>(a);
+            else if (fix_cols == 256) register_finish_kernel<256><<<(unsigned)fgrid, FIX_THREADS, 0, stream>>>(a);
+            else register_finish_kernel<128><<<(unsigned)fgrid, FIX_THREADS, 0, stream>>>(a);
             GENPC_CHECK_LAUNCH();
             continue;
         }
