@@ -12,6 +12,7 @@ RMSE 1e-6), voxel down-sampling and `remove_statistical_outlier` are restated fr
 import numpy as np
 import torch
 
+from . import _lib
 from .fps import furthest_point_sample
 from .loss_functions import chamfer_3DDist
 from .optim_registration.diff_obj_pose import object_pose_optimization_points
@@ -134,15 +135,33 @@ def remove_close_points(source_xyz, target_xyz, distance_threshold=0.0001):
     return d1[0] >= distance_threshold
 
 
-def remove_statistical_outlier(xyz, nb_neighbors=20, std_ratio=2.5, chunk=4096):
-    """Open3D remove_statistical_outlier restated: mean distance to the nb_neighbors nearest neighbours, keep points
-    below mean + std_ratio * std.  (utils/dataUtils.py:652-666; adjacent helper, torch.cdist in chunks.)"""
-    n = xyz.shape[0]
-    md = torch.empty(n, device=xyz.device)
-    for c0 in range(0, n, chunk):
-        d = torch.cdist(xyz[c0:c0 + chunk], xyz)
-        md[c0:c0 + chunk] = d.topk(nb_neighbors + 1, largest=False).values[:, 1:].mean(1)
-    return md <= md.mean() + std_ratio * md.std(unbiased=False)
+def knn_mean_distance(xyz, k, include_self=True):
+    """Mean distance from each point of xyz [N,3] (CUDA) to its k nearest points of the same cloud
+    (genpc_knn_mean_distance; include_self counts the point itself, as a KD-tree query of a cloud point does)."""
+    _lib.require_cuda(xyz)
+    x = xyz.contiguous().float()
+    out = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().genpc_knn_mean_distance(_lib.ptr(x), x.shape[0], int(k), int(bool(include_self)), _lib.ptr(out),
+                                                _lib.current_stream(x.device))
+    _lib.check(rc, "genpc_knn_mean_distance")
+    return out
+
+
+def remove_statistical_outlier(xyz, nb_neighbors=20, std_ratio=2.5):
+    """Open3D remove_statistical_outlier as the reference uses it (reg_xyz.py:219, utils/dataUtils.py:652-666),
+    restated on the k-NN kernel: per point the mean distance to its nb_neighbors nearest points -- the KD-tree query of
+    a cloud point returns the point itself first, so it is one of them -- then keep 0 < mean < cloud_mean + std_ratio *
+    sample_std (float64 statistics).  Returns the boolean keep mask.  (Open3D is not vendored: semantics from its
+    documented behaviour, parity unpinned; the oracle defines them.)"""
+    md = knn_mean_distance(xyz, nb_neighbors, include_self=True).double()
+    valid = md >= 0
+    nv = int(valid.sum())
+    if nv == 0:
+        return torch.zeros_like(valid)
+    mu = md[valid].sum() / nv
+    sd = torch.sqrt(((md[valid] - mu) ** 2).sum() / (nv - 1)) if nv > 1 else torch.zeros((), dtype=torch.float64, device=md.device)
+    return (md > 0) & (md < mu + std_ratio * sd)
 
 
 def reg_points(partial_xyz, complete_xyz, cd_inv_weight=0.5, diff_init=True, reg_fine_xyz=False, dataset="redwood",

@@ -135,6 +135,15 @@ int genpc_chamfer_sym_partial(const float *rows_shard, const float *cols, unsign
 int genpc_chamfer_sym_fixup(const float *rows_full, const float *cols, const unsigned long long *pcol, int B,
                             int nr_full, int nc, float *dist_cols, int *idx_cols, genpc_stream_t stream);
 
+/* ---- k-NN statistic of the fusion tail ----------------------------------------------------------
+ * Replaces the per-point part of Open3D's remove_statistical_outlier as the reference calls it on the fused cloud
+ * (reg_xyz.py:219 -> utils/dataUtils.py:652-666, nb_neighbors=20; third-party CPU KD-tree code, not vendored):
+ * mean_dist[i] = mean Euclidean distance from xyz[i] to its k nearest points of the same cloud (1 <= k <= 32);
+ * include_self != 0 counts the point itself (distance 0) among the k, as a KD-tree query of a cloud point does.
+ * Squared distances with the Chamfer rounding order, square roots added in ascending order in fp32: reproducible
+ * bit for bit (oracle_knn_mean_distance).  A cloud with fewer than k candidates averages what it has; none: -1. */
+int genpc_knn_mean_distance(const float *xyz, int n, int k, int include_self, float *mean_dist, genpc_stream_t stream);
+
 /* ---- Farthest point sampling -------------------------------------------------------------------
  * Replaces the reference's CPU call fpsample.fps_sampling(xyz, K) (main.py:21-22, reg_xyz.py:215,
  * DepthPrompting.py:88-90; un-vendored third-party package).  xyz [B][N][3] -> idx_out [B][K] int32,

@@ -41,6 +41,7 @@ def lib():
         L.oracle_emd_forward.restype = _int
         L.oracle_emd_backward.argtypes = [_int, _int, _f32p, _f32p, _f32p, _i32p, _f32p]
         L.oracle_fps.argtypes = [_int, _int, _int, _int, _f32p, _i32p, _vp]
+        L.oracle_knn_mean_distance.argtypes = [_int, _int, _int, _f32p, _f32p]
         L.oracle_project_uv.argtypes = [_int, _int, _f32p, _f32p, _int, _flt, _f32p, _f32p, _f32p]
         L.oracle_zbuffer.argtypes = [_int, _int, _int, _int, _f32p, _f32p, _vp, _u64p]
         L.oracle_zbuffer_resolve.argtypes = [_int, _int, _int, _u64p, _f32p, _f32p, _i32p, _f32p]
@@ -132,6 +133,31 @@ def fps(xyz, K, start=0, return_seq=False):
     seq = np.zeros((B, K), np.float32)
     lib().oracle_fps(B, N, K, int(start), xyz, idx, seq.ctypes.data_as(_vp))
     return (idx, seq) if return_seq else idx
+
+
+def knn_mean_distance(xyz, k, include_self=True):
+    """mean distance to the k nearest neighbours of each point of xyz [N,3] (Open3D remove_statistical_outlier's
+    per-point statistic, reg_xyz.py:219); float32 [N]."""
+    xyz = _c(xyz, np.float32)
+    if not 1 <= k <= 32:
+        raise ValueError("1 <= k <= 32")
+    out = np.zeros(xyz.shape[0], np.float32)
+    lib().oracle_knn_mean_distance(xyz.shape[0], int(k), int(bool(include_self)), xyz, out)
+    return out
+
+
+def statistical_outlier_mask(mean_dist, std_ratio):
+    """Open3D's threshold over the per-point means (float64 like its std::vector<double>): keep a point when
+    0 < mean < cloud_mean + std_ratio * sample_std; points whose query found nothing (mean < 0) are left out of the
+    statistics and dropped."""
+    m = np.asarray(mean_dist, np.float64)
+    valid = m >= 0
+    nv = int(valid.sum())
+    if nv == 0:
+        return np.zeros(m.shape, bool)
+    mu = m[valid].sum() / nv
+    sd = np.sqrt(((m[valid] - mu) ** 2).sum() / (nv - 1)) if nv > 1 else 0.0
+    return (m > 0) & (m < mu + std_ratio * sd)
 
 
 def project_uv(cams, xyz, rescale=True, padding=0.15):

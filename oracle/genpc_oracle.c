@@ -320,6 +320,41 @@ HOT void oracle_fps(int B, int N, int K, int start, const float *xyz, int *idx, 
 }
 
 /* ------------------------------------------------------------------------------------------------
+ * Mean distance to the k nearest neighbours of every point of one cloud -- the per-point statistic of Open3D's
+ * remove_statistical_outlier as the reference calls it on the fused cloud (reg_xyz.py:219, utils/dataUtils.py:652-666;
+ * Open3D is not vendored: semantics restated from its documented behaviour, parity unpinned).  Squared distances with
+ * the Chamfer rounding order, the k smallest kept, mean = (sum of their square roots, added in ascending order in
+ * fp32) / count.  include_self counts the point itself (distance 0), as a KD-tree query of a cloud point does.
+ * A cloud with fewer than k candidates averages what it has; none at all gives -1 (Open3D's marker).
+ * ---------------------------------------------------------------------------------------------- */
+HOT void oracle_knn_mean_distance(int n, int k, int include_self, const float *xyz, float *out) {
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < n; i++) {
+        float best[32];
+        for (int c = 0; c < k; c++) best[c] = INFINITY;
+        const float qx = xyz[i * 3 + 0], qy = xyz[i * 3 + 1], qz = xyz[i * 3 + 2];
+        for (int j = 0; j < n; j++) {
+            if (!include_self && j == i) continue;
+            float v = sqdist_ref(qx, qy, qz, xyz[j * 3 + 0], xyz[j * 3 + 1], xyz[j * 3 + 2]);
+            if (!(v < best[k - 1])) continue;
+            for (int c = 0; c < k; c++) { /* sorted insertion */
+                const float lo = best[c] < v ? best[c] : v;
+                v = best[c] < v ? v : best[c];
+                best[c] = lo;
+            }
+        }
+        float sum = 0.f;
+        int m = 0;
+        for (int c = 0; c < k; c++)
+            if (best[c] < INFINITY) {
+                sum = sum + sqrtf(best[c]);
+                m++;
+            }
+        out[i] = m > 0 ? sum / (float)m : -1.0f;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------
  * DepthPrompting geometry (DepthPrompting.py:239-271 getUvs, :179-184 pixel mapping, :292-391
  * paintPixels/getRawDepth).  Camera = 16 floats:
  *   [0..8]  R row-major (rows right / up / backward: camera looks down -z),  [9..11] t = -R*eye,

@@ -59,3 +59,26 @@ def test_remove_close_points_and_reg_points(cuda):
     out = reg_points(tp, tc * 1.2, cd_inv_weight=0.5, diff_init=False, reg_fine_xyz=False, n_fused=3000)
     assert out["fused"].shape[0] <= 3000 and out["fused"].shape[1] == 3 and torch.isfinite(out["fused"]).all()
     assert 0.8 <= out["best_scale"] <= 1.5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,k", [(1, 3), (7, 20), (300, 1), (5000, 20), (20000, 20), (4099, 32), (2048, 7)])
+def test_knn_mean_distance_gpu_bit_exact(cuda, n, k):
+    """genpc_knn_mean_distance against the oracle, bit for bit (same rounding order, ascending fp32 sum), on uniform,
+    lattice (many ties) and shape clouds; then remove_statistical_outlier against the oracle's mask."""
+    import oracle
+    import torch
+
+    from genpc_b200.reg_xyz import knn_mean_distance, remove_statistical_outlier
+    from util import lattice_cloud, rand_cloud, shape_cloud
+
+    for kind, x in (("rand", rand_cloud(n, 1, n)[0]), ("lattice", lattice_cloud(n + 1, 1, n, side=9)[0]),
+                    ("shape", shape_cloud(n + 2, 1, n)[0])):
+        t = torch.from_numpy(x).to(cuda)
+        for inc in (True, False):
+            got = knn_mean_distance(t, k, inc).cpu().numpy()
+            exp = oracle.knn_mean_distance(x, k, inc)
+            assert np.array_equal(got.view(np.int32), exp.view(np.int32)), (kind, inc)
+        if k == 20:
+            keep = remove_statistical_outlier(t, 20, 2.5).cpu().numpy()
+            assert np.array_equal(keep, oracle.statistical_outlier_mask(oracle.knn_mean_distance(x, 20, True), 2.5)), kind

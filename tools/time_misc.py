@@ -91,4 +91,23 @@ rb2 = RegistrationBatch(comp_s, part_s, n_starts=4, lr=0.01, max_iters=300)
 rb2.run(10); torch.cuda.synchronize()
 e0.record(); rb2.run(201); e1.record(); torch.cuda.synchronize()
 out["registration_small_2500x1000_4starts_201iters_ms"] = e0.elapsed_time(e1)
+# ---- section 8f rows: scale / ICP candidate search and the fusion tail (reg_xyz.py) ----
+from genpc_b200.reg_xyz import iterative_scale_search, knn_mean_distance, remove_close_points, remove_statistical_outlier  # noqa: E402
+from genpc_b200.utils.dataUtils import voxel_down_sample  # noqa: E402
+tgt_s = voxel_down_sample(tc[0], 0.03)
+src_s = voxel_down_sample(tc[0] / torch.tensor([1.1, 1.0, 0.9], device=dev), 0.03)
+iterative_scale_search(src_s, tgt_s, [(0.8, 1.2)] * 3, 4, None, 0.5); torch.cuda.synchronize()
+t0 = time.perf_counter(); iterative_scale_search(src_s, tgt_s, [(0.8, 1.2)] * 3, 10, None, 0.5); torch.cuda.synchronize()
+out["scale_search_1000_candidates_icp30_ms"] = {"ms": (time.perf_counter() - t0) * 1e3, "src_pts": int(src_s.shape[0]),
+                                                "tgt_pts": int(tgt_s.shape[0])}
+fused = torch.cat([tc[0], tp[0]])[:20000].contiguous()
+out["knn20_mean_distance_20000pts_ms"] = ev_time(lambda: knn_mean_distance(fused, 20, True))[0]
+out["remove_statistical_outlier_20000pts_ms"] = ev_time(lambda: remove_statistical_outlier(fused, 20, 2.5))[0]
+out["remove_close_points_16384x16384_ms"] = ev_time(lambda: remove_close_points(tp[0], tc[0], 1e-4))[0]
+def outlier_torch(x, k=20, chunk=4096):   # the library formulation this kernel replaces (torch.cdist + topk)
+    md = torch.empty(x.shape[0], device=x.device)
+    for c0 in range(0, x.shape[0], chunk):
+        md[c0:c0 + chunk] = torch.cdist(x[c0:c0 + chunk], x).topk(k, largest=False).values.mean(1)
+    return md
+out["knn20_torch_cdist_topk_20000pts_ms"] = ev_time(lambda: outlier_torch(fused))[0]
 print(json.dumps(out, indent=1))
