@@ -87,13 +87,15 @@ def shard_range_aligned(n, rank, world, align=128):
     return min(lo * align, n), min(hi * align, n)
 
 
-def sharded_chamfer_forward(xyz1, xyz2, group=None):
+def sharded_chamfer_forward(xyz1, xyz2, group=None, phase_ms=None):
     """Sharded Chamfer forward, every point pair evaluated ONCE across the job.  xyz1 [1,N,3], xyz2 [1,M,3]: the FULL
     clouds, identical on every rank.  Rank r scans its 128-aligned row slice of xyz1 against all of xyz2 with the
     symmetric kernel: exact (dist1, idx1) for its rows, partial (dist, row block) minima for every point of xyz2.
     ONE all-reduce-MIN over [packed rows | packed cols] (16 MB for 1M + 1M points) completes both, a local fix-up
     resolves idx2.  Returns (dist1, dist2, idx1, idx2) identical on every rank and bit-identical to chamfer_3DDist.
-    Batched inputs (B > 1) fall back to the target-sharded scan (sharded_chamfer_forward_targets)."""
+    Batched inputs (B > 1) fall back to the target-sharded scan (sharded_chamfer_forward_targets).
+    phase_ms: optional dict; filled with the device time of the three phases (scan / all-reduce / unpack + fix-up)
+    measured with CUDA events -- synchronises, for measurements only."""
     if xyz1.shape[0] != 1:
         return sharded_chamfer_forward_targets(xyz1, xyz2, group)
     _lib.require_cuda(xyz1, xyz2)
@@ -107,19 +109,28 @@ def sharded_chamfer_forward(xyz1, xyz2, group=None):
     lo, hi = shard_range_aligned(N, rank, world)
     packed = torch.full((N + M,), EMPTY, dtype=torch.int64, device=dev)   # [rows of cloud 1 | cols = cloud 2]
     L = _lib.lib()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if phase_ms is not None else None
     with torch.cuda.device(dev):
+        if ev: ev[0].record()
         rows = xyz1[0, lo:hi]
         rc = L.genpc_chamfer_sym_partial(_lib.ptr(rows) if hi > lo else None, _lib.ptr(xyz2),
                                          ctypes.c_void_p(packed.data_ptr() + lo * 8), ctypes.c_void_p(packed.data_ptr() + N * 8),
                                          1, hi - lo, M, lo, 0, _lib.current_stream(dev))
         _lib.check(rc, "genpc_chamfer_sym_partial")
+        if ev: ev[1].record()
         allreduce_min_packed(packed, group)
+        if ev: ev[2].record()
         d1, i1 = nn_unpack(packed[:N])
         d2 = torch.empty(M, dtype=torch.float32, device=dev)
         i2 = torch.empty(M, dtype=torch.int32, device=dev)
         rc = L.genpc_chamfer_sym_fixup(_lib.ptr(xyz1), _lib.ptr(xyz2), ctypes.c_void_p(packed.data_ptr() + N * 8), 1, N, M,
                                        _lib.ptr(d2), _lib.ptr(i2), _lib.current_stream(dev))
         _lib.check(rc, "genpc_chamfer_sym_fixup")
+        if ev:
+            ev[3].record()
+            torch.cuda.synchronize(dev)
+            phase_ms.update(scan=ev[0].elapsed_time(ev[1]), allreduce=ev[1].elapsed_time(ev[2]),
+                            unpack_fixup=ev[2].elapsed_time(ev[3]))
     return d1[None], d2[None], i1[None], i2[None]
 
 

@@ -1,4 +1,4 @@
-"""One small workload per kernel family, for ncu:  python tools/prof_targets.py {register|emd|fps|depth|sharded}"""
+"""One small workload per kernel family, for ncu:  python tools/prof_targets.py {register|emd|fps|depth|knn}"""
 import os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -30,5 +30,10 @@ elif what == "depth":
     cams, _ = D.create_cameras(8, 1.6, 49.1, 512, dev)
     for _ in range(2):
         ndc, uv, b = D.project_uv(cams, pts, True, 0.15); r = D.zbuffer_render(uv, ndc, 512, 2); D.unproject(cams, b, r["zbuf"], ndc, True)
+elif what == "knn":
+    from genpc_b200.reg_xyz import knn_mean_distance
+    from genpc_b200.synthetic import superquadric
+    pts = torch.from_numpy(superquadric(0, 20000)).to(dev)
+    knn_mean_distance(pts, 20, True); knn_mean_distance(pts, 20, True)
 torch.cuda.synchronize()
 print("done", what)

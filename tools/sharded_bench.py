@@ -37,6 +37,12 @@ for _ in range(args.reps):
 ms = min(ts)
 res = {"workload": "C5: 1M x 1M Chamfer forward, target-sharded", "n": n, "n_gpus": world, "ms": ms,
        "pairs_per_s": 2.0 * n * n / (ms * 1e-3), "scaling": "strong", "all_ms": ts}
+ph = {}
+if world > 1: dist.barrier()
+sharded_chamfer_forward(ta, tb, phase_ms=ph)          # one more pass with per-phase CUDA events (this rank's view)
+pt = torch.tensor([ph["scan"], ph["allreduce"], ph["unpack_fixup"]], dtype=torch.float64, device=dev)
+if world > 1: dist.all_reduce(pt, op=dist.ReduceOp.MAX)
+res["phase_ms_max_over_ranks"] = {"scan": float(pt[0]), "allreduce_min_packed": float(pt[1]), "unpack_fixup": float(pt[2])}
 if rank == 0:
     import oracle
     sel = np.random.default_rng(0).choice(n, 2000, replace=False)
