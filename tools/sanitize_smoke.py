@@ -24,4 +24,17 @@ for (nc, nr) in [(1500, 900), (20000, 12000)]:                      # single-lau
     rb = RegistrationBatch(torch.rand(1, nc, 3, generator=g).to(dev) - 0.5, torch.rand(1, nr, 3, generator=g).to(dev) - 0.5, n_starts=2)
     rb.run(2)
 p = nn_partial_packed(torch.rand(1, 2000, 3, generator=g).to(dev), torch.rand(1, 700, 3, generator=g).to(dev), 100); nn_unpack(p)
+# fused loss step (epilogue with loss reduction, zero-fill with odd tails, re-armed workspace), twice per shape; host-fed
+from genpc_b200.utils.loss_util import Completionloss
+from genpc_b200.reg_xyz import knn_mean_distance
+from genpc_b200.sharded import sharded_chamfer_forward
+cl = Completionloss("cd_l1")
+for (B, N, M) in [(3, 701, 1303), (1, 3001, 997), (2, 100, 37)]:
+    for _ in range(2):
+        a = torch.rand(B, N, 3, generator=g).to(dev).requires_grad_(True); b = torch.rand(B, M, 3, generator=g).to(dev).requires_grad_(True)
+        cl.get_loss(a, b).backward()
+ha, hb = torch.rand(4, 600, 3, generator=g).pin_memory(), torch.rand(4, 1500, 3, generator=g).pin_memory()
+loss, da, db = cl.get_loss_from_host(ha, hb, device=dev, chunks=2); loss.backward()
+knn_mean_distance(torch.rand(3001, 3, generator=g).to(dev), 20, True); knn_mean_distance(torch.rand(17, 3, generator=g).to(dev), 32, False)
+sharded_chamfer_forward(torch.rand(1, 5001, 3, generator=g).to(dev), torch.rand(1, 3003, 3, generator=g).to(dev))
 torch.cuda.synchronize(); print("sanitize smoke done")
