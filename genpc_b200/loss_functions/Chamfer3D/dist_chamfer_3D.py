@@ -23,12 +23,21 @@ def _outputs(like, count):
             torch.empty(shape, dtype=torch.int32, device=like.device))
 
 
+def _grad_buffers(ctx, xyz1, xyz2):
+    """Gradient accumulators for a forward whose inputs need gradients: allocated now, zero-filled by the forward's
+    epilogue launch (the reference zero-fills them with two launches in backward, :56-57)."""
+    if any(ctx.needs_input_grad[:2]) and xyz1.dtype == torch.float32 and xyz2.dtype == torch.float32:
+        return torch.empty_like(xyz1), torch.empty_like(xyz2)
+    return None, None
+
+
 class chamfer_3DFunction(Function):
     @staticmethod
     def forward(ctx, xyz1, xyz2):
         dist1, idx1 = _outputs(xyz1, xyz1.shape[1])
         dist2, idx2 = _outputs(xyz2, xyz2.shape[1])
-        chamfer_3D.forward(xyz1, xyz2, dist1, dist2, idx1, idx2)
+        ctx.grads = _grad_buffers(ctx, xyz1, xyz2)
+        chamfer_3D.forward_fused(xyz1, xyz2, dist1, dist2, idx1, idx2, ctx.grads[0], ctx.grads[1])
         ctx.save_for_backward(xyz1, xyz2, idx1, idx2)
         ctx.mark_non_differentiable(idx1, idx2)
         return dist1, dist2, idx1, idx2
@@ -36,8 +45,12 @@ class chamfer_3DFunction(Function):
     @staticmethod
     def backward(ctx, graddist1, graddist2, gradidx1, gradidx2):
         xyz1, xyz2, idx1, idx2 = ctx.saved_tensors
-        # the native backward ACCUMULATES (atomics), so the gradients start from zero as in the reference (:56-57)
-        grads = torch.zeros_like(xyz1), torch.zeros_like(xyz2)
+        # the native backward ACCUMULATES (atomics), so the gradients start from zero as in the reference (:56-57):
+        # the buffers zero-filled by the forward's epilogue, or fresh zeros for a second backward through the graph
+        grads = ctx.grads
+        ctx.grads = (None, None)
+        if grads[0] is None:
+            grads = torch.zeros_like(xyz1), torch.zeros_like(xyz2)
         chamfer_3D.backward(xyz1, xyz2, grads[0], grads[1], graddist1.contiguous(), graddist2.contiguous(), idx1, idx2)
         return grads
 
@@ -50,7 +63,8 @@ class chamfer_3DHostFunction(Function):
     def forward(ctx, xyz1, xyz2, h1, h2, chunks):
         dist1, idx1 = _outputs(xyz1, xyz1.shape[1])
         dist2, idx2 = _outputs(xyz2, xyz2.shape[1])
-        chamfer_3D.forward_host(h1, h2, xyz1, xyz2, dist1, dist2, idx1, idx2, chunks)
+        ctx.grads = _grad_buffers(ctx, xyz1, xyz2)
+        chamfer_3D.forward_fused(xyz1, xyz2, dist1, dist2, idx1, idx2, ctx.grads[0], ctx.grads[1], None, h1, h2, chunks)
         ctx.save_for_backward(xyz1, xyz2, idx1, idx2)
         ctx.mark_non_differentiable(idx1, idx2)
         return dist1, dist2, idx1, idx2

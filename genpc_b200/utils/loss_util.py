@@ -26,42 +26,6 @@ def _l1(d):
     return torch.sqrt(d).mean()
 
 
-_loss_ws = {}
-
-
-def _workspace(device):
-    """Reduction scratch, zeroed once per (device, stream) -- the kernel re-arms its own ticket."""
-    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
-    if key not in _loss_ws:
-        _loss_ws[key] = torch.zeros(_lib.lib().genpc_chamfer_loss_workspace_bytes(), dtype=torch.uint8, device=device)
-    return _loss_ws[key]
-
-
-class _StepWorkspace:
-    """Scratch of one fused loss step shape on one (device, stream): the packed-word workspace, which the epilogue leaves
-    re-armed (all-ones) so that the next step skips the memset, and the loss partials + ticket (zeroed once)."""
-
-    def __init__(self, device, B, N, M):
-        L = _lib.lib()
-        self.packed_bytes = L.genpc_chamfer_workspace_bytes(B, N, M)
-        self.packed = torch.empty(max(self.packed_bytes, 8), dtype=torch.uint8, device=device)
-        self.loss = torch.zeros(max(L.genpc_chamfer_fuse_workspace_bytes(B, N, M), 8), dtype=torch.uint8, device=device)
-        self.armed = False
-
-
-_step_ws = {}
-
-
-def _step_workspace(device, B, N, M):
-    key = (device.index, torch.cuda.current_stream(device).cuda_stream, B, N, M)
-    ws = _step_ws.get(key)
-    if ws is None:
-        if len(_step_ws) >= 16:   # a few live shapes at most: drop the oldest
-            _step_ws.pop(next(iter(_step_ws)))
-        ws = _step_ws[key] = _StepWorkspace(device, B, N, M)
-    return ws
-
-
 class _FusedChamferLoss(Function):
     """w1 * mean f(d1) + w2 * mean f(d2) in two launches forward (scan, epilogue: fix-up + unpack + loss reduction +
     zero-fill of the gradient accumulators + re-arming of the workspace -- genpc_chamfer_forward_fused) and one backward,
@@ -83,27 +47,8 @@ class _FusedChamferLoss(Function):
         need_grad = any(ctx.needs_input_grad[:2])
         ga = torch.empty_like(a) if need_grad else None   # zero-filled by the epilogue
         gb = torch.empty_like(b) if need_grad else None
-        L = _lib.lib()
-        with torch.cuda.device(dev):
-            ws = _step_workspace(dev, B, N, M)
-            fuse = _lib.ChamferFuse(int(ws.armed), int(use_sqrt), float(w1), float(w2), out.data_ptr(), ws.loss.data_ptr(),
-                                    ws.loss.numel(), ga.data_ptr() if need_grad else None,
-                                    gb.data_ptr() if need_grad else None)
-            ws.armed = False   # stays False if the call below fails half-way
-            stream = _lib.current_stream(dev)
-            if h1 is None:
-                rc = L.genpc_chamfer_forward_fused(_lib.ptr(a), _lib.ptr(b), _lib.ptr(d1), _lib.ptr(d2), _lib.ptr(i1),
-                                                   _lib.ptr(i2), B, N, M, _lib.ptr(ws.packed), ws.packed_bytes, fuse, stream)
-                _lib.check(rc, "genpc_chamfer_forward_fused")
-            else:  # host-fed: xyz1 / xyz2 are uninitialised leaves, filled from h1 / h2 while the scan runs
-                if h1.is_cuda or h2.is_cuda or h1.shape != a.shape or h2.shape != b.shape:
-                    raise _lib.GenpcError("host-fed loss takes CPU clouds shaped like the device leaves")
-                rc = L.genpc_chamfer_forward_host_fused(chamfer_3D._feed(dev), _lib.ptr(h1), _lib.ptr(h2), _lib.ptr(a),
-                                                        _lib.ptr(b), _lib.ptr(d1), _lib.ptr(d2), _lib.ptr(i1), _lib.ptr(i2),
-                                                        B, N, M, int(chunks), _lib.ptr(ws.packed), ws.packed_bytes, fuse,
-                                                        stream)
-                _lib.check(rc, "genpc_chamfer_forward_host_fused")
-            ws.armed = (max(N, M) >= 512 and min(N, M) > 0)   # the symmetric path re-arms the packed words
+        # host-fed when h1 / h2 are given: xyz1 / xyz2 are uninitialised leaves, filled from h1 / h2 while the scan runs
+        chamfer_3D.forward_fused(a, b, d1, d2, i1, i2, ga, gb, (out, use_sqrt, w1, w2), h1, h2, chunks)
         ctx.save_for_backward(a, b, d1, d2, i1, i2)
         ctx.cfg = (int(use_sqrt), float(w1), float(w2))
         ctx.grads = (ga, gb)
