@@ -15,6 +15,7 @@
 //   (reference_thread(k), k) -- the order in which the reference's thread slices visit targets (:136-139,:167);
 //   GetMax window +-1e-6 in double (:188); the reference's last-writer race is resolved as "highest j".
 #include <cooperative_groups.h>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -32,9 +33,12 @@ struct EmdArgs {
     float *bid_increments, *max_increments;
     int *unass_idx, *unass_cnt, *max_idx;
     int *flags, *tickets;  // workspace [B] each, zeroed by the host
+    float *pmin;           // workspace [B]: lowest price of the cloud at the start of the run (prices only rise)
     int B, n;
     float eps;
     int iters, group;      // group = CTAs per batch entry (1 when B >= grid)
+    int two_level_div;     // two-level pre-filter while U * two_level_div >= n (0: never)
+    int direct_p;          // items with at most this many bidders read the targets from global memory (no staging)
 };
 
 struct BidState {
@@ -76,22 +80,123 @@ __device__ __forceinline__ void st_release(int *p, int v) {
 }
 
 // ascending compaction of {j : assignment[j] == -1} into uidx; returns the count (valid in every thread).
-// Warp w owns the contiguous slice [w * n/8, (w+1) * n/8): pass 1 counts it with coalesced loads + ballots (no block
-// barrier inside, loads independent), one barrier publishes the eight warp totals, pass 2 re-reads the slice (L1) and
-// writes the indices.  (The first form walked the array 256 elements at a time with two block barriers per step:
-// 64 barriers at n = 8192, most of an iteration's serial tail.)
-__device__ int compact_unassigned(const int *__restrict__ asg, int *__restrict__ uidx, int *__restrict__ midx, int n,
+// Warp w owns the contiguous slice [w * n/8, (w+1) * n/8) and walks it 128 elements at a time with one LDG.128 per lane
+// (lane l holds elements 4l..4l+3 of the step: ascending order is (lane, component)).  Steps are independent, so the
+// loads of a whole batch of EMD_CSTEPS steps are in flight together; the flags of the batch stay in registers between the
+// counting pass and the writing pass.  One block barrier publishes the eight warp totals.  (The first form walked the
+// array 256 elements at a time with two block barriers per step -- 64 barriers at n = 8192; the second one element per
+// lane and step with four loads in flight -- both left the iteration's serial tail bound by L2 latency.)
+constexpr int EMD_CSTEPS = 8;  // 8 x 128 = 1024 elements per warp and batch (n = 8192: the whole slice)
+
+__device__ __noinline__ int compact_unassigned(const int *__restrict__ asg, int *__restrict__ uidx, int *__restrict__ midx, int n,
                                   int *sscan) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int WARPS = EMD_THREADS / 32;
-    const int per_warp = n / WARPS;  // n % 256 == 0
+    const int per_warp = n / WARPS;  // n % 256 == 0  =>  per_warp % 32 == 0
     const int j0 = warp * per_warp;
+    const unsigned lt = (1u << lane) - 1u;
+    const int4 minus1 = make_int4(-1, -1, -1, -1);
+    if (per_warp % 128 == 0 && per_warp <= 128 * EMD_CSTEPS) {
+        // fast path (n <= 8192, n % 1024 == 0): one batch, flags kept in registers across the barrier
+        const int steps = per_warp / 128;
+        unsigned fl[EMD_CSTEPS];  // 4 flag bits per step
+        int cnt = 0;
+#pragma unroll
+        for (int r = 0; r < EMD_CSTEPS; ++r) {
+            fl[r] = 0;
+            if (r < steps) {
+                const int j = j0 + r * 128 + lane * 4;
+                const int4 v = __ldcg(reinterpret_cast<const int4 *>(asg + j));
+                *reinterpret_cast<int4 *>(midx + j) = minus1;  // re-arm GetMax for the next iteration
+                fl[r] = (v.x == -1 ? 1u : 0u) | (v.y == -1 ? 2u : 0u) | (v.z == -1 ? 4u : 0u) | (v.w == -1 ? 8u : 0u);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < EMD_CSTEPS; ++r) cnt += __popc(fl[r]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        if (lane == 0) sscan[warp] = cnt;
+        __syncthreads();
+        int base = 0, tot = 0;
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) {
+            const int c = sscan[w];
+            base += (w < warp) ? c : 0;
+            tot += c;
+        }
+#pragma unroll
+        for (int r = 0; r < EMD_CSTEPS; ++r) {
+            if (r < steps) {
+                const unsigned b0 = __ballot_sync(0xffffffffu, fl[r] & 1u), b1 = __ballot_sync(0xffffffffu, fl[r] & 2u);
+                const unsigned b2 = __ballot_sync(0xffffffffu, fl[r] & 4u), b3 = __ballot_sync(0xffffffffu, fl[r] & 8u);
+                int pos = base + __popc(b0 & lt) + __popc(b1 & lt) + __popc(b2 & lt) + __popc(b3 & lt);
+                const int j = j0 + r * 128 + lane * 4;
+                if (fl[r] & 1u) uidx[pos++] = j;
+                if (fl[r] & 2u) uidx[pos++] = j + 1;
+                if (fl[r] & 4u) uidx[pos++] = j + 2;
+                if (fl[r] & 8u) uidx[pos++] = j + 3;
+                base += __popc(b0) + __popc(b1) + __popc(b2) + __popc(b3);
+            }
+        }
+        __syncthreads();  // sscan may be reused
+        return tot;
+    }
+    if (per_warp % (128 * EMD_CSTEPS) == 0) {
+        // larger clouds (n % 8192 == 0): the same 128-element steps in batches of EMD_CSTEPS, two passes over the slice
+        // (the second one re-reads it from L1 / L2 with all loads of a batch in flight again)
+        int cnt = 0;
+        for (int r0 = 0; r0 < per_warp; r0 += 128 * EMD_CSTEPS) {
+            int4 v[EMD_CSTEPS];
+#pragma unroll
+            for (int r = 0; r < EMD_CSTEPS; ++r) {
+                const int j = j0 + r0 + r * 128 + lane * 4;
+                v[r] = __ldcg(reinterpret_cast<const int4 *>(asg + j));
+                *reinterpret_cast<int4 *>(midx + j) = minus1;
+            }
+#pragma unroll
+            for (int r = 0; r < EMD_CSTEPS; ++r) cnt += (v[r].x == -1) + (v[r].y == -1) + (v[r].z == -1) + (v[r].w == -1);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        if (lane == 0) sscan[warp] = cnt;
+        __syncthreads();
+        int base = 0, tot = 0;
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) {
+            const int c = sscan[w];
+            base += (w < warp) ? c : 0;
+            tot += c;
+        }
+        if (cnt > 0) {
+            for (int r0 = 0; r0 < per_warp; r0 += 128 * EMD_CSTEPS) {
+                int4 v[EMD_CSTEPS];
+#pragma unroll
+                for (int r = 0; r < EMD_CSTEPS; ++r) v[r] = __ldcg(reinterpret_cast<const int4 *>(asg + j0 + r0 + r * 128 + lane * 4));
+#pragma unroll
+                for (int r = 0; r < EMD_CSTEPS; ++r) {
+                    const bool f0 = v[r].x == -1, f1 = v[r].y == -1, f2 = v[r].z == -1, f3 = v[r].w == -1;
+                    const unsigned b0 = __ballot_sync(0xffffffffu, f0), b1 = __ballot_sync(0xffffffffu, f1);
+                    const unsigned b2 = __ballot_sync(0xffffffffu, f2), b3 = __ballot_sync(0xffffffffu, f3);
+                    int pos = base + __popc(b0 & lt) + __popc(b1 & lt) + __popc(b2 & lt) + __popc(b3 & lt);
+                    const int j = j0 + r0 + r * 128 + lane * 4;
+                    if (f0) uidx[pos++] = j;
+                    if (f1) uidx[pos++] = j + 1;
+                    if (f2) uidx[pos++] = j + 2;
+                    if (f3) uidx[pos++] = j + 3;
+                    base += __popc(b0) + __popc(b1) + __popc(b2) + __popc(b3);
+                }
+            }
+        }
+        __syncthreads();  // sscan may be reused
+        return tot;
+    }
+    // general path: one element per lane and step, two passes over the slice
     int cnt = 0;
-#pragma unroll 4
+#pragma unroll 8
     for (int r = 0; r < per_warp; r += 32) {
         const int j = j0 + r + lane;
         const int f = (__ldcg(asg + j) == -1);
-        midx[j] = -1;  // re-arm GetMax for the next iteration
+        midx[j] = -1;
         cnt += __popc(__ballot_sync(0xffffffffu, f));
     }
     if (lane == 0) sscan[warp] = cnt;
@@ -104,12 +209,12 @@ __device__ int compact_unassigned(const int *__restrict__ asg, int *__restrict__
         tot += c;
     }
     if (cnt > 0) {
-#pragma unroll 4
+#pragma unroll 8
         for (int r = 0; r < per_warp; r += 32) {
             const int j = j0 + r + lane;
             const int f = (__ldcg(asg + j) == -1);
             const unsigned bal = __ballot_sync(0xffffffffu, f);
-            if (f) uidx[base + __popc(bal & ((1u << lane) - 1u))] = j;
+            if (f) uidx[base + __popc(bal & lt)] = j;
             base += __popc(bal);
         }
     }
@@ -117,10 +222,81 @@ __device__ int compact_unassigned(const int *__restrict__ asg, int *__restrict__
     return tot;
 }
 
-__global__ void __launch_bounds__(EMD_THREADS) emd_auction_kernel(const EmdArgs a) {
+// GetMax (emd_cuda.cu:181-194: highest j inside the +-1e-6 window wins) and Assign (:196-215) for the U bidders of one
+// cloud, run by ONE CTA (the iteration's serial tail).  Every bidder is a chain of dependent L2 reads
+// (uidx -> bid / increment -> max_increment / max_idx -> assignment_inv, price); a thread takes EMD_TAIL_R bidders at a
+// time and issues each level of the chain for all of them before it consumes any, so the tail costs about one L2
+// latency per level instead of one per level and bidder.  Bidders act on disjoint targets (one winner per target), so
+// the order in which they are processed does not matter.
+constexpr int EMD_TAIL_R = 2;
+
+__device__ __noinline__ void emd_getmax_assign(const int *__restrict__ uidx, const int *__restrict__ bd,
+                                               const float *__restrict__ binc, float *minc, int *midx, int *asg, int *asg_inv,
+                                               float *pr, int U, bool last) {
+    const int tid = threadIdx.x;
+    for (int u0 = 0; u0 < U; u0 += EMD_THREADS * EMD_TAIL_R) {
+        int j[EMD_TAIL_R], bid[EMD_TAIL_R];
+        float inc[EMD_TAIL_R], mx[EMD_TAIL_R];
+#pragma unroll
+        for (int r = 0; r < EMD_TAIL_R; ++r) {
+            const int u = u0 + r * EMD_THREADS + tid;
+            j[r] = (u < U) ? __ldcg(uidx + u) : -1;
+        }
+#pragma unroll
+        for (int r = 0; r < EMD_TAIL_R; ++r)
+            if (j[r] >= 0) bid[r] = __ldcg(bd + j[r]), inc[r] = __ldcg(binc + j[r]);
+#pragma unroll
+        for (int r = 0; r < EMD_TAIL_R; ++r)
+            if (j[r] >= 0) mx[r] = __ldcg(minc + bid[r]);
+#pragma unroll
+        for (int r = 0; r < EMD_TAIL_R; ++r)
+            if (j[r] >= 0 && (double)inc[r] - 1e-6 <= (double)mx[r] && (double)mx[r] <= (double)inc[r] + 1e-6)
+                atomicMax(midx + bid[r], j[r]);
+    }
+    __syncthreads();
+    for (int u0 = 0; u0 < U; u0 += EMD_THREADS * EMD_TAIL_R) {
+        int j[EMD_TAIL_R], bid[EMD_TAIL_R], win[EMD_TAIL_R], inv[EMD_TAIL_R];
+        float inc[EMD_TAIL_R], p[EMD_TAIL_R];
+#pragma unroll
+        for (int r = 0; r < EMD_TAIL_R; ++r) {
+            const int u = u0 + r * EMD_THREADS + tid;
+            j[r] = (u < U) ? __ldcg(uidx + u) : -1;
+        }
+#pragma unroll
+        for (int r = 0; r < EMD_TAIL_R; ++r)
+            if (j[r] >= 0) bid[r] = __ldcg(bd + j[r]), inc[r] = __ldcg(binc + j[r]);
+        if (last) {
+#pragma unroll
+            for (int r = 0; r < EMD_TAIL_R; ++r)
+                if (j[r] >= 0) {
+                    asg[j[r]] = bid[r];
+                    atomicMax(asg_inv + bid[r], j[r]);
+                    atomicAdd(pr + bid[r], inc[r]);
+                    minc[bid[r]] = -1e9f;
+                }
+            continue;
+        }
+#pragma unroll
+        for (int r = 0; r < EMD_TAIL_R; ++r) win[r] = (j[r] >= 0) && (__ldcg(midx + bid[r]) == j[r]);
+#pragma unroll
+        for (int r = 0; r < EMD_TAIL_R; ++r)
+            if (win[r]) inv[r] = __ldcg(asg_inv + bid[r]), p[r] = __ldcg(pr + bid[r]);
+#pragma unroll
+        for (int r = 0; r < EMD_TAIL_R; ++r)
+            if (win[r]) {
+                if (inv[r] != -1) asg[inv[r]] = -1;
+                asg_inv[bid[r]] = j[r];
+                asg[j[r]] = bid[r];
+                pr[bid[r]] = __fadd_rn(p[r], inc[r]);
+                minc[bid[r]] = -1e9f;
+            }
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(EMD_THREADS, 5) emd_auction_kernel(const EmdArgs a) {
     __shared__ __align__(16) float sx[EMD_CHUNK], sy[EMD_CHUNK], sz[EMD_CHUNK];  // targets, SoA (pairs feed FADD2/FFMA2)
-    __shared__ __align__(16) float sc[EMD_CHUNK];                                 // c = fl(3 - price): pre-filter operand
-    __shared__ float sprice[EMD_CHUNK];
+    __shared__ __align__(16) float sprice[EMD_CHUNK];
     __shared__ BidState smerge[EMD_THREADS];
     __shared__ int sscan[EMD_THREADS / 32];
     __shared__ int s_last;
@@ -145,9 +321,19 @@ __global__ void __launch_bounds__(EMD_THREADS) emd_auction_kernel(const EmdArgs 
 
         if (rank == 0) {  // initial compaction (calc_unass_cnt / calc_unass_idx of iteration 0)
             const int U0 = compact_unassigned(asg, uidx, midx, n, sscan);
+            // lowest initial price (0 with the reference's initial state, emd_module.py:45): the target-independent
+            // pre-filter below needs a lower bound of every price, and prices only ever rise during the auction
+            float pm = __int_as_float(0x7f800000);
+            for (int k = tid; k < n; k += EMD_THREADS) pm = fminf(pm, __ldcg(pr + k));
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) pm = fminf(pm, __shfl_xor_sync(0xffffffffu, pm, o));
+            if ((tid & 31) == 0) sscan[tid >> 5] = __float_as_int(pm);
             __threadfence();
             __syncthreads();
             if (tid == 0) {
+#pragma unroll
+                for (int w = 0; w < EMD_THREADS / 32; ++w) pm = fminf(pm, __int_as_float(sscan[w]));
+                a.pmin[b] = pm;
                 a.unass_cnt[b] = U0;
                 __threadfence();
                 st_release(flag, 1);
@@ -166,6 +352,8 @@ __global__ void __launch_bounds__(EMD_THREADS) emd_auction_kernel(const EmdArgs 
                 complete = true;
                 break;
             }
+            const float c_max = __fsub_rn(3.0f, __ldcg(a.pmin + b));
+            const bool two_level = (a.two_level_div > 0) && ((long long)U * a.two_level_div >= n);
             // ---- Bid (emd_cuda.cu:95-179) ----
             if (U > 0) {
                 const int upb_ref = (U + block_cnt - 1) / block_cnt;
@@ -188,56 +376,88 @@ __global__ void __launch_bounds__(EMD_THREADS) emd_auction_kernel(const EmdArgs 
                     }
                     BidState st;
                     st.best = -1e9f, st.better = -1e9f, st.bi = -1;
-                    float bm = -2e9f;  // better - margin (pre-filter threshold)
+                    float bm = -2e9f;   // better - margin (pre-filter threshold)
+                    float s_cap = __int_as_float(0x7f800000);  // target-independent bound on s (two-level filter)
+                    // exact evaluation of one candidate (the reference's arithmetic and tie rule)
+                    auto consider = [&](int k, float s, float pk) {
+                        const float d = (float)((3.0 - (double)__fsqrt_rn(s)) - (double)pk);
+                        if (d > st.best) {
+                            st.better = st.best;
+                            st.best = d;
+                            st.bi = k;
+                        } else {
+                            st.better = fmaxf(st.better, d);
+                            if (d == st.best && ref_visit_key(k, n, tpu_ref) < ref_visit_key(st.bi, n, tpu_ref)) st.bi = k;
+                        }
+                        bm = __fsub_rn(st.better, __fmul_rn(1e-4f, fmaxf(1.f, fabsf(st.better))));
+                        // every price >= pmin0, so a candidate that matters has sqrt(s) <= (3 - pmin0) - bm, whatever its target
+                        const float tq0 = __fsub_rn(c_max, bm);
+                        s_cap = tq0 > 0.f ? __fmul_rn(tq0, tq0) : -1.f;
+                    };
+                    // two targets per step on the packed FP32 pipe.  Conservative pre-filter (no sqrt, no FP64): a
+                    // candidate can only matter if its value d >= better, i.e. sqrt(s) <= 3 - price - better up to a few
+                    // ulps; bm = better - margin with margin = 1e-4*max(1,|better|) (hundreds of ulps) makes
+                    // "tq > 0 && s <= tq^2" a superset of those candidates; whatever passes takes the exact path above,
+                    // so the result is bit-identical to evaluating every candidate exactly.
+                    const float2 nx = make_float2(-x1, -x1), ny = make_float2(-y1, -y1), nz = make_float2(-z1, -z1);
+                    auto step2 = [&](int k, float2 tx, float2 ty, float2 tz, float2 pk) {
+                        const float2 tc = make_float2(__fsub_rn(3.0f, pk.x), __fsub_rn(3.0f, pk.y));
+                        const float2 s2 = sqdist_ref_x2(nx, ny, nz, tx, ty, tz);
+                        const float2 tq = __fadd2_rn(tc, make_float2(-bm, -bm));
+                        const float2 tq2 = __fmul2_rn(tq, tq);
+                        const bool c0 = tq.x > 0.f && s2.x <= tq2.x;
+                        const bool c1 = tq.y > 0.f && s2.y <= tq2.y;
+                        if (c0) consider(k, s2.x, pk.x);
+                        // bm may have risen while handling the first candidate; the filter stays conservative because it
+                        // was evaluated against the OLDER (lower) threshold
+                        if (c1) consider(k + 1, s2.y, pk.y);
+                    };
+                    if (P <= a.direct_p) {
+                        // thin items (few bidders per CTA, the late iterations): staging the whole target cloud through
+                        // shared memory for a handful of points costs more than the scan itself -- read the targets
+                        // straight from global memory (L1/L2 resident: 16 B per target), no block barriers
+                        if (active) {
+                            const float2 *t2 = reinterpret_cast<const float2 *>(p2);   // 3 float2 per target pair
+                            const float2 *pr2 = reinterpret_cast<const float2 *>(pr);
+#pragma unroll 2
+                            for (int kp = tpt; kp < (n >> 1); kp += T) {                // n is even (n % 256 == 0)
+                                const float2 q0 = __ldg(t2 + kp * 3), q1 = __ldg(t2 + kp * 3 + 1), q2 = __ldg(t2 + kp * 3 + 2);
+                                const float2 pk = __ldcg(pr2 + kp);
+                                // q0 = (x0, y0), q1 = (z0, x1), q2 = (y1, z1)
+                                step2(2 * kp, make_float2(q0.x, q1.y), make_float2(q0.y, q2.x), make_float2(q1.x, q2.y), pk);
+                            }
+                        }
+                    } else
                     for (int k2 = 0; k2 < n; k2 += EMD_CHUNK) {
                         const int end_k = min(EMD_CHUNK, n - k2);
                         __syncthreads();
                         for (int k = tid; k < end_k; k += EMD_THREADS) {
                             const float *tp = p2 + (size_t)(k2 + k) * 3;
-                            const float pk = __ldcg(pr + k2 + k);
                             sx[k] = __ldg(tp), sy[k] = __ldg(tp + 1), sz[k] = __ldg(tp + 2);
-                            sc[k] = __fsub_rn(3.0f, pk);
-                            sprice[k] = pk;
+                            sprice[k] = __ldcg(pr + k2 + k);
                         }
                         __syncthreads();
-                        if (active) {
-                            // exact evaluation of one candidate (the reference's arithmetic and tie rule)
-                            auto consider = [&](int kl, float s) {
-                                const float d = (float)((3.0 - (double)__fsqrt_rn(s)) - (double)sprice[kl]);
-                                if (d > st.best) {
-                                    st.better = st.best;
-                                    st.best = d;
-                                    st.bi = k2 + kl;
-                                } else {
-                                    st.better = fmaxf(st.better, d);
-                                    if (d == st.best &&
-                                        ref_visit_key(k2 + kl, n, tpu_ref) < ref_visit_key(st.bi, n, tpu_ref))
-                                        st.bi = k2 + kl;
-                                }
-                                bm = __fsub_rn(st.better, __fmul_rn(1e-4f, fmaxf(1.f, fabsf(st.better))));
-                            };
-                            // two targets per step on the packed FP32 pipe.  Conservative pre-filter (no sqrt, no FP64):
-                            // a candidate can only matter if its value d >= better, i.e. sqrt(s) <= 3 - price - better up
-                            // to a few ulps; bm = better - margin with margin = 1e-4*max(1,|better|) (hundreds of ulps)
-                            // makes "tq > 0 && s <= tq^2" a superset of those candidates; whatever passes takes the exact
-                            // path above, so the result is bit-identical to evaluating every candidate exactly.
-                            const float2 nx = make_float2(-x1, -x1), ny = make_float2(-y1, -y1), nz = make_float2(-z1, -z1);
-                            for (int kp = tpt; kp < (end_k >> 1); kp += T) {   // end_k is even (n % 256 == 0)
-                                const float2 tx = reinterpret_cast<const float2 *>(sx)[kp];
-                                const float2 ty = reinterpret_cast<const float2 *>(sy)[kp];
+                        if (active && two_level) {
+                            // early iterations (most points still bid, prices near their start): one compare per target
+                            // against the target-independent bound s_cap rejects almost everything before the price is
+                            // even read; survivors take the per-target filter + exact path.  Half the instructions of the
+                            // single-level loop while prices are small; later (bound loose) the single-level loop is used.
+                            for (int kp = tpt; kp < (end_k >> 1); kp += T) {
+                                const float2 tx = reinterpret_cast<const float2 *>(sx)[kp], ty = reinterpret_cast<const float2 *>(sy)[kp];
                                 const float2 tz = reinterpret_cast<const float2 *>(sz)[kp];
-                                const float2 tc = reinterpret_cast<const float2 *>(sc)[kp];
                                 const float2 s2 = sqdist_ref_x2(nx, ny, nz, tx, ty, tz);
-                                const float2 tq = __fadd2_rn(tc, make_float2(-bm, -bm));
-                                const float2 tq2 = __fmul2_rn(tq, tq);
-                                const bool c0 = tq.x > 0.f && s2.x <= tq2.x;
-                                const bool c1 = tq.y > 0.f && s2.y <= tq2.y;
-                                if (c0) consider(2 * kp, s2.x);
-                                if (c1) {
-                                    // bm may have risen while handling the first candidate; the filter stays conservative
-                                    // because it was evaluated against the OLDER (lower) threshold
-                                    consider(2 * kp + 1, s2.y);
+                                if (s2.x <= s_cap || s2.y <= s_cap) {
+                                    const float2 pk = reinterpret_cast<const float2 *>(sprice)[kp];
+                                    const float tq_x = __fsub_rn(__fsub_rn(3.0f, pk.x), bm);
+                                    if (tq_x > 0.f && s2.x <= __fmul_rn(tq_x, tq_x)) consider(k2 + 2 * kp, s2.x, pk.x);
+                                    const float tq_y = __fsub_rn(__fsub_rn(3.0f, pk.y), bm);   // bm as updated by the first
+                                    if (tq_y > 0.f && s2.y <= __fmul_rn(tq_y, tq_y)) consider(k2 + 2 * kp + 1, s2.y, pk.y);
                                 }
+                            }
+                        } else if (active) {
+                            for (int kp = tpt; kp < (end_k >> 1); kp += T) {   // end_k is even (n % 256 == 0)
+                                step2(k2 + 2 * kp, reinterpret_cast<const float2 *>(sx)[kp], reinterpret_cast<const float2 *>(sy)[kp],
+                                      reinterpret_cast<const float2 *>(sz)[kp], reinterpret_cast<const float2 *>(sprice)[kp]);
                             }
                         }
                     }
@@ -269,35 +489,7 @@ __global__ void __launch_bounds__(EMD_THREADS) emd_auction_kernel(const EmdArgs 
             __syncthreads();
             if (s_last) {
                 __threadfence();
-                // GetMax (:181-194): highest j inside the +-1e-6 window wins
-                for (int u = tid; u < U; u += EMD_THREADS) {
-                    const int j = __ldcg(uidx + u);
-                    const int bid_id = __ldcg(bd + j);
-                    const float bid_inc = __ldcg(binc + j);
-                    const float max_inc = __ldcg(minc + bid_id);
-                    if ((double)bid_inc - 1e-6 <= (double)max_inc && (double)max_inc <= (double)bid_inc + 1e-6)
-                        atomicMax(midx + bid_id, j);
-                }
-                __syncthreads();
-                // Assign (:196-215)
-                for (int u = tid; u < U; u += EMD_THREADS) {
-                    const int j = __ldcg(uidx + u);
-                    const int bid_id = __ldcg(bd + j);
-                    if (last) {
-                        asg[j] = bid_id;
-                        atomicMax(asg_inv + bid_id, j);
-                        atomicAdd(pr + bid_id, __ldcg(binc + j));
-                        minc[bid_id] = -1e9f;
-                    } else if (__ldcg(midx + bid_id) == j) {
-                        const int ass_inv = __ldcg(asg_inv + bid_id);
-                        if (ass_inv != -1) asg[ass_inv] = -1;
-                        asg_inv[bid_id] = j;
-                        asg[j] = bid_id;
-                        pr[bid_id] = __fadd_rn(__ldcg(pr + bid_id), __ldcg(binc + j));
-                        minc[bid_id] = -1e9f;
-                    }
-                }
-                __syncthreads();
+                emd_getmax_assign(uidx, bd, binc, minc, midx, asg, asg_inv, pr, U, last);
                 const int U2 = compact_unassigned(asg, uidx, midx, n, sscan);
                 __threadfence();
                 __syncthreads();
@@ -343,7 +535,7 @@ __global__ void emd_grad_kernel(const float *__restrict__ xyz1, const float *__r
 
 using namespace genpc;
 
-extern "C" size_t genpc_emd_workspace_bytes(int B) { return B < 0 ? 0 : (size_t)B * 2 * sizeof(int); }
+extern "C" size_t genpc_emd_workspace_bytes(int B) { return B < 0 ? 0 : (size_t)B * 3 * sizeof(int); }
 
 extern "C" int genpc_emd_forward(const float *xyz1, const float *xyz2, float *dist, int *assignment, float *price,
                                  int *assignment_inv, int *bid, float *bid_increments, float *max_increments,
@@ -367,7 +559,7 @@ extern "C" int genpc_emd_forward(const float *xyz1, const float *xyz2, float *di
     a.xyz1 = xyz1, a.xyz2 = xyz2, a.dist = dist, a.assignment = assignment, a.price = price;
     a.assignment_inv = assignment_inv, a.bid = bid, a.bid_increments = bid_increments;
     a.max_increments = max_increments, a.unass_idx = unass_idx, a.unass_cnt = unass_cnt, a.max_idx = max_idx;
-    a.flags = (int *)workspace, a.tickets = (int *)workspace + B;
+    a.flags = (int *)workspace, a.tickets = (int *)workspace + B, a.pmin = (float *)workspace + 2 * (size_t)B;
     a.B = B, a.n = n, a.eps = eps, a.iters = iters;
     int grid;
     if (B >= resident) {
@@ -381,6 +573,14 @@ extern "C" int genpc_emd_forward(const float *xyz1, const float *xyz2, float *di
         if (a.group < 1) a.group = 1;
         grid = a.group * B;
     }
+    // measured on B200 (profiles/r01j_emd_direct.txt)
+    a.direct_p = 8;
+    a.two_level_div = 8;
+    const char *tl = getenv("GENPC_EMD_TWO_LEVEL");  // experiments only
+    if (tl != nullptr) a.two_level_div = atoi(tl);
+    const char *dp = getenv("GENPC_EMD_DIRECT_P");  // experiments only
+    if (dp != nullptr) a.direct_p = atoi(dp);
+    if ((reinterpret_cast<size_t>(xyz2) & 7) != 0 || (reinterpret_cast<size_t>(price) & 7) != 0) a.direct_p = 0;  // LDG.64
     void *kargs[] = {(void *)&a};
     e = cudaLaunchCooperativeKernel((void *)emd_auction_kernel, dim3(grid), dim3(EMD_THREADS), kargs, 0, stream);
     if (e != cudaSuccess) return (int)e;
