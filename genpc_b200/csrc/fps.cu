@@ -343,6 +343,10 @@ static cudaError_t launch_fps_cluster(const float *xyz, int B, int N, int K, int
                                              (int)cfg.dynamicSmemBytes);
         if (e != cudaSuccess) return e;
     }
+    if (CS > 8) {  // 16-CTA clusters are beyond the portable size
+        cudaError_t e = cudaFuncSetAttribute(fps_cluster_kernel<PPT, CS, SMEMC>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        if (e != cudaSuccess) return e;
+    }
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -372,7 +376,23 @@ extern "C" int genpc_fps(const float *xyz, int B, int N, int K, int start, int *
     const char *fm = getenv("GENPC_FPS_MODE");
     const bool want_cluster = (fm == nullptr) ? (ppt > 8 && ppt <= 144 && B * 8 <= GENPC_NUM_SMS) : (strcmp(fm, "cluster") == 0 && ppt <= 144);
     if (want_cluster) {
-        cudaError_t e;
+        cudaError_t e = cudaErrorUnknown;
+        // big clouds (N > 49152, the 45 K - 170 K scans the reference feeds to fpsample): a 16-CTA cluster holds the whole
+        // cloud in registers (<= 9 points per thread) and halves the per-pick distance update of the 8-CTA form, whose
+        // coordinates live in shared memory; the exchange grows from 8 to 16 candidates.  Falls back to 8 CTAs when the
+        // device cannot co-schedule 16 (profiles/r01j_fps_cluster16.txt).
+        const char *c16 = getenv("GENPC_FPS_CLUSTER16");
+        // measured: 16 CTAs win from ~45 K points on (1.73 vs 2.06 us per pick at 71 372, 2.11 vs 2.56 at 139 138)
+        const bool try16 = (c16 == nullptr) ? (ppt > 48 && B * 16 <= GENPC_NUM_SMS) : (atoi(c16) != 0 && ppt > 8);
+        if (try16) {
+            if (ppt <= 16) e = launch_fps_cluster<1, 16, false>(xyz, B, N, K, start, idx_out, seq_out, stream);
+            else if (ppt <= 32) e = launch_fps_cluster<2, 16, false>(xyz, B, N, K, start, idx_out, seq_out, stream);
+            else if (ppt <= 64) e = launch_fps_cluster<4, 16, false>(xyz, B, N, K, start, idx_out, seq_out, stream);
+            else if (ppt <= 96) e = launch_fps_cluster<6, 16, false>(xyz, B, N, K, start, idx_out, seq_out, stream);
+            else e = launch_fps_cluster<9, 16, false>(xyz, B, N, K, start, idx_out, seq_out, stream);
+            if (e == cudaSuccess) return GENPC_OK;
+            (void)cudaGetLastError();  // not schedulable here: clear the error and use the portable size
+        }
         if (ppt <= 8) e = launch_fps_cluster<1, 8, false>(xyz, B, N, K, start, idx_out, seq_out, stream);
         else if (ppt <= 16) e = launch_fps_cluster<2, 8, false>(xyz, B, N, K, start, idx_out, seq_out, stream);
         else if (ppt <= 32) e = launch_fps_cluster<4, 8, false>(xyz, B, N, K, start, idx_out, seq_out, stream);

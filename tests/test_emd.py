@@ -42,7 +42,7 @@ def run_ours(x1, x2, eps, iters, dev):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("B,n,eps,iters", [(1, 256, 0.005, 50), (2, 512, 0.005, 50), (3, 1024, 0.002, 80),
-                                           (1, 2304, 0.005, 50), (32, 1024, 0.005, 50), (1, 8192, 0.005, 50),
+                                           (1, 2304, 0.005, 50), (32, 1024, 0.005, 50), (1, 8192, 0.005, 50), (1, 16384, 0.005, 50),
                                            (2, 2048, 0.05, 400)])
 def test_emd_gpu_bit_exact_vs_oracle(cuda, B, n, eps, iters):
     rng = np.random.default_rng(n + B)

@@ -67,7 +67,8 @@ def test_fps_gpu_ties_and_api(cuda):
                                          (1, 32768, 100, 0), (1, 1500, 200, 7), (1, 71372, 300, 11), (2, 100000, 40, 0),
                                          (1, 147000, 24, 146999)])
 def test_fps_cluster_kernel_bit_exact(cuda, B, N, K, start):
-    """The thread-block-cluster / DSMEM kernel (forced through GENPC_FPS_MODE) against the oracle."""
+    """The thread-block-cluster / DSMEM kernel (forced through GENPC_FPS_MODE) against the oracle, in its 8-CTA form
+    (coordinates in registers or shared memory), its 16-CTA form (everything in registers) and with the default choice."""
     import os
 
     import torch
@@ -75,12 +76,16 @@ def test_fps_cluster_kernel_bit_exact(cuda, B, N, K, start):
     from genpc_b200.fps import furthest_point_sample
 
     a = shape_cloud(N + 1, B, N)
-    os.environ["GENPC_FPS_MODE"] = "cluster"
-    try:
-        idx, seq = furthest_point_sample(torch.from_numpy(a).to(cuda), K, start, return_seq=True)
-        torch.cuda.synchronize()
-    finally:
-        del os.environ["GENPC_FPS_MODE"]
     eidx, eseq = oracle.fps(a, K, start, True)
-    assert np.array_equal(idx.cpu().numpy(), eidx)
-    assert np.array_equal(seq.cpu().numpy().view(np.int32), eseq.view(np.int32))
+    for c16 in (None, "0", "1"):
+        os.environ["GENPC_FPS_MODE"] = "cluster"
+        if c16 is not None:
+            os.environ["GENPC_FPS_CLUSTER16"] = c16
+        try:
+            idx, seq = furthest_point_sample(torch.from_numpy(a).to(cuda), K, start, return_seq=True)
+            torch.cuda.synchronize()
+        finally:
+            del os.environ["GENPC_FPS_MODE"]
+            os.environ.pop("GENPC_FPS_CLUSTER16", None)
+        assert np.array_equal(idx.cpu().numpy(), eidx), c16
+        assert np.array_equal(seq.cpu().numpy().view(np.int32), eseq.view(np.int32)), c16
