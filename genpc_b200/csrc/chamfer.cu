@@ -81,8 +81,27 @@ __global__ void nn_unpack_kernel(const unsigned long long *__restrict__ packed, 
     }
 }
 
+// += (x, y, z) on point `i` of an AoS [..][3] float array with TWO reductions instead of three: a point starts at byte
+// 12*i, so either its (x, y) or its (y, z) pair is 8-byte aligned -- that pair goes out as one RED.ADD.F32x2, the
+// remaining component as a scalar RED.  Addresses and operands are selected arithmetically (no divergence between the
+// even and odd lanes of a warp).  VEC = false (array base not 8-byte aligned): three scalar reductions.
+template <bool VEC>
+__device__ __forceinline__ void red_add3(float *arr, size_t i, float x, float y, float z) {
+    float *p = arr + i * 3;
+    if (VEC) {
+        const int odd = (int)(i & 1);
+        atomicAdd(reinterpret_cast<float2 *>(p + odd), odd ? make_float2(y, z) : make_float2(x, y));
+        atomicAdd(p + (odd ? 0 : 2), odd ? x : z);
+    } else {
+        atomicAdd(p, x);
+        atomicAdd(p + 1, y);
+        atomicAdd(p + 2, z);
+    }
+}
+
 // Backward: one thread per (direction, batch, point); same six terms as NmDistanceGradKernel
 // (chamfer3D.cu:155-174): g = 2*grad; own += g*(p - nn); nn's -= g*(p - nn).
+template <bool VEC>
 __global__ void chamfer_grad_kernel(const float *__restrict__ xyz1, const float *__restrict__ xyz2,
                                     const float *__restrict__ gd1, const float *__restrict__ gd2,
                                     const int *__restrict__ idx1, const int *__restrict__ idx2,
@@ -108,9 +127,8 @@ __global__ void chamfer_grad_kernel(const float *__restrict__ xyz1, const float 
         tx = __fmul_rn(g, __fsub_rn(x1, x2));
         ty = __fmul_rn(g, __fsub_rn(y1, y2));
         tz = __fmul_rn(g, __fsub_rn(z1, z2));
-        atomicAdd(ga + i * 3 + 0, tx);  // own term: one writer per element here, but the other direction scatters
-        atomicAdd(ga + i * 3 + 1, ty);  // into the same array concurrently -> atomic
-        atomicAdd(ga + i * 3 + 2, tz);
+        // own term: one writer per element here, but the other direction scatters into the same array concurrently -> atomic
+        red_add3<VEC>(ga, i, tx, ty, tz);
     }
     // scatter term, warp-aggregated: lanes that hit the same neighbour (common when many points of a dense cloud share
     // one nearest neighbour in a sparse one and the cloud is stored with spatial locality) are summed by shuffles
@@ -118,11 +136,7 @@ __global__ void chamfer_grad_kernel(const float *__restrict__ xyz1, const float 
     const unsigned long long key = valid ? ((unsigned long long)t * 2ull + (unsigned)dir) : (~0ull - (unsigned)lane);
     const unsigned peers = __match_any_sync(0xffffffffu, key);
     if (peers == (1u << lane)) {
-        if (valid) {
-            atomicAdd(go + t * 3 + 0, -tx);
-            atomicAdd(go + t * 3 + 1, -ty);
-            atomicAdd(go + t * 3 + 2, -tz);
-        }
+        if (valid) red_add3<VEC>(go, t, -tx, -ty, -tz);
         return;
     }
     const int leader = __ffs(peers) - 1;
@@ -132,11 +146,7 @@ __global__ void chamfer_grad_kernel(const float *__restrict__ xyz1, const float 
         const float ox = __shfl_sync(peers, -tx, src), oy = __shfl_sync(peers, -ty, src), oz = __shfl_sync(peers, -tz, src);
         sx += ox, sy += oy, sz += oz;
     }
-    if (lane == leader) {  // groups only form among valid lanes (invalid lanes carry unique keys)
-        atomicAdd(go + t * 3 + 0, sx);
-        atomicAdd(go + t * 3 + 1, sy);
-        atomicAdd(go + t * 3 + 2, sz);
-    }
+    if (lane == leader) red_add3<VEC>(go, t, sx, sy, sz);  // groups only form among valid lanes (invalid lanes carry unique keys)
 }
 
 static void fill_dir(NNDir &D, const float *q, const float *t, unsigned long long *out, int B, int nq, int mt,
@@ -376,8 +386,14 @@ extern "C" int genpc_chamfer_backward(const float *xyz1, const float *xyz2, cons
     if (B < 0 || N < 0 || M < 0) return GENPC_ERR_SHAPE;
     const size_t tot = (size_t)B * N + (size_t)B * M;
     if (tot == 0 || N == 0 || M == 0) return GENPC_OK;
-    chamfer_grad_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(xyz1, xyz2, graddist1, graddist2, idx1,
-                                                                            idx2, gradxyz1, gradxyz2, B, N, M);
+    // vector reductions need 8-byte aligned gradient arrays (every point then has one aligned component pair)
+    const bool vec = ((reinterpret_cast<size_t>(gradxyz1) | reinterpret_cast<size_t>(gradxyz2)) & 7) == 0;
+    if (vec)
+        chamfer_grad_kernel<true><<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(xyz1, xyz2, graddist1, graddist2, idx1, idx2,
+                                                                                      gradxyz1, gradxyz2, B, N, M);
+    else
+        chamfer_grad_kernel<false><<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(xyz1, xyz2, graddist1, graddist2, idx1, idx2,
+                                                                                       gradxyz1, gradxyz2, B, N, M);
     GENPC_CHECK_LAUNCH();
     return GENPC_OK;
 }
@@ -648,6 +664,7 @@ __global__ void __launch_bounds__(256) chamfer_loss_kernel(const float *__restri
 
 // Backward of the fused loss: graddist = upstream * w / n (* 0.5 / sqrt(d) for the L1 forms, inf at d == 0 exactly as
 // torch's sqrt backward, loss_util.py:37) folded into the gradient kernel: same six terms as NmDistanceGradKernel.
+template <bool VEC>
 __global__ void chamfer_loss_grad_kernel(const float *__restrict__ xyz1, const float *__restrict__ xyz2,
                                          const float *__restrict__ d1, const float *__restrict__ d2,
                                          const int *__restrict__ idx1, const int *__restrict__ idx2,
@@ -676,18 +693,12 @@ __global__ void chamfer_loss_grad_kernel(const float *__restrict__ xyz1, const f
         tx = __fmul_rn(g, __fsub_rn(x1, x2));
         ty = __fmul_rn(g, __fsub_rn(y1, y2));
         tz = __fmul_rn(g, __fsub_rn(z1, z2));
-        atomicAdd(ga + i * 3 + 0, tx);
-        atomicAdd(ga + i * 3 + 1, ty);
-        atomicAdd(ga + i * 3 + 2, tz);
+        red_add3<VEC>(ga, i, tx, ty, tz);
     }
     const unsigned long long key = valid ? ((unsigned long long)t * 2ull + (unsigned)dir) : (~0ull - (unsigned)lane);
     const unsigned peers = __match_any_sync(0xffffffffu, key);
     if (peers == (1u << lane)) {
-        if (valid) {
-            atomicAdd(go + t * 3 + 0, -tx);
-            atomicAdd(go + t * 3 + 1, -ty);
-            atomicAdd(go + t * 3 + 2, -tz);
-        }
+        if (valid) red_add3<VEC>(go, t, -tx, -ty, -tz);
         return;
     }
     const int leader = __ffs(peers) - 1;
@@ -697,11 +708,7 @@ __global__ void chamfer_loss_grad_kernel(const float *__restrict__ xyz1, const f
         const float ox = __shfl_sync(peers, -tx, src), oy = __shfl_sync(peers, -ty, src), oz = __shfl_sync(peers, -tz, src);
         sx += ox, sy += oy, sz += oz;
     }
-    if (lane == leader) {
-        atomicAdd(go + t * 3 + 0, sx);
-        atomicAdd(go + t * 3 + 1, sy);
-        atomicAdd(go + t * 3 + 2, sz);
-    }
+    if (lane == leader) red_add3<VEC>(go, t, sx, sy, sz);
 }
 }  // namespace genpc
 
@@ -727,8 +734,13 @@ extern "C" int genpc_chamfer_loss_backward(const float *xyz1, const float *xyz2,
     if (B < 0 || N < 0 || M < 0) return GENPC_ERR_SHAPE;
     if (N == 0 || M == 0 || B == 0) return GENPC_OK;
     const size_t tot = (size_t)B * N + ((w2 != 0.f) ? (size_t)B * M : 0);
-    chamfer_loss_grad_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(xyz1, xyz2, dist1, dist2, idx1, idx2, upstream,
-                                                                                 use_sqrt, w1, w2, gradxyz1, gradxyz2, B, N, M);
+    const bool vec = ((reinterpret_cast<size_t>(gradxyz1) | reinterpret_cast<size_t>(gradxyz2)) & 7) == 0;
+    if (vec)
+        chamfer_loss_grad_kernel<true><<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(
+            xyz1, xyz2, dist1, dist2, idx1, idx2, upstream, use_sqrt, w1, w2, gradxyz1, gradxyz2, B, N, M);
+    else
+        chamfer_loss_grad_kernel<false><<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(
+            xyz1, xyz2, dist1, dist2, idx1, idx2, upstream, use_sqrt, w1, w2, gradxyz1, gradxyz2, B, N, M);
     GENPC_CHECK_LAUNCH();
     return GENPC_OK;
 }
