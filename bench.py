@@ -33,7 +33,7 @@ B, N, M = 32, 2048, 16384
 FLOP_PER_PAIR = 8            # 3 sub, 3 mul, 2 add
 FP32_NOMINAL_TFLOPS = 74.4   # 148 SM x 128 lanes x 2 x 1.965 GHz (not in MEASURED_PEAKS.json)
 L2_FLUSH_BYTES = 256 << 20
-NCU_DRAM_BYTES_NN_SYM = 11819776  # ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of one nn_sym_kernel launch (profiles/r01j_nn_sym_ncu.txt)
+NCU_DRAM_BYTES_NN_SYM = 11819776  # ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of one nn_sym_kernel launch (profiles/r01k_nn_sym_ncu.txt)
 
 
 def env_int(k, d):
@@ -481,7 +481,7 @@ def main():
                             "ms": t_fwd, "pairs_per_s": 2.0 * B * N * M / (t_fwd * 1e-3),
                             "algorithmic_bytes_per_launch": 20.0 * B * (N + M),
                             "traffic": NCU_DRAM_BYTES_NN_SYM, "traffic_source": "ncu --set full, dram__bytes_read.sum + "
-                            "dram__bytes_write.sum per launch of nn_sym_kernel (profiles/r01j_nn_sym_ncu.txt)"}
+                            "dram__bytes_write.sum per launch of nn_sym_kernel (profiles/r01k_nn_sym_ncu.txt)"}
         if m and "ffma2" in m:
             line["roofline"]["measured_ffma2_tflops"] = m["ffma2"].get("tflops")
         bwd_bytes = 44.0 * B * (N + M)
