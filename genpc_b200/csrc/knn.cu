@@ -4,7 +4,8 @@
 // (reg_xyz.py:219, utils/dataUtils.py:652-666; third-party CPU KD-tree code, not vendored): per point the mean distance
 // to its nb_neighbors nearest neighbours, then a mean + std_ratio * std threshold over the cloud.  The per-point part is a
 // k-NN extension of the Chamfer scan:
-//   * one thread per query point, the cloud swept through shared memory in SoA tiles (broadcast LDS.128);
+//   * four adjacent lanes per query point (each scans a quarter of every tile; the four sorted lists are merged by a
+//     shuffle butterfly at the end), the cloud swept through shared memory in SoA tiles (LDS.128);
 //   * squared distance with the Chamfer rounding order fma(dz,dz,fma(dx,dx,dy*dy));
 //   * the k smallest squared distances are kept SORTED in registers; a candidate below the current k-th value is
 //     inserted by a branch-free min/max ripple (2 instructions per slot), others cost one compare;
@@ -16,16 +17,30 @@
 namespace genpc {
 
 constexpr int KNN_THREADS = 128;
+constexpr int KNN_SPLIT = 4;    // lanes per query point: each scans a quarter of every tile, lists merged by shuffles
 constexpr int KNN_TILE = 2048;  // targets staged per step (24 KB)
+
+// insert v into the ascending list best[0..K) (branch-free ripple, 2 instructions per slot)
+template <int K>
+__device__ __forceinline__ void knn_insert(float (&best)[K], float v) {
+#pragma unroll
+    for (int c = 0; c < K; ++c) {
+        const float lo = fminf(best[c], v);
+        v = fmaxf(best[c], v);
+        best[c] = lo;
+    }
+}
 
 template <int K>
 __global__ void __launch_bounds__(KNN_THREADS) knn_mean_kernel(const float *__restrict__ xyz, int n, int include_self,
                                                                float *__restrict__ mean_out) {
     __shared__ __align__(16) float s[3][KNN_TILE];
-    const int i = blockIdx.x * KNN_THREADS + threadIdx.x;
-    const bool valid = i < n;
-    float qx = 0.f, qy = 0.f, qz = 0.f;
-    if (valid) qx = __ldg(xyz + (size_t)i * 3), qy = __ldg(xyz + (size_t)i * 3 + 1), qz = __ldg(xyz + (size_t)i * 3 + 2);
+    // KNN_SPLIT adjacent lanes share one query (a thread per query leaves one warp per scheduler on a 20 000-point cloud:
+    // latency bound); out-of-range queries are clamped so that whole lane groups stay converged for the shuffles
+    const int q = (blockIdx.x * KNN_THREADS + threadIdx.x) / KNN_SPLIT, sub = threadIdx.x & (KNN_SPLIT - 1);
+    const bool valid = q < n;
+    const int i = valid ? q : n - 1;
+    const float qx = __ldg(xyz + (size_t)i * 3), qy = __ldg(xyz + (size_t)i * 3 + 1), qz = __ldg(xyz + (size_t)i * 3 + 2);
     const float inf = __int_as_float(0x7f800000);
     float best[K];
 #pragma unroll
@@ -43,8 +58,7 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_mean_kernel(const float *__re
             s[0][k] = x, s[1][k] = y, s[2][k] = z;
         }
         __syncthreads();
-        if (!valid) continue;
-        for (int g = 0; g < cnt4 / 4; ++g) {
+        for (int g = sub; g < cnt4 / 4; g += KNN_SPLIT) {
             const float4 X = sx4[g], Y = sy4[g], Z = sz4[g];
             float d[4];
             d[0] = sqdist_ref(qx, qy, qz, X.x, Y.x, Z.x);
@@ -57,21 +71,22 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_mean_kernel(const float *__re
             }
             if (fmin3(fminf(d[0], d[1]), d[2], d[3]) < best[K - 1]) {  // rare once the list has settled
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    float v = d[e];
-                    if (v < best[K - 1]) {
-#pragma unroll
-                        for (int c = 0; c < K; ++c) {  // ripple: best stays sorted ascending
-                            const float lo = fminf(best[c], v);
-                            v = fmaxf(best[c], v);
-                            best[c] = lo;
-                        }
-                    }
-                }
+                for (int e = 0; e < 4; ++e)
+                    if (d[e] < best[K - 1]) knn_insert<K>(best, d[e]);
             }
         }
     }
-    if (!valid) return;
+    // merge the KNN_SPLIT lists of a query: butterfly over the lane group, every lane ends with the same K smallest values
+#pragma unroll
+    for (int o = 1; o < KNN_SPLIT; o <<= 1) {
+        float other[K];
+#pragma unroll
+        for (int c = 0; c < K; ++c) other[c] = __shfl_xor_sync(0xffffffffu, best[c], o);
+#pragma unroll
+        for (int c = 0; c < K; ++c)
+            if (other[c] < best[K - 1]) knn_insert<K>(best, other[c]);
+    }
+    if (!valid || sub != 0) return;
     float sum = 0.f;
     int m = 0;
 #pragma unroll
@@ -81,7 +96,7 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_mean_kernel(const float *__re
             ++m;
         }
     }
-    mean_out[i] = m > 0 ? __fdiv_rn(sum, (float)m) : -1.0f;  // Open3D: mean = -1 when the query finds nothing
+    mean_out[q] = m > 0 ? __fdiv_rn(sum, (float)m) : -1.0f;  // Open3D: mean = -1 when the query finds nothing
 }
 
 }  // namespace genpc
@@ -93,7 +108,7 @@ extern "C" int genpc_knn_mean_distance(const float *xyz, int n, int k, int inclu
     cudaStream_t stream = (cudaStream_t)stream_;
     if (n < 0 || k < 1 || k > 32) return GENPC_ERR_SHAPE;
     if (n == 0) return GENPC_OK;
-    const unsigned grid = (unsigned)((n + KNN_THREADS - 1) / KNN_THREADS);
+    const unsigned grid = (unsigned)(((size_t)n * KNN_SPLIT + KNN_THREADS - 1) / KNN_THREADS);
 #define KNN_CASE(KK) \
     if (k <= KK) { knn_mean_kernel<KK><<<grid, KNN_THREADS, 0, stream>>>(xyz, n, include_self, mean_dist); GENPC_CHECK_LAUNCH(); return GENPC_OK; }
     // a list longer than k is NOT equivalent (the mean runs over the whole list), so every k has its own size
