@@ -120,3 +120,31 @@ def test_emd_shape_errors_and_completionloss(cuda):
     d1, d2, _, _ = cl.chamfer_dist(p1, p2)
     assert torch.allclose(cl.chamfer_partial_l1(p1, p2), torch.sqrt(d1).mean())
     assert torch.allclose(cl.chamfer_l1(p1, p2), (torch.sqrt(d1).mean() + torch.sqrt(d2).mean()) / 2)
+
+
+@pytest.mark.gpu
+def test_emd_unaligned_pointers(cuda):
+    """xyz2 / price that are only 4-byte aligned (the direct Bid path reads them with LDG.64 and must step aside)."""
+    rng = np.random.default_rng(77)
+    B, n = 1, 2048
+    x1, x2 = rng.random((B, n, 3), dtype=np.float32), rng.random((B, n, 3), dtype=np.float32)
+    import torch
+
+    from genpc_b200 import emd as E
+
+    def off(t):
+        flat = torch.empty(t.numel() + 5, dtype=t.dtype, device=t.device)
+        v = flat[1:1 + t.numel()].view(t.shape)
+        v.copy_(t)
+        assert v.data_ptr() % 8 != 0
+        return v
+
+    t1, t2 = off(torch.from_numpy(x1).to(cuda)), off(torch.from_numpy(x2).to(cuda))
+    dist = torch.zeros(B, n, device=cuda); asg = torch.full((B, n), -1, dtype=torch.int32, device=cuda)
+    asg_inv = torch.full((B, n), -1, dtype=torch.int32, device=cuda); price = off(torch.zeros(B, n, device=cuda))
+    bid = torch.zeros(B, n, dtype=torch.int32, device=cuda); binc = torch.zeros(B, n, device=cuda); minc = torch.zeros(B, n, device=cuda)
+    uidx = torch.zeros(B * n, dtype=torch.int32, device=cuda); midx = torch.zeros(B * n, dtype=torch.int32, device=cuda)
+    z = [torch.zeros(512, dtype=torch.int32, device=cuda) for _ in range(3)]
+    E.forward(t1, t2, dist, asg, price, asg_inv, bid, binc, minc, uidx, z[0], z[1], z[2], midx, 0.005, 50)
+    ed, ea = oracle.emd_forward(x1, x2, 0.005, 50)
+    assert np.array_equal(asg.cpu().numpy(), ea) and np.array_equal(dist.cpu().numpy().view(np.int32), ed.view(np.int32))
