@@ -482,6 +482,11 @@ def main():
                             "algorithmic_bytes_per_launch": 20.0 * B * (N + M),
                             "traffic": NCU_DRAM_BYTES_NN_SYM, "traffic_source": "ncu --set full, dram__bytes_read.sum + "
                             "dram__bytes_write.sum per launch of nn_sym_kernel (profiles/r01k_nn_sym_ncu.txt)"}
+        # transparency: the symmetric kernel EXECUTES each distance once (6 FMA-pipe lane-ops, counted as 8 flop), i.e. half of
+        # the algorithmic work; ncu's FMA-pipe utilisation of the same launch is recorded beside it
+        line["roofline"]["executed"] = {"tflops": ach / 2.0, "frac_of_peak": ach / 2.0 / FP32_NOMINAL_TFLOPS,
+                                        "fma_pipe_cycles_active_pct_ncu": 71.2,
+                                        "source": "profiles/r01k_nn_sym_ncu.txt (sm__pipe_fma_cycles_active)"}
         if m and "ffma2" in m:
             line["roofline"]["measured_ffma2_tflops"] = m["ffma2"].get("tflops")
         bwd_bytes = 44.0 * B * (N + M)
