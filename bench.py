@@ -484,9 +484,12 @@ def main():
                             "dram__bytes_write.sum per launch of nn_sym_kernel (profiles/r01k_nn_sym_ncu.txt)"}
         # transparency: the symmetric kernel EXECUTES each distance once (6 FMA-pipe lane-ops, counted as 8 flop), i.e. half of
         # the algorithmic work; ncu's FMA-pipe utilisation of the same launch is recorded beside it
-        line["roofline"]["executed"] = {"tflops": ach / 2.0, "frac_of_peak": ach / 2.0 / FP32_NOMINAL_TFLOPS,
+        lane_ops = 6.0 * B * N * M / (t_fwd * 1e-3)      # 3 sub + 1 mul + 2 fma per distance, each distance evaluated once
+        line["roofline"]["executed"] = {"fma_pipe_lane_ops_per_s": lane_ops,
+                                        "frac_of_fma_pipe_lane_rate": lane_ops / (148 * 128 * 1.965e9),
                                         "fma_pipe_cycles_active_pct_ncu": 71.2,
-                                        "source": "profiles/r01k_nn_sym_ncu.txt (sm__pipe_fma_cycles_active)"}
+                                        "note": "over the whole forward op (memset + scan + epilogue); the ncu figure is the scan "
+                                                "kernel alone, profiles/r01k_nn_sym_ncu.txt (sm__pipe_fma_cycles_active)"}
         if m and "ffma2" in m:
             line["roofline"]["measured_ffma2_tflops"] = m["ffma2"].get("tflops")
         bwd_bytes = 44.0 * B * (N + M)
