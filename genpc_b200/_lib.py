@@ -49,6 +49,7 @@ _SIGNATURES = {
     "genpc_nn_unpack": (_int, [_vp, _vp, _vp, _sz, _vp]),
     "genpc_chamfer_sym_partial": (_int, [_vp, _vp, _vp, _vp, _int, _int, _int, _int, _int, _vp]),
     "genpc_chamfer_sym_fixup": (_int, [_vp, _vp, _vp, _int, _int, _int, _vp, _vp, _vp]),
+    "genpc_icp_step": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _int, _int, _flt, _flt, _flt, _int, _vp]),
     "genpc_knn_mean_distance": (_int, [_vp, _int, _int, _int, _vp, _vp]),
     "genpc_fps_workspace_bytes": (_sz, [_int, _int, _int]),
     "genpc_fps": (_int, [_vp, _int, _int, _int, _int, _vp, _vp, _vp, _sz, _vp]),

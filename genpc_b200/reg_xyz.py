@@ -2,13 +2,16 @@
 
 The reference scores 11 isotropic + 1000 anisotropic scale candidates one at a time: deepcopy -> Open3D ICP on the
 CPU -> H2D -> two Chamfer extension calls (4 NN scans) -> `cd < best_loss` D2H sync (reg_xyz.py:60-96, 146-173).
-Here the candidates ARE the batch dimension: one batched point-to-point ICP (NN from the Chamfer kernel + a
-batched 3x3 Kabsch/SVD) and one Chamfer call score all of them, everything stays on the device.
+Here the candidates ARE the batch dimension: one batched point-to-point ICP (NN from the Chamfer kernel + one
+genpc_icp_step launch per iteration: inliers, covariance, Horn's closed-form rotation, convergence) and one Chamfer call
+score all of them, everything stays on the device.
 
 Open3D is not vendored: `registration_icp` (point-to-point, default criteria: 30 iterations, relative fitness /
 RMSE 1e-6), voxel down-sampling and `remove_statistical_outlier` are restated from their documented behaviour
 (parity unpinned).  Function names and argument meaning follow the reference.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -35,8 +38,46 @@ def chamfer_partial_l1_batched(src, tgt, cd_inv_weight=0.0):
 
 def icp_point_to_point(source, target, max_correspondence_distance=0.05, init_transform=None, max_iteration=30,
                        relative_fitness=1e-6, relative_rmse=1e-6):
-    """Batched Open3D-style registration_icp (TransformationEstimationPointToPoint, no scaling).
-    source [K,Ns,3], target [K,Nt,3] (or [1,Nt,3]) -> (T [K,4,4], fitness [K], inlier_rmse [K])."""
+    """Batched Open3D-style registration_icp (TransformationEstimationPointToPoint, no scaling), reg_xyz.py:9-38.
+    source [K,Ns,3], target [K,Nt,3] (or [1,Nt,3]) -> (T [K,4,4], fitness [K], inlier_rmse [K]).
+    Per iteration: transform (one bmm), nearest neighbours of all candidates (one Chamfer launch pair) and ONE
+    genpc_icp_step launch (inliers, fitness / rmse / convergence, covariance, Horn rotation, T update) -- no host
+    synchronisation except a convergence poll every 4 iterations.  GENPC_ICP_TORCH=1 selects the torch formulation
+    (batched float64 SVD, ~25 launches and a host sync per iteration) the kernel replaced; both agree to rounding."""
+    if os.environ.get("GENPC_ICP_TORCH") == "1":
+        return _icp_point_to_point_torch(source, target, max_correspondence_distance, init_transform, max_iteration,
+                                         relative_fitness, relative_rmse)
+    _lib.require_cuda(source, target)
+    K, Ns, _ = source.shape
+    dev = source.device
+    source = source.contiguous().float()
+    tgt = target.float()
+    if tgt.shape[0] == 1 and K > 1:
+        tgt = tgt.expand(K, -1, -1)
+    tgt = tgt.contiguous()
+    Nt = tgt.shape[1]
+    T = torch.eye(4, device=dev).repeat(K, 1, 1) if init_transform is None else \
+        torch.as_tensor(init_transform, dtype=torch.float32, device=dev).expand(K, 4, 4).clone()
+    T = T.contiguous()
+    state = torch.zeros(K, 4, device=dev)
+    thr2 = float(max_correspondence_distance) ** 2
+    L = _lib.lib()
+    with torch.no_grad(), torch.cuda.device(dev):
+        for it in range(max_iteration + 1):
+            cur = _apply(T, source).contiguous()
+            d1, _, i1, _ = _cd(cur, tgt)
+            rc = L.genpc_icp_step(_lib.ptr(cur), _lib.ptr(tgt), _lib.ptr(d1), _lib.ptr(i1), _lib.ptr(T), _lib.ptr(state), K, Ns,
+                                  K, Nt, thr2, float(relative_fitness), float(relative_rmse), int(it < max_iteration),
+                                  _lib.current_stream(dev))
+            _lib.check(rc, "genpc_icp_step")
+            if it % 4 == 3 and bool(state[:, 2].all()):   # every candidate converged: the remaining iterations are no-ops
+                break
+    return T, state[:, 0].clone(), state[:, 1].clone()
+
+
+def _icp_point_to_point_torch(source, target, max_correspondence_distance=0.05, init_transform=None, max_iteration=30,
+                              relative_fitness=1e-6, relative_rmse=1e-6):
+    """The torch formulation of icp_point_to_point (kept for A/B checks: tests/test_reg_xyz.py)."""
     K, Ns, _ = source.shape
     dev = source.device
     if target.shape[0] == 1 and K > 1:

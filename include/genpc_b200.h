@@ -144,6 +144,23 @@ int genpc_chamfer_sym_fixup(const float *rows_full, const float *cols, const uns
  * bit for bit (oracle_knn_mean_distance).  A cloud with fewer than k candidates averages what it has; none: -1. */
 int genpc_knn_mean_distance(const float *xyz, int n, int k, int include_self, float *mean_dist, genpc_stream_t stream);
 
+/* ---- point-to-point ICP step (scale / ICP candidate search) ----------------------------------------
+ * Replaces one iteration of Open3D registration_icp(TransformationEstimationPointToPoint) as the reference calls it for
+ * every scale candidate (reg_xyz.py:9-38 inside the sweeps :60-96 and :146-173; third-party CPU code), batched over K
+ * candidates; the nearest neighbours come from genpc_chamfer_forward (dist1 / idx1 of cur vs target).
+ *   cur [K][Ns][3]    the candidates' source clouds under their current transforms
+ *   target [Kt][Nt][3], Kt = K or 1 (one target shared by all candidates)
+ *   T [K][16]         row-major 4x4 transforms, updated in place: T <- [R|t] T, (R, t) = the least-squares rigid motion of
+ *                     the inlier pairs (dist < max_dist2) -- Horn's closed form, identical optimum to Kabsch/SVD
+ *   state [K][4]      fitness, inlier_rmse, converged (0/1), calls -- zeroed by the caller before the first call; a
+ *                     candidate converges when both |fitness - previous| < rel_fitness and |rmse - previous| < rel_rmse
+ *                     (Open3D ICPConvergenceCriteria) and is left unchanged from then on, like one with < 3 inliers
+ *   update = 0        statistics only (the evaluation after the last iteration)
+ * One CTA per candidate, deterministic double accumulation, no host synchronisation. */
+int genpc_icp_step(const float *cur, const float *target, const float *dist, const int *idx, float *T, float *state, int K,
+                   int Ns, int Kt, int Nt, float max_dist2, float rel_fitness, float rel_rmse, int update,
+                   genpc_stream_t stream);
+
 /* ---- Farthest point sampling -------------------------------------------------------------------
  * Replaces the reference's CPU call fpsample.fps_sampling(xyz, K) (main.py:21-22, reg_xyz.py:215,
  * DepthPrompting.py:88-90; un-vendored third-party package).  xyz [B][N][3] -> idx_out [B][K] int32,

@@ -82,3 +82,46 @@ def test_knn_mean_distance_gpu_bit_exact(cuda, n, k):
         if k == 20:
             keep = remove_statistical_outlier(t, 20, 2.5).cpu().numpy()
             assert np.array_equal(keep, oracle.statistical_outlier_mask(oracle.knn_mean_distance(x, 20, True), 2.5)), kind
+
+
+def test_icp_step_kernel_matches_the_torch_formulation(cuda):
+    """genpc_icp_step (Horn closed form, on-device convergence) against the torch formulation it replaced (batched
+    float64 Kabsch/SVD): transforms within 1e-4, fitness / rmse within 1e-5, over candidates that converge at different
+    iterations, one that never gets 3 inliers, and a shared ([1,Nt,3]) as well as a per-candidate target."""
+    import os
+
+    import torch
+
+    from genpc_b200.reg_xyz import icp_point_to_point
+    from genpc_b200.synthetic import superquadric
+
+    tgt = torch.from_numpy(superquadric(9, 2500)).to(cuda)
+    K = 7
+    g = torch.Generator().manual_seed(5)
+    src = []
+    for k in range(K):
+        ang = 0.02 * (k + 1)
+        R = torch.tensor([[math.cos(ang), -math.sin(ang), 0], [math.sin(ang), math.cos(ang), 0], [0, 0, 1.0]])
+        t = (torch.rand(3, generator=g) - 0.5) * 0.04
+        s = (tgt.cpu()[k::3][:700] - t) @ R * (1.0 + 0.03 * (k - 3))
+        src.append(s)
+    src[-1] = src[-1] + 5.0                                    # far away: no inliers, must stay at the identity
+    source = torch.stack(src).to(cuda)
+    res = {}
+    for mode in ("kernel", "torch"):
+        for shared in (True, False):
+            if mode == "torch":
+                os.environ["GENPC_ICP_TORCH"] = "1"
+            try:
+                tg = tgt[None] if shared else tgt[None].expand(K, -1, -1).contiguous()
+                res[mode, shared] = icp_point_to_point(source, tg, 0.075)
+            finally:
+                os.environ.pop("GENPC_ICP_TORCH", None)
+    for shared in (True, False):
+        Tk, fk, rk = res["kernel", shared]
+        Tt, ft, rt = res["torch", shared]
+        assert torch.allclose(Tk, Tt, atol=1e-4), (Tk - Tt).abs().max()
+        assert torch.allclose(fk, ft, atol=1e-5) and torch.allclose(rk, rt, atol=1e-5)
+        assert torch.equal(Tk[-1], torch.eye(4, device=cuda)) and float(fk[-1]) == 0.0
+        assert float(fk[:-1].min()) > 0.9
+    assert torch.equal(res["kernel", True][0], res["kernel", False][0])     # deterministic, same arithmetic
