@@ -13,5 +13,6 @@ timeout 300 ncu --set full --clock-control none -k regex:"register_sym_scan|regi
 timeout 300 ncu --set full --clock-control none -k regex:emd_auction -s 1 -c 1 -f -o gpurun_out/prof_emd python tools/prof_targets.py emd > gpurun_out/ncu_emd.log 2>&1
 timeout 300 ncu --set full --clock-control none -k regex:fps_ -s 1 -c 2 -f -o gpurun_out/prof_fps python tools/prof_targets.py fps > gpurun_out/ncu_fps.log 2>&1
 timeout 300 ncu --set full --clock-control none -k regex:knn_mean -s 1 -c 1 -f -o gpurun_out/prof_knn python tools/prof_targets.py knn > gpurun_out/ncu_knn.log 2>&1
+timeout 300 ncu --set full --clock-control none -k regex:icp_step -s 1 -c 1 -f -o gpurun_out/prof_icp python tools/prof_targets.py icp > gpurun_out/ncu_icp.log 2>&1
 timeout 300 ncu --set full --clock-control none -k regex:"project_kernel|uv_kernel|zsplat|zresolve|unproject" -s 5 -c 5 -f -o gpurun_out/prof_depth python tools/prof_targets.py depth > gpurun_out/ncu_depth.log 2>&1
 head -c 2500 gpurun_out/bench.json; echo; for f in ncu_emd ncu_fps ncu_reg ncu_knn; do tail -n 2 gpurun_out/$f.log; done; exit 0

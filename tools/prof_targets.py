@@ -1,4 +1,4 @@
-"""One small workload per kernel family, for ncu:  python tools/prof_targets.py {register|emd|fps|depth|knn}"""
+"""One small workload per kernel family, for ncu:  python tools/prof_targets.py {register|emd|fps|depth|knn|icp}"""
 import os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -35,5 +35,11 @@ elif what == "knn":
     from genpc_b200.synthetic import superquadric
     pts = torch.from_numpy(superquadric(0, 20000)).to(dev)
     knn_mean_distance(pts, 20, True); knn_mean_distance(pts, 20, True)
+elif what == "icp":
+    from genpc_b200.reg_xyz import icp_point_to_point
+    from genpc_b200.synthetic import superquadric
+    tgt = torch.from_numpy(superquadric(0, 1800)).to(dev)
+    src = (tgt[None] * torch.linspace(0.8, 1.2, 250, device=dev)[:, None, None]).contiguous()
+    icp_point_to_point(src, tgt[None], 0.075, max_iteration=4)
 torch.cuda.synchronize()
 print("done", what)

@@ -37,4 +37,6 @@ ha, hb = torch.rand(4, 600, 3, generator=g).pin_memory(), torch.rand(4, 1500, 3,
 loss, da, db = cl.get_loss_from_host(ha, hb, device=dev, chunks=2); loss.backward()
 knn_mean_distance(torch.rand(3001, 3, generator=g).to(dev), 20, True); knn_mean_distance(torch.rand(17, 3, generator=g).to(dev), 32, False)
 sharded_chamfer_forward(torch.rand(1, 5001, 3, generator=g).to(dev), torch.rand(1, 3003, 3, generator=g).to(dev))
+from genpc_b200.reg_xyz import icp_point_to_point
+icp_point_to_point(torch.rand(5, 333, 3, generator=g).to(dev), torch.rand(1, 777, 3, generator=g).to(dev), 0.3, max_iteration=3)
 torch.cuda.synchronize(); print("sanitize smoke done")
