@@ -106,6 +106,83 @@ __global__ void __launch_bounds__(FPS_THREADS, 1) fps_reg_kernel(const float *__
     }
 }
 
+// Shared-memory form of the single-CTA kernel for 4096 < N <= 16384: the cloud is staged ONCE as SoA x[] / y[] / z[] in
+// the CTA's dynamic shared memory (12 B per point, 196 KB at N = 16384) and a thread owns PPT/4 groups of FOUR consecutive
+// points (indices k*4096 + 4*tid + j), so a pick reads its coordinates with three conflict-free LDS.128 per four points
+// instead of twelve LDG through L1 with their address arithmetic (fps_reg_kernel<.., false>): about a third fewer
+// instructions per pick in the kernel that serves batched FPS (one CTA per cloud).  Same arithmetic, same tie rule
+// (ascending (k, j) == ascending index inside a thread; the block arg-max takes the lowest index among equal values).
+template <int PPT>
+__global__ void __launch_bounds__(FPS_THREADS, 1) fps_smem_kernel(const float *__restrict__ xyz, int N, int K, int start,
+                                                                    int *__restrict__ idx_out, float *__restrict__ seq_out) {
+    static_assert(PPT % 4 == 0, "a thread owns groups of four consecutive points");
+    extern __shared__ __align__(16) float dyn_xyz[];
+    constexpr int NP = PPT * FPS_THREADS;  // padded cloud size
+    float *sx = dyn_xyz, *sy = dyn_xyz + NP, *sz = dyn_xyz + 2 * NP;
+    __shared__ unsigned sval[2][FPS_WARPS];
+    __shared__ int sidx[2][FPS_WARPS];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float *p = xyz + (size_t)b * N * 3;
+    for (int i = tid; i < NP; i += FPS_THREADS) {
+        float x = 0.f, y = 0.f, z = 0.f;
+        if (i < N) x = __ldg(p + (size_t)i * 3), y = __ldg(p + (size_t)i * 3 + 1), z = __ldg(p + (size_t)i * 3 + 2);
+        sx[i] = x, sy[i] = y, sz[i] = z;
+    }
+    float run[PPT];
+#pragma unroll
+    for (int k = 0; k < PPT / 4; ++k)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) run[k * 4 + j] = (k * 4 * FPS_THREADS + 4 * tid + j < N) ? __int_as_float(0x7f800000) : -1.f;
+    __syncthreads();
+    const float4 *sx4 = reinterpret_cast<const float4 *>(sx), *sy4 = reinterpret_cast<const float4 *>(sy);
+    const float4 *sz4 = reinterpret_cast<const float4 *>(sz);
+    int cur = start;
+    for (int s = 0; s < K; ++s) {
+        if (tid == 0) idx_out[(size_t)b * K + s] = cur;
+        const float lx = sx[cur], ly = sy[cur], lz = sz[cur];
+        float best = -2.f;
+        int best_i = 0x7fffffff;
+#pragma unroll
+        for (int k = 0; k < PPT / 4; ++k) {
+            const float4 X = sx4[k * FPS_THREADS + tid], Y = sy4[k * FPS_THREADS + tid], Z = sz4[k * FPS_THREADS + tid];
+            const float xs[4] = {X.x, X.y, X.z, X.w}, ys[4] = {Y.x, Y.y, Y.z, Y.w}, zs[4] = {Z.x, Z.y, Z.z, Z.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float dx = __fsub_rn(xs[j], lx), dy = __fsub_rn(ys[j], ly), dz = __fsub_rn(zs[j], lz);
+                const float d = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+                const float r = (run[k * 4 + j] < d) ? run[k * 4 + j] : d;  // as oracle_fps; padding (-1) stays -1
+                run[k * 4 + j] = r;
+                if (r > best) {  // strict: (k, j) ascending == index ascending -> lowest index kept
+                    best = r;
+                    best_i = k * 4 * FPS_THREADS + 4 * tid + j;
+                }
+            }
+        }
+        int winner;
+        fps_block_argmax(best, best_i, sval, sidx, s & 1, lane, warp, winner);
+        if (seq_out != nullptr && tid == 0) {
+            if (s == 0) seq_out[(size_t)b * K] = __int_as_float(0x7f800000);
+            if (s + 1 < K) {
+                unsigned m = 0;
+#pragma unroll
+                for (int w = 0; w < FPS_WARPS; ++w) m = max(m, sval[s & 1][w]);
+                seq_out[(size_t)b * K + s + 1] = __uint_as_float(m - 1u);
+            }
+        }
+        cur = winner;
+    }
+}
+
+template <int PPT>
+static cudaError_t launch_fps_smem(const float *xyz, int B, int N, int K, int start, int *idx_out, float *seq_out,
+                                   cudaStream_t stream) {
+    const size_t bytes = (size_t)3 * PPT * FPS_THREADS * sizeof(float);
+    cudaError_t e = cudaFuncSetAttribute(fps_smem_kernel<PPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return e;
+    fps_smem_kernel<PPT><<<B, FPS_THREADS, bytes, stream>>>(xyz, N, K, start, idx_out, seq_out);
+    return cudaGetLastError();
+}
+
 // Generic fallback: points and running distances stay in global memory (L2-resident for any realistic N).
 __global__ void __launch_bounds__(FPS_THREADS, 1) fps_gmem_kernel(const float *__restrict__ xyz, int N, int K,
                                                                     int start, int *__restrict__ idx_out,
@@ -403,6 +480,16 @@ extern "C" int genpc_fps(const float *xyz, int B, int N, int K, int start, int *
         return GENPC_OK;
     }
 #define FPS_LAUNCH(P) fps_reg_kernel<P, (P <= 4)><<<B, FPS_THREADS, 0, stream>>>(xyz, N, K, start, idx_out, seq_out)
+    // 4096 < N <= 16384: coordinates in shared memory (LDS.128) instead of re-reads through L1; GENPC_FPS_SMEM=0 keeps
+    // the L1 form (measured: profiles/r01k_fps_smem.txt)
+    const char *fs = getenv("GENPC_FPS_SMEM");
+    const bool use_smem = (fs == nullptr) ? true : (atoi(fs) != 0);
+    if (use_smem && ppt > 4 && ppt <= 16) {
+        const cudaError_t e = (ppt <= 8) ? launch_fps_smem<8>(xyz, B, N, K, start, idx_out, seq_out, stream)
+                                         : launch_fps_smem<16>(xyz, B, N, K, start, idx_out, seq_out, stream);
+        if (e != cudaSuccess) return (int)e;
+        return GENPC_OK;
+    }
     if (ppt <= 1) FPS_LAUNCH(1);
     else if (ppt <= 2) FPS_LAUNCH(2);
     else if (ppt <= 4) FPS_LAUNCH(4);

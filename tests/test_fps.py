@@ -89,3 +89,28 @@ def test_fps_cluster_kernel_bit_exact(cuda, B, N, K, start):
             os.environ.pop("GENPC_FPS_CLUSTER16", None)
         assert np.array_equal(idx.cpu().numpy(), eidx), c16
         assert np.array_equal(seq.cpu().numpy().view(np.int32), eseq.view(np.int32)), c16
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,N,K,start", [(2, 16384, 300, 5), (20, 12000, 50, 3), (1, 8193, 100, 0), (3, 4097, 200, 4096),
+                                         (2, 8192, 64, 1), (1, 6001, 6001, 17)])
+def test_fps_single_cta_shared_memory_and_l1_forms(cuda, B, N, K, start):
+    """One CTA per cloud (batched FPS, forced with GENPC_FPS_MODE=cta) for 4096 < N <= 16384: the shared-memory form
+    (LDS.128, the default) and the L1 form (GENPC_FPS_SMEM=0) against the oracle, indices and running distances."""
+    import os
+
+    import torch
+
+    from genpc_b200.fps import furthest_point_sample
+
+    a = lattice_cloud(N, B, N, side=12) if N % 2 else shape_cloud(N, B, N)
+    eidx, eseq = oracle.fps(a, K, start, True)
+    for smem in ("1", "0"):
+        os.environ["GENPC_FPS_MODE"], os.environ["GENPC_FPS_SMEM"] = "cta", smem
+        try:
+            idx, seq = furthest_point_sample(torch.from_numpy(a).to(cuda), K, start, return_seq=True)
+            torch.cuda.synchronize()
+        finally:
+            del os.environ["GENPC_FPS_MODE"], os.environ["GENPC_FPS_SMEM"]
+        assert np.array_equal(idx.cpu().numpy(), eidx), smem
+        assert np.array_equal(seq.cpu().numpy().view(np.int32), eseq.view(np.int32)), smem
