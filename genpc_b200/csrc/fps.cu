@@ -408,9 +408,48 @@ __global__ void __launch_bounds__(FPS_THREADS, 1) fps_cluster_kernel(const float
     cluster.sync();  // no CTA may exit while a sibling can still write into its shared memory
 }
 
+// A cluster needs CS SMs of ONE GPC: the number of clusters that can be resident together is what the occupancy query
+// says, not SMs / CS (B200: 16 clusters of 8 CTAs, although 148 / 8 = 18).  More clouds than that run in waves -- the
+// single-CTA kernel is the better choice then.  Returns 0 when the query fails.
+template <int PPT, int CS, bool SMEMC>
+static int fps_max_active_clusters() {
+    static int cached = -1;  // per template instance; the answer depends only on the device
+    if (cached >= 0) return cached;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(CS * 64));
+    cfg.blockDim = dim3(FPS_THREADS);
+    cfg.dynamicSmemBytes = SMEMC ? (size_t)3 * PPT * FPS_THREADS * sizeof(float) : 0;
+    if (SMEMC && cudaFuncSetAttribute(fps_cluster_kernel<PPT, CS, SMEMC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)cfg.dynamicSmemBytes) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return 0;
+    }
+    if (CS > 8 && cudaFuncSetAttribute(fps_cluster_kernel<PPT, CS, SMEMC>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) !=
+                      cudaSuccess) {
+        (void)cudaGetLastError();
+        return 0;
+    }
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CS, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr, cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, fps_cluster_kernel<PPT, CS, SMEMC>, &cfg) != cudaSuccess) {
+        (void)cudaGetLastError();
+        n = 0;
+    }
+    cached = n;
+    return n;
+}
+
 template <int PPT, int CS, bool SMEMC>
 static cudaError_t launch_fps_cluster(const float *xyz, int B, int N, int K, int start, int *idx_out, float *seq_out,
                                       cudaStream_t stream) {
+    // clouds of up to 16384 points have a fast single-CTA kernel (2.9 ms for 16384 -> 2048 whatever B): when the clusters
+    // would run in waves (4.7 ms at B = 18) the caller falls through to it; larger clouds stay here (waves of clusters
+    // still beat the L1 / global-memory single-CTA forms)
+    if (PPT * CS <= 16 && getenv("GENPC_FPS_MODE") == nullptr && B > fps_max_active_clusters<PPT, CS, SMEMC>())
+        return cudaErrorLaunchOutOfResources;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(B * CS));
     cfg.blockDim = dim3(FPS_THREADS);
@@ -476,8 +515,9 @@ extern "C" int genpc_fps(const float *xyz, int B, int N, int K, int start, int *
         else if (ppt <= 64) e = launch_fps_cluster<8, 8, true>(xyz, B, N, K, start, idx_out, seq_out, stream);
         else if (ppt <= 96) e = launch_fps_cluster<12, 8, true>(xyz, B, N, K, start, idx_out, seq_out, stream);
         else e = launch_fps_cluster<18, 8, true>(xyz, B, N, K, start, idx_out, seq_out, stream);
-        if (e != cudaSuccess) return (int)e;
-        return GENPC_OK;
+        if (e == cudaSuccess) return GENPC_OK;
+        if (e != cudaErrorLaunchOutOfResources || fm != nullptr) return (int)e;
+        (void)cudaGetLastError();  // more clouds than co-resident clusters: one CTA per cloud below
     }
 #define FPS_LAUNCH(P) fps_reg_kernel<P, (P <= 4)><<<B, FPS_THREADS, 0, stream>>>(xyz, N, K, start, idx_out, seq_out)
     // 4096 < N <= 16384: coordinates in shared memory (LDS.128) instead of re-reads through L1; GENPC_FPS_SMEM=0 keeps
