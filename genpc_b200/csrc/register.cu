@@ -366,7 +366,20 @@ extern "C" int genpc_register_run(const float *complete, const float *center, co
     a.counters = (int *)(a.partials + (size_t)S * ((Nc + 128 - 1) / 128) * 14);
     a.loss_hist = loss_hist;
     a.S = S, a.n_starts = n_starts, a.Nc = Nc, a.Nr = Nr, a.T = T;
-    const int QT = nn_pick_qt(Nc < Nr ? Nc : Nr);
+    // queries per thread of the single-launch path: the real pipeline registers 1-3 K-point clouds with 4 starts -- a few
+    // dozen CTAs; fewer queries per thread (more, shorter CTAs) while the grid does not fill the GPU twice over
+    int QT = nn_pick_qt(Nc < Nr ? Nc : Nr);
+    const char *fq = getenv("GENPC_REGISTER_QT");  // experiments only
+    if (fq != nullptr && (atoi(fq) == 1 || atoi(fq) == 2 || atoi(fq) == 4)) {
+        QT = atoi(fq);
+    } else {
+        while (QT > 1) {
+            const long long items = (long long)((Nc + NN_THREADS * QT - 1) / (NN_THREADS * QT)) * ((Nr + NN_SPAN - 1) / NN_SPAN) +
+                                    (long long)((Nr + NN_THREADS * QT - 1) / (NN_THREADS * QT)) * ((Nc + NN_SPAN - 1) / NN_SPAN);
+            if ((long long)S * items >= 2LL * GENPC_NUM_SMS) break;
+            QT >>= 1;
+        }
+    }
     a.qtilesA = (Nc + NN_THREADS * QT - 1) / (NN_THREADS * QT);
     a.tsplitsA = (Nr + NN_SPAN - 1) / NN_SPAN;
     a.itemsA = a.qtilesA * a.tsplitsA;
