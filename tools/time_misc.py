@@ -67,8 +67,10 @@ from genpc_b200.DepthPrompting import DepthPrompting  # noqa: E402
 dp = DepthPrompting(dict(view_num=1024, res=256, cam_res=256, downsample_num=10000))
 rgb = torch.rand(71372, 3, device=dev)
 dp.getDepth(pts, rgb); torch.cuda.synchronize()
-t0 = time.perf_counter(); dp.getDepth(pts, rgb); torch.cuda.synchronize()
-out["depthprompting_getDepth_1024views_res256_71372pts_ms"] = (time.perf_counter() - t0) * 1e3
+ts = []
+for _ in range(3):   # wall clock (the call synchronises on the selected view): best of three
+    t0 = time.perf_counter(); dp.getDepth(pts, rgb); torch.cuda.synchronize(); ts.append((time.perf_counter() - t0) * 1e3)
+out["depthprompting_getDepth_1024views_res256_71372pts_ms"] = min(ts)
 
 # ---- C3: registration, 64 scans x 16384 pts, 1 start each (scan-iters/s) ----
 S = int(os.environ.get("REG_SCANS", 64))
