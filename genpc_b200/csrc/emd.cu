@@ -13,9 +13,11 @@
 //   value = (float)((3.0 - (double)sqrtf(fma(dz,dz,fma(dx,dx,dy*dy)))) - (double)price)   (emd_cuda.cu:146)
 //   best / second-best with multiplicity; among equal best values the winner is the target with the smallest
 //   (reference_thread(k), k) -- the order in which the reference's thread slices visit targets (:136-139,:167);
-//   GetMax window +-1e-6 in double (:188); the reference's last-writer race is resolved as "highest j".
+//   GetMax window +-1e-6 in double (:188); the reference's last-writer race is resolved as "highest j" (default) or
+//   "lowest j" (GENPC_EMD_GETMAX=lowest): the reference itself lands on either, depending on block timing.
 #include <cooperative_groups.h>
 #include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
 
@@ -38,6 +40,7 @@ struct EmdArgs {
     float eps;
     int iters, group;      // group = CTAs per batch entry (1 when B >= grid)
     int two_level_div;     // two-level pre-filter while U * two_level_div >= n (0: never)
+    int getmax_lowest;     // GetMax race resolved as lowest (1) or highest (0, default) bidder index
     int direct_p;          // items with at most this many bidders read the targets from global memory (no staging)
 };
 
@@ -222,7 +225,7 @@ __device__ __noinline__ int compact_unassigned(const int *__restrict__ asg, int 
     return tot;
 }
 
-// GetMax (emd_cuda.cu:181-194: highest j inside the +-1e-6 window wins) and Assign (:196-215) for the U bidders of one
+// GetMax (emd_cuda.cu:181-194: highest -- or, on request, lowest -- j inside the +-1e-6 window wins) and Assign (:196-215) for the U bidders of one
 // cloud, run by ONE CTA (the iteration's serial tail).  Every bidder is a chain of dependent L2 reads
 // (uidx -> bid / increment -> max_increment / max_idx -> assignment_inv, price); a thread takes EMD_TAIL_R bidders at a
 // time and issues each level of the chain for all of them before it consumes any, so the tail costs about one L2
@@ -232,7 +235,7 @@ constexpr int EMD_TAIL_R = 2;
 
 __device__ __noinline__ void emd_getmax_assign(const int *__restrict__ uidx, const int *__restrict__ bd,
                                                const float *__restrict__ binc, float *minc, int *midx, int *asg, int *asg_inv,
-                                               float *pr, int U, bool last) {
+                                               float *pr, int U, bool last, bool lowest) {
     const int tid = threadIdx.x;
     for (int u0 = 0; u0 < U; u0 += EMD_THREADS * EMD_TAIL_R) {
         int j[EMD_TAIL_R], bid[EMD_TAIL_R];
@@ -251,7 +254,10 @@ __device__ __noinline__ void emd_getmax_assign(const int *__restrict__ uidx, con
 #pragma unroll
         for (int r = 0; r < EMD_TAIL_R; ++r)
             if (j[r] >= 0 && (double)inc[r] - 1e-6 <= (double)mx[r] && (double)mx[r] <= (double)inc[r] + 1e-6)
-                atomicMax(midx + bid[r], j[r]);
+            {
+                if (lowest) atomicMin(reinterpret_cast<unsigned *>(midx + bid[r]), (unsigned)j[r]);  // -1 (re-armed) is UINT_MAX
+                else atomicMax(midx + bid[r], j[r]);
+            }
     }
     __syncthreads();
     for (int u0 = 0; u0 < U; u0 += EMD_THREADS * EMD_TAIL_R) {
@@ -489,7 +495,7 @@ __global__ void __launch_bounds__(EMD_THREADS, 5) emd_auction_kernel(const EmdAr
             __syncthreads();
             if (s_last) {
                 __threadfence();
-                emd_getmax_assign(uidx, bd, binc, minc, midx, asg, asg_inv, pr, U, last);
+                emd_getmax_assign(uidx, bd, binc, minc, midx, asg, asg_inv, pr, U, last, a.getmax_lowest != 0);
                 const int U2 = compact_unassigned(asg, uidx, midx, n, sscan);
                 __threadfence();
                 __syncthreads();
@@ -576,6 +582,8 @@ extern "C" int genpc_emd_forward(const float *xyz1, const float *xyz2, float *di
     // measured on B200 (profiles/r01j_emd_direct.txt)
     a.direct_p = 8;
     a.two_level_div = 8;
+    const char *gm = getenv("GENPC_EMD_GETMAX");  // "lowest": the other legitimate outcome of the reference's race
+    a.getmax_lowest = (gm != nullptr && strcmp(gm, "lowest") == 0) ? 1 : 0;
     const char *tl = getenv("GENPC_EMD_TWO_LEVEL");  // experiments only
     if (tl != nullptr) a.two_level_div = atoi(tl);
     const char *dp = getenv("GENPC_EMD_DIRECT_P");  // experiments only

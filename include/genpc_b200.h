@@ -207,7 +207,8 @@ int genpc_unproject(const float *cams, const float *bounds, int rescale, const u
  * max_increments = 0; unass_cnt has >= B ints (the reference allocates 512).  The reference's
  * unass_cnt_sum / cnt_tmp scratch is not needed.  Returns GENPC_ERR_SHAPE for n != m, B > 512, n % 256 != 0
  * (emd_cuda.cu:236-249).  Outputs dist[B][n], assignment[B][n] bit-identical to the reference wherever the
- * reference itself is deterministic (its GetMax race is resolved as "highest bidder index").
+ * reference itself is deterministic (its GetMax store race is resolved as "highest bidder index"; the environment
+ * variable GENPC_EMD_GETMAX=lowest selects the other outcome the reference is seen to produce).
  * workspace: genpc_emd_workspace_bytes(B). */
 size_t genpc_emd_workspace_bytes(int B);
 int genpc_emd_forward(const float *xyz1, const float *xyz2, float *dist, int *assignment, float *price,

@@ -93,8 +93,10 @@ def chamfer_backward(xyz1, xyz2, g1, g2, i1, i2):
     return gx1, gx2
 
 
-def emd_forward(xyz1, xyz2, eps, iters, return_state=False):
-    """(dist[B,n], assignment[B,n]) -- emd_cuda.cu:228-282 with emd_module.py:43-54 initial state."""
+def emd_forward(xyz1, xyz2, eps, iters, return_state=False, getmax_lowest=False):
+    """(dist[B,n], assignment[B,n]) -- emd_cuda.cu:228-282 with emd_module.py:43-54 initial state.
+    getmax_lowest: resolve the reference's GetMax store race (:188-191) as "lowest bidder index wins" instead of the
+    default "highest" (both are legitimate outcomes of the race; see the comment in genpc_oracle.c)."""
     xyz1, xyz2 = _c(xyz1, np.float32), _c(xyz2, np.float32)
     B, n, _ = xyz1.shape
     m = xyz2.shape[1]
@@ -107,8 +109,12 @@ def emd_forward(xyz1, xyz2, eps, iters, return_state=False):
     minc = np.zeros((B, m), np.float32)
     uidx = np.zeros(B * n, np.int32)
     midx = np.zeros(B * m, np.int32)
-    rc = lib().oracle_emd_forward(B, n, m, xyz1, xyz2, dist, asg, price, asg_inv, bid, binc, minc, uidx,
-                                  midx, float(eps), int(iters))
+    lib().oracle_emd_set_getmax_rule(1 if getmax_lowest else 0)
+    try:
+        rc = lib().oracle_emd_forward(B, n, m, xyz1, xyz2, dist, asg, price, asg_inv, bid, binc, minc, uidx,
+                                      midx, float(eps), int(iters))
+    finally:
+        lib().oracle_emd_set_getmax_rule(0)
     if rc != 1:
         raise ValueError(f"oracle_emd_forward rejected the shapes (rc={rc})")
     if return_state:

@@ -138,13 +138,16 @@ void oracle_chamfer_backward(int B, int N, int M, const float *xyz1, const float
  *   calc_unass_idx (:85-93) compacts with atomicAdd -> order nondeterministic; the order only
  *     decides which block/group handles a point, never the result, so ascending order is used.
  *   GetMax (:181-194): every bidder within +-1e-6 (double) of the max writes max_idx, last writer
- *     wins -> racy in the reference.  ORACLE RULE: highest j wins.
+ *     wins -> racy in the reference.  ORACLE RULE: highest j wins (lowest j selectable, see the loop).
  *   Assign (:196-215) incl. the `last` iteration (no eviction, duplicates allowed).
  *   CalcDist (:217-226): dist = fma order of `deltax*deltax+deltay*deltay+deltaz*deltaz`,
  *     delta = xyz1 - xyz2.
  * Scratch arrays mirror the reference's caller-allocated tensors so state can be inspected.
  * Returns 1 on success, -1 on the shape violations of :236-249.
  * ---------------------------------------------------------------------------------------------- */
+static int g_emd_getmax_lowest = 0;
+void oracle_emd_set_getmax_rule(int lowest) { g_emd_getmax_lowest = lowest != 0; }
+
 HOT int oracle_emd_forward(int B, int n, int m, const float *xyz1, const float *xyz2, float *dist,
                            int *assignment, float *price, int *assignment_inv, int *bid,
                            float *bid_increments, float *max_increments, int *unass_idx, int *max_idx,
@@ -228,8 +231,14 @@ HOT int oracle_emd_forward(int B, int n, int m, const float *xyz1, const float *
                     if (inc > minc[best_i]) minc[best_i] = inc;
                 }
             }
-            /* GetMax: highest j inside the +-1e-6 window wins (oracle rule for the reference's race) */
-            for (int j = 0; j < n; j++) {
+            /* GetMax: every bidder inside the +-1e-6 window stores its index, the last store wins (:188-191): a race with
+             * no defined winner.  The oracle resolves it deterministically: HIGHEST j wins by default (the later thread /
+             * block writes last -- what the reference did in every live comparison at n = 8192 / 16384 on B200), LOWEST j
+             * when oracle_emd_set_getmax_rule(1) was called.  tests/golden/emd_ref_centered.npz is a witness of the race:
+             * the reference's (run-to-run identical) output there equals the "lowest j" resolution and differs from the
+             * "highest j" one in 44 of 1024 assignments; the other goldens have no decisive collision. */
+            for (int jj = 0; jj < n; jj++) {
+                const int j = g_emd_getmax_lowest ? n - 1 - jj : jj;
                 if (asg[j] == -1) {
                     int bid_id = bd[j];
                     float bid_inc = binc[j];

@@ -26,7 +26,11 @@ def main():
     ch = oracle.load_ref_ext("chamfer_3D")
     cases = {"rand": (rand_cloud(11, 2, 700), rand_cloud(12, 2, 1900)),
              "shape": (shape_cloud(13, 1, 2048), shape_cloud(14, 1, 4096)),
-             "lattice": (lattice_cloud(15, 2, 500), lattice_cloud(16, 2, 1500))}
+             "lattice": (lattice_cloud(15, 2, 500), lattice_cloud(16, 2, 1500)),
+             # edge shapes: ragged sizes below / across the reference's 512-target chunks, negative and large coordinates
+             "ragged": (rand_cloud(17, 3, 37), rand_cloud(18, 3, 513)),
+             "negative": (shape_cloud(19, 1, 1025), shape_cloud(20, 1, 255)),
+             "chunked": (rand_cloud(21, 1, 600, 10.0, -5.0), rand_cloud(22, 1, 1300, 10.0, -5.0))}
     for name, (a, b) in cases.items():
         B, N, M = a.shape[0], a.shape[1], b.shape[1]
         ta, tb = torch.from_numpy(a).to(dev), torch.from_numpy(b).to(dev)
@@ -39,8 +43,11 @@ def main():
     em = oracle.load_ref_ext("emd")
     rng = np.random.default_rng(21)
     for name, (B, n, eps, iters) in {"small": (2, 512, 0.005, 50), "n2048": (1, 2048, 0.005, 50),
-                                     "n4096": (1, 4096, 0.002, 100)}.items():
+                                     "n4096": (1, 4096, 0.002, 100), "centered": (1, 1024, 0.005, 50),
+                                     "b3_n256": (3, 256, 0.01, 30)}.items():
         x1 = rng.random((B, n, 3), dtype=np.float32); x2 = rng.random((B, n, 3), dtype=np.float32)
+        if name == "centered":   # the metric path feeds [-0.5, 0.5] data un-normalised (main.py:26-33)
+            x1, x2 = x1 - np.float32(0.5), x2 - np.float32(0.5)
         runs = []
         for rep in range(3):  # the reference is racy (GetMax): record its own run-to-run spread
             t1, t2 = torch.from_numpy(x1).to(dev), torch.from_numpy(x2).to(dev)
