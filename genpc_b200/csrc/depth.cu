@@ -263,6 +263,7 @@ extern "C" int genpc_project_uv(const float *cams, const float *xyz, int V, int 
                                 genpc_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (V < 0 || N < 0) return GENPC_ERR_SHAPE;
+    if ((reinterpret_cast<size_t>(uv) & 7) != 0) return GENPC_ERR_SHAPE;  // uv is accessed as float2 (8-byte aligned pairs)
     if (V == 0 || N == 0) return GENPC_OK;
     if (workspace == nullptr || workspace_bytes < genpc_depth_workspace_bytes(V)) return GENPC_ERR_WORKSPACE;
     unsigned *keys = (unsigned *)workspace;  // [V][4]: min x, min y, max x, max y
@@ -285,6 +286,7 @@ extern "C" int genpc_zbuffer_render(const float *uv, const float *ndc, const uns
                                     float *zminmax, void *workspace, size_t workspace_bytes, genpc_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (V < 0 || N < 0 || res <= 0 || point_size < 1) return GENPC_ERR_SHAPE;
+    if ((reinterpret_cast<size_t>(uv) & 7) != 0) return GENPC_ERR_SHAPE;  // uv is accessed as float2 (8-byte aligned pairs)
     if (V == 0) return GENPC_OK;
     if (workspace == nullptr || workspace_bytes < genpc_depth_workspace_bytes(V)) return GENPC_ERR_WORKSPACE;
     unsigned *zkeys = (unsigned *)workspace + (size_t)V * 4;  // [V][2]: min z key, max z key

@@ -99,7 +99,9 @@ __device__ __noinline__ int compact_unassigned(const int *__restrict__ asg, int 
     const int j0 = warp * per_warp;
     const unsigned lt = (1u << lane) - 1u;
     const int4 minus1 = make_int4(-1, -1, -1, -1);
-    if (per_warp % 128 == 0 && per_warp <= 128 * EMD_CSTEPS) {
+    // the LDG.128 / STG.128 forms need 16-byte aligned arrays (the C ABI takes plain pointers: fall back otherwise)
+    const bool vec_ok = ((reinterpret_cast<size_t>(asg) | reinterpret_cast<size_t>(midx)) & 15) == 0;
+    if (vec_ok && per_warp % 128 == 0 && per_warp <= 128 * EMD_CSTEPS) {
         // fast path (n <= 8192, n % 1024 == 0): one batch, flags kept in registers across the barrier
         const int steps = per_warp / 128;
         unsigned fl[EMD_CSTEPS];  // 4 flag bits per step
@@ -144,7 +146,7 @@ __device__ __noinline__ int compact_unassigned(const int *__restrict__ asg, int 
         __syncthreads();  // sscan may be reused
         return tot;
     }
-    if (per_warp % (128 * EMD_CSTEPS) == 0) {
+    if (vec_ok && per_warp % (128 * EMD_CSTEPS) == 0) {
         // larger clouds (n % 8192 == 0): the same 128-element steps in batches of EMD_CSTEPS, two passes over the slice
         // (the second one re-reads it from L1 / L2 with all loads of a batch in flight again)
         int cnt = 0;

@@ -187,7 +187,9 @@ int genpc_fps(const float *xyz, int B, int N, int K, int start, int *idx_out, fl
  *   gathered from colors[N][3], zminmax[V][2].
  * genpc_unproject (no reference counterpart; defined in DESIGN.md 3.4): every non-empty pixel, in raster
  *   order, back to a 3-D point at the pixel centre: out[V][res*res][3], own[V][res*res], counts[V].
- * workspace for the first two: genpc_depth_workspace_bytes(V). */
+ * workspace for the first two: genpc_depth_workspace_bytes(V).  uv must be 8-byte aligned (it is accessed as float pairs;
+ * GENPC_ERR_SHAPE otherwise); no other entry of this header needs more than the natural 4-byte alignment of its
+ * arrays -- wider accesses are chosen at run time when the pointers allow them. */
 size_t genpc_depth_workspace_bytes(int V);
 int genpc_project_uv(const float *cams, const float *xyz, int V, int N, int rescale, float padding, float *ndc,
                      float *uv, float *bounds, void *workspace, size_t workspace_bytes, genpc_stream_t stream);

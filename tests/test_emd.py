@@ -150,7 +150,8 @@ def test_emd_shape_errors_and_completionloss(cuda):
 
 @pytest.mark.gpu
 def test_emd_unaligned_pointers(cuda):
-    """xyz2 / price that are only 4-byte aligned (the direct Bid path reads them with LDG.64 and must step aside)."""
+    """xyz2 / price / assignment / max_idx that are only 4-byte aligned (the direct Bid path reads with LDG.64, the
+    compaction with LDG.128 / STG.128: both must step aside)."""
     rng = np.random.default_rng(77)
     B, n = 1, 2048
     x1, x2 = rng.random((B, n, 3), dtype=np.float32), rng.random((B, n, 3), dtype=np.float32)
@@ -166,10 +167,10 @@ def test_emd_unaligned_pointers(cuda):
         return v
 
     t1, t2 = off(torch.from_numpy(x1).to(cuda)), off(torch.from_numpy(x2).to(cuda))
-    dist = torch.zeros(B, n, device=cuda); asg = torch.full((B, n), -1, dtype=torch.int32, device=cuda)
+    dist = torch.zeros(B, n, device=cuda); asg = off(torch.full((B, n), -1, dtype=torch.int32, device=cuda))
     asg_inv = torch.full((B, n), -1, dtype=torch.int32, device=cuda); price = off(torch.zeros(B, n, device=cuda))
     bid = torch.zeros(B, n, dtype=torch.int32, device=cuda); binc = torch.zeros(B, n, device=cuda); minc = torch.zeros(B, n, device=cuda)
-    uidx = torch.zeros(B * n, dtype=torch.int32, device=cuda); midx = torch.zeros(B * n, dtype=torch.int32, device=cuda)
+    uidx = torch.zeros(B * n, dtype=torch.int32, device=cuda); midx = off(torch.zeros(B * n, dtype=torch.int32, device=cuda))
     z = [torch.zeros(512, dtype=torch.int32, device=cuda) for _ in range(3)]
     E.forward(t1, t2, dist, asg, price, asg_inv, bid, binc, minc, uidx, z[0], z[1], z[2], midx, 0.005, 50)
     ed, ea = oracle.emd_forward(x1, x2, 0.005, 50)
