@@ -109,7 +109,7 @@ __global__ void chamfer_grad_kernel(const float *__restrict__ xyz1, const float 
     const size_t n1 = (size_t)B * N, n2 = (size_t)B * M;
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
-    const bool valid = i < n1 + n2;
+    bool valid = i < n1 + n2;
     const int dir = (valid && i >= n1) ? 1 : 0;
     if (dir) i -= n1;
     const float *a = dir ? xyz2 : xyz1, *o = dir ? xyz1 : xyz2, *gd = dir ? gd2 : gd1;
@@ -118,10 +118,13 @@ __global__ void chamfer_grad_kernel(const float *__restrict__ xyz1, const float 
     const int na = dir ? M : N, no = dir ? N : M;
     size_t t = 0;
     float tx = 0.f, ty = 0.f, tz = 0.f;
+    // an index outside [0, no) (caller-supplied garbage) contributes nothing instead of touching foreign memory
+    const int nn = valid ? __ldg(idx + i) : 0;
+    valid = valid && (unsigned)nn < (unsigned)no;
     if (valid) {
         const size_t b = i / na;
         const float x1 = __ldg(a + i * 3), y1 = __ldg(a + i * 3 + 1), z1 = __ldg(a + i * 3 + 2);
-        t = b * no + __ldg(idx + i);
+        t = b * no + nn;
         const float x2 = __ldg(o + t * 3), y2 = __ldg(o + t * 3 + 1), z2 = __ldg(o + t * 3 + 2);
         const float g = __fmul_rn(__ldg(gd + i), 2.f);
         tx = __fmul_rn(g, __fsub_rn(x1, x2));
@@ -673,7 +676,7 @@ __global__ void chamfer_loss_grad_kernel(const float *__restrict__ xyz1, const f
     const size_t n1 = (size_t)B * N, n2 = (w2 != 0.f) ? (size_t)B * M : 0;
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
-    const bool valid = i < n1 + n2;
+    bool valid = i < n1 + n2;
     const int dir = (valid && i >= n1) ? 1 : 0;
     if (dir) i -= n1;
     const float *a = dir ? xyz2 : xyz1, *o = dir ? xyz1 : xyz2, *dd = dir ? d2 : d1;
@@ -682,10 +685,12 @@ __global__ void chamfer_loss_grad_kernel(const float *__restrict__ xyz1, const f
     const int na = dir ? M : N, no = dir ? N : M;
     size_t t = 0;
     float tx = 0.f, ty = 0.f, tz = 0.f;
+    const int nn = valid ? __ldg(idx + i) : 0;
+    valid = valid && (unsigned)nn < (unsigned)no;   // see chamfer_grad_kernel
     if (valid) {
         const size_t b = i / na;
         const float x1 = __ldg(a + i * 3), y1 = __ldg(a + i * 3 + 1), z1 = __ldg(a + i * 3 + 2);
-        t = b * no + __ldg(idx + i);
+        t = b * no + nn;
         const float x2 = __ldg(o + t * 3), y2 = __ldg(o + t * 3 + 1), z2 = __ldg(o + t * 3 + 2);
         float gd = __fmul_rn(__ldg(upstream), __fdiv_rn(dir ? w2 : w1, (float)(dir ? (size_t)B * M : n1)));
         if (use_sqrt) gd = __fmul_rn(gd, __fdiv_rn(0.5f, __fsqrt_rn(__ldg(dd + i))));

@@ -197,8 +197,10 @@ __device__ __forceinline__ void nn_sym_item(float (*s)[SYM_SPAN_MAX], const floa
 #else
         const float cmin = butterfly_min32(cacc, lane);
 #endif
+        // every in-range column publishes, also when its minimum is +inf (NaN / overflowing coordinates): no packed word
+        // is ever left unarmed, so the epilogue and the gradient kernels always see an in-range block / index
         const int col = blk * 32 + lane;
-        if (col < cnt && cmin < inf) atomicMin(pcol + col, pack_dist_idx(cmin, rblock_base + rblock));
+        if (col < cnt) atomicMin(pcol + col, pack_dist_idx(cmin, rblock_base + rblock));
     }
 
     // ---- row side: exact lowest column index inside the winning chunk, merged across column spans ----
@@ -206,7 +208,11 @@ __device__ __forceinline__ void nn_sym_item(float (*s)[SYM_SPAN_MAX], const floa
 #pragma unroll
     for (int qi = 0; qi < QT; ++qi) {
         const int j = jbase + qi * 32;
-        if (j >= nr || !(best[qi] < inf)) continue;
+        if (j >= nr) continue;
+        if (!(best[qi] < inf)) {  // NaN / overflow: publish (inf, first column of the span) like nn_scan_item does
+            atomicMin(prow + j, pack_dist_idx(inf, c0));
+            continue;
+        }
         const float qx = -nqx[qi].x, qy = -nqy[qi].x, qz = -nqz[qi].x;
         const int cb = bchunk[qi] * SYM_CHUNK;
         int kbest = 0;

@@ -3,12 +3,15 @@ scope, BASELINE.json north_star).  numpy only; used by bench.py, smoke() and the
 import numpy as np
 
 
-def superquadric(seed, n, exps=None):
-    """n points on a superquadric surface, normalised like normalize_numpy(range=0.5)
-    (reference utils/dataUtils.py:561-581): centred, longest bbox side = 1 -> coords in [-0.5, 0.5]."""
+def _superquadric_params(seed, exps=None):
     rng = np.random.default_rng(seed)
     e1, e2 = exps if exps is not None else rng.uniform(0.3, 1.6, size=2)
     ax = rng.uniform(0.4, 1.0, size=3)
+    return rng, (e1, e2, ax)
+
+
+def _superquadric_raw(params, rng, n):
+    e1, e2, ax = params
     eta = rng.uniform(-np.pi / 2, np.pi / 2, n)
     om = rng.uniform(-np.pi, np.pi, n)
 
@@ -18,10 +21,28 @@ def superquadric(seed, n, exps=None):
     x = ax[0] * f(np.cos(eta), e1) * f(np.cos(om), e2)
     y = ax[1] * f(np.cos(eta), e1) * f(np.sin(om), e2)
     z = ax[2] * f(np.sin(eta), e1)
-    p = np.stack([x, y, z], 1)
+    return np.stack([x, y, z], 1)
+
+
+def superquadric(seed, n, exps=None):
+    """n points on a superquadric surface, normalised like normalize_numpy(range=0.5)
+    (reference utils/dataUtils.py:561-581): centred, longest bbox side = 1 -> coords in [-0.5, 0.5]."""
+    rng, params = _superquadric_params(seed, exps)
+    p = _superquadric_raw(params, rng, n)
     lo, hi = p.min(0), p.max(0)
     p = (p - (lo + hi) / 2) / (hi - lo).max()
     return p.astype(np.float32)
+
+
+def superquadric_pair(seed, n, n_second):
+    """Two INDEPENDENT samplings of the same surface in the same frame (the first one defines the normalisation): a
+    complete cloud and the raw material of a partial scan that shares no sample with it."""
+    rng, params = _superquadric_params(seed)
+    p = _superquadric_raw(params, rng, n)
+    q = _superquadric_raw(params, np.random.default_rng(seed + 15485863), n_second)
+    lo, hi = p.min(0), p.max(0)
+    c, s = (lo + hi) / 2, (hi - lo).max()
+    return ((p - c) / s).astype(np.float32), ((q - c) / s).astype(np.float32)
 
 
 def partial_view(points, seed, n_out):
@@ -50,7 +71,13 @@ def rigid_perturb(points, seed, max_rot_deg=30.0, max_t=0.1, scale_range=(0.7, 1
 
 
 def pcn_batch(seed0, B, n_partial=2048, n_complete=16384):
-    """BASELINE config C2: B shapes, complete = n_complete surface samples, partial = n_partial visible points."""
-    comp = np.stack([superquadric(seed0 + b, n_complete) for b in range(B)])
-    part = np.stack([partial_view(comp[b], seed0 + b, n_partial) for b in range(B)])
-    return part, comp
+    """BASELINE config C2: B shapes, complete = n_complete surface samples, partial = n_partial points of a SEPARATE
+    sampling of the same surface seen from a random direction.  The two clouds share no sample, so
+    neither direction's distances are trivially zero (r01 drew the partial cloud from the complete one: dist1 == 0,
+    which would flatter any filtering / pruning kernel)."""
+    comp, part = [], []
+    for b in range(B):
+        c, raw = superquadric_pair(seed0 + b, n_complete, 3 * n_partial)
+        comp.append(c)
+        part.append(partial_view(raw, seed0 + b, n_partial))
+    return np.stack(part), np.stack(comp)

@@ -319,3 +319,83 @@ def test_unaligned_pointers_take_the_scalar_paths(cuda):
     e = oracle.chamfer_forward(a.cpu().numpy(), b.cpu().numpy())
     for k in range(4):
         assert np.array_equal(res[1][k].cpu().numpy(), e[k]), k
+
+
+def test_full_c2_bit_exact_vs_oracle_and_reference(cuda):
+    """BASELINE config C2 AT FULL BATCH (B=32, 2048 x 16384, the bench's own synthetic PCN batch): bit-exact against the
+    oracle (all 32 scans: ~0.3 s of OpenMP CPU work) AND against the live reference extension; gradients of
+    chamfer_l2 within 1e-5 of the double-accumulated oracle."""
+    from genpc_b200.synthetic import pcn_batch
+    from genpc_b200.utils.loss_util import Completionloss
+
+    part, comp = pcn_batch(0, 32, 2048, 16384)
+    got = run_ours(part, comp, cuda)
+    exp = oracle.chamfer_forward(part, comp)
+    for g, e, name in zip(got, exp, ("dist1", "dist2", "idx1", "idx2")):
+        assert np.array_equal(g.view(np.int32), e.view(np.int32)), f"{name} differs ({(g != e).sum()} entries)"
+    assert (exp[0] > 0).mean() > 0.99, "the partial cloud must not be a subset of the complete one (r01 finding)"
+    ref = oracle.load_ref_ext("chamfer_3D")
+    if ref is not None:
+        a, b = torch.from_numpy(part).to(cuda), torch.from_numpy(comp).to(cuda)
+        d1 = torch.zeros(32, 2048, device=cuda); d2 = torch.zeros(32, 16384, device=cuda)
+        i1 = torch.zeros(32, 2048, dtype=torch.int32, device=cuda); i2 = torch.zeros(32, 16384, dtype=torch.int32, device=cuda)
+        ref.forward(a, b, d1, d2, i1, i2)
+        for g, r, name in zip(got, (d1, d2, i1, i2), ("dist1", "dist2", "idx1", "idx2")):
+            assert np.array_equal(g, r.cpu().numpy()), f"{name} differs from the reference extension"
+    ta = torch.from_numpy(part).to(cuda).requires_grad_(True)
+    tb = torch.from_numpy(comp).to(cuda).requires_grad_(True)
+    loss = Completionloss("cd_l2").get_loss(ta, tb)
+    loss.backward()
+    want = exp[0].astype(np.float64).mean() + exp[1].astype(np.float64).mean()
+    assert abs(float(loss) - want) <= 1e-6 * want
+    g1 = np.full((32, 2048), 1.0 / (32 * 2048), np.float32)
+    g2 = np.full((32, 16384), 1.0 / (32 * 16384), np.float32)
+    e1, e2 = oracle.chamfer_backward(part, comp, g1, g2, exp[2], exp[3])
+    assert np.abs(ta.grad.cpu().numpy() - e1).max() <= 1e-5 * np.abs(e1).max()
+    assert np.abs(tb.grad.cpu().numpy() - e2).max() <= 1e-5 * np.abs(e2).max()
+
+
+@pytest.mark.parametrize("N,M", [(300, 200), (700, 600), (5000, 1300), (2048, 16384)])
+def test_nan_and_inf_points_stay_in_range(cuda, N, M):
+    """a NaN / Inf / overflowing point must not leave a packed word unarmed -- every returned index is
+    inside [0, other cloud), the finite points' results are unchanged, and the backward writes nothing outside its two
+    gradient arrays (guard bands around them stay intact)."""
+    from genpc_b200 import chamfer_3D
+
+    B = 2
+    a, b = rand_cloud(81, B, N), rand_cloud(82, B, M)
+    clean = oracle.chamfer_forward(a, b)
+    a[0, 3] = np.nan                       # a NaN query / row
+    b[0, 5, 1] = np.nan                    # a NaN target / column
+    a[1, 7] = 3e38                         # squared distance overflows to +inf
+    b[1, M - 1] = np.inf
+    ta, tb = torch.from_numpy(a).to(cuda), torch.from_numpy(b).to(cuda)
+    d1 = torch.empty(B, N, device=cuda); d2 = torch.empty(B, M, device=cuda)
+    i1 = torch.full((B, N), -7, dtype=torch.int32, device=cuda); i2 = torch.full((B, M), -7, dtype=torch.int32, device=cuda)
+    chamfer_3D.forward(ta, tb, d1, d2, i1, i2)
+    torch.cuda.synchronize()
+    assert int(i1.min()) >= 0 and int(i1.max()) < M and int(i2.min()) >= 0 and int(i2.max()) < N
+    # rows / columns that never met a poisoned point keep their exact answers
+    keep1 = np.ones((B, N), bool); keep1[0, 3] = keep1[1, 7] = False
+    keep1 &= ~((clean[2] == 5) & (np.arange(B)[:, None] == 0)) & ~((clean[2] == M - 1) & (np.arange(B)[:, None] == 1))
+    keep2 = np.ones((B, M), bool); keep2[0, 5] = keep2[1, M - 1] = False
+    keep2 &= ~((clean[3] == 3) & (np.arange(B)[:, None] == 0)) & ~((clean[3] == 7) & (np.arange(B)[:, None] == 1))
+    assert np.array_equal(d1.cpu().numpy()[keep1], clean[0][keep1]) and np.array_equal(i1.cpu().numpy()[keep1], clean[2][keep1])
+    assert np.array_equal(d2.cpu().numpy()[keep2], clean[1][keep2]) and np.array_equal(i2.cpu().numpy()[keep2], clean[3][keep2])
+    # backward between guard bands
+    guard = 64
+    buf1 = torch.full((B * N * 3 + 2 * guard,), 123.0, device=cuda); buf2 = torch.full((B * M * 3 + 2 * guard,), 321.0, device=cuda)
+    gx1 = buf1[guard:guard + B * N * 3].view(B, N, 3); gx2 = buf2[guard:guard + B * M * 3].view(B, M, 3)
+    gx1.zero_(); gx2.zero_()
+    chamfer_3D.backward(ta, tb, gx1, gx2, torch.ones(B, N, device=cuda), torch.ones(B, M, device=cuda), i1, i2)
+    torch.cuda.synchronize()
+    for buf, v in ((buf1, 123.0), (buf2, 321.0)):
+        assert bool((buf[:guard] == v).all()) and bool((buf[-guard:] == v).all())
+    # caller-supplied garbage indices contribute nothing instead of touching foreign memory
+    bad1 = torch.full_like(i1, -1); bad2 = torch.full_like(i2, 2 ** 30)
+    gx1.zero_(); gx2.zero_()
+    chamfer_3D.backward(ta, tb, gx1, gx2, torch.ones(B, N, device=cuda), torch.ones(B, M, device=cuda), bad1, bad2)
+    torch.cuda.synchronize()
+    assert not gx1.any() and not gx2.any()
+    for buf, v in ((buf1, 123.0), (buf2, 321.0)):
+        assert bool((buf[:guard] == v).all()) and bool((buf[-guard:] == v).all())
