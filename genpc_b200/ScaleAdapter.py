@@ -2,8 +2,8 @@
 
 Same class and method names.  `scaleReg` / `reg` run entirely on the GPU (genpc_b200.reg_xyz); the generator-facing
 methods (`remove_bg`, `img2shape`: background removal and image-to-3D, ScaleAdapter.py:19-44,70-72) are out of
-scope (BASELINE.json north_star) and raise.  File hand-off mirrors the reference's workspace layout, with the
-generated shape read from `<flag>_<generative_model>.ply` (mesh sampling of the .glb is generator-side).
+scope (BASELINE.json north_star) and raise.  File hand-off mirrors the reference's workspace layout: the generated shape is
+`<flag>_<generative_model>.glb` (reg_xyz.py:105-107), parsed and surface-sampled here (utils/glb.py, csrc/mesh.cu).
 """
 import os
 from types import SimpleNamespace
@@ -13,23 +13,44 @@ import torch
 
 from .reg_xyz import reg_points
 from .utils.dataUtils import load_xyz, write_ply_xyz
+from .utils.glb import read_glb, sample_mesh
 
 
-def reg(cfg, flag, cd_inv_weight=0.5, diff_init=True, reg_fine_xyz=False):
-    """reg_xyz.reg (reg_xyz.py:99-223) on files: color_point.ply + generated shape -> <flag>_fused.ply."""
+def reg(cfg, flag, cd_inv_weight=0.5, diff_init=True, reg_fine_xyz=False, seed=0):
+    """reg_xyz.reg (reg_xyz.py:99-223) on the reference's workspace layout:
+        <output_path>/<flag>/color_point.ply                      the coloured partial scan
+        <output_path>/<flag>/<flag>_<generative_model>.glb        the generated mesh
+     -> <output_path>/<flag>/<flag>_fused.ply                     (:220)
+    The mesh is sampled on the GPU (utils/glb.glb2point: 163 840 points for the fusion :125, 120 000 for the
+    differentiable init diff_obj_pose.py:504; seeded -- trimesh's sampler is not).  A `<flag>_<generative_model>.ply`
+    point cloud is accepted in place of the .glb (r01 layout)."""
     path = cfg.output_path
     scan = f"{path}/{flag}/color_point.ply"
-    gen = f"{path}/{flag}/{flag}_{cfg.generative_model}.ply"
-    for p in (scan, gen):
-        if not os.path.exists(p):
-            print(f"Path {p} does not exist.")
-            raise FileNotFoundError(f"Path {p} does not exist.")
+    glb = f"{path}/{flag}/{flag}_{cfg.generative_model}.glb"
+    ply = f"{path}/{flag}/{flag}_{cfg.generative_model}.ply"
+    if not os.path.exists(scan):
+        print(f"Path {scan} does not exist.")
+        raise FileNotFoundError(f"Path {scan} does not exist.")
+    if not os.path.exists(glb) and not os.path.exists(ply):
+        print(f"Path {glb} does not exist.")
+        raise FileNotFoundError(f"Path {glb} does not exist.")
     dev = torch.device(cfg.device)
-    partial, _ = load_xyz(scan)
-    complete, _ = load_xyz(gen)
-    out = reg_points(torch.from_numpy(partial).to(dev), torch.from_numpy(complete).to(dev), cd_inv_weight, diff_init,
-                     reg_fine_xyz, getattr(cfg, "dataset", "redwood"))
-    write_ply_xyz(f"{path}/{flag}/{flag}_fused.ply", out["fused"].cpu().numpy())
+    partial, partial_rgb = load_xyz(scan)
+    diff_complete = None
+    if os.path.exists(glb):
+        verts, faces, vcol = read_glb(glb)
+        tv, tf = torch.from_numpy(verts).to(dev), torch.from_numpy(faces).to(dev)
+        tc = None if vcol is None else torch.from_numpy(vcol).to(dev)
+        complete, complete_rgb = sample_mesh(tv, tf, 163840, seed, tc)
+        if diff_init:
+            diff_complete, _ = sample_mesh(tv, tf, 120000, seed + 1, tc)
+    else:
+        c, crgb = load_xyz(ply)
+        complete, complete_rgb = torch.from_numpy(c).to(dev), torch.from_numpy(crgb).to(dev)
+    out = reg_points(torch.from_numpy(partial).to(dev), complete, cd_inv_weight, diff_init, reg_fine_xyz,
+                     getattr(cfg, "dataset", "redwood"), partial_rgb=torch.from_numpy(partial_rgb).to(dev),
+                     complete_rgb=complete_rgb, generative_model=cfg.generative_model, diff_complete_xyz=diff_complete)
+    write_ply_xyz(f"{path}/{flag}/{flag}_fused.ply", out["fused"].cpu().numpy(), out["fused_rgb"].cpu().numpy())
     return out
 
 

@@ -51,6 +51,8 @@ _SIGNATURES = {
     "genpc_chamfer_sym_fixup": (_int, [_vp, _vp, _vp, _int, _int, _int, _vp, _vp, _vp]),
     "genpc_icp_step": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _int, _int, _flt, _flt, _flt, _int, _vp]),
     "genpc_knn_mean_distance": (_int, [_vp, _int, _int, _int, _vp, _vp]),
+    "genpc_mesh_face_areas": (_int, [_vp, _vp, _int, _int, _vp, _vp]),
+    "genpc_mesh_sample": (_int, [_vp, _vp, _vp, _vp, _int, _int, ctypes.c_ulonglong, _vp, _vp, _vp, _vp]),
     "genpc_fps_workspace_bytes": (_sz, [_int, _int, _int]),
     "genpc_fps": (_int, [_vp, _int, _int, _int, _int, _vp, _vp, _vp, _sz, _vp]),
     "genpc_depth_workspace_bytes": (_sz, [_int]),

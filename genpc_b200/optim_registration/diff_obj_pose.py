@@ -181,16 +181,28 @@ def object_pose_optimization_points(complete_xyz, partial_xyz, lr=0.005, iters=3
     return rb.transforms()[0].detach().cpu().numpy()
 
 
+def load_point_cloud(point_path, device, radius=0.05, num_points=5000, seed=0):
+    """:136-165 -- a .ply is read and voxel down-sampled, a .glb is surface-sampled (num_points) then down-sampled.
+    -> (vert_pos [N,3], vert_col [N,3]) float32 tensors on `device`."""
+    from ..utils.dataUtils import load_xyz
+    from ..utils.glb import glb2point
+
+    if str(point_path).endswith(".ply"):
+        xyz, color = load_xyz(point_path, down_sample=radius)
+        return torch.as_tensor(xyz, dtype=torch.float32, device=device), torch.as_tensor(color, dtype=torch.float32, device=device)
+    if str(point_path).endswith(".glb"):
+        return glb2point(point_path, down_sample=radius, num_points=num_points, seed=seed, device=device)
+    raise ValueError("Unsupported point cloud format")
+
+
 def object_pose_optimization(glb_path, point_path, radius=0.005, lr=0.005, iters=300, render_size=224, vis=False,
                              save_path=None, device=None, cam_bias_num=4):
-    """Reference signature (:496).  Both inputs must be point clouds (.ply): sampling a .glb mesh (glb2point,
-    trimesh) belongs to the generator side and is out of scope -- export the generated shape as .ply first."""
-    from ..utils.dataUtils import load_xyz
-
-    if not (str(glb_path).endswith(".ply") and str(point_path).endswith(".ply")):
-        raise NotImplementedError("object_pose_optimization: only .ply inputs are supported (mesh sampling is out of scope)")
-    partial_xyz, _ = load_xyz(point_path, down_sample=radius)
-    complete_xyz, _ = load_xyz(glb_path, down_sample=radius)
+    """Reference signature and inputs (:496-594): `point_path` = the partial scan (.ply), `glb_path` = the generated mesh
+    (.glb, sampled with 120 000 points :504; a .ply is accepted too).  The Pulsar render / mask terms are out of scope:
+    the loss is the Chamfer term (:326-327).  Returns the 4x4 numpy transform and saves it like the reference (:593)."""
+    device = device or torch.device("cuda:0")
+    partial_xyz, _ = load_point_cloud(point_path, device, radius, 8000)          # :502
+    complete_xyz, _ = load_point_cloud(glb_path, device, radius, 120000)         # :504
     T = object_pose_optimization_points(complete_xyz, partial_xyz, lr, iters, cam_bias_num, device)
     np.save("final_transform.npy", T)
     return T

@@ -193,33 +193,65 @@ def remove_statistical_outlier(xyz, nb_neighbors=20, std_ratio=2.5):
     """Open3D remove_statistical_outlier as the reference uses it (reg_xyz.py:219, utils/dataUtils.py:652-666),
     restated on the k-NN kernel: per point the mean distance to its nb_neighbors nearest points -- the KD-tree query of
     a cloud point returns the point itself first, so it is one of them -- then keep 0 < mean < cloud_mean + std_ratio *
-    sample_std (float64 statistics).  Returns the boolean keep mask.  (Open3D is not vendored: semantics from its
+    std_dev (float64 statistics; means of exactly 0 -- duplicated points -- stay out of both sums, as in Open3D).  Returns the boolean keep mask.  (Open3D is not vendored: semantics from its
     documented behaviour, parity unpinned; the oracle defines them.)"""
     md = knn_mean_distance(xyz, nb_neighbors, include_self=True).double()
-    valid = md >= 0
-    nv = int(valid.sum())
+    nv = int((md >= 0).sum())
     if nv == 0:
-        return torch.zeros_like(valid)
-    mu = md[valid].sum() / nv
-    sd = torch.sqrt(((md[valid] - mu) ** 2).sum() / (nv - 1)) if nv > 1 else torch.zeros((), dtype=torch.float64, device=md.device)
-    return (md > 0) & (md < mu + std_ratio * sd)
+        return torch.zeros_like(md, dtype=torch.bool)
+    pos = md > 0            # Open3D: only positive means enter the sums, the divisors count every answered query
+    mu = md[pos].sum() / nv
+    sd = torch.sqrt(((md[pos] - mu) ** 2).sum() / (nv - 1)) if nv > 1 else torch.zeros((), dtype=torch.float64, device=md.device)
+    return pos & (md < mu + std_ratio * sd)
+
+
+def get_rotate_matrix(axis, angle):
+    """utils/dataUtils.py:455-471 (degrees)."""
+    a = angle * np.pi / 180
+    c, s_ = np.cos(a), np.sin(a)
+    if axis == "x":
+        return np.array([[1, 0, 0], [0, c, -s_], [0, s_, c]])
+    if axis == "y":
+        return np.array([[c, 0, s_], [0, 1, 0], [-s_, 0, c]])
+    if axis == "z":
+        return np.array([[c, -s_, 0], [s_, c, 0], [0, 0, 1]])
+    raise ValueError("axis should be x,y,z")
+
+
+GENERATIVE_MODELS = ("instantmesh", "trellis", "sf3d")
 
 
 def reg_points(partial_xyz, complete_xyz, cd_inv_weight=0.5, diff_init=True, reg_fine_xyz=False, dataset="redwood",
-               n_fused=20000, lr=0.01, iters=200):
-    """In-memory form of reg() (reg_xyz.py:99-223): differentiable init -> 11-scale coarse ICP sweep -> optional
-    per-axis scale grid -> fuse (drop generated points that coincide with scan points, FPS to n_fused, outlier filter).
-    partial_xyz = the scan (`color_point.ply`), complete_xyz = the generated shape.  Returns dict of device tensors."""
+               n_fused=20000, lr=0.01, iters=200, partial_rgb=None, complete_rgb=None, generative_model="trellis",
+               diff_complete_xyz=None):
+    """In-memory form of reg() (reg_xyz.py:99-223): differentiable init -> generator-specific frame fix-up -> 11-scale
+    coarse ICP sweep -> optional per-axis scale grid -> fuse (drop generated points that coincide with scan points, FPS to
+    n_fused, outlier filter).  partial_xyz = the scan (`color_point.ply`), complete_xyz = the generated shape (163 840
+    surface samples in the reference, :125); colours ride along through every selection (:211-219).  diff_complete_xyz:
+    the cloud the differentiable init registers (the reference samples the mesh a second time, 120 000 points,
+    diff_obj_pose.py:504); default = complete_xyz.  Returns a dict of device tensors.
+    Deviations from the reference, all forced by unseeded / unvendored third-party calls: FPS
+    starts at index 0 (fpsample: random start) and is skipped when the fused cloud already has <= n_fused points."""
+    if generative_model not in GENERATIVE_MODELS:
+        raise ValueError(f"generative_model {generative_model!r} not supported (reg_xyz.py:133-140 knows {GENERATIVE_MODELS})")
     dev = partial_xyz.device
     source, target = partial_xyz.float(), complete_xyz.float()
+    src_rgb = None if partial_rgb is None else partial_rgb.float().to(dev)
+    tgt_rgb = None if complete_rgb is None else complete_rgb.float().to(dev)
     diff_T = np.eye(4)
     if diff_init:
-        T = object_pose_optimization_points(voxel_down_sample(target, 0.02), voxel_down_sample(source, 0.02), lr=lr,
+        dc = target if diff_complete_xyz is None else diff_complete_xyz.float()
+        T = object_pose_optimization_points(voxel_down_sample(dc, 0.02), voxel_down_sample(source, 0.02), lr=lr,
                                             iters=iters, device=dev)
         diff_T = np.linalg.inv(T)                                   # reg_xyz.py:122
     dT = torch.as_tensor(diff_T, dtype=torch.float32, device=dev)
     source = source @ dT[:3, :3].T + dT[:3, 3]                      # partial into the generated shape's frame (:126)
     tn, _, _ = normalize_numpy(target.cpu().numpy(), range=0.5)     # :131
+    if generative_model == "instantmesh":                           # :133-138
+        keep0 = remove_statistical_outlier(source, 20, 1.5)         # remove_noise_from_point_cloud(source_pcd)
+        source = source[keep0]
+        src_rgb = None if src_rgb is None else src_rgb[keep0]
+        tn = np.dot(np.dot(tn, get_rotate_matrix("x", 90).T), get_rotate_matrix("y", 90).T)
     target = torch.as_tensor(tn, dtype=torch.float32, device=dev)
     # coarse sweep (:146-173), all 11 scales at once
     scales = np.linspace(1.5, 0.8, 11)
@@ -230,7 +262,8 @@ def reg_points(partial_xyz, complete_xyz, cd_inv_weight=0.5, diff_init=True, reg
     cd = chamfer_partial_l1_batched(s_down[None].expand(len(scales), -1, -1), t_moved, cd_inv_weight)
     k = int(torch.argmin(cd))
     coarse = Ts[k]
-    out = {"best_scale": float(scales[k]), "coarse_loss": float(cd[k]), "coarse_transformation": coarse}
+    out = {"best_scale": float(scales[k]), "coarse_loss": float(cd[k]), "coarse_transformation": coarse,
+           "diff_transform": diff_T}
     tgt_full = target
     if reg_fine_xyz:
         source = source @ coarse[:3, :3].T + coarse[:3, 3]          # :176
@@ -248,10 +281,15 @@ def reg_points(partial_xyz, complete_xyz, cd_inv_weight=0.5, diff_init=True, reg
     di = torch.as_tensor(np.linalg.inv(diff_T), dtype=torch.float32, device=dev)
     source = source @ di[:3, :3].T + di[:3, 3]                      # :206
     keep = remove_close_points(source, tgt_full, 0.0001)            # :210
-    fused = torch.cat([source, tgt_full[keep]])
+    fused = torch.cat([source, tgt_full[keep]])                     # :211 fused = source + filtered target
+    with_rgb = src_rgb is not None and tgt_rgb is not None
+    fused_rgb = torch.cat([src_rgb, tgt_rgb[keep]]) if with_rgb else None
     if fused.shape[0] > n_fused:
-        idx = furthest_point_sample(fused[None].contiguous(), n_fused, 0)[0].long()   # :215
+        idx = furthest_point_sample(fused[None].contiguous(), n_fused, 0)[0].long()   # :215-217
         fused = fused[idx]
-    fused = fused[remove_statistical_outlier(fused, std_ratio=2.5)]                   # :219
-    out.update(fused=fused, source=source, target=tgt_full)
+        fused_rgb = fused_rgb[idx] if with_rgb else None
+    ok = remove_statistical_outlier(fused, std_ratio=2.5)                             # :219
+    fused = fused[ok]
+    fused_rgb = fused_rgb[ok] if with_rgb else None
+    out.update(fused=fused, fused_rgb=fused_rgb, source=source, target=tgt_full)
     return out

@@ -81,3 +81,29 @@ def pcn_batch(seed0, B, n_partial=2048, n_complete=16384):
         comp.append(c)
         part.append(partial_view(raw, seed0 + b, n_partial))
     return np.stack(part), np.stack(comp)
+
+
+def superquadric_mesh(seed, n_eta=48, n_om=96):
+    """Triangle mesh of the same surface family (a stand-in for the generators' .glb output): a latitude / longitude
+    grid over the parametric domain, two triangles per cell, normalised like `superquadric`.  -> (verts f32 [V,3],
+    faces i32 [F,3], vertex colours f32 [V,3] = min-max normalised coordinates)."""
+    _, (e1, e2, ax) = _superquadric_params(seed)
+    eta = np.linspace(-np.pi / 2, np.pi / 2, n_eta)
+    om = np.linspace(-np.pi, np.pi, n_om, endpoint=False)
+    E, O = np.meshgrid(eta, om, indexing="ij")
+
+    def f(w, e):
+        return np.sign(w) * np.abs(w) ** e
+
+    p = np.stack([ax[0] * f(np.cos(E), e1) * f(np.cos(O), e2), ax[1] * f(np.cos(E), e1) * f(np.sin(O), e2),
+                  ax[2] * f(np.sin(E), e1)], -1).reshape(-1, 3)
+    lo, hi = p.min(0), p.max(0)
+    p = (p - (lo + hi) / 2) / (hi - lo).max()
+    i, j = np.meshgrid(np.arange(n_eta - 1), np.arange(n_om), indexing="ij")
+    a = (i * n_om + j).reshape(-1)
+    b = (i * n_om + (j + 1) % n_om).reshape(-1)
+    c = ((i + 1) * n_om + j).reshape(-1)
+    d = ((i + 1) * n_om + (j + 1) % n_om).reshape(-1)
+    faces = np.concatenate([np.stack([a, b, c], 1), np.stack([b, d, c], 1)]).astype(np.int32)
+    col = (p - p.min(0)) / (p.max(0) - p.min(0) + 1e-8)
+    return p.astype(np.float32), faces, col.astype(np.float32)

@@ -69,16 +69,20 @@ def write_ply_xyz(path, points, colors=None):
         f.write(rec.tobytes())
 
 
-def voxel_down_sample(points, voxel_size):
+def voxel_down_sample(points, voxel_size, colors=None):
     """Open3D semantics: one output point per occupied voxel = mean of its points (voxel grid anchored at
-    min_bound - voxel/2).  torch, runs on whatever device `points` lives on; output order = sorted voxel key."""
+    min_bound - voxel/2); colours, when given, are averaged the same way.  torch, runs on whatever device `points`
+    lives on; output order = sorted voxel key.  -> points, or (points, colors) when colors is given."""
     p = torch.as_tensor(points)
     lo = p.min(0).values - voxel_size * 0.5
     key = torch.floor((p - lo) / voxel_size).long()
     uniq, inv = torch.unique(key, dim=0, return_inverse=True)
-    out = torch.zeros(uniq.shape[0], 3, dtype=p.dtype, device=p.device).index_add_(0, inv, p)
     cnt = torch.zeros(uniq.shape[0], dtype=p.dtype, device=p.device).index_add_(0, inv, torch.ones_like(p[:, 0]))
-    return out / cnt[:, None]
+    out = torch.zeros(uniq.shape[0], 3, dtype=p.dtype, device=p.device).index_add_(0, inv, p) / cnt[:, None]
+    if colors is None:
+        return out
+    c = torch.as_tensor(colors).to(p.dtype)
+    return out, torch.zeros(uniq.shape[0], c.shape[1], dtype=p.dtype, device=p.device).index_add_(0, inv, c) / cnt[:, None]
 
 
 def load_xyz(path, down_sample=None):

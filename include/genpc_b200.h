@@ -144,6 +144,23 @@ int genpc_chamfer_sym_fixup(const float *rows_full, const float *cols, const uns
  * bit for bit (oracle_knn_mean_distance).  A cloud with fewer than k candidates averages what it has; none: -1. */
 int genpc_knn_mean_distance(const float *xyz, int n, int k, int include_self, float *mean_dist, genpc_stream_t stream);
 
+/* ---- surface sampling of the generated mesh -------------------------------------------------------
+ * Replaces the sampling step of glb2point (utils/dataUtils.py:217-250: trimesh mesh.sample(num_points, return_index=True)
+ * and the barycentric colour interpolation :231-243; third-party CPU code, unseeded), which turns the generated .glb
+ * into the 163 840-point cloud reg() registers (reg_xyz.py:125) and the 120 000-point cloud of the differentiable init
+ * (diff_obj_pose.py:504).  Semantics defined here (csrc/mesh.cu header, oracle/mesh.py): fp32 face areas without fma,
+ * integer weights floor(area / max_area * 2^32) whose inclusive uint64 prefix sums the CALLER provides (exact, so the
+ * face choice does not depend on summation order), counter-based splitmix64 draws from (seed, sample index).
+ *   verts [n_verts][3] f32, faces [n_faces][3] i32, vertex_rgb [n_verts][3] f32 in [0,1] or NULL (-> 0.5 grey)
+ *   areas [n_faces] f32 out (0 for degenerate / out-of-range faces)
+ *   cum_weights [n_faces] u64 inclusive prefix sums, cum_weights[n_faces-1] > 0
+ *   out_xyz [n_samples][3], out_rgb [n_samples][3] or NULL, out_face [n_samples] or NULL */
+int genpc_mesh_face_areas(const float *verts, const int *faces, int n_verts, int n_faces, float *areas,
+                          genpc_stream_t stream);
+int genpc_mesh_sample(const float *verts, const int *faces, const float *vertex_rgb,
+                      const unsigned long long *cum_weights, int n_faces, int n_samples, unsigned long long seed,
+                      float *out_xyz, float *out_rgb, int *out_face, genpc_stream_t stream);
+
 /* ---- point-to-point ICP step (scale / ICP candidate search) ----------------------------------------
  * Replaces one iteration of Open3D registration_icp(TransformationEstimationPointToPoint) as the reference calls it for
  * every scale candidate (reg_xyz.py:9-38 inside the sweeps :60-96 and :146-173; third-party CPU code), batched over K

@@ -154,16 +154,17 @@ def knn_mean_distance(xyz, k, include_self=True):
 
 def statistical_outlier_mask(mean_dist, std_ratio):
     """Open3D's threshold over the per-point means (float64 like its std::vector<double>): keep a point when
-    0 < mean < cloud_mean + std_ratio * sample_std; points whose query found nothing (mean < 0) are left out of the
-    statistics and dropped."""
+    0 < mean < cloud_mean + std_ratio * std_dev.  As in Open3D's RemoveStatisticalOutliers, only means > 0 enter the two
+    sums, while the divisors count every point whose query found something (mean >= 0): cloud_mean = sum / n_valid,
+    std_dev = sqrt(sum((mean - cloud_mean)^2 over mean > 0) / (n_valid - 1))."""
     m = np.asarray(mean_dist, np.float64)
-    valid = m >= 0
-    nv = int(valid.sum())
+    nv = int((m >= 0).sum())
     if nv == 0:
         return np.zeros(m.shape, bool)
-    mu = m[valid].sum() / nv
-    sd = np.sqrt(((m[valid] - mu) ** 2).sum() / (nv - 1)) if nv > 1 else 0.0
-    return (m > 0) & (m < mu + std_ratio * sd)
+    pos = m > 0
+    mu = m[pos].sum() / nv
+    sd = np.sqrt(((m[pos] - mu) ** 2).sum() / (nv - 1)) if nv > 1 else 0.0
+    return pos & (m < mu + std_ratio * sd)
 
 
 def project_uv(cams, xyz, rescale=True, padding=0.15):

@@ -15,6 +15,9 @@ KEYS = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
         "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed",
         "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
         "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_tmem.avg.pct_of_peak_sustained_active",
+        "smsp__sass_inst_executed_op_tmem_ldt.sum",
         "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
         "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_bytes.sum",
