@@ -33,7 +33,43 @@ B, N, M = 32, 2048, 16384
 FLOP_PER_PAIR = 8            # 3 sub, 3 mul, 2 add
 FP32_NOMINAL_TFLOPS = 74.4   # 148 SM x 128 lanes x 2 x 1.965 GHz (not in MEASURED_PEAKS.json)
 L2_FLUSH_BYTES = 256 << 20
-NCU_DRAM_BYTES_NN_SYM = 11819776  # ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of one nn_sym_kernel launch (profiles/r01k_nn_sym_ncu.txt)
+
+
+def read_ncu_profile(stem, kernel_substr):
+    """Latest committed ncu --set full summary profiles/r*_<stem>_ncu.txt (written by tools/ncu_summary.py from the capture
+    of THIS bench command): -> {metric: (value, unit)} of the first kernel whose name contains kernel_substr, plus 'file'.
+    The bench line quotes DRAM traffic / pipe utilisation from that file at run time instead of pasting constants."""
+    import glob
+    import re
+
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", f"r*_{stem}_ncu.txt")))
+    for f in reversed(files):
+        cur, out = None, {}
+        for line in open(f):
+            if line.startswith("== "):
+                if out:
+                    break
+                cur = line if kernel_substr in line else None
+                continue
+            m = re.match(r"\s+(\S+)\s+([-0-9.eE+]+)\s*(\S*)", line)
+            if cur and m:
+                out[m.group(1)] = (float(m.group(2)), m.group(3))
+        if out:
+            out["file"] = os.path.relpath(f, ROOT)
+            return out
+    return None
+
+
+def ncu_dram_bytes(prof):
+    if not prof:
+        return None
+    mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tot = 0.0
+    for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+        if k not in prof:
+            return None
+        tot += prof[k][0] * mult.get(prof[k][1], 1.0)
+    return tot
 
 
 def env_int(k, d):
@@ -117,7 +153,7 @@ def measured_fp32_peak():
 # ---------------------------------------------------------------------------------------------------
 # CPU baselines (rank 0, N=1 only) -- oracle/ is used here strictly as the thing that is timed beside us
 # ---------------------------------------------------------------------------------------------------
-def cpu_baseline(part, comp, budget_b=None):
+def cpu_baseline(part, comp, budget_b=None, keep_forward=False):
     import oracle
 
     cores = os.cpu_count()
@@ -132,6 +168,8 @@ def cpu_baseline(part, comp, budget_b=None):
     pairs = 2.0 * nb * N * M
     out = {"value": pairs / dt, "unit": "pairs/s", "cores": cores, "kind": "port",
            "sample": f"oracle C port (OpenMP), fwd+bwd on {nb} of the {B} scans of C2, {dt:.2f} s"}
+    if keep_forward:
+        out["_oracle_forward"] = (d1, d2, i1, i2)   # popped by the caller: full-batch parity assert of the GPU arm
     # the reference's stated CPU path (BASELINE.json): torch.cdist (no-mm) + min both ways
     try:
         torch.set_num_threads(cores)
@@ -359,6 +397,7 @@ def registration_metric(rank, world, dev, iters=10, total_scans=64, pts=16384):
     Returns scan-iterations per second, whole job (max time over ranks)."""
     import torch.distributed as dist
 
+    from genpc_b200 import _lib
     from genpc_b200.optim_registration.diff_obj_pose import RegistrationBatch
     from genpc_b200.sharded import shard_range
     from genpc_b200.synthetic import partial_view, rigid_perturb, superquadric
@@ -384,9 +423,206 @@ def registration_metric(rank, world, dev, iters=10, total_scans=64, pts=16384):
     L = rb.losses()
     return {"metric": "registration_scan_iters_per_sec", "value": total_scans * iters / (ms * 1e-3), "unit": "scan-iters/s",
             "scans": total_scans, "pts": pts, "iters_timed": iters, "ms_per_iter": ms / iters, "scaling": "strong",
-            "pairs_per_s": total_scans * iters * 2.0 * pts * pts / (ms * 1e-3), "launches_per_iter": 1,
+            "pairs_per_s": total_scans * iters * 2.0 * pts * pts / (ms * 1e-3),
+            "launches_per_iter": int(_lib.lib().genpc_register_launches_per_iter(hi - lo, pts, pts)),
             "loss_first_last_scan0": [float(L[0, 0]), float(L[0, rb.t - 1])],
             "workload": "C3: pose+scale Adam steps on 3*(CDp-L1(pts->ref)+0.5*CDp-L1(ref->pts)), 1 start per scan"}
+
+
+def ev_best(fn, reps=3, warm=1):
+    """Best-of CUDA-event time (ms) of fn() on the current stream."""
+    for _ in range(warm):
+        fn()
+    ts = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return min(ts)
+
+
+def c5_sharded_metric(rank, world, dev, n=1_000_000, reps=2):
+    """BASELINE config C5: n x n-point Chamfer forward, rows of cloud 1 sharded over the ranks (every point pair evaluated
+    once across the job), ONE NCCL all-reduce-MIN over the packed (dist, idx) words, local fix-up.  Strong scaling.  All
+    ranks call this (collective inside); device time, max over ranks; rank 0 checks 2000 sampled points bit-exactly against
+    the oracle (a full CPU scan of 1e12 pairs is out of reach)."""
+    import torch.distributed as dist
+
+    from genpc_b200.sharded import sharded_chamfer_forward
+    from genpc_b200.synthetic import lidar_scene_pair
+
+    a, b = lidar_scene_pair(n, 0)
+    ta, tb = a[None].to(dev), b[None].to(dev)
+    out = sharded_chamfer_forward(ta, tb)
+    torch.cuda.synchronize(dev)
+    ts = []
+    for _ in range(reps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = sharded_chamfer_forward(ta, tb)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ts.append(float(t))
+    ph = {}
+    if world > 1:
+        dist.barrier()
+    sharded_chamfer_forward(ta, tb, phase_ms=ph)   # one more pass with per-phase CUDA events
+    pt = torch.tensor([ph["scan"], ph["allreduce"], ph["unpack_fixup"]], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(pt, op=dist.ReduceOp.MAX)
+    ms = min(ts)
+    res = {"workload": f"C5: {n} x {n} Chamfer forward (LiDAR-like scene), row-sharded symmetric scan + all-reduce-MIN of packed "
+                       "(dist, idx) words + local fix-up", "n": n, "n_gpus": world, "scaling": "strong", "ms": ms,
+           "pairs_per_s": 2.0 * n * n / (ms * 1e-3),
+           "phase_ms_max_over_ranks": {"scan": float(pt[0]), "allreduce_min_packed": float(pt[1]), "unpack_fixup": float(pt[2])},
+           "collective": "torch.distributed all_reduce(MIN, int64) over NCCL" if world > 1 else "none (1 rank)",
+           "allreduce_bytes": 8 * 2 * n}
+    if rank == 0:
+        import oracle
+
+        sel = np.random.default_rng(0).choice(n, 2000, replace=False)
+        ed, ei = oracle.nn_distance(a[sel][None].numpy(), b[None].numpy())
+        ed2, ei2 = oracle.nn_distance(b[sel][None].numpy(), a[None].numpy())
+        d1, d2, i1, i2 = out
+        ok = (np.array_equal(d1[0, sel].cpu().numpy(), ed[0]) and np.array_equal(i1[0, sel].cpu().numpy(), ei[0]) and
+              np.array_equal(d2[0, sel].cpu().numpy(), ed2[0]) and np.array_equal(i2[0, sel].cpu().numpy(), ei2[0]))
+        res["sample_check_bit_exact_vs_oracle"] = bool(ok)
+        assert ok, "C5: sharded Chamfer differs from the oracle on the sampled points"
+    return res
+
+
+def _emd_buffers(Bn, n, dev):
+    z = lambda *s, dt=torch.float32: torch.zeros(*s, dtype=dt, device=dev)   # noqa: E731
+    return dict(dist=z(Bn, n), asg=z(Bn, n, dt=torch.int32) - 1, price=z(Bn, n), asg_inv=z(Bn, n, dt=torch.int32) - 1,
+                bid=z(Bn, n, dt=torch.int32), binc=z(Bn, n), minc=z(Bn, n), uidx=z(Bn * n, dt=torch.int32),
+                ucnt=z(512, dt=torch.int32), ucs=z(512, dt=torch.int32), ctmp=z(512, dt=torch.int32), midx=z(Bn * n, dt=torch.int32))
+
+
+def emd_c5_metric(dev, n=8192, eps=0.005, iters=50):
+    """BASELINE config C5, EMD leg (emd_module.py:98-118 `test_emd` inputs: torch.rand pairs, eps 0.005, 50 iterations):
+    ours through the mirror of the pybind module, the unmodified reference extension beside it on the same GPU."""
+    import oracle
+    from genpc_b200 import emd as ours
+
+    ref = oracle.load_ref_ext("emd")
+    out = {"workload": f"C5 EMD: auction matching of torch.rand(B,{n},3) pairs, eps {eps}, {iters} iterations", "n": n}
+    for Bn in (1, 32):
+        g = torch.Generator().manual_seed(0)
+        x1, x2 = torch.rand(Bn, n, 3, generator=g).to(dev), torch.rand(Bn, n, 3, generator=g).to(dev)
+        row = {}
+        for name, mod in (("ours", ours), ("reference_ext", ref)):
+            if mod is None:
+                continue
+            best = None
+            for rep in range(3):
+                bf = _emd_buffers(Bn, n, dev)
+                torch.cuda.synchronize(dev)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                mod.forward(x1, x2, bf["dist"], bf["asg"], bf["price"], bf["asg_inv"], bf["bid"], bf["binc"], bf["minc"], bf["uidx"],
+                            bf["ucnt"], bf["ucs"], bf["ctmp"], bf["midx"], eps, iters)
+                e1.record()
+                torch.cuda.synchronize(dev)
+                ms = e0.elapsed_time(e1)
+                best = ms if best is None or (rep > 0 and ms < best) else best
+            row[name + "_ms"] = best
+            row[name + "_emd_cost"] = float(torch.sqrt(bf["dist"]).mean())
+            row[name + "_unassigned"] = int((bf["asg"] < 0).sum())
+        if "reference_ext_ms" in row:
+            row["speedup_vs_reference_ext"] = row["reference_ext_ms"] / row["ours_ms"]
+            row["cost_rel_diff"] = abs(row["ours_emd_cost"] - row["reference_ext_emd_cost"]) / row["reference_ext_emd_cost"]
+        row["matchings_per_s"] = Bn / (row["ours_ms"] * 1e-3)
+        out[f"B{Bn}"] = row
+    return out
+
+
+def c4_metric(dev):
+    """BASELINE config C4: 8-view 512 x 512 point -> depth z-buffer render + depth -> point unprojection of the reference scan
+    (data/01184.ply, 71 372 points; committed fixture) and FPS 16384 -> 2048; z-buffer owners and FPS indices checked bit
+    for bit against the oracle."""
+    import oracle
+    from genpc_b200 import depth as D
+    from genpc_b200.fps import furthest_point_sample
+    from genpc_b200.synthetic import superquadric
+
+    fix = os.path.join(ROOT, "tests", "golden", "scan_01184_xyz.npz")
+    scan = np.load(fix)["xyz"] if os.path.exists(fix) else superquadric(0, 71372)
+    pts = torch.from_numpy(scan).to(dev)
+    V, res = 8, 512
+    cams, _ = D.create_cameras(V, 1.6, 49.1, res, dev)
+    out = {"workload": f"C4: {V} views x {res}^2, project + z-buffer render + unproject of {scan.shape[0]} points "
+                       "(data/01184.ply); FPS 16384 -> 2048", "views": V, "res": res, "points": int(scan.shape[0])}
+    for ps in (1, 2):
+        def run(ps=ps):
+            ndc, uv, b = D.project_uv(cams, pts, True, 0.15)
+            r = D.zbuffer_render(uv, ndc, res, ps)
+            return ndc, uv, b, r, D.unproject(cams, b, r["zbuf"], ndc, True)
+        ms = ev_best(run, reps=5, warm=2)
+        ndc, uv, b, r, un = run()
+        e_ndc, e_uv, e_b = oracle.project_uv(cams.cpu().numpy(), scan, True, 0.15)
+        e_zb = oracle.zbuffer(e_uv, e_ndc, res, ps)
+        zb_ok = bool(np.array_equal(r["zbuf"].cpu().numpy().view(np.uint64), np.asarray(e_zb).view(np.uint64)))
+        out[f"point_size_{ps}"] = {"ms": ms, "points_per_s": V * scan.shape[0] / (ms * 1e-3),
+                                   "pixels_per_s": V * res * res / (ms * 1e-3), "zbuffer_bit_exact_vs_oracle": zb_ok}
+        assert zb_ok, "C4: z-buffer differs from the oracle"
+    for name, cloud in (("uniform_cube", np.random.default_rng(0).random((1, 16384, 3), dtype=np.float32)),
+                        ("c2_shape", superquadric(0, 16384)[None])):
+        x = torch.from_numpy(cloud).to(dev)
+        ms = ev_best(lambda: furthest_point_sample(x, 2048, 0), reps=3, warm=1)
+        idx = furthest_point_sample(x, 2048, 0).cpu().numpy()
+        ok = bool(np.array_equal(idx.astype(np.int64), np.asarray(oracle.fps(cloud, 2048, 0)).astype(np.int64)))
+        out[f"fps_16384_to_2048_{name}"] = {"ms": ms, "picks_per_s": 2048 / (ms * 1e-3), "indices_bit_exact_vs_oracle": ok}
+        assert ok, "C4: FPS indices differ from the oracle"
+    xb = torch.rand(32, 16384, 3, device=dev)
+    out["fps_16384_to_2048_B32_ms"] = ev_best(lambda: furthest_point_sample(xb, 2048, 0), reps=2, warm=1)
+    return out
+
+
+def c1_metric(dev):
+    """BASELINE config C1 on the real scan: data/01184.ply (71 372 pts, committed fixture) vs the 16 384-pt synthetic shape,
+    batch 1, CD-L1 forward + backward through the module; indices checked against the reference extension's golden."""
+    import hashlib
+
+    from genpc_b200.loss_functions import chamfer_3DDist
+    from genpc_b200.synthetic import superquadric
+
+    fix = os.path.join(ROOT, "tests", "golden", "scan_01184_xyz.npz")
+    gold = os.path.join(ROOT, "tests", "golden", "c1_ref_chamfer.npz")
+    if not os.path.exists(fix):
+        return {"error": "tests/golden/scan_01184_xyz.npz missing"}
+    scan, shape = np.load(fix)["xyz"], superquadric(0, 16384)
+    a = torch.from_numpy(scan[None]).to(dev).requires_grad_(True)
+    b = torch.from_numpy(shape[None]).to(dev).requires_grad_(True)
+    cd = chamfer_3DDist()
+
+    def step():
+        a.grad = None
+        b.grad = None
+        d1, d2, _, _ = cd(a, b)
+        ((torch.sqrt(d1).mean() + torch.sqrt(d2).mean()) / 2).backward()
+
+    ms = ev_best(step, reps=10, warm=3)
+    d1, d2, i1, i2 = cd(a.detach(), b.detach())
+    res = {"workload": "C1: CD-L1 fwd+bwd, data/01184.ply (71372 pts) vs 16384-pt synthetic shape, B=1", "ms_fwd_bwd": ms,
+           "pairs_per_s": 2.0 * scan.shape[0] * 16384 / (ms * 1e-3),
+           "cd_l1": float((torch.sqrt(d1).mean() + torch.sqrt(d2).mean()) / 2)}
+    if os.path.exists(gold):
+        g = np.load(gold)
+        h = hashlib.sha256()
+        for t in (d1, d2, i1, i2):
+            h.update(np.ascontiguousarray(t.cpu().numpy()[0]).tobytes())
+        res["bit_exact_vs_reference_ext_golden"] = bool(h.hexdigest() == str(g["sha256"]))
+        assert res["bit_exact_vs_reference_ext_golden"], "C1: differs from the reference extension's golden"
+    return res
 
 
 def main():
@@ -396,6 +632,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the C1 / C4 / C5 legs (profiling runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank, local, world = env_int("RANK", 0), env_int("LOCAL_RANK", 0), env_int("WORLD_SIZE", 1)
@@ -473,14 +710,26 @@ def main():
     line.update(res)
     # per step: nn_sym_kernel, nn_sym_epilogue_kernel<fused> (fix-up + unpack + loss + zero-fill), chamfer_loss_grad_kernel
     line["gpu_launches"] = 3 * args.steps
-    line["config"]["api"] = "genpc_b200.utils.loss_util.Completionloss('cd_l2').get_loss(gen, gt); loss.backward()"
+    line["api"] = "genpc_b200.utils.loss_util.Completionloss('cd_l2').get_loss(gen, gt); loss.backward()"
+    # ---- the other BASELINE configs ride in the same line (outside the C2 timed region) ----
+    cfgs = {}
     try:
-        reg = registration_metric(rank, world, dev)
+        cfgs["C3_registration"] = registration_metric(rank, world, dev)
     except Exception as e:  # pragma: no cover
-        reg = {"error": str(e)}
-    line["registration"] = reg
+        cfgs["C3_registration"] = {"error": str(e)}
+    line["registration"] = cfgs["C3_registration"]
+    if not args.no_extras:
+        try:
+            cfgs["C5_sharded_chamfer"] = c5_sharded_metric(rank, world, dev)   # collective: every rank takes part
+        except AssertionError:
+            raise
+        except Exception as e:  # pragma: no cover
+            cfgs["C5_sharded_chamfer"] = {"error": str(e)}
+    line["baseline_configs"] = cfgs
     if rank == 0:
         t_fwd, t_bwd = time_kernels_ours(dev, a, b, flush)
+        prof_scan = read_ncu_profile("nn_sym", "nn_sym")
+        prof_grad = read_ncu_profile("fix_grad", "chamfer_loss_grad_kernel")
         flops = 2.0 * B * N * M * FLOP_PER_PAIR
         ach = flops / (t_fwd * 1e-3) / 1e12
         m = measured_fp32_peak()
@@ -495,23 +744,29 @@ def main():
                                            "figure; measured issue rates in profiles/fp32_peak_b200.json)",
                             "ms": t_fwd, "pairs_per_s": 2.0 * B * N * M / (t_fwd * 1e-3),
                             "algorithmic_bytes_per_launch": 20.0 * B * (N + M),
-                            "traffic": NCU_DRAM_BYTES_NN_SYM, "traffic_source": "ncu --set full, dram__bytes_read.sum + "
-                            "dram__bytes_write.sum per launch of nn_sym_kernel (profiles/r01k_nn_sym_ncu.txt)"}
+                            "traffic": ncu_dram_bytes(prof_scan),
+                            "traffic_source": ("ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch of the scan "
+                                               f"kernel, read at run time from {prof_scan['file']}") if prof_scan else None}
         # transparency: the symmetric kernel EXECUTES each distance once (6 FMA-pipe lane-ops, counted as 8 flop), i.e. half of
         # the algorithmic work; ncu's FMA-pipe utilisation of the same launch is recorded beside it
         lane_ops = 6.0 * B * N * M / (t_fwd * 1e-3)      # 3 sub + 1 mul + 2 fma per distance, each distance evaluated once
         line["roofline"]["executed"] = {"fma_pipe_lane_ops_per_s": lane_ops,
                                         "frac_of_fma_pipe_lane_rate": lane_ops / (148 * 128 * 1.965e9),
-                                        "fma_pipe_cycles_active_pct_ncu": 71.2,
+                                        "fma_pipe_cycles_active_pct_ncu":
+                                            prof_scan["sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"][0]
+                                            if prof_scan and "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active" in prof_scan
+                                            else None,
                                         "note": "over the whole forward op (memset + scan + epilogue); the ncu figure is the scan "
-                                                "kernel alone, profiles/r01k_nn_sym_ncu.txt (sm__pipe_fma_cycles_active)"}
+                                                "kernel alone, from the same profile file"}
         if m and "ffma2" in m:
             line["roofline"]["measured_ffma2_tflops"] = m["ffma2"].get("tflops")
         bwd_bytes = 44.0 * B * (N + M)
         gbs = bwd_bytes / (t_bwd * 1e-3) / 1e9
         line["roofline_bwd"] = {"bound": "hbm", "kernel": "chamfer_grad_kernel", "achieved": gbs, "peak": hbm_peak,
                                 "unit": "GB/s", "frac": gbs / hbm_peak, "peak_source": peak_src, "ms": t_bwd,
-                                "traffic": None}
+                                "algorithmic_bytes_per_launch": bwd_bytes, "traffic": ncu_dram_bytes(prof_grad),
+                                "traffic_source": (f"ncu --set full of chamfer_loss_grad_kernel (the fused-loss form of the same "
+                                                   f"kernel), {prof_grad['file']}") if prof_grad else None}
         if world == 1:
             try:
                 import oracle
@@ -535,7 +790,24 @@ def main():
             except Exception as e:  # pragma: no cover
                 line["ref_cuda_ext"] = {"error": str(e)}
             if not args.no_cpu_baseline:
-                line["cpu_baseline"] = cpu_baseline(part, comp)
+                cb = cpu_baseline(part, comp, keep_forward=True)
+                # full-batch parity of the arm that was just timed: every one of the 32 scans, bit for bit, against the oracle
+                exp = cb.pop("_oracle_forward")
+                from genpc_b200.loss_functions import chamfer_3DDist
+
+                got = chamfer_3DDist()(a.detach(), b.detach())
+                ok = all(np.array_equal(g_.cpu().numpy().view(np.int32), e_.view(np.int32)) for g_, e_ in zip(got, exp))
+                line["parity"] = {"c2_full_batch_bit_exact_vs_oracle": bool(ok), "scans": B}
+                assert ok, "C2: the timed kernels differ from the oracle"
+                line["cpu_baseline"] = cb
+            if not args.no_extras:
+                for key, fn in (("C1_real_scan", c1_metric), ("C4_depth_fps", c4_metric), ("C5_emd", emd_c5_metric)):
+                    try:
+                        cfgs[key] = fn(dev)
+                    except AssertionError:
+                        raise
+                    except Exception as e:  # pragma: no cover
+                        cfgs[key] = {"error": f"{type(e).__name__}: {e}"}
         print(json.dumps(line))
     if world > 1:
         torch.distributed.destroy_process_group()

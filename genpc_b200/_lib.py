@@ -64,6 +64,7 @@ _SIGNATURES = {
     "genpc_emd_forward": (_int, [_vp] * 12 + [_int, _int, _int, _flt, _int, _vp, _sz, _vp]),
     "genpc_emd_backward": (_int, [_vp, _vp, _vp, _vp, _vp, _int, _int, _vp]),
     "genpc_register_workspace_bytes": (_sz, [_int, _int, _int]),
+    "genpc_register_launches_per_iter": (_int, [_int, _int, _int]),
     "genpc_register_run": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _int, _int, _int, _int, _int,
                                   _dbl, _dbl, _dbl, _flt, _flt, _flt, _vp, _sz, _int, _vp]),
 }

@@ -343,10 +343,26 @@ __global__ void __launch_bounds__(FIX_THREADS, 2) register_finish_kernel(const R
 
 using namespace genpc;
 
+// symmetric path (default for big problems): rows = fixed cloud, cols = moving cloud; the one-scan-per-direction kernel
+// stays for tiny fixed clouds and for A/B runs (GENPC_REGISTER_MODE=scan).  Measured on B200
+// (profiles/r01d_registration.txt): 64 x 16384^2 -> 5.32 ms/iter (sym) vs 7.12 (scan); tiny problems (2500 x 1000 x 4
+// starts) are launch bound and keep the single-launch kernel.
+static bool register_takes_sym_path(int S, int Nc, int Nr) {
+    const char *mode = getenv("GENPC_REGISTER_MODE");
+    const bool big = (double)S * (double)Nc * (double)Nr >= 2e8;
+    return (mode == nullptr ? big : strcmp(mode, "sym") == 0) && Nr >= 512;
+}
+
 extern "C" size_t genpc_register_workspace_bytes(int S, int Nc, int Nr) {
     if (S < 0 || Nc < 0 || Nr < 0) return 0;
     const size_t fix_ctas = ((size_t)Nc + 128 - 1) / 128;  // sized for the finest CTA granularity
     return ((size_t)S * Nc + (size_t)S * Nr) * 8 + (size_t)S * fix_ctas * 14 * sizeof(double) + (size_t)S * sizeof(int);
+}
+
+// Kernel launches one Adam iteration costs at this problem size (1: single-launch path, 2: symmetric scan + finish).
+extern "C" int genpc_register_launches_per_iter(int S, int Nc, int Nr) {
+    if (S <= 0 || Nc <= 0 || Nr <= 0) return GENPC_ERR_SHAPE;
+    return register_takes_sym_path(S, Nc, Nr) ? 2 : 1;
 }
 
 extern "C" int genpc_register_run(const float *complete, const float *center, const float *ref, float *params,
@@ -389,13 +405,7 @@ extern "C" int genpc_register_run(const float *complete, const float *center, co
     a.ticket_total = a.items_per_scan;
     const long long grid = (long long)S * a.items_per_scan;
     if (grid > 0x7fffffffLL) return GENPC_ERR_RANGE;
-    // symmetric path (default): rows = fixed cloud, cols = moving cloud; the one-scan-per-direction kernel stays for
-    // tiny fixed clouds and for A/B runs (GENPC_REGISTER_MODE=scan)
-    const char *mode = getenv("GENPC_REGISTER_MODE");
-    // measured on B200 (profiles/r01d_registration.txt): 64 x 16384^2 -> 5.32 ms/iter (sym) vs 7.12 (scan); tiny problems
-    // (2500 x 1000 x 4 starts) are launch bound and keep the single-launch kernel
-    const bool big = (double)S * (double)Nc * (double)Nr >= 2e8;
-    const bool sym = (mode == nullptr ? big : strcmp(mode, "sym") == 0) && Nr >= 512;
+    const bool sym = register_takes_sym_path(S, Nc, Nr);
     const int SQT = Nr >= 1024 ? 4 : 2;
     long long sgrid = 0, fgrid = 0;
     const int fix_cols = fix_cols_per_cta(S, Nc);

@@ -107,3 +107,20 @@ def superquadric_mesh(seed, n_eta=48, n_om=96):
     faces = np.concatenate([np.stack([a, b, c], 1), np.stack([b, d, c], 1)]).astype(np.int32)
     col = (p - p.min(0)) / (p.max(0) - p.min(0) + 1e-8)
     return p.astype(np.float32), faces, col.astype(np.float32)
+
+
+def lidar_scene_pair(n, seed=0):
+    """BASELINE config C5 (SURVEY.md section 8d): two n-point LiDAR-like clouds -- ground plane + ~100 object blobs, shuffled;
+    the second = the first rigidly perturbed (1 cm-scale motion) + 2 cm jitter.  torch CPU tensors [n,3] float32."""
+    import torch
+
+    g = torch.Generator().manual_seed(seed)
+    ground = torch.rand(n // 2, 3, generator=g) * torch.tensor([80.0, 80.0, 0.05]) - torch.tensor([40.0, 40.0, 0.0])
+    centers = torch.rand(100, 3, generator=g) * torch.tensor([70.0, 70.0, 0.0]) - torch.tensor([35.0, 35.0, -1.0])
+    objs = centers[torch.randint(0, 100, (n - n // 2,), generator=g)] + \
+        torch.randn(n - n // 2, 3, generator=g) * torch.tensor([1.5, 0.8, 0.7])
+    a = torch.cat([ground, objs])[torch.randperm(n, generator=g)].contiguous()
+    ang = 0.01
+    R = torch.tensor([[np.cos(ang), -np.sin(ang), 0], [np.sin(ang), np.cos(ang), 0], [0, 0, 1]], dtype=torch.float32)
+    b = (a @ R.T + torch.tensor([0.05, -0.03, 0.01]) + torch.randn(n, 3, generator=g) * 0.02).contiguous()
+    return a, b

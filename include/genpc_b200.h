@@ -253,6 +253,8 @@ int genpc_emd_backward(const float *xyz1, const float *xyz2, float *gradxyz, con
  * workspace: genpc_register_workspace_bytes(S,Nc,Nr); pass reset_workspace=1 on the first call of a run
  * (later calls continuing the same run pass 0 and t_start = iterations already done). */
 size_t genpc_register_workspace_bytes(int S, int Nc, int Nr);
+/* Kernel launches per Adam iteration at this problem size: 1 (single fused launch) or 2 (symmetric scan + finish). */
+int genpc_register_launches_per_iter(int S, int Nc, int Nr);
 int genpc_register_run(const float *complete, const float *center, const float *ref, float *params,
                        float *adam_m, float *adam_v, float *loss_hist, int S, int n_starts, int Nc, int Nr,
                        int iters, int t_start, int T, double lr_rot, double lr_trans, double lr_scale,

@@ -13,16 +13,9 @@ rank, local, world = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_R
 dev = torch.device(f"cuda:{local}"); torch.cuda.set_device(dev)
 if world > 1:
     dist.init_process_group("nccl", device_id=dev)
-# LiDAR-like scene: ground plane + ~100 object blobs; second cloud = rigidly perturbed + jittered copy (seed 0)
-g = torch.Generator().manual_seed(0)
+from genpc_b200.synthetic import lidar_scene_pair
 n = args.n
-ground = torch.rand(n // 2, 3, generator=g) * torch.tensor([80.0, 80.0, 0.05]) - torch.tensor([40.0, 40.0, 0.0])
-centers = torch.rand(100, 3, generator=g) * torch.tensor([70.0, 70.0, 0.0]) - torch.tensor([35.0, 35.0, -1.0])
-objs = centers[torch.randint(0, 100, (n - n // 2,), generator=g)] + torch.randn(n - n // 2, 3, generator=g) * torch.tensor([1.5, 0.8, 0.7])
-a = torch.cat([ground, objs])[torch.randperm(n, generator=g)].contiguous()
-ang = 0.01
-R = torch.tensor([[np.cos(ang), -np.sin(ang), 0], [np.sin(ang), np.cos(ang), 0], [0, 0, 1]], dtype=torch.float32)
-b = (a @ R.T + torch.tensor([0.05, -0.03, 0.01]) + torch.randn(n, 3, generator=g) * 0.02).contiguous()
+a, b = lidar_scene_pair(n, 0)   # LiDAR-like scene (same generator as bench.py's C5 leg)
 ta, tb = a[None].to(dev), b[None].to(dev)
 out = sharded_chamfer_forward(ta, tb); torch.cuda.synchronize()
 ts = []
