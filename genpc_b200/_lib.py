@@ -28,11 +28,14 @@ class ChamferFuse(ctypes.Structure):
 
 _SIGNATURES = {
     "genpc_version": (ctypes.c_char_p, []),
+    "genpc_set_tunable": (_int, [ctypes.c_char_p, ctypes.c_char_p]),
+    "genpc_get_tunable": (ctypes.c_char_p, [ctypes.c_char_p]),
     "genpc_chamfer_workspace_bytes": (_sz, [_int, _int, _int]),
     "genpc_chamfer_forward": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _int, _vp, _sz, _vp]),
     "genpc_host_feed_create": (_int, [ctypes.POINTER(_vp)]),
     "genpc_host_feed_destroy": (_int, [_vp]),
     "genpc_host_feed_error": (_int, [_vp, _vp]),
+    "genpc_host_feed_inject_error": (_int, [_vp, _vp]),
     "genpc_chamfer_forward_host": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _int, _int, _vp, _sz,
                                           _vp]),
     "genpc_chamfer_fuse_workspace_bytes": (_sz, [_int, _int, _int]),
@@ -85,6 +88,28 @@ def lib():
             fn.argtypes = args
         _lib = L
     return _lib
+
+
+class tunable:
+    """Context manager: set an experiment knob of the library (GENPC_* name) for the duration of a block.  The library reads
+    the environment only once, at load time, so tests / tools flip knobs through this instead of os.environ."""
+
+    def __init__(self, **knobs):
+        self.knobs = {k: (None if v is None else str(v)) for k, v in knobs.items()}
+        self.old = {}
+
+    def __enter__(self):
+        L = lib()
+        for k, v in self.knobs.items():
+            self.old[k] = L.genpc_get_tunable(k.encode())
+            check(L.genpc_set_tunable(k.encode(), None if v is None else v.encode()), f"genpc_set_tunable({k})")
+        return self
+
+    def __exit__(self, *exc):
+        L = lib()
+        for k, v in self.old.items():
+            L.genpc_set_tunable(k.encode(), v)
+        return False
 
 
 def check(rc, what):

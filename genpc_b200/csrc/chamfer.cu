@@ -14,6 +14,8 @@
 //     lowest-index tie rule), then unpacked to dist/idx.
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
+#include <new>
 
 #include "nn_core.cuh"
 #include "nn_sym.cuh"
@@ -187,25 +189,25 @@ static int chamfer_forward_sym(const float *xyz1, const float *xyz2, float *dist
     // measured on B200 (profiles/r01c_sym_variants.txt): QT=4 at 3 CTAs/SM is within 1 % of QT=8 at 2 CTAs/SM on
     // large clouds and clearly better when the grid is small
     int QT = p.nr >= 1024 ? 4 : 2;
-    const char *fq = getenv("GENPC_SYM_QT");  // experiments only
+    const char *fq = tunable("GENPC_SYM_QT");  // experiments only
     if (gate == nullptr && fq != nullptr && (atoi(fq) == 8 || atoi(fq) == 6 || atoi(fq) == 4 || atoi(fq) == 2)) QT = atoi(fq);
     p.rtiles = (p.nr + SYM_THREADS * QT - 1) / (SYM_THREADS * QT);
     // column span: the largest that still gives >= 2 waves of work items (3 CTAs x 148 SMs), at least 256 columns
     int span = SYM_SPAN_MAX;
     const long long want = 2LL * 3 * GENPC_NUM_SMS;
     while (span > 256 && (long long)B * p.rtiles * ((p.nc + span - 1) / span) < want) span >>= 1;
-    const char *fs = getenv("GENPC_SYM_SPAN");
+    const char *fs = tunable("GENPC_SYM_SPAN");
     if (fs != nullptr && atoi(fs) >= 32 && atoi(fs) <= SYM_SPAN_MAX && atoi(fs) % 32 == 0) span = atoi(fs);
     p.span = span;
     p.cspans = (p.nc + span - 1) / span;
     const long long items = (long long)B * p.rtiles * p.cspans;
     if (items > 0x7fffffffLL) return GENPC_ERR_RANGE;
-    const char *pm = getenv("GENPC_SYM_PERSIST");
+    const char *pm = tunable("GENPC_SYM_PERSIST");
     const bool persist = (pm == nullptr) ? GENPC_DEFAULT_PERSIST : (atoi(pm) != 0);
     // measured on B200 (profiles/r01h_sym_balanced_vs_grid.txt): with fewer than two waves of full-span work items the
     // balanced form wins (B=1 16384^2 +5 %, 3 x 5000 x 3333 +12 %); with more, one CTA per item is 4-5 % faster (resident
     // CTAs drift out of phase, so staging / publishing of one overlaps the scan of the other)
-    const char *bm = getenv("GENPC_SYM_BALANCED");
+    const char *bm = tunable("GENPC_SYM_BALANCED");
     const bool few_items = (long long)B * p.rtiles * ((p.nc + SYM_SPAN_MAX - 1) / SYM_SPAN_MAX) < 4LL * GENPC_NUM_SMS;
     const bool balanced = (bm == nullptr) ? (GENPC_DEFAULT_BALANCED && few_items) : (atoi(bm) != 0);
     if (gate != nullptr) {
@@ -251,6 +253,7 @@ static int chamfer_forward_sym(const float *xyz1, const float *xyz2, float *dist
         if (fuse->loss_out != nullptr) f.partial = fuse_partial, f.ticket = fuse_ticket, f.loss_out = fuse->loss_out;
         f.zero[0] = fuse->zero1, f.nzero[0] = (size_t)B * N * 3;
         f.zero[1] = fuse->zero2, f.nzero[1] = (size_t)B * M * 3;
+        f.err_flag = gate != nullptr ? gate + GATE_ERR_SLOT : nullptr;
         nn_sym_epilogue_kernel<true><<<fix_blocks + unpack_blocks, 256, 0, stream>>>(
             p.rows, p.cols, p.prow, p.pcol, B, p.nr, p.nc, 32 * QT, fix_blocks, dist_r, idx_r, dist_c, idx_c, f);
     }
@@ -275,7 +278,7 @@ extern "C" size_t genpc_chamfer_workspace_bytes(int B, int N, int M) {
 
 static bool takes_sym_path(int N, int M) {
     // "sym": one evaluation of every distance feeds both directions (nn_sym.cuh); "scan": one scan per direction
-    const char *mode = getenv("GENPC_CHAMFER_MODE");
+    const char *mode = tunable("GENPC_CHAMFER_MODE");
     const bool want_sym = (mode == nullptr) ? GENPC_DEFAULT_SYM : (strcmp(mode, "sym") == 0);
     return want_sym && N > 0 && M > 0 && (N > M ? N : M) >= 512;
 }
@@ -345,7 +348,7 @@ extern "C" int genpc_chamfer_forward_fused(const float *xyz1, const float *xyz2,
     }
     if (sym) {
         int *counter = (int *)(packed + n1 + n2);  // work-item counter of the persistent kernel (after the packed words)
-        const char *pm = getenv("GENPC_SYM_PERSIST");
+        const char *pm = tunable("GENPC_SYM_PERSIST");
         if ((pm == nullptr) ? GENPC_DEFAULT_PERSIST : (atoi(pm) != 0)) {
             e = cudaMemsetAsync(counter, 0, 16, stream);
             if (e != cudaSuccess) return (int)e;
@@ -418,13 +421,15 @@ struct genpc_host_feed {
     unsigned *h_ring;  // pinned: source words of the gate writes
     unsigned gen;
     int device;
+    std::mutex lock;   // one call at a time per handle: the generation counter, the ring slot and the gate words are shared
 };
 static constexpr int FEED_RING = 256;
 
 extern "C" int genpc_host_feed_create(genpc_host_feed_t **out) {
     if (out == nullptr) return GENPC_ERR_SHAPE;
-    genpc_host_feed *f = (genpc_host_feed *)calloc(1, sizeof(genpc_host_feed));
+    genpc_host_feed *f = new (std::nothrow) genpc_host_feed();
     if (f == nullptr) return (int)cudaErrorMemoryAllocation;
+    f->copy_stream = nullptr, f->ready = nullptr, f->copied = nullptr, f->gate = nullptr, f->h_ring = nullptr, f->gen = 0;
     cudaError_t e = cudaGetDevice(&f->device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&f->copy_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&f->ready, cudaEventDisableTiming);
@@ -447,7 +452,7 @@ extern "C" int genpc_host_feed_destroy(genpc_host_feed_t *f) {
     if (f->copied) cudaEventDestroy(f->copied);
     if (f->gate) cudaFree(f->gate);
     if (f->h_ring) cudaFreeHost(f->h_ring);
-    free(f);
+    delete f;
     return GENPC_OK;
 }
 
@@ -480,6 +485,7 @@ extern "C" int genpc_chamfer_forward_host_fused(genpc_host_feed_t *f, const floa
         return genpc_chamfer_forward_fused(xyz1, xyz2, dist1, dist2, idx1, idx2, B, N, M, workspace, workspace_bytes, fuse, stream_);
     }
     if (workspace == nullptr || workspace_bytes < genpc_chamfer_workspace_bytes(B, N, M)) return GENPC_ERR_WORKSPACE;
+    std::lock_guard<std::mutex> guard(f->lock);   // host threads sharing the handle take turns
     if (chunks > GATE_MAX_CHUNKS) chunks = GATE_MAX_CHUNKS;
     if (chunks > B) chunks = B;
     const int pairs = (B + chunks - 1) / chunks;  // cloud pairs per chunk
@@ -515,14 +521,24 @@ extern "C" int genpc_chamfer_forward_host_fused(genpc_host_feed_t *f, const floa
     return GENPC_OK;
 }
 
-// 1 if a gated launch of this feed ever timed out waiting for its data (results of that call are invalid).
+// 1 if a gated launch of this feed timed out waiting for its data since the last call of this function (results of that
+// launch are invalid; its fused loss, if any, is NaN).  Synchronises `stream`; the error word is cleared once reported.
 extern "C" int genpc_host_feed_error(genpc_host_feed_t *f, genpc_stream_t stream_) {
     if (f == nullptr) return GENPC_ERR_SHAPE;
+    std::lock_guard<std::mutex> guard(f->lock);
     unsigned v = 0;
     cudaError_t e = cudaMemcpyAsync(&v, f->gate + GATE_ERR_SLOT, sizeof(unsigned), cudaMemcpyDeviceToHost, (cudaStream_t)stream_);
     if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream_);
+    if (e == cudaSuccess && v) e = cudaMemsetAsync(f->gate + GATE_ERR_SLOT, 0, sizeof(unsigned), (cudaStream_t)stream_);
     if (e != cudaSuccess) return (int)e;
     return v ? 1 : 0;
+}
+
+// Test hook: raise the feed's error word as a timed-out gate would (the 2-second timeout itself cannot be provoked cheaply).
+extern "C" int genpc_host_feed_inject_error(genpc_host_feed_t *f, genpc_stream_t stream_) {
+    if (f == nullptr) return GENPC_ERR_SHAPE;
+    cudaError_t e = cudaMemsetAsync(f->gate + GATE_ERR_SLOT, 1, 1, (cudaStream_t)stream_);
+    return e == cudaSuccess ? GENPC_OK : (int)e;
 }
 
 // ---- target-sharded Chamfer (million-point clouds over several GPUs) ---------------------------------------

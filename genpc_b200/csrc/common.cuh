@@ -13,6 +13,10 @@
 
 namespace genpc {
 
+// Experiment knob `name` (GENPC_*): its value as read from the environment when the library was loaded or as set through
+// genpc_set_tunable(); nullptr when unset.  Never calls getenv() (tunables.cu).
+const char *tunable(const char *name);
+
 // The whole library is compiled with -fmad=false: every contraction below is explicit, because the
 // reference's indices depend on the exact rounding order.
 

@@ -551,7 +551,11 @@ extern "C" int genpc_emd_forward(const float *xyz1, const float *xyz2, float *di
                                  void *workspace, size_t workspace_bytes, genpc_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     // the reference's checks (emd_cuda.cu:236-249)
-    if (n != m || B > 512 || n % 256 != 0 || B < 0 || n < 0 || iters < 0) return GENPC_ERR_SHAPE;
+    if (n != m || B > 512 || n % 256 != 0 || B < 0 || n < 0) return GENPC_ERR_SHAPE;
+    // eps <= 0: the bid increments best - better + eps are no longer all positive and the integer atomicMax over their bit
+    // patterns would order them differently from the reference's float atomicMax; iters <= 0 leaves assignment = -1 and the
+    // distance / gradient kernels would index xyz2[-1] (the reference does, emd_cuda.cu:217-226).  Both rejected.
+    if (!(eps > 0.f) || iters <= 0) return GENPC_ERR_SHAPE;
     if (B == 0 || n == 0) return GENPC_OK;
     if (workspace == nullptr || workspace_bytes < genpc_emd_workspace_bytes(B)) return GENPC_ERR_WORKSPACE;
     cudaError_t e = cudaMemsetAsync(workspace, 0, genpc_emd_workspace_bytes(B), stream);
@@ -584,11 +588,11 @@ extern "C" int genpc_emd_forward(const float *xyz1, const float *xyz2, float *di
     // measured on B200 (profiles/r01j_emd_direct.txt)
     a.direct_p = 8;
     a.two_level_div = 8;
-    const char *gm = getenv("GENPC_EMD_GETMAX");  // "lowest": the other legitimate outcome of the reference's race
+    const char *gm = tunable("GENPC_EMD_GETMAX");  // "lowest": the other legitimate outcome of the reference's race
     a.getmax_lowest = (gm != nullptr && strcmp(gm, "lowest") == 0) ? 1 : 0;
-    const char *tl = getenv("GENPC_EMD_TWO_LEVEL");  // experiments only
+    const char *tl = tunable("GENPC_EMD_TWO_LEVEL");  // experiments only
     if (tl != nullptr) a.two_level_div = atoi(tl);
-    const char *dp = getenv("GENPC_EMD_DIRECT_P");  // experiments only
+    const char *dp = tunable("GENPC_EMD_DIRECT_P");  // experiments only
     if (dp != nullptr) a.direct_p = atoi(dp);
     if ((reinterpret_cast<size_t>(xyz2) & 7) != 0 || (reinterpret_cast<size_t>(price) & 7) != 0) a.direct_p = 0;  // LDG.64
     void *kargs[] = {(void *)&a};

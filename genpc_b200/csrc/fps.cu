@@ -448,7 +448,7 @@ static cudaError_t launch_fps_cluster(const float *xyz, int B, int N, int K, int
     // clouds of up to 16384 points have a fast single-CTA kernel (2.9 ms for 16384 -> 2048 whatever B): when the clusters
     // would run in waves (4.7 ms at B = 18) the caller falls through to it; larger clouds stay here (waves of clusters
     // still beat the L1 / global-memory single-CTA forms)
-    if (PPT * CS <= 16 && getenv("GENPC_FPS_MODE") == nullptr && B > fps_max_active_clusters<PPT, CS, SMEMC>())
+    if (PPT * CS <= 16 && tunable("GENPC_FPS_MODE") == nullptr && B > fps_max_active_clusters<PPT, CS, SMEMC>())
         return cudaErrorLaunchOutOfResources;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(B * CS));
@@ -489,7 +489,7 @@ extern "C" int genpc_fps(const float *xyz, int B, int N, int K, int start, int *
     // clusters of 8 CTAs when the batch alone cannot fill the chip and the cloud is big enough to be LSU/L1 bound.
     // Measured on B200 (profiles/r01d_fps.txt): a pick costs 1.15 us through the cluster exchange whatever N is, and
     // 0.35 / 0.51 / 1.02 / 1.78 / 4.23 us in the single CTA at N = 1024 / 4096 / 8192 / 16384 / 32768.
-    const char *fm = getenv("GENPC_FPS_MODE");
+    const char *fm = tunable("GENPC_FPS_MODE");
     const bool want_cluster = (fm == nullptr) ? (ppt > 8 && ppt <= 144 && B * 8 <= GENPC_NUM_SMS) : (strcmp(fm, "cluster") == 0 && ppt <= 144);
     if (want_cluster) {
         cudaError_t e = cudaErrorUnknown;
@@ -497,7 +497,7 @@ extern "C" int genpc_fps(const float *xyz, int B, int N, int K, int start, int *
         // cloud in registers (<= 9 points per thread) and halves the per-pick distance update of the 8-CTA form, whose
         // coordinates live in shared memory; the exchange grows from 8 to 16 candidates.  Falls back to 8 CTAs when the
         // device cannot co-schedule 16 (profiles/r01j_fps_cluster16.txt).
-        const char *c16 = getenv("GENPC_FPS_CLUSTER16");
+        const char *c16 = tunable("GENPC_FPS_CLUSTER16");
         // measured: 16 CTAs win from ~45 K points on (1.73 vs 2.06 us per pick at 71 372, 2.11 vs 2.56 at 139 138)
         const bool try16 = (c16 == nullptr) ? (ppt > 48 && B * 16 <= GENPC_NUM_SMS) : (atoi(c16) != 0 && ppt > 8);
         if (try16) {
@@ -522,7 +522,7 @@ extern "C" int genpc_fps(const float *xyz, int B, int N, int K, int start, int *
 #define FPS_LAUNCH(P) fps_reg_kernel<P, (P <= 4)><<<B, FPS_THREADS, 0, stream>>>(xyz, N, K, start, idx_out, seq_out)
     // 4096 < N <= 16384: coordinates in shared memory (LDS.128) instead of re-reads through L1; GENPC_FPS_SMEM=0 keeps
     // the L1 form (measured: profiles/r01k_fps_smem.txt)
-    const char *fs = getenv("GENPC_FPS_SMEM");
+    const char *fs = tunable("GENPC_FPS_SMEM");
     const bool use_smem = (fs == nullptr) ? true : (atoi(fs) != 0);
     if (use_smem && ppt > 4 && ppt <= 16) {
         const cudaError_t e = (ppt <= 8) ? launch_fps_smem<8>(xyz, B, N, K, start, idx_out, seq_out, stream)

@@ -209,10 +209,8 @@ __device__ __forceinline__ void nn_sym_item(float (*s)[SYM_SPAN_MAX], const floa
     for (int qi = 0; qi < QT; ++qi) {
         const int j = jbase + qi * 32;
         if (j >= nr) continue;
-        if (!(best[qi] < inf)) {  // NaN / overflow: publish (inf, first column of the span) like nn_scan_item does
-            atomicMin(prow + j, pack_dist_idx(inf, c0));
-            continue;
-        }
+        // every in-range row publishes, also when its minimum stayed +inf (NaN / overflowing coordinates: the re-scan finds
+        // no match and reports the first column of the span, like nn_scan_item) -- no packed word is ever left unarmed
         const float qx = -nqx[qi].x, qy = -nqy[qi].x, qz = -nqz[qi].x;
         const int cb = bchunk[qi] * SYM_CHUNK;
         int kbest = 0;
@@ -440,6 +438,7 @@ struct EpiFuse {
     int rearm;              // store all-ones back into every packed word after reading it
     float *zero[2];         // buffers to zero-fill, or nullptr
     size_t nzero[2];        // their sizes in floats
+    const unsigned *err_flag;  // host-fed launches: the feed's error word -- a timed-out gate poisons the loss with NaN
 };
 
 __device__ __forceinline__ void epi_zero_fill(float *z, size_t n, size_t g, size_t total_threads) {
@@ -568,6 +567,9 @@ static __global__ void __launch_bounds__(256) nn_sym_epilogue_kernel(const float
             double loss = 0.0;
             if (f.fcol != 0.0) loss += f.fcol * sc;
             if (f.frow != 0.0) loss += f.frow * sr;
+            // a gated scan that gave up waiting for its data (nn_sym_gated_kernel) worked on garbage: the caller sees it at
+            // the first natural synchronisation point -- the loss it reads back is NaN
+            if (f.err_flag != nullptr && __ldcg(f.err_flag) != 0u) loss = __longlong_as_double(0x7ff8000000000000LL);
             f.loss_out[0] = (float)loss;
             *f.ticket = 0;
         }

@@ -235,7 +235,7 @@ constexpr int FIX_THREADS = 512;
 // 128 -> 4.41, 256 -> 4.32, 512 -> 4.28 ms per iteration (fewer tickets / partial reductions per point); the largest
 // size that still gives every resident-CTA slot (2 per SM) one CTA is used.
 static int fix_cols_per_cta(int S, int Nc) {
-    const char *e = getenv("GENPC_FIX_COLS");  // experiments only
+    const char *e = tunable("GENPC_FIX_COLS");  // experiments only
     if (e != nullptr && (atoi(e) == 128 || atoi(e) == 256 || atoi(e) == 512)) return atoi(e);
     for (int cols = 512; cols > 128; cols >>= 1)
         if ((long long)S * ((Nc + cols - 1) / cols) >= 2LL * GENPC_NUM_SMS) return cols;
@@ -348,7 +348,7 @@ using namespace genpc;
 // (profiles/r01d_registration.txt): 64 x 16384^2 -> 5.32 ms/iter (sym) vs 7.12 (scan); tiny problems (2500 x 1000 x 4
 // starts) are launch bound and keep the single-launch kernel.
 static bool register_takes_sym_path(int S, int Nc, int Nr) {
-    const char *mode = getenv("GENPC_REGISTER_MODE");
+    const char *mode = tunable("GENPC_REGISTER_MODE");
     const bool big = (double)S * (double)Nc * (double)Nr >= 2e8;
     return (mode == nullptr ? big : strcmp(mode, "sym") == 0) && Nr >= 512;
 }
@@ -385,7 +385,7 @@ extern "C" int genpc_register_run(const float *complete, const float *center, co
     // queries per thread of the single-launch path: the real pipeline registers 1-3 K-point clouds with 4 starts -- a few
     // dozen CTAs; fewer queries per thread (more, shorter CTAs) while the grid does not fill the GPU twice over
     int QT = nn_pick_qt(Nc < Nr ? Nc : Nr);
-    const char *fq = getenv("GENPC_REGISTER_QT");  // experiments only
+    const char *fq = tunable("GENPC_REGISTER_QT");  // experiments only
     if (fq != nullptr && (atoi(fq) == 1 || atoi(fq) == 2 || atoi(fq) == 4)) {
         QT = atoi(fq);
     } else {

@@ -188,3 +188,66 @@ class sharded_chamfer_3DDist(torch.nn.Module):
 
     def forward(self, input1, input2):
         return ShardedChamferFunction.apply(input1, input2, self.group)
+
+
+# ---- independent units: batch sharding -----------------------------------------------------------
+# The reference scatters a batch over its visible GPUs with nn.DataParallel(emdModule) inside ONE process
+# (utils/loss_util.py:12).  Here every rank is one process with one GPU and the same (replicated) batch: rank r computes
+# its contiguous batch slice, then ONE all-gather hands every rank the full result -- no data-path collective inside the
+# compute, results bit-identical to the single-GPU call because batch entries never interact.
+
+def _gather_batch(parts_shape, local, lo, hi, group):
+    """All-gather of per-rank batch slices [lo:hi] of a [B, ...] tensor (uneven slices allowed)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return local
+    world = dist.get_world_size(group)
+    out = torch.empty(parts_shape, dtype=local.dtype, device=local.device)
+    sizes = [shard_range(parts_shape[0], r, world) for r in range(world)]
+    chunks = [out[a:b] for a, b in sizes]
+    if all(b - a == sizes[0][1] - sizes[0][0] for a, b in sizes):
+        dist.all_gather(chunks, local.contiguous(), group=group)       # equal slices: views into `out`, no extra copy
+    else:
+        for r, (a, b) in enumerate(sizes):                             # uneven: one broadcast per owner
+            if a == b:
+                continue
+            buf = local.contiguous() if r == dist.get_rank(group) else chunks[r]
+            dist.broadcast(buf, src=dist.get_global_rank(group, r) if group is not None else r, group=group)
+            if r == dist.get_rank(group):
+                chunks[r].copy_(buf)
+    return out
+
+
+def data_parallel_batch(fn, *tensors, group=None):
+    """out = fn(*tensors) with the batch dimension (dim 0 of every tensor) sharded over the ranks of `group`: every rank
+    runs fn on its slice, the outputs (a tensor or a tuple of tensors, batch first) are all-gathered.  Forward only."""
+    if dist.is_available() and dist.is_initialized():
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+    else:
+        rank, world = 0, 1
+    B = tensors[0].shape[0]
+    lo, hi = shard_range(B, rank, world)
+    if hi > lo:
+        local = fn(*[t[lo:hi].contiguous() for t in tensors])
+    else:   # more ranks than batch entries: run one entry to learn the output shapes, contribute nothing
+        local = fn(*[t[:1].contiguous() for t in tensors])
+        local = tuple(o[:0] for o in local) if isinstance(local, (tuple, list)) else local[:0]
+    if isinstance(local, (tuple, list)):
+        return tuple(_gather_batch((B,) + tuple(o.shape[1:]), o, lo, hi, group) for o in local)
+    return _gather_batch((B,) + tuple(local.shape[1:]), local, lo, hi, group)
+
+
+def data_parallel_emd(input1, input2, eps, iters, group=None):
+    """emdModule()(input1, input2, eps, iters) with the batch sharded over the ranks: the one-process-per-GPU equivalent of
+    the reference's nn.DataParallel(emdModule) (utils/loss_util.py:12).  -> (dist [B,n], assignment [B,n]) on every rank."""
+    from .loss_functions import emdModule
+
+    mod = emdModule()
+    with torch.no_grad():
+        return data_parallel_batch(lambda a, b: mod(a, b, eps, iters), input1, input2, group=group)
+
+
+def data_parallel_fps(xyz, K, start=0, group=None):
+    """furthest_point_sample over a batch sharded by cloud (FPS batches / views are independent units)."""
+    from .fps import furthest_point_sample
+
+    return data_parallel_batch(lambda x: furthest_point_sample(x, K, start), xyz, group=group)

@@ -127,7 +127,9 @@ class Completionloss:
     def get_loss_from_host(self, gen, gt, device=None, chunks=6):
         """`get_loss(gen.cuda(), gt.cuda())` for CPU (pinned) clouds, with the host-to-device copy overlapped with the
         scan (genpc_chamfer_forward_host): returns (loss, gen_cuda, gt_cuda); after `loss.backward()` the gradients are
-        in gen_cuda.grad / gt_cuda.grad.  Chamfer metrics only (the EMD auction needs every point before it starts)."""
+        in gen_cuda.grad / gt_cuda.grad.  Chamfer metrics only (the EMD auction needs every point before it starts).
+        If the copy never arrives (the scan gives up after ~2 s) the returned loss is NaN and
+        genpc_b200.chamfer_3D.host_feed_error(device) reports and clears the condition."""
         if self.loss_func not in self._HOST_CFG:
             raise Exception("get_loss_from_host supports cd_l1 / cd_l2")
         from ..loss_functions.Chamfer3D.dist_chamfer_3D import host_leaves

@@ -31,6 +31,12 @@ typedef void *genpc_stream_t; /* cudaStream_t */
 #define GENPC_ERR_WORKSPACE (-2) /* workspace NULL or too small */
 #define GENPC_ERR_RANGE (-3)     /* B*N does not fit the 32-bit index space of the reference */
 
+/* Experiment knobs (GENPC_* names, e.g. GENPC_FPS_MODE=cluster): the environment is read ONCE when the library is loaded;
+ * genpc_set_tunable overrides a knob at run time (value NULL = unset), genpc_get_tunable returns the current value or NULL.
+ * For tests and measurements; not synchronised with launches issued from other threads.  Unknown name: GENPC_ERR_SHAPE. */
+int genpc_set_tunable(const char *name, const char *value);
+const char *genpc_get_tunable(const char *name);
+
 /* Library / build identification: returns a static string such as "genpc_b200 0.1 sm_100a". */
 const char *genpc_version(void);
 
@@ -52,12 +58,16 @@ int genpc_chamfer_forward(const float *xyz1, const float *xyz2, float *dist1, fl
  * scan launch on `stream` consumes each group as soon as its copy has landed.  This is the reference's stock flow
  * `xyz.cuda()` + chamfer_3D.forward (dist_chamfer_3D.py:33-47) with the 7 MB PCIe transfer of a PCN batch hidden
  * behind 0.27 ms of compute.  On return, all work is queued; `stream` is ordered after the copies, so xyz1 / xyz2 can
- * be used by later work on `stream` (e.g. genpc_chamfer_backward).  A handle serves one call at a time per device;
- * genpc_host_feed_error reports (and synchronises `stream`) whether a launch ever timed out waiting for its data.
+ * be used by later work on `stream` (e.g. genpc_chamfer_backward).  A handle serves one call at a time (host threads
+ * sharing it are serialised by a lock inside the handle).  A gated launch that waits more than ~2 s for its data gives
+ * up and raises the handle's error word: the fused form then returns loss = NaN, so the failure is seen at the first
+ * natural synchronisation point; genpc_host_feed_error reports (synchronising `stream`) whether that happened since it
+ * was last asked, and clears the word.
  * Every 256th call waits on the host for the previous call's copies (recycling of the pinned flag source ring). */
 typedef struct genpc_host_feed genpc_host_feed_t;
 int genpc_host_feed_create(genpc_host_feed_t **feed);
 int genpc_host_feed_destroy(genpc_host_feed_t *feed);
+int genpc_host_feed_inject_error(genpc_host_feed_t *feed, genpc_stream_t stream); /* test hook: raise the error word */
 int genpc_host_feed_error(genpc_host_feed_t *feed, genpc_stream_t stream);
 int genpc_chamfer_forward_host(genpc_host_feed_t *feed, const float *h_xyz1, const float *h_xyz2, float *xyz1,
                                float *xyz2, float *dist1, float *dist2, int *idx1, int *idx2, int B, int N, int M,
@@ -225,9 +235,10 @@ int genpc_unproject(const float *cams, const float *bounds, int rescale, const u
  * reference's (emd_module.py:43-54): assignment = assignment_inv = -1, price = bid_increments =
  * max_increments = 0; unass_cnt has >= B ints (the reference allocates 512).  The reference's
  * unass_cnt_sum / cnt_tmp scratch is not needed.  Returns GENPC_ERR_SHAPE for n != m, B > 512, n % 256 != 0
- * (emd_cuda.cu:236-249).  Outputs dist[B][n], assignment[B][n] bit-identical to the reference wherever the
- * reference itself is deterministic (its GetMax store race is resolved as "highest bidder index"; the environment
- * variable GENPC_EMD_GETMAX=lowest selects the other outcome the reference is seen to produce).
+ * (emd_cuda.cu:236-249) and for eps <= 0 or iters <= 0 (the reference reads xyz2[-1] / mis-orders bids there).  Outputs dist[B][n], assignment[B][n] bit-identical to the reference wherever the
+ * reference itself is deterministic (its GetMax store race is resolved as "highest bidder index"; the knob
+ * GENPC_EMD_GETMAX=lowest -- environment at load time or genpc_set_tunable -- selects the other outcome the reference is
+ * seen to produce).
  * workspace: genpc_emd_workspace_bytes(B). */
 size_t genpc_emd_workspace_bytes(int B);
 int genpc_emd_forward(const float *xyz1, const float *xyz2, float *dist, int *assignment, float *price,

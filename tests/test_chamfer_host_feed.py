@@ -84,3 +84,29 @@ def test_host_fed_rejects_cuda_inputs(cuda):
     x = torch.zeros(2, 600, 3, device=cuda)
     with pytest.raises(_lib.GenpcError):
         chamfer_3DDist().forward_from_host(x, x, device=cuda)
+
+
+@pytest.mark.gpu
+def test_host_feed_error_surfaces_as_nan_loss_and_clears(cuda):
+    """a gated launch that timed out must not hand back a plausible number.  The error word of the feed (raised
+    here through the test hook -- the 2 s timeout itself cannot be provoked cheaply) turns the fused loss into NaN;
+    host_feed_error() reports it once and clears it; the next step is clean again."""
+    import torch
+
+    from genpc_b200 import _lib, chamfer_3D
+    from genpc_b200.utils.loss_util import Completionloss
+
+    g = torch.Generator().manual_seed(0)
+    ha = torch.rand(8, 600, 3, generator=g).pin_memory()
+    hb = torch.rand(8, 2000, 3, generator=g).pin_memory()
+    cl = Completionloss("cd_l2")
+    loss, a, b = cl.get_loss_from_host(ha, hb, device=cuda)
+    good = float(loss)
+    assert np.isfinite(good) and not chamfer_3D.host_feed_error(cuda)
+    _lib.check(_lib.lib().genpc_host_feed_inject_error(chamfer_3D._feed(cuda), _lib.current_stream(cuda)), "inject")
+    loss, a, b = cl.get_loss_from_host(ha, hb, device=cuda)
+    assert np.isnan(float(loss))
+    assert chamfer_3D.host_feed_error(cuda) is True
+    assert chamfer_3D.host_feed_error(cuda) is False          # cleared once reported
+    loss, a, b = cl.get_loss_from_host(ha, hb, device=cuda)
+    assert float(loss) == good

@@ -118,3 +118,61 @@ def test_depthprompting_class_runs_and_is_deterministic(cuda):
     for x, y in zip(a[1:], b[1:]):
         assert torch.equal(x, y)
     assert a[2].shape == (3, 128, 128) and 0.1 <= float(a[2][a[2] > 0].min()) and float(a[2].max()) <= 0.9 + 1e-6
+
+
+def _oracle_visible(cams, pts, res, rescale=True, padding=0.15):
+    """Z-buffer visibility restated on the oracle (a point is visible in a view iff it owns a pixel)."""
+    ndc, uv, _ = oracle.project_uv(cams, pts, rescale, padding)
+    zb = oracle.zbuffer(uv, ndc, res, 1)
+    V, N = uv.shape[0], uv.shape[1]
+    vis = np.zeros((V, N), bool)
+    for v in range(V):
+        w = zb[v][zb[v] != np.uint64(0xFFFFFFFFFFFFFFFF)]
+        vis[v, (w & np.uint64(0xFFFFFFFF)).astype(np.int64)] = True
+    return vis
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("V,N,res", [(4, 3000, 64), (16, 20000, 128), (64, 10000, 256)])
+def test_get_visible_points_vs_oracle(cuda, V, N, res):
+    """DepthPrompting.getVisiblePoints (reference :273-290 uses Open3D hidden_point_removal; here z-buffer ownership)
+    against the oracle's z-buffer: the boolean [V,N] mask bit for bit, and the properties the stage relies on -- a visible
+    point is the nearest of its pixel, points on the far side of a closed surface are mostly hidden."""
+    import torch
+
+    from genpc_b200.DepthPrompting import DepthPrompting
+
+    pts = shape_cloud(7, 1, N)[0]
+    dp = DepthPrompting(dict(view_num=V, res=res, cam_res=res))
+    vis = dp.getVisiblePoints(torch.from_numpy(pts).to(cuda)).cpu().numpy()
+    exp = _oracle_visible(dp.cameras.cpu().numpy(), pts, res)
+    assert vis.shape == (V, N) and np.array_equal(vis, exp)
+    # at most one owner per pixel; a closed surface seen from outside hides its far side (back-facing points are
+    # visible through sampling gaps only)
+    assert (vis.sum(1) <= res * res).all() and (vis.sum(1) > 0).all()
+    eyes = np.asarray(dp.viewpoints, np.float32)
+    facing = np.einsum("vk,nk->vn", eyes / np.linalg.norm(eyes, axis=1, keepdims=True), pts / np.linalg.norm(pts, axis=1, keepdims=True))
+    if N >= 10000 and res <= 128:
+        assert (vis & (facing > 0.3)).sum() > 3 * (vis & (facing < -0.3)).sum()
+
+
+@pytest.mark.gpu
+def test_viewpoint_select_vs_oracle(cuda):
+    """viewpoint_select (:87-98: FPS down-sample, visibility per view, argmax of the visible count) against the oracle
+    pipeline (oracle.fps -> oracle z-buffer -> first maximum): same view, same counts."""
+    import torch
+
+    from genpc_b200.DepthPrompting import DepthPrompting
+
+    rng = np.random.default_rng(3)
+    pts = shape_cloud(11, 1, 25000)[0]
+    pts = pts[pts @ np.array([0.3, 0.8, 0.5], np.float32) > -0.05]          # a partial scan: one side missing
+    rng.shuffle(pts)
+    dp = DepthPrompting(dict(view_num=32, res=128, cam_res=128, downsample_num=5000))
+    t = torch.from_numpy(pts).to(cuda)
+    best = int(dp.viewpoint_select(t))
+    sel = np.asarray(oracle.fps(pts[None], 5000, 0))[0].astype(np.int64)
+    counts = _oracle_visible(dp.cameras.cpu().numpy(), pts[sel], 128).sum(1)
+    assert best == int(np.argmax(counts))
+    got = dp.getVisiblePoints(t[torch.from_numpy(sel).to(cuda)]).sum(1).cpu().numpy()
+    assert np.array_equal(got, counts)

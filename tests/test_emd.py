@@ -60,12 +60,10 @@ def test_emd_gpu_golden_and_centered_data(cuda):
         # emd_ref_centered.npz is the witness of the reference's GetMax race (tests/test_oracle_golden.py): the reference
         # landed on the "lowest bidder index" outcome there, which the kernel produces on request
         lowest = os.path.basename(f) == "emd_ref_centered.npz"
-        if lowest:
-            os.environ["GENPC_EMD_GETMAX"] = "lowest"
-        try:
+        from genpc_b200 import _lib
+
+        with _lib.tunable(GENPC_EMD_GETMAX="lowest" if lowest else None):
             d, a = run_ours(z["xyz1"], z["xyz2"], float(z["eps"]), int(z["iters"]), cuda)
-        finally:
-            os.environ.pop("GENPC_EMD_GETMAX", None)
         assert np.array_equal(a, z["assignment"]) and np.array_equal(d.view(np.int32), z["dist"].view(np.int32)), f
         ed, ea = oracle.emd_forward(z["xyz1"], z["xyz2"], float(z["eps"]), int(z["iters"]), getmax_lowest=lowest)
         assert np.array_equal(a, ea) and np.array_equal(d.view(np.int32), ed.view(np.int32)), f
@@ -110,13 +108,10 @@ def test_emd_gpu_vs_reference_extension_and_backward(cuda):
     # The reference's GetMax is a store race (emd_cuda.cu:188-191): where a decisive collision
     # occurs it lands on the "highest index" or the "lowest index" outcome depending on block timing, or on a mixture.
     # Accept the other pure outcome bit for bit, or a mixture that differs in few assignments and not in cost.
-    import os
+    from genpc_b200 import _lib
 
-    os.environ["GENPC_EMD_GETMAX"] = "lowest"
-    try:
+    with _lib.tunable(GENPC_EMD_GETMAX="lowest"):
         d2, a2 = emdModule()(x1.detach(), x2, 0.005, 50)
-    finally:
-        os.environ.pop("GENPC_EMD_GETMAX", None)
     if torch.equal(asg, a2) and torch.equal(dist, d2):
         return
     frac = float((asg != a).float().mean())
@@ -137,6 +132,12 @@ def test_emd_shape_errors_and_completionloss(cuda):
         emd.forward(x, x, z(1, 300), z(1, 300, dt=torch.int32), z(1, 300), z(1, 300, dt=torch.int32),
                     z(1, 300, dt=torch.int32), z(1, 300), z(1, 300), z(300, dt=torch.int32), z(512, dt=torch.int32),
                     z(512, dt=torch.int32), z(512, dt=torch.int32), z(300, dt=torch.int32), 0.005, 5)
+    y = torch.rand(1, 256, 3, device=cuda)
+    for eps, iters in ((0.0, 5), (-0.01, 5), (0.005, 0), (float("nan"), 5)):   # rejected, not mis-ordered / OOB
+        with pytest.raises(_lib.GenpcError):
+            emd.forward(y, y, z(1, 256), z(1, 256, dt=torch.int32) - 1, z(1, 256), z(1, 256, dt=torch.int32) - 1,
+                        z(1, 256, dt=torch.int32), z(1, 256), z(1, 256), z(256, dt=torch.int32), z(512, dt=torch.int32),
+                        z(512, dt=torch.int32), z(512, dt=torch.int32), z(256, dt=torch.int32), eps, iters)
     g = torch.Generator().manual_seed(0)
     p1, p2 = torch.rand(2, 1024, 3, generator=g).to(cuda), torch.rand(2, 1024, 3, generator=g).to(cuda)
     for name in ("cd_l1", "cd_l2", "emd"):

@@ -77,16 +77,12 @@ def test_fps_cluster_kernel_bit_exact(cuda, B, N, K, start):
 
     a = shape_cloud(N + 1, B, N)
     eidx, eseq = oracle.fps(a, K, start, True)
+    from genpc_b200 import _lib
+
     for c16 in (None, "0", "1"):
-        os.environ["GENPC_FPS_MODE"] = "cluster"
-        if c16 is not None:
-            os.environ["GENPC_FPS_CLUSTER16"] = c16
-        try:
+        with _lib.tunable(GENPC_FPS_MODE="cluster", GENPC_FPS_CLUSTER16=c16):
             idx, seq = furthest_point_sample(torch.from_numpy(a).to(cuda), K, start, return_seq=True)
             torch.cuda.synchronize()
-        finally:
-            del os.environ["GENPC_FPS_MODE"]
-            os.environ.pop("GENPC_FPS_CLUSTER16", None)
         assert np.array_equal(idx.cpu().numpy(), eidx), c16
         assert np.array_equal(seq.cpu().numpy().view(np.int32), eseq.view(np.int32)), c16
 
@@ -105,12 +101,11 @@ def test_fps_single_cta_shared_memory_and_l1_forms(cuda, B, N, K, start):
 
     a = lattice_cloud(N, B, N, side=12) if N % 2 else shape_cloud(N, B, N)
     eidx, eseq = oracle.fps(a, K, start, True)
+    from genpc_b200 import _lib
+
     for smem in ("1", "0"):
-        os.environ["GENPC_FPS_MODE"], os.environ["GENPC_FPS_SMEM"] = "cta", smem
-        try:
+        with _lib.tunable(GENPC_FPS_MODE="cta", GENPC_FPS_SMEM=smem):
             idx, seq = furthest_point_sample(torch.from_numpy(a).to(cuda), K, start, return_seq=True)
             torch.cuda.synchronize()
-        finally:
-            del os.environ["GENPC_FPS_MODE"], os.environ["GENPC_FPS_SMEM"]
         assert np.array_equal(idx.cpu().numpy(), eidx), smem
         assert np.array_equal(seq.cpu().numpy().view(np.int32), eseq.view(np.int32)), smem

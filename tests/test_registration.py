@@ -106,9 +106,10 @@ def test_trajectory_vs_oracle(cuda):
         hist.append(rb.params.cpu().numpy()[0].copy())
     ehist, elosses = OR.run(comp, part, iters, lr=0.01, center=rb.center[0].cpu().numpy())
     losses = rb.losses().cpu().numpy()[0]
-    # tolerance: 1e-5 relative on the loss for the whole trajectory, parameters within 2e-5 absolute
-    assert np.abs(losses - elosses).max() <= 1e-5 * np.abs(elosses).max() * 5, np.abs(losses - elosses).max()
-    assert np.abs(np.stack(hist) - ehist).max() <= 5e-5, np.abs(np.stack(hist) - ehist).max()
+    # tolerance (north_star): 1e-5 relative on every loss of the trajectory, every parameter within 1e-5 absolute
+    # (r01 used 5e-5 / 5e-5; measured drift against the oracle is <= 3e-6 over 500 steps, profiles/r02b_c3_spread_500iters.json)
+    assert (np.abs(losses - elosses) <= 1e-5 * np.abs(elosses)).all(), np.abs(losses - elosses).max()
+    assert np.abs(np.stack(hist) - ehist).max() <= 1e-5, np.abs(np.stack(hist) - ehist).max()
 
 
 @pytest.mark.gpu
@@ -139,8 +140,8 @@ def test_trajectory_vs_reference_machinery_on_gpu(cuda):
     autograd, the forward expression of ObjectPoseOptim.forward (diff_obj_pose.py:419-423), the Chamfer term of
     compute_loss_function (:326-327, weight 3.0 :334) and torch.optim.Adam with the three lr groups (:524-528), all
     fp32 -- against the fused kernels.  The reference's backward accumulates with unordered float atomics, so it is
-    not bit-reproducible itself; tolerance: 1e-5 relative on every loss of the trajectory, 1e-4 absolute on parameters
-    after 30 steps."""
+    not bit-reproducible itself (its run-to-run spread after 30 steps is ~5e-10, profiles/r02b_c3_spread_500iters.json);
+    tolerance: 1e-5 relative on every loss of the trajectory, 1e-5 absolute on the parameters after 30 steps."""
     import torch
 
     from genpc_b200.optim_registration.diff_obj_pose import RegistrationBatch, rotation_6d_to_matrix
@@ -192,6 +193,81 @@ def test_trajectory_vs_reference_machinery_on_gpu(cuda):
     rb.run(iters)
     ours = rb.losses()[0].cpu().numpy()
     ref_losses = np.array(ref_losses)
-    assert np.abs(ours - ref_losses).max() <= 1e-5 * np.abs(ref_losses).max() * 3, np.abs(ours - ref_losses).max()
+    assert (np.abs(ours - ref_losses) <= 1e-5 * np.abs(ref_losses)).all(), np.abs(ours - ref_losses).max()
     ref_p = torch.cat([rot, trans, ls]).detach().cpu().numpy()
-    assert np.abs(rb.params[0].cpu().numpy() - ref_p).max() <= 1e-4, np.abs(rb.params[0].cpu().numpy() - ref_p).max()
+    assert np.abs(rb.params[0].cpu().numpy() - ref_p).max() <= 1e-5, np.abs(rb.params[0].cpu().numpy() - ref_p).max()
+
+
+@pytest.mark.gpu
+def test_c3_length_500_iterations_vs_oracle_and_reference_self_spread(cuda):
+    """BASELINE config C3 runs 500 Adam iterations; north_star: registered pose / scale within 1e-5.  Three arms on the same
+    pair: the fused kernels, the oracle (C-oracle NN indices + float64 autograd + torch Adam, oracle/registration.py) and the
+    reference's machinery run TWICE (its backward sums with unordered float atomics).  tools/c3_spread.py recorded the full
+    picture (profiles/r02b_c3_spread_500iters.json): on this pair the kernels stay within 3e-6 of the oracle for all 500
+    steps while the reference drifts up to 3.6e-4 from ITSELF mid-trajectory; on a second pair (4096 x 3000) every arm --
+    reference vs reference included -- bifurcates around iteration 200 (one flipped nearest neighbour, amplified by Adam's
+    normalisation) and ends 1e-3..5e-3 apart in the parameters with losses still equal to 2e-6.
+    Tolerances: final loss 1e-5 relative; every parameter, at EVERY step, within max(1e-5, 2 x the reference's own
+    run-to-run spread over the trajectory)."""
+    import torch
+
+    from genpc_b200.optim_registration.diff_obj_pose import RegistrationBatch, rotation_6d_to_matrix
+
+    iters, lr = 500, 0.01
+    comp, part, _ = make_pair(11, 2048, 1500)
+    V, Rf = torch.from_numpy(comp).to(cuda), torch.from_numpy(part).to(cuda)
+    rb = RegistrationBatch(V[None], Rf[None], n_starts=1, lr=lr, max_iters=iters)
+    center, p0 = rb.center[0].clone(), rb.params[0].clone()
+    ours = []
+    for _ in range(iters):
+        rb.run(1)
+        ours.append(rb.params[0].cpu().numpy().copy())
+    ours = np.stack(ours)
+    ours_l = rb.losses()[0].cpu().numpy()
+    eh, el = OR.run(comp, part, iters, lr=lr, center=center.cpu().numpy())
+    eh = eh[1:]
+    assert abs(ours_l[-1] - el[-1]) <= 1e-5 * abs(el[-1])
+    assert (np.abs(ours_l - el) <= 1e-5 * np.abs(el)).all()
+    spread = 0.0
+    ext = oracle.load_ref_ext("chamfer_3D")
+    if ext is not None:
+        class RefChamfer(torch.autograd.Function):
+            @staticmethod
+            def forward(ctx, a, b):
+                B, n, _ = a.shape
+                m = b.shape[1]
+                d1 = torch.zeros(B, n, device=a.device); d2 = torch.zeros(B, m, device=a.device)
+                i1 = torch.zeros(B, n, dtype=torch.int32, device=a.device); i2 = torch.zeros(B, m, dtype=torch.int32, device=a.device)
+                ext.forward(a, b, d1, d2, i1, i2)
+                ctx.save_for_backward(a, b, i1, i2)
+                return d1, d2, i1, i2
+
+            @staticmethod
+            def backward(ctx, g1, g2, _a, _b):
+                a, b, i1, i2 = ctx.saved_tensors
+                ga, gb = torch.zeros_like(a), torch.zeros_like(b)
+                ext.backward(a, b, ga, gb, g1.contiguous(), g2.contiguous(), i1, i2)
+                return ga, gb
+
+        def run_ref():
+            rot = p0[:6].clone().requires_grad_(True); trans = p0[6:9].clone().requires_grad_(True); ls = p0[9:].clone().requires_grad_(True)
+            opt = torch.optim.Adam([{"params": [rot], "lr": lr}, {"params": [trans], "lr": lr * 0.2}, {"params": [ls], "lr": lr * 0.1}])
+            hist = []
+            for _ in range(iters):
+                opt.zero_grad()
+                R = rotation_6d_to_matrix(rot[None])[0]
+                pts = (R @ ((V - center) * torch.exp(ls)[0]).T).T + center + trans
+                pl1 = lambda p, q: torch.sqrt(RefChamfer.apply(p.contiguous(), q.contiguous())[0]).mean()   # noqa: E731
+                loss = 3.0 * (pl1(pts[None], Rf[None]) + 0.5 * pl1(Rf[None], pts[None]))
+                loss.backward()
+                opt.step()
+                hist.append(torch.cat([rot, trans, ls]).detach().cpu().numpy().copy())
+            return np.stack(hist)
+
+        r1, r2 = run_ref(), run_ref()
+        spread = float(np.abs(r1 - r2).max())
+        tol_ref = max(1e-5, 2.0 * spread)
+        assert np.abs(ours - r1).max() <= tol_ref, (np.abs(ours - r1).max(), spread)
+    tol = max(1e-5, 2.0 * spread)
+    assert np.abs(ours - eh).max() <= tol, (np.abs(ours - eh).max(), spread)
+    assert np.abs(ours[-1] - eh[-1]).max() <= 1e-5, np.abs(ours[-1] - eh[-1]).max()     # the registered pose / scale itself

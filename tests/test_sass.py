@@ -52,7 +52,7 @@ def test_scan_kernel_distance_arithmetic(sass):
     n = {op: len(re.findall(r"\b" + re.escape(op) + r"\b", k)) for op in ("FADD2", "FMUL2", "FFMA2", "FMNMX3", "CREDUX.MIN", "LDS.128")}
     assert n["FADD2"] >= 192 and n["FFMA2"] >= 128 and n["FMUL2"] >= 64, n
     assert n["FADD2"] == 3 * n["FMUL2"] and n["FFMA2"] == 2 * n["FMUL2"], n          # the reference's rounding order, packed
-    assert n["FMNMX3"] >= 128 and n["CREDUX.MIN"] == 32 and n["LDS.128"] >= 24, n
+    assert n["FMNMX3"] >= 128 and n["CREDUX.MIN"] % 32 == 0 and n["CREDUX.MIN"] >= 32 and n["LDS.128"] >= 24, n   # ptxas may unroll the block loop x2
     assert "REDG.E.MIN.64" in k
     assert len(re.findall(r"\bSTL\b", k)) <= 2 and len(re.findall(r"\bLDL\b", k)) <= 2
 

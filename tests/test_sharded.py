@@ -176,3 +176,56 @@ def test_full_size_c5_million_points_sampled(cuda):
     ed, ei = oracle.nn_distance(bn[:, sel], an)
     assert np.array_equal(d2[0, sel].cpu().numpy().view(np.int32), ed[0].view(np.int32))
     assert np.array_equal(i2[0, sel].cpu().numpy(), ei[0])
+
+
+@pytest.mark.gpu
+def test_nccl_two_ranks_sharded_chamfer_and_batch_sharded_emd(cuda):
+    """Real NCCL, one process per GPU (torchrun, 2 ranks): sharded Chamfer forward bit-identical to the single-GPU kernels
+    on every rank (random, lattice-tie and ragged clouds), its autograd form within 1e-5, and the batch-sharded EMD helper
+    (the reference's nn.DataParallel(emdModule), utils/loss_util.py:12) equal to the single-GPU call.  Skipped on a
+    one-GPU box (the driver's round-end suite runs on one GPU; `gpurun --gpus 2` runs it for real)."""
+    import subprocess
+    import sys
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    worker = os.path.join(os.path.dirname(os.path.abspath(__file__)), "nccl_sharded_worker.py")
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", str(port), worker], capture_output=True, text=True, timeout=600)
+    lines = [ln for ln in p.stdout.splitlines() if ln.startswith("RANK")]
+    assert p.returncode == 0 and len(lines) == 2, p.stdout[-2000:] + p.stderr[-2000:]
+    for ln in lines:
+        assert '"all_ranks_ok": true' in ln, ln
+
+
+def _dp_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from genpc_b200.sharded import data_parallel_batch
+
+    g = torch.Generator().manual_seed(0)
+    res = {}
+    for B in (1, 2, 5, 8):                                  # fewer entries than ranks, uneven and even splits
+        x, y = torch.rand(B, 7, 3, generator=g), torch.rand(B, 4, generator=g)
+        fn = lambda a, b: ((a * 2).sum(-1), b.cumsum(-1) + a[:, :4, 0])   # noqa: E731
+        got = data_parallel_batch(fn, x, y)
+        exp = fn(x, y)
+        res[B] = all(torch.equal(g_, e_) for g_, e_ in zip(got, exp))
+        single = data_parallel_batch(lambda a: a.mean(1), x)
+        res[(B, "single")] = torch.equal(single, x.mean(1))
+    out[rank] = res
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_gloo_batch_sharding_helper(world):
+    """data_parallel_batch (the one-process-per-GPU stand-in for nn.DataParallel, utils/loss_util.py:12): every rank ends up
+    with the full-batch result, whatever the split (host logic on CPU, gloo)."""
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_dp_worker, args=(world, port, out), nprocs=world, join=True)
+    for r in range(world):
+        assert all(out[r].values()), (r, dict(out[r]))

@@ -19,9 +19,12 @@ elif what == "emd":
     emdModule()(x, y, 0.005, 50); emdModule()(x, y, 0.005, 50)
 elif what == "fps":
     from genpc_b200.fps import furthest_point_sample
+from genpc_b200 import _lib
+def setk(name, value):   # the library reads the environment once at load time: flip knobs through the C ABI
+    _lib.check(_lib.lib().genpc_set_tunable(name.encode(), None if value is None else str(value).encode()), name)
     x = torch.rand(1, 16384, 3, generator=g).to(dev)
     furthest_point_sample(x, 2048, 0); furthest_point_sample(x, 2048, 0)
-    os.environ["GENPC_FPS_MODE"] = "cta"
+    setk("GENPC_FPS_MODE", "cta")
     furthest_point_sample(x, 2048, 0)
 elif what == "depth":
     from genpc_b200 import depth as D
