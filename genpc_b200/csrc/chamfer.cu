@@ -19,6 +19,7 @@
 
 #include "nn_core.cuh"
 #include "nn_sym.cuh"
+#include "nn_tc.cuh"
 
 #ifndef GENPC_DEFAULT_SYM
 #define GENPC_DEFAULT_SYM true
@@ -170,6 +171,19 @@ static cudaError_t launch_scan(const NNParams &p, cudaStream_t stream) {
     return cudaGetLastError();
 }
 
+static unsigned *g_tc_stats = nullptr;   // diagnostics counters of the filter (genpc_chamfer_tc_stats), nullptr in production
+
+// Tensor-core filter (nn_tc.cuh).  MEASURED r02 (profiles/r02c_nn_tc_*): bit-identical results, but the C2 forward takes
+// 0.438 ms against 0.272 ms of the FP32 symmetric scan -- the exact re-evaluation of the winning chunks (every point, once
+// per item) and the stalls it causes in the drain pipeline cost more than the tensor pipe saves at dim = 3 -- so it is
+// OFF by default: GENPC_CHAMFER_TC=1 selects it for any shape with at least one full row block (tests, experiments).
+static bool tc_eligible(int B, int nr, int nc) {
+    (void)B;
+    const char *k = tunable("GENPC_CHAMFER_TC");
+    if (k == nullptr || atoi(k) != 1) return false;
+    return nr >= TC_RBLK && nc >= 1;
+}
+
 // Symmetric path: rows = the larger cloud (registers), cols = the smaller one (shared-memory sweep).
 // gate != nullptr: host-fed launch (nn_sym_gated_kernel), see genpc_chamfer_forward_host.
 static int chamfer_forward_sym(const float *xyz1, const float *xyz2, float *dist1, float *dist2, int *idx1, int *idx2,
@@ -186,6 +200,36 @@ static int chamfer_forward_sym(const float *xyz1, const float *xyz2, float *dist
     p.prow = packed, p.pcol = packed + (size_t)B * p.nr;
     p.rblock_base = 0;
     p.gate = gate, p.gate_gen = gate_gen, p.gate_pairs = gate_pairs;
+    p.select = nullptr;
+    // ---- tensor-core filter (nn_tc.cuh): both launches are queued, a device-side flag written by the precheck decides which
+    // one does the work (coordinates at unit scale -> nn_tc_kernel, anything else -> the FP32 kernel below) ----
+    int *ctl = counter;   // [0] persistent work counter, [1] selection flag, [2] precheck accumulator, [3] precheck ticket
+    const bool use_tc = ctl != nullptr && tc_eligible(B, p.nr, p.nc);
+    if (use_tc) {
+        static bool attr_done = false;   // opt in to 166 KB of dynamic shared memory once per process
+        if (!attr_done) {
+            cudaError_t ea = cudaFuncSetAttribute(nn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TcSmem));
+            if (ea == cudaSuccess) ea = cudaFuncSetAttribute(nn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TcSmem));
+            if (ea != cudaSuccess) return (int)ea;
+            attr_done = true;
+        }
+        const char *lim = tunable("GENPC_TC_LIMIT");
+        const float limit = lim != nullptr ? (float)atof(lim) : 2.0f;
+        if (gate == nullptr) {
+            nn_tc_precheck_kernel<<<2 * GENPC_NUM_SMS, 256, 0, stream>>>(p.rows, (size_t)B * p.nr * 3, p.cols, (size_t)B * p.nc * 3, limit, ctl);
+            GENPC_CHECK_LAUNCH();
+            p.select = ctl + 1;
+        }   // host-fed launches cannot look at data that has not arrived: the caller vouches for the range (get_loss_from_host)
+        TcParams t;
+        t.rows = p.rows, t.cols = p.cols, t.prow = p.prow, t.pcol = p.pcol, t.B = B, t.nr = p.nr, t.nc = p.nc;
+        t.rblks = (p.nr + TC_RBLK - 1) / TC_RBLK, t.total_units = B * t.rblks;
+        t.select = p.select, t.gate = gate, t.gate_gen = gate_gen, t.gate_pairs = gate_pairs, t.stats = g_tc_stats;
+        const int grid = t.total_units < GENPC_NUM_SMS ? t.total_units : GENPC_NUM_SMS;
+        if (gate != nullptr) nn_tc_kernel<true><<<grid, TC_THREADS, sizeof(TcSmem), stream>>>(t);
+        else nn_tc_kernel<false><<<grid, TC_THREADS, sizeof(TcSmem), stream>>>(t);
+        GENPC_CHECK_LAUNCH();
+    }
+    const bool fp32_needed = !use_tc || gate == nullptr;   // gated + filter: the filter is the only launch
     // measured on B200 (profiles/r01c_sym_variants.txt): QT=4 at 3 CTAs/SM is within 1 % of QT=8 at 2 CTAs/SM on
     // large clouds and clearly better when the grid is small
     int QT = p.nr >= 1024 ? 4 : 2;
@@ -210,7 +254,9 @@ static int chamfer_forward_sym(const float *xyz1, const float *xyz2, float *dist
     const char *bm = tunable("GENPC_SYM_BALANCED");
     const bool few_items = (long long)B * p.rtiles * ((p.nc + SYM_SPAN_MAX - 1) / SYM_SPAN_MAX) < 4LL * GENPC_NUM_SMS;
     const bool balanced = (bm == nullptr) ? (GENPC_DEFAULT_BALANCED && few_items) : (atoi(bm) != 0);
-    if (gate != nullptr) {
+    if (!fp32_needed) {
+        // nothing: nn_tc_kernel<true> does the whole scan
+    } else if (gate != nullptr) {
         if (QT >= 4) nn_sym_gated_kernel<4><<<(unsigned)items, SYM_THREADS, 0, stream>>>(p);
         else nn_sym_gated_kernel<2><<<(unsigned)items, SYM_THREADS, 0, stream>>>(p);
     } else if (balanced && !persist && (QT == 4 || QT == 2)) {
@@ -241,6 +287,9 @@ static int chamfer_forward_sym(const float *xyz1, const float *xyz2, float *dist
     const unsigned unpack_blocks = (unsigned)((nrw + EPI_ROWS_PER_CTA - 1) / EPI_ROWS_PER_CTA);
     EpiFuse f;
     memset(&f, 0, sizeof(f));
+    // column words are exact iff the filter did the work: ctl[1] == 0 after the precheck; a gated launch has no precheck and
+    // points at ctl[2], which is zero between launches
+    f.select = use_tc ? (gate == nullptr ? ctl + 1 : ctl + 2) : nullptr;
     if (fuse == nullptr) {
         nn_sym_epilogue_kernel<false><<<fix_blocks + unpack_blocks, 256, 0, stream>>>(
             p.rows, p.cols, p.prow, p.pcol, B, p.nr, p.nc, 32 * QT, fix_blocks, dist_r, idx_r, dist_c, idx_c, f);
@@ -344,6 +393,7 @@ extern "C" int genpc_chamfer_forward_fused(const float *xyz1, const float *xyz2,
     const bool sym = takes_sym_path(N, M);
     if (!(sym && fuse != nullptr && fuse->workspace_armed)) {  // an armed workspace already holds all-ones words
         e = cudaMemsetAsync(packed, 0xff, (n1 + n2) * 8, stream);
+        if (e == cudaSuccess) e = cudaMemsetAsync(packed + n1 + n2, 0, 16, stream);   // control words (counter, filter flag / ticket)
         if (e != cudaSuccess) return (int)e;
     }
     if (sym) {
@@ -400,6 +450,21 @@ extern "C" int genpc_chamfer_backward(const float *xyz1, const float *xyz2, cons
     else
         chamfer_grad_kernel<false><<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(xyz1, xyz2, graddist1, graddist2, idx1, idx2,
                                                                                        gradxyz1, gradxyz2, B, N, M);
+    GENPC_CHECK_LAUNCH();
+    return GENPC_OK;
+}
+
+// Diagnostics of the tensor-core filter: while `stats4` (device, 4 x u32, zeroed by the caller) is set, every filter launch
+// adds {runner-up chunk re-evaluations, whole-tile exact scans, degenerate items, items} to it.  nullptr switches it off.
+extern "C" int genpc_chamfer_tc_stats(unsigned *stats4) {
+    g_tc_stats = stats4;
+    return GENPC_OK;
+}
+
+// Test probe: e(x,y) = u(x).v(y) of one 128 x 256 tile as the tensor pipe computes it (rows128 [128][3], cols256 [256][3],
+// e_out [128][256], all device memory).
+extern "C" int genpc_tc_probe(const float *rows128, const float *cols256, float *e_out, genpc_stream_t stream_) {
+    nn_tc_probe_kernel<<<1, 128, 0, (cudaStream_t)stream_>>>(rows128, cols256, e_out);
     GENPC_CHECK_LAUNCH();
     return GENPC_OK;
 }
@@ -509,11 +574,14 @@ extern "C" int genpc_chamfer_forward_host_fused(genpc_host_feed_t *f, const floa
         FEED_CHECK(cudaMemcpyAsync(f->gate + c, src, sizeof(unsigned), cudaMemcpyHostToDevice, f->copy_stream));
     }
     unsigned long long *packed = (unsigned long long *)workspace;
-    if (!(fuse != nullptr && fuse->workspace_armed)) FEED_CHECK(cudaMemsetAsync(packed, 0xff, (n1 + n2) * 8, stream));
+    if (!(fuse != nullptr && fuse->workspace_armed)) {
+        FEED_CHECK(cudaMemsetAsync(packed, 0xff, (n1 + n2) * 8, stream));
+        FEED_CHECK(cudaMemsetAsync(packed + n1 + n2, 0, 16, stream));
+    }
     double *partial = fuse ? (double *)fuse->loss_workspace : nullptr;
     unsigned *ticket = partial ? (unsigned *)(partial + sym_epilogue_ctas(B, N, M)) : nullptr;
-    const int rc = chamfer_forward_sym(xyz1, xyz2, dist1, dist2, idx1, idx2, B, N, M, packed, nullptr, stream, f->gate, gen, pairs,
-                                       fuse, partial, ticket);
+    const int rc = chamfer_forward_sym(xyz1, xyz2, dist1, dist2, idx1, idx2, B, N, M, packed, (int *)(packed + n1 + n2), stream, f->gate,
+                                       gen, pairs, fuse, partial, ticket);
     if (rc != GENPC_OK) return rc;
     FEED_CHECK(cudaEventRecord(f->copied, f->copy_stream));
     FEED_CHECK(cudaStreamWaitEvent(stream, f->copied, 0));  // later work on the caller's stream sees complete clouds

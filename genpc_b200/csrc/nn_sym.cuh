@@ -44,6 +44,9 @@ struct SymParams {
     const unsigned *gate;
     unsigned gate_gen;
     int gate_pairs;
+    // tensor-core filter selection (nn_tc.cuh): when set, this FP32 launch only runs if *select != 0, i.e. the precheck
+    // found coordinates outside the filter's range; nullptr: always run
+    const int *select;
 };
 
 // Coordinates arriving by DMA while the kernel is resident must not go through the non-coherent path (ld.global.nc
@@ -226,6 +229,7 @@ __device__ __forceinline__ void nn_sym_item(float (*s)[SYM_SPAN_MAX], const floa
 template <int QT>
 __global__ void __launch_bounds__(SYM_THREADS, GENPC_SYM_MINB(QT)) nn_sym_kernel(const SymParams p) {
     __shared__ __align__(16) float s[3][SYM_SPAN_MAX];
+    if (p.select != nullptr && *p.select == 0) return;
     int item = blockIdx.x;
     const int cs = item % p.cspans;
     item /= p.cspans;
@@ -248,6 +252,7 @@ constexpr long long GATE_TIMEOUT_CLK = 4000000000LL;  // ~2 s at 1.965 GHz
 template <int QT>
 __global__ void __launch_bounds__(SYM_THREADS, GENPC_SYM_MINB(QT)) nn_sym_gated_kernel(const SymParams p) {
     __shared__ __align__(16) float s[3][SYM_SPAN_MAX];
+    if (p.select != nullptr && *p.select == 0) return;
     int item = blockIdx.x;
     const int cs = item % p.cspans;
     item /= p.cspans;
@@ -282,6 +287,7 @@ template <int QT>
 __global__ void __launch_bounds__(SYM_THREADS, GENPC_SYM_MINB(QT)) nn_sym_balanced_kernel(const SymParams p, int total_units,
                                                                                          int units_per_job) {
     __shared__ __align__(16) float s[3][SYM_SPAN_MAX];
+    if (p.select != nullptr && *p.select == 0) return;
     int u = (int)((long long)total_units * blockIdx.x / gridDim.x);
     const int u_end = (int)((long long)total_units * (blockIdx.x + 1) / gridDim.x);
     int job = u / units_per_job;
@@ -439,6 +445,7 @@ struct EpiFuse {
     float *zero[2];         // buffers to zero-fill, or nullptr
     size_t nzero[2];        // their sizes in floats
     const unsigned *err_flag;  // host-fed launches: the feed's error word -- a timed-out gate poisons the loss with NaN
+    const int *select;         // tensor-core filter selection flag: *select == 0 -> the column words already hold exact indices
 };
 
 __device__ __forceinline__ void epi_zero_fill(float *z, size_t n, size_t g, size_t total_threads) {
@@ -474,6 +481,7 @@ static __global__ void __launch_bounds__(256) nn_sym_epilogue_kernel(const float
                                                                      float *__restrict__ dist_c, int *__restrict__ idx_c,
                                                                      const EpiFuse f) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool cols_exact = f.select != nullptr && *f.select == 0;   // nn_tc_kernel ran: nothing to fix up (warp-uniform)
     double term = 0.0;  // sum of f(d) over the output elements this thread owns
     if (blockIdx.x >= fix_blocks) {
         const size_t n = (size_t)B * nr;
@@ -516,8 +524,9 @@ static __global__ void __launch_bounds__(256) nn_sym_epilogue_kernel(const float
             const unsigned long long word = __shfl_sync(0xffffffffu, my_w, k);
             const float cx = __shfl_sync(0xffffffffu, mx, k), cy = __shfl_sync(0xffffffffu, my, k), cz = __shfl_sync(0xffffffffu, mz, k);
             const size_t base = __shfl_sync(0xffffffffu, my_base, k);
-            const int found = sym_fix_column(rows + base, nr, rows_per_block, cx, cy, cz, __uint_as_float((unsigned)(word >> 32)),
-                                             (int)(unsigned)(word & 0xffffffffu), lane);
+            const int found = cols_exact ? (int)(unsigned)(word & 0xffffffffu)
+                                         : sym_fix_column(rows + base, nr, rows_per_block, cx, cy, cz,
+                                                          __uint_as_float((unsigned)(word >> 32)), (int)(unsigned)(word & 0xffffffffu), lane);
             if (lane == k) my_found = found;
         }
         if (lane < EPI_CPW && mine < n) {

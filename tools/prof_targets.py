@@ -3,9 +3,19 @@ import os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 dev = torch.device("cuda:0")
+from genpc_b200 import _lib
+def setk(name, value):   # the library reads the environment once at load time: flip knobs through the C ABI
+    _lib.check(_lib.lib().genpc_set_tunable(name.encode(), None if value is None else str(value).encode()), name)
 what = sys.argv[1]
 g = torch.Generator().manual_seed(0)
-if what == "register":
+if what == "chamfer":   # C2 forward (tensor-core filter by default), three calls
+    from genpc_b200.loss_functions import chamfer_3DDist
+    from genpc_b200.synthetic import pcn_batch
+    part, comp = pcn_batch(0, 32, 2048, 16384)
+    a, b = torch.from_numpy(part).to(dev), torch.from_numpy(comp).to(dev)
+    for _ in range(3):
+        chamfer_3DDist()(a, b)
+elif what == "register":
     from genpc_b200.optim_registration.diff_obj_pose import RegistrationBatch
     from genpc_b200.synthetic import partial_view, rigid_perturb, superquadric
     import numpy as np
@@ -19,9 +29,6 @@ elif what == "emd":
     emdModule()(x, y, 0.005, 50); emdModule()(x, y, 0.005, 50)
 elif what == "fps":
     from genpc_b200.fps import furthest_point_sample
-from genpc_b200 import _lib
-def setk(name, value):   # the library reads the environment once at load time: flip knobs through the C ABI
-    _lib.check(_lib.lib().genpc_set_tunable(name.encode(), None if value is None else str(value).encode()), name)
     x = torch.rand(1, 16384, 3, generator=g).to(dev)
     furthest_point_sample(x, 2048, 0); furthest_point_sample(x, 2048, 0)
     setk("GENPC_FPS_MODE", "cta")
