@@ -281,7 +281,7 @@ def chamfer_l2_loss(fn, a, b):
     return torch.mean(d1) + torch.mean(d2)
 
 
-def run_gpu_arm(args, loss_fn, rank, world, dev, part, comp, tag, host_loss_fn=None):
+def run_gpu_arm(args, loss_fn, rank, world, dev, part, comp, tag, host_loss_fn=None, graphed_factory=None):
     """Times K steps device-resident (`value`) and K steps end-to-end from pinned host buffers (`e2e`).
     loss_fn(a, b) -> scalar loss is the public API call: Completionloss('cd_l2').get_loss of either implementation.
     host_loss_fn(ha, hb) -> (loss, a_cuda, b_cuda): our host-fed public call (H2D copy overlapped with the scan); when
@@ -341,7 +341,12 @@ def run_gpu_arm(args, loss_fn, rank, world, dev, part, comp, tag, host_loss_fn=N
 
     sampler = ClockSampler(dev.index)
     sampler.start()
-    ms_res = timed(step_resident, args.steps, args.warmup)
+    ms_eager = timed(step_resident, args.steps, args.warmup)
+    ms_res = ms_eager
+    if graphed_factory is not None:
+        # the same step (same kernels, same device-resident inputs) captured once into a CUDA graph: one graph launch per step
+        gstep = graphed_factory(a.detach(), b.detach())
+        ms_res = timed(lambda: gstep(), args.steps, args.warmup)
     clocks = sampler.stop()
     ms_plain = timed(step_e2e, args.steps, args.warmup)
     ms_e2e = timed(step_e2e_hostfed, args.steps, args.warmup) if host_loss_fn is not None else ms_plain
@@ -354,6 +359,10 @@ def run_gpu_arm(args, loss_fn, rank, world, dev, part, comp, tag, host_loss_fn=N
                 "ms_per_step": ms_e2e / args.steps},
         "clocks": clocks,
     }
+    if graphed_factory is not None:
+        res["api_value"] = "GraphedLossStep(Completionloss('cd_l2'), gen, gt)(): the fused step replayed as one CUDA graph"
+        res["eager"] = {"value": pairs_per_step * args.steps / (ms_eager * 1e-3), "unit": "pairs/s", "ms_per_step": ms_eager / args.steps,
+                        "api": "Completionloss('cd_l2').get_loss(gen, gt); loss.backward()  (Python + autograd per step)"}
     if host_loss_fn is not None:
         res["e2e"]["api"] = ("Completionloss('cd_l2').get_loss_from_host(gen_pinned, gt_pinned); loss.backward(); loss -> host "
                              "(genpc_chamfer_forward_host: H2D copy in 6 chunks overlapped with the one scan launch)")
@@ -705,8 +714,11 @@ def main():
     from genpc_b200.utils.loss_util import Completionloss
 
     ours_loss = Completionloss("cd_l2")   # the reference's facade name and call: get_loss == chamfer_l2
+    from genpc_b200.utils.loss_util import GraphedLossStep
+
     res, (a, b, flush) = run_gpu_arm(args, ours_loss.get_loss, rank, world, dev, part, comp, "ours",
-                                     host_loss_fn=lambda ha, hb: ours_loss.get_loss_from_host(ha, hb, device=dev))
+                                     host_loss_fn=lambda ha, hb: ours_loss.get_loss_from_host(ha, hb, device=dev),
+                                     graphed_factory=lambda ga, gb: GraphedLossStep(ours_loss, ga, gb))
     line.update(res)
     # per step: nn_sym_kernel, nn_sym_epilogue_kernel<fused> (fix-up + unpack + loss + zero-fill), chamfer_loss_grad_kernel
     line["gpu_launches"] = 3 * args.steps

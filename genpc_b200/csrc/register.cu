@@ -98,7 +98,21 @@ __device__ __forceinline__ void accum_term(const RegArgs &a, const Similarity &T
 
 // Single thread: Gram-Schmidt backward on the 13 reduced gradient scalars, Adam step, loss record,
 // ticket re-armed.  tot = {dL/dt[3], dL/dR[9] row-major, dL/dlog_s, loss}.
-__device__ __noinline__ void pose_update(const RegArgs &a, int scan, const Similarity &T, const double *tot) {
+// per-iteration Adam scalars (torch.optim.Adam: step_size = lr / (1 - beta1^t), denominator uses sqrt(1 - beta2^t))
+struct AdamStep {
+    float step_size[3];
+    float bc2_sqrt;
+    int t_index;
+};
+
+__device__ __forceinline__ AdamStep adam_step_from_args(const RegArgs &a) {
+    AdamStep st;
+    st.step_size[0] = a.step_size[0], st.step_size[1] = a.step_size[1], st.step_size[2] = a.step_size[2];
+    st.bc2_sqrt = a.bc2_sqrt, st.t_index = a.t_index;
+    return st;
+}
+
+__device__ __noinline__ void pose_update(const RegArgs &a, int scan, const Similarity &T, const double *tot, const AdamStep &st) {
     float *par = a.params + (size_t)scan * REG_NPAR;
     float *am = a.adam_m + (size_t)scan * REG_NPAR;
     float *av = a.adam_v + (size_t)scan * REG_NPAR;
@@ -127,19 +141,19 @@ __device__ __noinline__ void pose_update(const RegArgs &a, int scan, const Simil
     // ---- Adam (torch.optim.Adam defaults; lr groups of diff_obj_pose.py:524-528), fp32 like torch ----
 #pragma unroll
     for (int i = 0; i < REG_NPAR; ++i) {
-        const float step = a.step_size[i < 6 ? 0 : (i < 9 ? 1 : 2)];
+        const float step = st.step_size[i < 6 ? 0 : (i < 9 ? 1 : 2)];
         const float g = grad[i];
         const float m = am[i] + (g - am[i]) * a.omb1;        // exp_avg.lerp_(grad, 1-beta1)
         const float v = a.beta2 * av[i] + a.omb2 * g * g;    // exp_avg_sq.mul_(beta2).addcmul_(g, g, 1-beta2)
         am[i] = m, av[i] = v;
-        const float denom = sqrtf(v) / a.bc2_sqrt + a.eps;
+        const float denom = sqrtf(v) / st.bc2_sqrt + a.eps;
         par[i] = par[i] - step * (m / denom);                // param.addcdiv_(exp_avg, denom, value=-step_size)
     }
-    if (a.loss_hist != nullptr) a.loss_hist[(size_t)scan * a.T + a.t_index] = (float)tot[13];
+    if (a.loss_hist != nullptr) a.loss_hist[(size_t)scan * a.T + st.t_index] = (float)tot[13];
     a.counters[scan] = 0;
 }
 
-__device__ __noinline__ void finalize_scan(const RegArgs &a, int scan, const Similarity &T, double *sh) {
+__device__ __noinline__ void finalize_scan(const RegArgs &a, int scan, const Similarity &T, double *sh, const AdamStep &st) {
     const int cloud = scan / a.n_starts;
     const float *V = a.complete + (size_t)cloud * a.Nc * 3;
     const float *Rf = a.ref + (size_t)cloud * a.Nr * 3;
@@ -169,7 +183,7 @@ __device__ __noinline__ void finalize_scan(const RegArgs &a, int scan, const Sim
     for (int i = 0; i < 14; ++i) tot[i] = block_sum(acc[i], sh);
     if (threadIdx.x != 0) return;
 
-    pose_update(a, scan, T, tot);
+    pose_update(a, scan, T, tot, st);
 }
 
 template <int QT>
@@ -202,7 +216,134 @@ __global__ void __launch_bounds__(NN_THREADS, NN_MINBLOCKS) register_step_kernel
     __syncthreads();
     if (is_last) {
         __threadfence();
-        finalize_scan(a, scan, T, sh);
+        finalize_scan(a, scan, T, sh, adam_step_from_args(a));
+    }
+}
+
+// ---- persistent form of the single-launch path: ALL iterations in ONE cooperative launch -----------------------------
+// The real pipeline registers 1-3 K-point clouds with 4 starts (diff_obj_pose.py:502-504 after voxel down-sampling): a few
+// dozen CTAs per iteration.  With one launch per iteration an iteration costs 37 us (profiles/r01k_registration_small.json),
+// and r02 measured that launch latency is NOT what it is made of: a first persistent version that kept the single-CTA
+// finalize ran at 36 us -- the chain is scan (7 us) -> ticket -> ONE CTA gathering all Nc + Nr loss / gradient terms with
+// dependent L2 round trips (20 us) -> Adam.  Here the grid (one CTA per work item, all co-resident: cooperative launch)
+// loops over the iterations on the device and EVERY CTA of a scan takes a slice of the terms:
+//   phase 1  scan item -> packed atomicMin                                  | per-scan barrier (monotonic arrival counter)
+//   phase 2  this CTA's slice of moving / fixed points: loss + 13 gradient  | ticket: the last CTA adds the per-CTA partials
+//            scalars in double, packed words re-armed, partial stored       | in index order (deterministic), steps Adam and
+//                                                                           | releases `iter_done[scan] = k + 1`
+// Scans never wait for each other.  Adam's per-iteration scalars are computed on the device from t (same double formulas
+// as the host loop).
+template <int QT>
+__global__ void __launch_bounds__(NN_THREADS, NN_MINBLOCKS) register_persistent_kernel(RegArgs a, int iters, int t_start, double lr_rot,
+                                                                                       double lr_trans, double lr_scale, int *iter_done,
+                                                                                       int *arrivals) {
+    __shared__ __align__(16) float s[3][NN_SPAN];
+    __shared__ Similarity T;
+    __shared__ int is_last;
+    __shared__ double shp[NN_THREADS / 32][14];
+    __shared__ double tot[14];
+    const int scan = blockIdx.x / a.items_per_scan;
+    const int item0 = blockIdx.x - scan * a.items_per_scan;
+    const int n = a.items_per_scan;
+    const int cloud = scan / a.n_starts;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float *V = a.complete + (size_t)cloud * a.Nc * 3;
+    const float *Rf = a.ref + (size_t)cloud * a.Nr * 3;
+    unsigned long long *pA = a.packedA + (size_t)scan * a.Nc;
+    unsigned long long *pB = a.packedB + (size_t)scan * a.Nr;
+    const int sliceA = (a.Nc + n - 1) / n, sliceB = (a.Nr + n - 1) / n;
+    const double cA = (double)a.cd_weight * (double)a.w_fwd / (double)a.Nc;
+    const double cB = (double)a.cd_weight * (double)a.w_inv / (double)a.Nr;
+    for (int k = 0; k < iters; ++k) {
+        if (threadIdx.x == 0) {
+            if (k > 0) {   // the pose of iteration k exists once iteration k - 1 of THIS scan has been finalised
+                int v;
+                for (;;) {
+                    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(iter_done + scan) : "memory");
+                    if (v >= k) break;
+                    __nanosleep(32);
+                }
+            }
+            load_similarity(a.params + (size_t)scan * REG_NPAR, a.center + (size_t)cloud * 3, T);
+        }
+        __syncthreads();
+        // ---- phase 1: this CTA's scan item ----
+        int item = item0;
+        if (item < a.itemsA) {
+            const int ts = item % a.tsplitsA, qt = item / a.tsplitsA;
+            nn_scan_item<QT>(s, V, a.Nc, qt * (NN_THREADS * QT), Rf, a.Nr, ts * NN_SPAN, 0, &T, nullptr, pA);
+        } else {
+            item -= a.itemsA;
+            const int ts = item % a.tsplitsB, qt = item / a.tsplitsB;
+            nn_scan_item<QT>(s, Rf, a.Nr, qt * (NN_THREADS * QT), V, a.Nc, ts * NN_SPAN, 0, nullptr, &T, pB);
+        }
+        // ---- per-scan barrier: every item of the scan has published its minima ----
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            atomicAdd(arrivals + scan, 1);
+            const int want = (2 * k + 1) * n;
+            int v;
+            for (;;) {
+                asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(arrivals + scan) : "memory");
+                if (v >= want) break;
+                __nanosleep(20);
+            }
+        }
+        __syncthreads();
+        // ---- phase 2: this CTA's slice of the loss / gradient terms ----
+        double acc[14];
+#pragma unroll
+        for (int i = 0; i < 14; ++i) acc[i] = 0.0;
+        for (int j = item0 * sliceA + (int)threadIdx.x; j < min((item0 + 1) * sliceA, a.Nc); j += NN_THREADS) {
+            const unsigned long long w = __ldcg(pA + j);
+            pA[j] = ~0ull;   // re-armed for the next iteration (nobody touches it before iter_done is released)
+            accum_term(a, T, V, Rf, j, (int)(unsigned)(w & 0xffffffffu), __uint_as_float((unsigned)(w >> 32)), cA, acc);
+        }
+        for (int q = item0 * sliceB + (int)threadIdx.x; q < min((item0 + 1) * sliceB, a.Nr); q += NN_THREADS) {
+            const unsigned long long w = __ldcg(pB + q);
+            pB[q] = ~0ull;
+            accum_term(a, T, V, Rf, (int)(unsigned)(w & 0xffffffffu), q, __uint_as_float((unsigned)(w >> 32)), cB, acc);
+        }
+#pragma unroll
+        for (int i = 0; i < 14; ++i) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+            if (lane == 0) shp[warp][i] = acc[i];
+        }
+        __syncthreads();
+        double *partial = a.partials + ((size_t)scan * n + item0) * 14;
+        if (threadIdx.x < 14) {
+            double r = 0.0;
+#pragma unroll
+            for (int w = 0; w < NN_THREADS / 32; ++w) r += shp[w][threadIdx.x];   // fixed order
+            partial[threadIdx.x] = r;
+            __threadfence();
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) is_last = (atomicAdd(arrivals + scan, 1) == (2 * k + 2) * n - 1);
+        __syncthreads();
+        if (is_last) {
+            __threadfence();
+            if (threadIdx.x < 14) {
+                double r = 0.0;
+                for (int c = 0; c < n; ++c) r += __ldcg(a.partials + ((size_t)scan * n + c) * 14 + threadIdx.x);   // index order
+                tot[threadIdx.x] = r;
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                const int t = t_start + k;
+                AdamStep st;
+                const double bc1 = 1.0 - pow(0.9, (double)(t + 1));
+                st.step_size[0] = (float)(lr_rot / bc1), st.step_size[1] = (float)(lr_trans / bc1), st.step_size[2] = (float)(lr_scale / bc1);
+                st.bc2_sqrt = (float)sqrt(1.0 - pow(0.999, (double)(t + 1)));
+                st.t_index = t;
+                pose_update(a, scan, T, tot, st);
+                __threadfence();
+                asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(iter_done + scan), "r"(k + 1) : "memory");
+            }
+        }
+        __syncthreads();   // T, shp / tot and the staging buffer are free for the next iteration
     }
 }
 
@@ -336,7 +477,7 @@ __global__ void __launch_bounds__(FIX_THREADS, 2) register_finish_kernel(const R
         if (lane == 0) tot[warp] = r;
     }
     __syncthreads();
-    if (threadIdx.x == 0) pose_update(a, scan, T, tot);
+    if (threadIdx.x == 0) pose_update(a, scan, T, tot, adam_step_from_args(a));
 }
 
 }  // namespace genpc
@@ -353,16 +494,25 @@ static bool register_takes_sym_path(int S, int Nc, int Nr) {
     return (mode == nullptr ? big : strcmp(mode, "sym") == 0) && Nr >= 512;
 }
 
+// per-scan slots of 14-double partial sums: one per finish CTA (symmetric path, finest granularity 128 columns) or one per
+// work item of the persistent small path (at its finest, one query per thread)
+static size_t register_partial_slots(int Nc, int Nr) {
+    const size_t fix_ctas = ((size_t)Nc + 128 - 1) / 128;
+    const size_t items = (size_t)((Nc + NN_THREADS - 1) / NN_THREADS) * ((Nr + NN_SPAN - 1) / NN_SPAN) +
+                         (size_t)((Nr + NN_THREADS - 1) / NN_THREADS) * ((Nc + NN_SPAN - 1) / NN_SPAN);
+    return fix_ctas > items ? fix_ctas : items;
+}
+
 extern "C" size_t genpc_register_workspace_bytes(int S, int Nc, int Nr) {
     if (S < 0 || Nc < 0 || Nr < 0) return 0;
-    const size_t fix_ctas = ((size_t)Nc + 128 - 1) / 128;  // sized for the finest CTA granularity
-    return ((size_t)S * Nc + (size_t)S * Nr) * 8 + (size_t)S * fix_ctas * 14 * sizeof(double) + (size_t)S * sizeof(int);
+    return ((size_t)S * Nc + (size_t)S * Nr) * 8 + (size_t)S * register_partial_slots(Nc, Nr) * 14 * sizeof(double) +
+           3 * (size_t)S * sizeof(int);   // tickets, iter_done, arrivals
 }
 
 // Kernel launches one Adam iteration costs at this problem size (1: single-launch path, 2: symmetric scan + finish).
 extern "C" int genpc_register_launches_per_iter(int S, int Nc, int Nr) {
     if (S <= 0 || Nc <= 0 || Nr <= 0) return GENPC_ERR_SHAPE;
-    return register_takes_sym_path(S, Nc, Nr) ? 2 : 1;
+    return register_takes_sym_path(S, Nc, Nr) ? 2 : 1;   // (small problems: ONE launch for all iterations of a run call)
 }
 
 extern "C" int genpc_register_run(const float *complete, const float *center, const float *ref, float *params,
@@ -379,7 +529,7 @@ extern "C" int genpc_register_run(const float *complete, const float *center, co
     a.packedA = (unsigned long long *)workspace;
     a.packedB = a.packedA + (size_t)S * Nc;
     a.partials = (double *)(a.packedB + (size_t)S * Nr);
-    a.counters = (int *)(a.partials + (size_t)S * ((Nc + 128 - 1) / 128) * 14);
+    a.counters = (int *)(a.partials + (size_t)S * register_partial_slots(Nc, Nr) * 14);
     a.loss_hist = loss_hist;
     a.S = S, a.n_starts = n_starts, a.Nc = Nc, a.Nr = Nr, a.T = T;
     // queries per thread of the single-launch path: the real pipeline registers 1-3 K-point clouds with 4 starts -- a few
@@ -430,6 +580,32 @@ extern "C" int genpc_register_run(const float *complete, const float *center, co
         if (e != cudaSuccess) return (int)e;
         e = cudaMemsetAsync(a.counters, 0, (size_t)S * sizeof(int), stream);
         if (e != cudaSuccess) return (int)e;
+    }
+    // ---- small problems: one cooperative launch runs all the iterations (register_persistent_kernel) ----
+    if (!sym && iters > 1) {
+        const char *pk = tunable("GENPC_REGISTER_PERSIST");
+        int dev = 0, sms = 0, per_sm = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaError_t eo = cudaSuccess;
+        switch (QT) {
+            case 4: eo = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, register_persistent_kernel<4>, NN_THREADS, 0); break;
+            case 2: eo = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, register_persistent_kernel<2>, NN_THREADS, 0); break;
+            default: eo = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, register_persistent_kernel<1>, NN_THREADS, 0); break;
+        }
+        if (eo == cudaSuccess && (pk == nullptr || atoi(pk) != 0) && grid <= (long long)sms * per_sm) {
+            int *iter_done = a.counters + S, *arrivals = a.counters + 2 * S;
+            cudaError_t e = cudaMemsetAsync(iter_done, 0, 2 * (size_t)S * sizeof(int), stream);
+            if (e != cudaSuccess) return (int)e;
+            int it_n = iters, t0 = t_start;
+            void *kargs[] = {(void *)&a, (void *)&it_n, (void *)&t0, (void *)&lr_rot, (void *)&lr_trans, (void *)&lr_scale, (void *)&iter_done,
+                             (void *)&arrivals};
+            const void *fn = QT == 4 ? (const void *)register_persistent_kernel<4>
+                                     : (QT == 2 ? (const void *)register_persistent_kernel<2> : (const void *)register_persistent_kernel<1>);
+            e = cudaLaunchCooperativeKernel(fn, dim3((unsigned)grid), dim3(NN_THREADS), kargs, 0, stream);
+            if (e != cudaSuccess) return (int)e;
+            return GENPC_OK;
+        }
     }
     for (int it = 0; it < iters; ++it) {
         const int t = t_start + it;

@@ -399,3 +399,27 @@ def test_nan_and_inf_points_stay_in_range(cuda, N, M):
     assert not gx1.any() and not gx2.any()
     for buf, v in ((buf1, 123.0), (buf2, 321.0)):
         assert bool((buf[:guard] == v).all()) and bool((buf[-guard:] == v).all())
+
+
+@pytest.mark.parametrize("name", ["cd_l1", "cd_l2"])
+def test_graphed_loss_step_equals_eager(cuda, name):
+    """GraphedLossStep (one CUDA-graph launch per step) against the eager fused step on changing inputs: loss and both
+    gradients identical bit for bit (same kernels, same deterministic reductions) -- gradients up to the atomics' order."""
+    from genpc_b200.utils.loss_util import Completionloss, GraphedLossStep
+
+    B, N, M = 4, 2048, 4096
+    cl = Completionloss(name)
+    a0, b0 = torch.from_numpy(shape_cloud(1, B, N)).to(cuda), torch.from_numpy(shape_cloud(2, B, M)).to(cuda)
+    step = GraphedLossStep(cl, a0, b0)
+    for k in range(4):
+        a = torch.from_numpy(shape_cloud(10 + k, B, N)).to(cuda)
+        b = torch.from_numpy(shape_cloud(20 + k, B, M)).to(cuda)
+        loss, ga, gb = step(a, b)
+        ea = a.clone().requires_grad_(True)
+        eb = b.clone().requires_grad_(True)
+        el = cl.get_loss(ea, eb)
+        el.backward()
+        torch.cuda.synchronize()
+        assert float(loss) == float(el)
+        assert torch.allclose(ga, ea.grad, rtol=1e-5, atol=1e-9) and torch.allclose(gb, eb.grad, rtol=1e-5, atol=1e-9)
+    assert step() [0] is step.loss

@@ -207,8 +207,9 @@ def test_c3_length_500_iterations_vs_oracle_and_reference_self_spread(cuda):
     steps while the reference drifts up to 3.6e-4 from ITSELF mid-trajectory; on a second pair (4096 x 3000) every arm --
     reference vs reference included -- bifurcates around iteration 200 (one flipped nearest neighbour, amplified by Adam's
     normalisation) and ends 1e-3..5e-3 apart in the parameters with losses still equal to 2e-6.
-    Tolerances: final loss 1e-5 relative; every parameter, at EVERY step, within max(1e-5, 2 x the reference's own
-    run-to-run spread over the trajectory)."""
+    Tolerances: against the oracle -- every loss 1e-5 relative, every parameter at EVERY step within max(1e-5, 2 x the
+    reference's own run-to-run spread), the final pose / scale within 1e-5; against the reference's two runs -- the nearer
+    one within 1e-3 at every step and 1e-4 at the end (a loose bound: its own twin runs can sit 3.6e-4 apart)."""
     import torch
 
     from genpc_b200.optim_registration.diff_obj_pose import RegistrationBatch, rotation_6d_to_matrix
@@ -266,8 +267,39 @@ def test_c3_length_500_iterations_vs_oracle_and_reference_self_spread(cuda):
 
         r1, r2 = run_ref(), run_ref()
         spread = float(np.abs(r1 - r2).max())
-        tol_ref = max(1e-5, 2.0 * spread)
-        assert np.abs(ours - r1).max() <= tol_ref, (np.abs(ours - r1).max(), spread)
+        # against the reference itself only a loose bound can be asserted without flakiness: one of its runs may take another
+        # branch at a near-tie for a few dozen steps (3.6e-4 from its twin in the recorded session) -- two samples do not
+        # bound that.  The strict 1e-5 checks are the ones against the deterministic oracle below.
+        near = min(np.abs(ours - r1).max(), np.abs(ours - r2).max())
+        assert near <= max(1e-3, 2.0 * spread), (near, spread)
+        assert min(np.abs(ours[-1] - r1[-1]).max(), np.abs(ours[-1] - r2[-1]).max()) <= max(1e-4, 2.0 * spread)
     tol = max(1e-5, 2.0 * spread)
     assert np.abs(ours - eh).max() <= tol, (np.abs(ours - eh).max(), spread)
     assert np.abs(ours[-1] - eh[-1]).max() <= 1e-5, np.abs(ours[-1] - eh[-1]).max()     # the registered pose / scale itself
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nc,nr,starts", [(2500, 1000, 4), (900, 1400, 2), (3000, 3000, 4)])
+def test_persistent_small_registration_equals_launch_per_iteration(cuda, nc, nr, starts):
+    """Small clouds (the real pipeline's 1-3 K points, 4 starts): run(n) is ONE cooperative launch that iterates on the device
+    (register_persistent_kernel); it must reproduce the launch-per-iteration path -- same kernels' arithmetic, Adam scalars
+    computed on the device instead of the host -- to float rounding of those scalars (1e-6), and be deterministic."""
+    import torch
+
+    from genpc_b200 import _lib
+    from genpc_b200.optim_registration.diff_obj_pose import RegistrationBatch
+
+    comp, part, _ = make_pair(21, nc, nr)
+    V, Rf = torch.from_numpy(comp[None]).to(cuda), torch.from_numpy(part[None]).to(cuda)
+    iters = 60
+    res = []
+    for persist in ("1", "1", "0"):
+        with _lib.tunable(GENPC_REGISTER_PERSIST=persist):
+            rb = RegistrationBatch(V, Rf, n_starts=starts, lr=0.01, max_iters=iters)
+            rb.run(iters)
+            torch.cuda.synchronize()
+        res.append((rb.params.cpu().numpy().copy(), rb.losses().cpu().numpy().copy()))
+    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])      # deterministic
+    assert np.abs(res[0][0] - res[2][0]).max() <= 1e-6, np.abs(res[0][0] - res[2][0]).max()
+    assert np.abs(res[0][1] - res[2][1]).max() <= 1e-6 * np.abs(res[2][1]).max()
+    assert (res[0][1][:, -1] < res[0][1][:, 0]).all()
