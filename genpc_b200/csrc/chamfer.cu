@@ -274,6 +274,9 @@ static int chamfer_forward_sym(const float *xyz1, const float *xyz2, float *dist
         if (QT == 4) nn_sym_persistent_kernel<4><<<grid, SYM_THREADS, 0, stream>>>(p, (int)items, counter);
         else nn_sym_persistent_kernel<2><<<grid, SYM_THREADS, 0, stream>>>(p, (int)items, counter);
 #endif
+    } else if (QT == 4 && tunable("GENPC_SYM_TMA") != nullptr && atoi(tunable("GENPC_SYM_TMA")) == 1 && p.nc % 4 == 0 && p.span % 4 == 0 &&
+               (reinterpret_cast<size_t>(p.cols) & 15) == 0) {
+        nn_sym_tma_kernel<4><<<(unsigned)items, SYM_THREADS, 0, stream>>>(p);   // r02 experiment: TMA bulk staging
     } else
     switch (QT) {
         case 8: nn_sym_kernel<8><<<(unsigned)items, SYM_THREADS, 0, stream>>>(p); break;

@@ -239,6 +239,56 @@ __global__ void __launch_bounds__(SYM_THREADS, GENPC_SYM_MINB(QT)) nn_sym_kernel
                     nullptr, p.prow + (size_t)b * p.nr, p.pcol + (size_t)b * p.nc, p.rblock_base);
 }
 
+// TMA-staged form (r02 experiment, GENPC_SYM_TMA=1): the column span is contiguous in the AoS cloud (span * 12 bytes), so ONE
+// bulk asynchronous copy (cp.async.bulk.shared::cluster.global, completion on an mbarrier -- the TMA engine, UBLKCP in SASS)
+// brings it into a raw shared-memory buffer while the threads load their rows; the AoS -> SoA transposition is then a
+// shared -> shared pass (12-byte lane stride: conflict free) instead of three scalar LDG -> STS per point.  Needs a 16-byte
+// aligned span start and a span size that is a multiple of 16 bytes; the caller falls back to nn_sym_kernel otherwise.
+// Measured (profiles/r02d_sym_tma.txt): no gain on C2 -- see DESIGN.md section 4.1.
+template <int QT>
+__global__ void __launch_bounds__(SYM_THREADS, GENPC_SYM_MINB(QT)) nn_sym_tma_kernel(const SymParams p) {
+    __shared__ __align__(16) float s[3][SYM_SPAN_MAX];
+    __shared__ __align__(128) float raw[3 * SYM_SPAN_MAX];
+    __shared__ __align__(8) unsigned long long bar;
+    if (p.select != nullptr && *p.select == 0) return;
+    int item = blockIdx.x;
+    const int cs = item % p.cspans;
+    item /= p.cspans;
+    const int rt = item % p.rtiles;
+    const int b = item / p.rtiles;
+    const int tid = threadIdx.x;
+    const int c0 = cs * p.span, cnt = min(p.span, p.nc - c0), cnt32 = (cnt + 31) & ~31;
+    const float *cp = p.cols + ((size_t)b * p.nc + c0) * 3;
+    const unsigned bytes = (unsigned)cnt * 12u;
+    const unsigned bar_a = (unsigned)__cvta_generic_to_shared(&bar);
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         (unsigned)__cvta_generic_to_shared(raw)),
+                     "l"(cp), "r"(bytes), "r"(bar_a)
+                     : "memory");
+    }
+    __syncthreads();   // the barrier is initialised before anybody polls it
+    {
+        unsigned ok = 0;
+        while (!ok)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(ok)
+                         : "r"(bar_a)
+                         : "memory");
+    }
+    const float qnan = __int_as_float(0x7fc00000);
+    for (int k = tid; k < cnt32; k += SYM_THREADS) {
+        const bool in = k < cnt;
+        s[0][k] = in ? raw[3 * k] : qnan, s[1][k] = in ? raw[3 * k + 1] : qnan, s[2][k] = in ? raw[3 * k + 2] : qnan;
+    }
+    __syncthreads();
+    nn_sym_item<QT, true>(s, p.rows + (size_t)b * p.nr * 3, p.nr, rt, p.cols + (size_t)b * p.nc * 3, p.nc, c0, p.span, nullptr,
+                          p.prow + (size_t)b * p.nr, p.pcol + (size_t)b * p.nc, p.rblock_base);
+}
+
 // Host-fed form: same work items, but the clouds are still arriving from pinned host memory while the kernel runs.
 // Thread 0 of every CTA waits (acquire, system scope) until the generation word of its cloud pair's chunk has been
 // written by the copy stream, then the CTA proceeds exactly like nn_sym_kernel.  CTAs are dispatched in blockIdx
