@@ -706,7 +706,7 @@ extern "C" int genpc_chamfer_sym_fixup(const float *rows_full, const float *cols
 // One launch, deterministic: fixed-size grid, per-CTA partial sums in double, the last CTA (ticket) adds the partials
 // in index order.  Replaces the ~8 tiny torch launches (sqrt, mean, add, div and their backward) per call.
 namespace genpc {
-constexpr int LOSS_CTAS = 2 * GENPC_NUM_SMS;
+constexpr int LOSS_CTAS = 2 * GENPC_NUM_SMS_B200;   // a fixed reduction grid (workspace size depends on it), not a tuning knob
 
 __global__ void __launch_bounds__(256) chamfer_loss_kernel(const float *__restrict__ d1, const float *__restrict__ d2,
                                                            size_t n1, size_t n2, int use_sqrt, float w1, float w2,

@@ -9,7 +9,14 @@
 #error "libgenpc_b200 is written for sm_100a (B200) only"
 #endif
 
-#define GENPC_NUM_SMS 148
+#define GENPC_NUM_SMS_B200 148   // compile-time sizes only (fixed-size reduction grids); launch shaping asks the device
+
+namespace genpc {
+// SMs of the CURRENT device (cached per device ordinal; tunables.cu).  B200: 148.  Grid sizes and the balanced / persistent
+// heuristics use this, so a part with fewer SMs or a process driving several different devices is tuned correctly.
+int num_sms();
+}  // namespace genpc
+#define GENPC_NUM_SMS (genpc::num_sms())
 
 namespace genpc {
 

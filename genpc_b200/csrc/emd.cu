@@ -73,6 +73,14 @@ __device__ __forceinline__ void bid_merge(BidState &a, const BidState &b, int n,
     }
 }
 
+// 16-byte shared-memory load through a 32-bit shared-window address: the generic-pointer form makes ptxas rebuild the
+// window base (S2UR SR_CgaCtaId + ULEA) in every iteration of the Bid scan
+__device__ __forceinline__ float4 lds128(unsigned addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+
 __device__ __forceinline__ int ld_acquire(const int *p) {
     int v;
     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -303,14 +311,21 @@ __device__ __noinline__ void emd_getmax_assign(const int *__restrict__ uidx, con
 }
 
 __global__ void __launch_bounds__(EMD_THREADS, 5) emd_auction_kernel(const EmdArgs a) {
-    __shared__ __align__(16) float sx[EMD_CHUNK], sy[EMD_CHUNK], sz[EMD_CHUNK];  // targets, SoA (pairs feed FADD2/FFMA2)
-    __shared__ __align__(16) float sprice[EMD_CHUNK];
+    // targets + prices of one chunk, two float4 planes per target PAIR p: stg[p] = (x0, x1, y0, y1), stg[EMD_CHUNK/2 + p] =
+    // (z0, z1, price0, price1) -- one address register (second plane at a constant offset) and two LDS.128 per step of the
+    // Bid scan (r02; four separate SoA arrays cost four LEA, four LDS.64 and six uniform address instructions per step:
+    // 31 -> 21 instructions per target pair on the reject path).  Consecutive pairs are 16 B apart inside a plane, so the
+    // lanes of a bidder hit distinct banks (a first r02 layout interleaved the two float4 of a pair: 32-byte lane stride,
+    // 2-way conflict on every load -- 930 M of 2000 M wavefronts).
+    __shared__ __align__(16) float4 stg[EMD_CHUNK];
+    constexpr unsigned STG_PLANE = (EMD_CHUNK / 2) * 16;
     __shared__ BidState smerge[EMD_THREADS];
     __shared__ int sscan[EMD_THREADS / 32];
     __shared__ int s_last;
     const int tid = threadIdx.x;
     const int n = a.n;
     const int block_cnt = n / 256;
+    const unsigned stg_addr = (unsigned)__cvta_generic_to_shared(stg);
 
     for (int b = (a.group > 1 ? (int)blockIdx.x / a.group : (int)blockIdx.x); b < a.B;
          b += (a.group > 1 ? a.B : (int)gridDim.x)) {
@@ -441,8 +456,9 @@ __global__ void __launch_bounds__(EMD_THREADS, 5) emd_auction_kernel(const EmdAr
                         __syncthreads();
                         for (int k = tid; k < end_k; k += EMD_THREADS) {
                             const float *tp = p2 + (size_t)(k2 + k) * 3;
-                            sx[k] = __ldg(tp), sy[k] = __ldg(tp + 1), sz[k] = __ldg(tp + 2);
-                            sprice[k] = __ldcg(pr + k2 + k);
+                            float *q = reinterpret_cast<float *>(stg + (k >> 1)) + (k & 1);
+                            q[0] = __ldg(tp), q[2] = __ldg(tp + 1);
+                            q[STG_PLANE / 4] = __ldg(tp + 2), q[STG_PLANE / 4 + 2] = __ldcg(pr + k2 + k);
                         }
                         __syncthreads();
                         if (active && two_level) {
@@ -450,12 +466,13 @@ __global__ void __launch_bounds__(EMD_THREADS, 5) emd_auction_kernel(const EmdAr
                             // against the target-independent bound s_cap rejects almost everything before the price is
                             // even read; survivors take the per-target filter + exact path.  Half the instructions of the
                             // single-level loop while prices are small; later (bound loose) the single-level loop is used.
-                            for (int kp = tpt; kp < (end_k >> 1); kp += T) {
-                                const float2 tx = reinterpret_cast<const float2 *>(sx)[kp], ty = reinterpret_cast<const float2 *>(sy)[kp];
-                                const float2 tz = reinterpret_cast<const float2 *>(sz)[kp];
-                                const float2 s2 = sqdist_ref_x2(nx, ny, nz, tx, ty, tz);
+                            unsigned sa = stg_addr + (unsigned)tpt * 16u;
+                            for (int kp = tpt; kp < (end_k >> 1); kp += T, sa += (unsigned)T * 16u) {
+                                const float4 q0 = lds128(sa), q1 = lds128(sa + STG_PLANE);
+                                const float2 s2 = sqdist_ref_x2(nx, ny, nz, make_float2(q0.x, q0.y), make_float2(q0.z, q0.w),
+                                                                make_float2(q1.x, q1.y));
                                 if (s2.x <= s_cap || s2.y <= s_cap) {
-                                    const float2 pk = reinterpret_cast<const float2 *>(sprice)[kp];
+                                    const float2 pk = make_float2(q1.z, q1.w);
                                     const float tq_x = __fsub_rn(__fsub_rn(3.0f, pk.x), bm);
                                     if (tq_x > 0.f && s2.x <= __fmul_rn(tq_x, tq_x)) consider(k2 + 2 * kp, s2.x, pk.x);
                                     const float tq_y = __fsub_rn(__fsub_rn(3.0f, pk.y), bm);   // bm as updated by the first
@@ -463,9 +480,11 @@ __global__ void __launch_bounds__(EMD_THREADS, 5) emd_auction_kernel(const EmdAr
                                 }
                             }
                         } else if (active) {
-                            for (int kp = tpt; kp < (end_k >> 1); kp += T) {   // end_k is even (n % 256 == 0)
-                                step2(k2 + 2 * kp, reinterpret_cast<const float2 *>(sx)[kp], reinterpret_cast<const float2 *>(sy)[kp],
-                                      reinterpret_cast<const float2 *>(sz)[kp], reinterpret_cast<const float2 *>(sprice)[kp]);
+                            unsigned sa = stg_addr + (unsigned)tpt * 16u;
+                            for (int kp = tpt; kp < (end_k >> 1); kp += T, sa += (unsigned)T * 16u) {   // end_k is even (n % 256 == 0)
+                                const float4 q0 = lds128(sa), q1 = lds128(sa + STG_PLANE);
+                                step2(k2 + 2 * kp, make_float2(q0.x, q0.y), make_float2(q0.z, q0.w), make_float2(q1.x, q1.y),
+                                      make_float2(q1.z, q1.w));
                             }
                         }
                     }

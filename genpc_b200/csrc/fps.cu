@@ -413,8 +413,11 @@ __global__ void __launch_bounds__(FPS_THREADS, 1) fps_cluster_kernel(const float
 // single-CTA kernel is the better choice then.  Returns 0 when the query fails.
 template <int PPT, int CS, bool SMEMC>
 static int fps_max_active_clusters() {
-    static int cached = -1;  // per template instance; the answer depends only on the device
-    if (cached >= 0) return cached;
+    static int cache[64];     // per template instance AND per device ordinal (0 = not asked yet, -1 = query failed)
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+    int &cached = cache[dev];
+    if (cached != 0) return cached < 0 ? 0 : cached;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(CS * 64));
     cfg.blockDim = dim3(FPS_THREADS);
@@ -422,6 +425,7 @@ static int fps_max_active_clusters() {
     if (SMEMC && cudaFuncSetAttribute(fps_cluster_kernel<PPT, CS, SMEMC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)cfg.dynamicSmemBytes) != cudaSuccess) {
         (void)cudaGetLastError();
+        cached = -1;
         return 0;
     }
     if (CS > 8 && cudaFuncSetAttribute(fps_cluster_kernel<PPT, CS, SMEMC>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) !=
@@ -438,7 +442,7 @@ static int fps_max_active_clusters() {
         (void)cudaGetLastError();
         n = 0;
     }
-    cached = n;
+    cached = n > 0 ? n : -1;
     return n;
 }
 

@@ -48,6 +48,18 @@ const char *tunable(const char *name) {
     return nullptr;
 }
 
+int num_sms() {
+    static int cache[64] = {0};   // 0 = not asked yet; racing first calls write the same value
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return GENPC_NUM_SMS_B200;
+    int n = cache[dev];
+    if (n <= 0) {
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = GENPC_NUM_SMS_B200;
+        cache[dev] = n;
+    }
+    return n;
+}
+
 }  // namespace genpc
 
 extern "C" int genpc_set_tunable(const char *name, const char *value) {
