@@ -102,43 +102,17 @@ __device__ __forceinline__ void red_add3(float *arr, size_t i, float x, float y,
     }
 }
 
-// Backward: one thread per (direction, batch, point); same six terms as NmDistanceGradKernel
-// (chamfer3D.cu:155-174): g = 2*grad; own += g*(p - nn); nn's -= g*(p - nn).
+// Backward: same six terms as NmDistanceGradKernel (chamfer3D.cu:155-174): g = 2*grad; own += g*(p - nn); nn's -= g*(p - nn).
+// GRAD_R points per thread, `nthreads` apart (coalesced): the chain idx -> gathered neighbour -> reductions is three dependent
+// memory round trips per point, so every level is issued for all GRAD_R points before any is consumed (r02: one point per
+// thread left the kernel latency bound at 0.17 of the HBM roofline).
+constexpr int GRAD_R = 4;
+
+// scatter term of one point, warp-aggregated: lanes that hit the same neighbour (common when many points of a dense cloud
+// share one nearest neighbour in a sparse one and the cloud is stored with spatial locality) are summed by shuffles and issue
+// ONE set of atomics.  Every lane of the warp must call this (invalid lanes carry unique keys).
 template <bool VEC>
-__global__ void chamfer_grad_kernel(const float *__restrict__ xyz1, const float *__restrict__ xyz2,
-                                    const float *__restrict__ gd1, const float *__restrict__ gd2,
-                                    const int *__restrict__ idx1, const int *__restrict__ idx2,
-                                    float *gx1, float *gx2, int B, int N, int M) {
-    const size_t n1 = (size_t)B * N, n2 = (size_t)B * M;
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int lane = threadIdx.x & 31;
-    bool valid = i < n1 + n2;
-    const int dir = (valid && i >= n1) ? 1 : 0;
-    if (dir) i -= n1;
-    const float *a = dir ? xyz2 : xyz1, *o = dir ? xyz1 : xyz2, *gd = dir ? gd2 : gd1;
-    const int *idx = dir ? idx2 : idx1;
-    float *ga = dir ? gx2 : gx1, *go = dir ? gx1 : gx2;
-    const int na = dir ? M : N, no = dir ? N : M;
-    size_t t = 0;
-    float tx = 0.f, ty = 0.f, tz = 0.f;
-    // an index outside [0, no) (caller-supplied garbage) contributes nothing instead of touching foreign memory
-    const int nn = valid ? __ldg(idx + i) : 0;
-    valid = valid && (unsigned)nn < (unsigned)no;
-    if (valid) {
-        const size_t b = i / na;
-        const float x1 = __ldg(a + i * 3), y1 = __ldg(a + i * 3 + 1), z1 = __ldg(a + i * 3 + 2);
-        t = b * no + nn;
-        const float x2 = __ldg(o + t * 3), y2 = __ldg(o + t * 3 + 1), z2 = __ldg(o + t * 3 + 2);
-        const float g = __fmul_rn(__ldg(gd + i), 2.f);
-        tx = __fmul_rn(g, __fsub_rn(x1, x2));
-        ty = __fmul_rn(g, __fsub_rn(y1, y2));
-        tz = __fmul_rn(g, __fsub_rn(z1, z2));
-        // own term: one writer per element here, but the other direction scatters into the same array concurrently -> atomic
-        red_add3<VEC>(ga, i, tx, ty, tz);
-    }
-    // scatter term, warp-aggregated: lanes that hit the same neighbour (common when many points of a dense cloud share
-    // one nearest neighbour in a sparse one and the cloud is stored with spatial locality) are summed by shuffles
-    // and issue ONE set of atomics.
+__device__ __forceinline__ void scatter_aggregated(float *go, bool valid, size_t t, int dir, float tx, float ty, float tz, int lane) {
     const unsigned long long key = valid ? ((unsigned long long)t * 2ull + (unsigned)dir) : (~0ull - (unsigned)lane);
     const unsigned peers = __match_any_sync(0xffffffffu, key);
     if (peers == (1u << lane)) {
@@ -152,7 +126,68 @@ __global__ void chamfer_grad_kernel(const float *__restrict__ xyz1, const float 
         const float ox = __shfl_sync(peers, -tx, src), oy = __shfl_sync(peers, -ty, src), oz = __shfl_sync(peers, -tz, src);
         sx += ox, sy += oy, sz += oz;
     }
-    if (lane == leader) red_add3<VEC>(go, t, sx, sy, sz);  // groups only form among valid lanes (invalid lanes carry unique keys)
+    if (lane == leader) red_add3<VEC>(go, t, sx, sy, sz);  // groups only form among valid lanes
+}
+
+// LOSS = false: gd1 / gd2 are the upstream gradients of dist1 / dist2 (chamfer_3D.backward).
+// LOSS = true : backward of the fused loss -- graddist = upstream[0] * w / n (* 0.5 / sqrt(d) for the L1 forms, inf at d == 0
+//               exactly as torch's sqrt backward, loss_util.py:37); gd1 / gd2 are the forward's distances; w2 == 0 drops the
+//               second direction.
+template <bool VEC, bool LOSS>
+__global__ void __launch_bounds__(256) chamfer_grad_kernel(const float *__restrict__ xyz1, const float *__restrict__ xyz2,
+                                                          const float *__restrict__ gd1, const float *__restrict__ gd2,
+                                                          const int *__restrict__ idx1, const int *__restrict__ idx2,
+                                                          const float *__restrict__ upstream, int use_sqrt, float w1, float w2,
+                                                          float *gx1, float *gx2, int B, int N, int M) {
+    const size_t n1 = (size_t)B * N, n2 = (LOSS && w2 == 0.f) ? 0 : (size_t)B * M;
+    const size_t nthreads = (size_t)gridDim.x * blockDim.x, g0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    bool valid[GRAD_R];
+    int dir[GRAD_R], nn[GRAD_R];
+    size_t i[GRAD_R], t[GRAD_R];
+    float x1[GRAD_R], y1[GRAD_R], z1[GRAD_R], gsc[GRAD_R], tx[GRAD_R], ty[GRAD_R], tz[GRAD_R];
+    const float up = LOSS ? __ldg(upstream) : 0.f;
+#pragma unroll
+    for (int r = 0; r < GRAD_R; ++r) {   // level 1: index, own point, gradient scale
+        i[r] = g0 + (size_t)r * nthreads;
+        valid[r] = i[r] < n1 + n2;
+        dir[r] = (valid[r] && i[r] >= n1) ? 1 : 0;
+        if (dir[r]) i[r] -= n1;
+        nn[r] = 0, x1[r] = y1[r] = z1[r] = gsc[r] = 0.f;
+        if (valid[r]) {
+            const float *a = dir[r] ? xyz2 : xyz1;
+            nn[r] = __ldg((dir[r] ? idx2 : idx1) + i[r]);
+            x1[r] = __ldg(a + i[r] * 3), y1[r] = __ldg(a + i[r] * 3 + 1), z1[r] = __ldg(a + i[r] * 3 + 2);
+            gsc[r] = __ldg((dir[r] ? gd2 : gd1) + i[r]);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < GRAD_R; ++r) {   // level 2: the gathered neighbour
+        const int no = dir[r] ? N : M, na = dir[r] ? M : N;
+        // an index outside [0, no) (caller-supplied garbage) contributes nothing instead of touching foreign memory
+        valid[r] = valid[r] && (unsigned)nn[r] < (unsigned)no;
+        t[r] = 0, tx[r] = ty[r] = tz[r] = 0.f;
+        if (valid[r]) {
+            const float *o = dir[r] ? xyz1 : xyz2;
+            t[r] = (i[r] / na) * no + nn[r];
+            const float x2 = __ldg(o + t[r] * 3), y2 = __ldg(o + t[r] * 3 + 1), z2 = __ldg(o + t[r] * 3 + 2);
+            float gd = gsc[r];
+            if (LOSS) {
+                gd = __fmul_rn(up, __fdiv_rn(dir[r] ? w2 : w1, (float)(dir[r] ? (size_t)B * M : n1)));
+                if (use_sqrt) gd = __fmul_rn(gd, __fdiv_rn(0.5f, __fsqrt_rn(gsc[r])));
+            }
+            const float g = __fmul_rn(gd, 2.f);
+            tx[r] = __fmul_rn(g, __fsub_rn(x1[r], x2));
+            ty[r] = __fmul_rn(g, __fsub_rn(y1[r], y2));
+            tz[r] = __fmul_rn(g, __fsub_rn(z1[r], z2));
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < GRAD_R; ++r) {   // level 3: reductions
+        // own term: one writer per element here, but the other direction scatters into the same array concurrently -> atomic
+        if (valid[r]) red_add3<VEC>(dir[r] ? gx2 : gx1, i[r], tx[r], ty[r], tz[r]);
+        scatter_aggregated<VEC>(dir[r] ? gx1 : gx2, valid[r], t[r], dir[r], tx[r], ty[r], tz[r], lane);
+    }
 }
 
 static void fill_dir(NNDir &D, const float *q, const float *t, unsigned long long *out, int B, int nq, int mt,
@@ -447,12 +482,13 @@ extern "C" int genpc_chamfer_backward(const float *xyz1, const float *xyz2, cons
     if (tot == 0 || N == 0 || M == 0) return GENPC_OK;
     // vector reductions need 8-byte aligned gradient arrays (every point then has one aligned component pair)
     const bool vec = ((reinterpret_cast<size_t>(gradxyz1) | reinterpret_cast<size_t>(gradxyz2)) & 7) == 0;
+    const unsigned grid = (unsigned)((tot + 256 * GRAD_R - 1) / (256 * GRAD_R));
     if (vec)
-        chamfer_grad_kernel<true><<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(xyz1, xyz2, graddist1, graddist2, idx1, idx2,
-                                                                                      gradxyz1, gradxyz2, B, N, M);
+        chamfer_grad_kernel<true, false><<<grid, 256, 0, stream>>>(xyz1, xyz2, graddist1, graddist2, idx1, idx2, nullptr, 0, 0.f, 0.f,
+                                                                  gradxyz1, gradxyz2, B, N, M);
     else
-        chamfer_grad_kernel<false><<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(xyz1, xyz2, graddist1, graddist2, idx1, idx2,
-                                                                                       gradxyz1, gradxyz2, B, N, M);
+        chamfer_grad_kernel<false, false><<<grid, 256, 0, stream>>>(xyz1, xyz2, graddist1, graddist2, idx1, idx2, nullptr, 0, 0.f, 0.f,
+                                                                   gradxyz1, gradxyz2, B, N, M);
     GENPC_CHECK_LAUNCH();
     return GENPC_OK;
 }
@@ -752,56 +788,6 @@ __global__ void __launch_bounds__(256) chamfer_loss_kernel(const float *__restri
     }
 }
 
-// Backward of the fused loss: graddist = upstream * w / n (* 0.5 / sqrt(d) for the L1 forms, inf at d == 0 exactly as
-// torch's sqrt backward, loss_util.py:37) folded into the gradient kernel: same six terms as NmDistanceGradKernel.
-template <bool VEC>
-__global__ void chamfer_loss_grad_kernel(const float *__restrict__ xyz1, const float *__restrict__ xyz2,
-                                         const float *__restrict__ d1, const float *__restrict__ d2,
-                                         const int *__restrict__ idx1, const int *__restrict__ idx2,
-                                         const float *__restrict__ upstream, int use_sqrt, float w1, float w2, float *gx1,
-                                         float *gx2, int B, int N, int M) {
-    const size_t n1 = (size_t)B * N, n2 = (w2 != 0.f) ? (size_t)B * M : 0;
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int lane = threadIdx.x & 31;
-    bool valid = i < n1 + n2;
-    const int dir = (valid && i >= n1) ? 1 : 0;
-    if (dir) i -= n1;
-    const float *a = dir ? xyz2 : xyz1, *o = dir ? xyz1 : xyz2, *dd = dir ? d2 : d1;
-    const int *idx = dir ? idx2 : idx1;
-    float *ga = dir ? gx2 : gx1, *go = dir ? gx1 : gx2;
-    const int na = dir ? M : N, no = dir ? N : M;
-    size_t t = 0;
-    float tx = 0.f, ty = 0.f, tz = 0.f;
-    const int nn = valid ? __ldg(idx + i) : 0;
-    valid = valid && (unsigned)nn < (unsigned)no;   // see chamfer_grad_kernel
-    if (valid) {
-        const size_t b = i / na;
-        const float x1 = __ldg(a + i * 3), y1 = __ldg(a + i * 3 + 1), z1 = __ldg(a + i * 3 + 2);
-        t = b * no + nn;
-        const float x2 = __ldg(o + t * 3), y2 = __ldg(o + t * 3 + 1), z2 = __ldg(o + t * 3 + 2);
-        float gd = __fmul_rn(__ldg(upstream), __fdiv_rn(dir ? w2 : w1, (float)(dir ? (size_t)B * M : n1)));
-        if (use_sqrt) gd = __fmul_rn(gd, __fdiv_rn(0.5f, __fsqrt_rn(__ldg(dd + i))));
-        const float g = __fmul_rn(gd, 2.f);
-        tx = __fmul_rn(g, __fsub_rn(x1, x2));
-        ty = __fmul_rn(g, __fsub_rn(y1, y2));
-        tz = __fmul_rn(g, __fsub_rn(z1, z2));
-        red_add3<VEC>(ga, i, tx, ty, tz);
-    }
-    const unsigned long long key = valid ? ((unsigned long long)t * 2ull + (unsigned)dir) : (~0ull - (unsigned)lane);
-    const unsigned peers = __match_any_sync(0xffffffffu, key);
-    if (peers == (1u << lane)) {
-        if (valid) red_add3<VEC>(go, t, -tx, -ty, -tz);
-        return;
-    }
-    const int leader = __ffs(peers) - 1;
-    float sx = -tx, sy = -ty, sz = -tz;
-    for (unsigned m = peers & (peers - 1u); m; m &= m - 1u) {
-        const int src = __ffs(m) - 1;
-        const float ox = __shfl_sync(peers, -tx, src), oy = __shfl_sync(peers, -ty, src), oz = __shfl_sync(peers, -tz, src);
-        sx += ox, sy += oy, sz += oz;
-    }
-    if (lane == leader) red_add3<VEC>(go, t, sx, sy, sz);
-}
 }  // namespace genpc
 
 extern "C" size_t genpc_chamfer_loss_workspace_bytes(void) { return (size_t)LOSS_CTAS * 2 * sizeof(double) + 16; }
@@ -827,12 +813,13 @@ extern "C" int genpc_chamfer_loss_backward(const float *xyz1, const float *xyz2,
     if (N == 0 || M == 0 || B == 0) return GENPC_OK;
     const size_t tot = (size_t)B * N + ((w2 != 0.f) ? (size_t)B * M : 0);
     const bool vec = ((reinterpret_cast<size_t>(gradxyz1) | reinterpret_cast<size_t>(gradxyz2)) & 7) == 0;
+    const unsigned grid = (unsigned)((tot + 256 * GRAD_R - 1) / (256 * GRAD_R));
     if (vec)
-        chamfer_loss_grad_kernel<true><<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(
-            xyz1, xyz2, dist1, dist2, idx1, idx2, upstream, use_sqrt, w1, w2, gradxyz1, gradxyz2, B, N, M);
+        chamfer_grad_kernel<true, true><<<grid, 256, 0, stream>>>(xyz1, xyz2, dist1, dist2, idx1, idx2, upstream, use_sqrt, w1, w2,
+                                                                 gradxyz1, gradxyz2, B, N, M);
     else
-        chamfer_loss_grad_kernel<false><<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(
-            xyz1, xyz2, dist1, dist2, idx1, idx2, upstream, use_sqrt, w1, w2, gradxyz1, gradxyz2, B, N, M);
+        chamfer_grad_kernel<false, true><<<grid, 256, 0, stream>>>(xyz1, xyz2, dist1, dist2, idx1, idx2, upstream, use_sqrt, w1, w2,
+                                                                  gradxyz1, gradxyz2, B, N, M);
     GENPC_CHECK_LAUNCH();
     return GENPC_OK;
 }

@@ -58,8 +58,8 @@ def test_scan_kernel_distance_arithmetic(sass):
 
 
 def test_other_kernels_use_the_instructions_claimed(sass):
-    assert "REDG.E.ADD.F32x2" in _one(sass, "chamfer_loss_grad_kernelILb1E")           # vector reductions in the backward
-    assert "MATCH.ANY" in _one(sass, "chamfer_loss_grad_kernelILb1E")                  # warp-aggregated scatter
+    assert "REDG.E.ADD.F32x2" in _one(sass, "chamfer_grad_kernelILb1ELb1E")           # vector reductions in the backward
+    assert "MATCH.ANY" in _one(sass, "chamfer_grad_kernelILb1ELb1E")                  # warp-aggregated scatter
     epi = _one(sass, "nn_sym_epilogue_kernelILb1E")
     assert "LDG.E.128" in epi                                                          # row-block fix-up with LDG.128
     fps = _one(sass, "fps_cluster_kernelILi2ELi8ELb0E")

@@ -7,7 +7,7 @@ timeout 600 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err
 timeout 600 python bench.py --impl reference > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/ncu_bench.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:nn_sym_kernel -s 3 -c 1 -f -o gpurun_out/prof_nn_sym python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/ncu_full.log 2>&1
-timeout 300 ncu --set full --clock-control none -k regex:"nn_sym_epilogue|chamfer_loss_grad" -s 6 -c 2 -f -o gpurun_out/prof_fix_grad python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/ncu_full2.log 2>&1
+timeout 300 ncu --set full --clock-control none -k regex:"nn_sym_epilogue|chamfer_grad_kernel" -s 6 -c 2 -f -o gpurun_out/prof_fix_grad python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/ncu_full2.log 2>&1
 timeout 300 ncu --set full --clock-control none -k regex:nn_sym_gated -s 2 -c 1 -f -o gpurun_out/prof_nn_gated python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/ncu_full3.log 2>&1
 timeout 300 ncu --set full --clock-control none -k regex:"register_sym_scan|register_finish" -s 2 -c 2 -f -o gpurun_out/prof_register python tools/prof_targets.py register > gpurun_out/ncu_reg.log 2>&1
 timeout 300 ncu --set full --clock-control none -k regex:emd_auction -s 1 -c 1 -f -o gpurun_out/prof_emd python tools/prof_targets.py emd > gpurun_out/ncu_emd.log 2>&1
