@@ -481,6 +481,7 @@ __global__ void __launch_bounds__(EMD_THREADS, 5) emd_auction_kernel(const EmdAr
                             }
                         } else if (active) {
                             unsigned sa = stg_addr + (unsigned)tpt * 16u;
+#pragma unroll 2
                             for (int kp = tpt; kp < (end_k >> 1); kp += T, sa += (unsigned)T * 16u) {   // end_k is even (n % 256 == 0)
                                 const float4 q0 = lds128(sa), q1 = lds128(sa + STG_PLANE);
                                 step2(k2 + 2 * kp, make_float2(q0.x, q0.y), make_float2(q0.z, q0.w), make_float2(q1.x, q1.y),
