@@ -176,3 +176,48 @@ def test_emd_unaligned_pointers(cuda):
     E.forward(t1, t2, dist, asg, price, asg_inv, bid, binc, minc, uidx, z[0], z[1], z[2], midx, 0.005, 50)
     ed, ea = oracle.emd_forward(x1, x2, 0.005, 50)
     assert np.array_equal(asg.cpu().numpy(), ea) and np.array_equal(dist.cpu().numpy().view(np.int32), ed.view(np.int32))
+
+
+@pytest.mark.gpu
+def test_emd_c5_batch32_n8192_against_the_racy_reference(cuda):
+    """BASELINE C5's EMD leg at full size (B=32, n=8192, eps 0.005, 50 iterations, torch.rand inputs as `test_emd`,
+    emd_module.py:98-118).  At this size the reference's GetMax store race (emd_cuda.cu:188-191) is decided differently in
+    different clouds of the batch, so its output equals NEITHER pure resolution of the race ("highest" / "lowest" bidder index)
+    -- r01 found 0.0362958 for the reference against 0.0362955 / 0.0362985 for the two resolutions.  What can be asserted, and
+    is: ours == the oracle bit for bit in both resolutions (sampled clouds), every cloud fully assigned, the matching cost within
+    2e-4 relative of the reference's and the assignments equal for more than 90 % of the points.  north_star's 1e-5 on the EMD
+    cost holds wherever the reference is race-free (goldens, B=1 sizes); here the reference's own run-to-run spread is printed."""
+    import torch
+
+    from genpc_b200 import _lib
+    from genpc_b200.loss_functions import emdModule
+
+    B, n = 32, 8192
+    g = torch.Generator().manual_seed(0)
+    x1, x2 = torch.rand(B, n, 3, generator=g).to(cuda), torch.rand(B, n, 3, generator=g).to(cuda)
+    d_hi, a_hi = emdModule()(x1, x2, 0.005, 50)
+    with _lib.tunable(GENPC_EMD_GETMAX="lowest"):
+        d_lo, a_lo = emdModule()(x1, x2, 0.005, 50)
+    for b in (0, 17):                                       # the CPU oracle takes ~2 s per cloud at this size
+        ed, ea = oracle.emd_forward(x1[b:b + 1].cpu().numpy(), x2[b:b + 1].cpu().numpy(), 0.005, 50)
+        assert np.array_equal(a_hi[b].cpu().numpy(), ea[0]) and np.array_equal(d_hi[b].cpu().numpy().view(np.int32), ed[0].view(np.int32))
+    ed, ea = oracle.emd_forward(x1[5:6].cpu().numpy(), x2[5:6].cpu().numpy(), 0.005, 50, getmax_lowest=True)
+    assert np.array_equal(a_lo[5].cpu().numpy(), ea[0])
+    assert int((a_hi < 0).sum()) == 0 and int((a_lo < 0).sum()) == 0
+    ref = oracle.load_ref_ext("emd")
+    if ref is None:
+        pytest.skip("oracle/_ref/emd not built")
+    costs = []
+    for rep in range(2):
+        z = lambda *s, dt=torch.float32: torch.zeros(*s, dtype=dt, device=cuda)   # noqa: E731
+        dist, asg = z(B, n), z(B, n, dt=torch.int32) - 1
+        ref.forward(x1, x2, dist, asg, z(B, n), z(B, n, dt=torch.int32) - 1, z(B, n, dt=torch.int32), z(B, n), z(B, n),
+                    z(B * n, dt=torch.int32), z(512, dt=torch.int32), z(512, dt=torch.int32), z(512, dt=torch.int32),
+                    z(B * n, dt=torch.int32), 0.005, 50)
+        torch.cuda.synchronize()
+        costs.append(float(torch.sqrt(dist).mean()))
+    c_hi, c_lo = float(torch.sqrt(d_hi).mean()), float(torch.sqrt(d_lo).mean())
+    print(f"EMD B=32 n=8192 cost: reference runs {costs}, ours highest {c_hi}, lowest {c_lo}; "
+          f"assignments equal to the reference: {float((asg == a_hi).float().mean()):.4f} / {float((asg == a_lo).float().mean()):.4f}")
+    assert min(abs(c_hi - costs[-1]), abs(c_lo - costs[-1])) <= 2e-4 * costs[-1]
+    assert max(float((asg == a_hi).float().mean()), float((asg == a_lo).float().mean())) > 0.9

@@ -203,3 +203,41 @@ def test_scale_adapter_on_reference_workspace_layout(cuda, tmp_path, model):
         finally:
             os.chdir(cwd)
         assert T.shape == (4, 4) and np.isfinite(T).all() and os.path.exists(tmp_path / "final_transform.npy")
+
+
+def test_glb_reader_base_colour_texture(tmp_path):
+    """Colours from the base-colour texture at TEXCOORD_0 (the reference bakes TextureVisuals to vertex colours,
+    utils/dataUtils.py:223-224): a 2 x 2 PNG embedded in the GLB, nearest texel, glTF's top-left uv origin."""
+    cv2 = pytest.importorskip("cv2")
+    from genpc_b200.utils.glb import read_glb
+
+    img = np.array([[[255, 0, 0], [0, 255, 0]], [[0, 0, 255], [255, 255, 0]]], np.uint8)       # RGB, row 0 = top
+    ok, png = cv2.imencode(".png", img[..., ::-1])
+    assert ok
+    png = png.tobytes()
+    pos = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [1, 1, 0]], np.float32)
+    uv = np.array([[0.0, 0.0], [1.0, 0.0], [0.0, 1.0], [1.0, 1.0]], np.float32)                  # -> texels (0,0) (0,1) (1,0) (1,1)
+    idx = np.array([0, 1, 2, 1, 3, 2], np.uint16)
+    parts = [pos.tobytes(), uv.tobytes(), idx.tobytes(), png]
+    offs, blob = [], b""
+    for part in parts:
+        offs.append(len(blob))
+        blob += part + b"\\0" * (-len(part) % 4)
+    js = {"asset": {"version": "2.0"}, "scene": 0, "scenes": [{"nodes": [0]}], "nodes": [{"mesh": 0}],
+          "meshes": [{"primitives": [{"attributes": {"POSITION": 0, "TEXCOORD_0": 1}, "indices": 2, "material": 0}]}],
+          "materials": [{"pbrMetallicRoughness": {"baseColorTexture": {"index": 0}}}],
+          "textures": [{"source": 0}], "images": [{"bufferView": 3, "mimeType": "image/png"}],
+          "accessors": [{"bufferView": 0, "componentType": 5126, "count": 4, "type": "VEC3"},
+                        {"bufferView": 1, "componentType": 5126, "count": 4, "type": "VEC2"},
+                        {"bufferView": 2, "componentType": 5123, "count": 6, "type": "SCALAR"}],
+          "bufferViews": [{"buffer": 0, "byteOffset": offs[k], "byteLength": len(parts[k])} for k in range(4)],
+          "buffers": [{"byteLength": len(blob)}]}
+    jb = json.dumps(js).encode()
+    jb += b" " * (-len(jb) % 4)
+    p = str(tmp_path / "t.glb")
+    with open(p, "wb") as fh:
+        fh.write(struct.pack("<III", 0x46546C67, 2, 12 + 8 + len(jb) + 8 + len(blob)))
+        fh.write(struct.pack("<II", len(jb), 0x4E4F534A) + jb + struct.pack("<II", len(blob), 0x004E4942) + blob)
+    v, f, c = read_glb(p)
+    assert np.array_equal(v, pos) and np.array_equal(f, [[0, 1, 2], [1, 3, 2]])
+    assert np.allclose(c, np.array([[1, 0, 0], [0, 1, 0], [0, 0, 1], [1, 1, 0]], np.float32))
