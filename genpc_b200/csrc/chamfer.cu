@@ -227,7 +227,7 @@ static int chamfer_forward_sym(const float *xyz1, const float *xyz2, float *dist
                                const genpc_chamfer_fuse_t *fuse = nullptr, double *fuse_partial = nullptr,
                                unsigned *fuse_ticket = nullptr) {
     const bool swap = M > N;
-    SymParams p;
+    SymParams p = {};
     p.rows = swap ? xyz2 : xyz1, p.cols = swap ? xyz1 : xyz2;
     p.nr = swap ? M : N, p.nc = swap ? N : M;
     float *dist_r = swap ? dist2 : dist1, *dist_c = swap ? dist1 : dist2;
@@ -255,7 +255,7 @@ static int chamfer_forward_sym(const float *xyz1, const float *xyz2, float *dist
             GENPC_CHECK_LAUNCH();
             p.select = ctl + 1;
         }   // host-fed launches cannot look at data that has not arrived: the caller vouches for the range (get_loss_from_host)
-        TcParams t;
+        TcParams t = {};
         t.rows = p.rows, t.cols = p.cols, t.prow = p.prow, t.pcol = p.pcol, t.B = B, t.nr = p.nr, t.nc = p.nc;
         t.rblks = (p.nr + TC_RBLK - 1) / TC_RBLK, t.total_units = B * t.rblks;
         t.select = p.select, t.gate = gate, t.gate_gen = gate_gen, t.gate_pairs = gate_pairs, t.stats = g_tc_stats;
@@ -704,10 +704,11 @@ extern "C" int genpc_chamfer_sym_partial(const float *rows_shard, const float *c
     e = cudaMemsetAsync(prow_shard, 0xff, (size_t)B * nr_shard * 8, stream);
     if (e != cudaSuccess) return (int)e;
     if (nc == 0) return GENPC_OK;
-    SymParams p;
+    SymParams p = {};
     p.rows = rows_shard, p.cols = cols, p.prow = prow_shard, p.pcol = pcol;
     p.nr = nr_shard, p.nc = nc, p.rblock_base = row_base / 128;
     p.gate = nullptr, p.gate_gen = 0, p.gate_pairs = 1;
+    p.select = nullptr;
     p.rtiles = (nr_shard + SYM_THREADS * 4 - 1) / (SYM_THREADS * 4);
     int span = SYM_SPAN_MAX;
     const long long want = 2LL * 3 * GENPC_NUM_SMS;

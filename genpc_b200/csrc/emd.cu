@@ -587,7 +587,7 @@ extern "C" int genpc_emd_forward(const float *xyz1, const float *xyz2, float *di
     if (e != cudaSuccess) return (int)e;
     const int resident = sms * per_sm;
     if (resident <= 0) return (int)cudaErrorLaunchOutOfResources;
-    EmdArgs a;
+    EmdArgs a = {};
     a.xyz1 = xyz1, a.xyz2 = xyz2, a.dist = dist, a.assignment = assignment, a.price = price;
     a.assignment_inv = assignment_inv, a.bid = bid, a.bid_increments = bid_increments;
     a.max_increments = max_increments, a.unass_idx = unass_idx, a.unass_cnt = unass_cnt, a.max_idx = max_idx;

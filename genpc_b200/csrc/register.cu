@@ -524,7 +524,7 @@ extern "C" int genpc_register_run(const float *complete, const float *center, co
     if (S <= 0 || n_starts <= 0 || S % n_starts != 0 || Nc <= 0 || Nr <= 0 || iters < 0 || t_start < 0) return GENPC_ERR_SHAPE;
     if (loss_hist != nullptr && t_start + iters > T) return GENPC_ERR_SHAPE;
     if (workspace == nullptr || workspace_bytes < genpc_register_workspace_bytes(S, Nc, Nr)) return GENPC_ERR_WORKSPACE;
-    RegArgs a;
+    RegArgs a = {};
     a.complete = complete, a.center = center, a.ref = ref, a.params = params, a.adam_m = adam_m, a.adam_v = adam_v;
     a.packedA = (unsigned long long *)workspace;
     a.packedB = a.packedA + (size_t)S * Nc;
