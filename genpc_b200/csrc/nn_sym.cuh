@@ -77,6 +77,9 @@ __device__ __forceinline__ float butterfly_min32(float (&v)[32], int lane) {
 #ifndef GENPC_SYM_MINB4
 #define GENPC_SYM_MINB4 2
 #endif
+#ifndef GENPC_SYM_EXPAND
+#define GENPC_SYM_EXPAND 0
+#endif
 #define GENPC_SYM_MINB(QT) ((QT) >= 8 ? GENPC_SYM_MINB8 : GENPC_SYM_MINB4)
 
 // One work item: row tile `rt` (SYM_THREADS*QT rows) x column span [c0, c0+span) of ONE cloud pair.
@@ -92,6 +95,12 @@ __device__ __forceinline__ void nn_sym_item(float (*s)[SYM_SPAN_MAX], const floa
 #if GENPC_SYM_REDUX == 2
     __shared__ unsigned scol[SYM_THREADS / 32][32];
 #endif
+#if GENPC_SYM_EXPAND
+    // TIMING EXPERIMENT ONLY (tools/nn_variants.cu -DGENPC_SYM_EXPAND=1): e = |y|^2 - 2 x.y + |x|^2 in 4 packed
+    // instructions per two pairs instead of 6 -- results are NOT the reference's bits; upper bound of the norm-expansion
+    // filter without any of the exactness machinery.  See DESIGN.md section 4.1b.
+    __shared__ __align__(16) float sn[SYM_SPAN_MAX];
+#endif
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int cnt = min(span, nc - c0);
     const int cnt32 = (cnt + 31) & ~31;
@@ -106,12 +115,18 @@ __device__ __forceinline__ void nn_sym_item(float (*s)[SYM_SPAN_MAX], const floa
                 if (colT != nullptr) apply_similarity(*colT, x, y, z);
             }
             s[0][k] = x, s[1][k] = y, s[2][k] = z;
+#if GENPC_SYM_EXPAND
+            sn[k] = fmaf(x, x, fmaf(y, y, z * z));
+#endif
         }
     }
     // ---- rows into registers (negated; NaN for out-of-range rows: they never win a min on either side) ----
     float2 nqx[QT], nqy[QT], nqz[QT];
     float best[QT];
     int bchunk[QT];
+#if GENPC_SYM_EXPAND
+    float nrm[QT];
+#endif
     const int rblock = rt * (SYM_THREADS / 32) + warp;          // global id of this warp's 32*QT-row block
     const int jbase = rblock * (32 * QT) + lane;
     const float *rp = rows;
@@ -122,9 +137,16 @@ __device__ __forceinline__ void nn_sym_item(float (*s)[SYM_SPAN_MAX], const floa
         if (j < nr)
             x = ld_coord<COHERENT>(rp + (size_t)j * 3), y = ld_coord<COHERENT>(rp + (size_t)j * 3 + 1),
             z = ld_coord<COHERENT>(rp + (size_t)j * 3 + 2);
+#if GENPC_SYM_EXPAND
+        nqx[qi] = make_float2(-2.f * x, -2.f * x);
+        nqy[qi] = make_float2(-2.f * y, -2.f * y);
+        nqz[qi] = make_float2(-2.f * z, -2.f * z);
+        nrm[qi] = fmaf(x, x, fmaf(y, y, z * z));
+#else
         nqx[qi] = make_float2(-x, -x);
         nqy[qi] = make_float2(-y, -y);
         nqz[qi] = make_float2(-z, -z);
+#endif
         best[qi] = __int_as_float(0x7f800000);
         bchunk[qi] = 0;
     }
@@ -149,6 +171,32 @@ __device__ __forceinline__ void nn_sym_item(float (*s)[SYM_SPAN_MAX], const floa
                 const int g = blk * 8 + sub * (SYM_CHUNK / 4) + kk;  // float4 group index
                 const float4 X = sx4[g], Y = sy4[g], Z = sz4[g];
                 const int t = sub * SYM_CHUNK + kk * 4;               // column offset inside the block
+#if GENPC_SYM_EXPAND
+                const float4 NY = reinterpret_cast<const float4 *>(sn)[g];
+                const float2 nlo = make_float2(NY.x, NY.y), nhi = make_float2(NY.z, NY.w);
+                auto expand_x2 = [](float2 ax, float2 ay, float2 az, float2 tx, float2 ty, float2 tz, float2 ny, float nx) {
+                    return __fadd2_rn(__ffma2_rn(ax, tx, __ffma2_rn(ay, ty, __ffma2_rn(az, tz, ny))), make_float2(nx, nx));
+                };
+#pragma unroll
+                for (int qi = 0; qi < QT; qi += 2) {
+                    const float2 a0 = expand_x2(nqx[qi], nqy[qi], nqz[qi], make_float2(X.x, X.y), make_float2(Y.x, Y.y),
+                                                make_float2(Z.x, Z.y), nlo, nrm[qi]);
+                    const float2 e0 = expand_x2(nqx[qi], nqy[qi], nqz[qi], make_float2(X.z, X.w), make_float2(Y.z, Y.w),
+                                                make_float2(Z.z, Z.w), nhi, nrm[qi]);
+                    const float2 a1 = expand_x2(nqx[qi + 1], nqy[qi + 1], nqz[qi + 1], make_float2(X.x, X.y),
+                                                make_float2(Y.x, Y.y), make_float2(Z.x, Z.y), nlo, nrm[qi + 1]);
+                    const float2 e1 = expand_x2(nqx[qi + 1], nqy[qi + 1], nqz[qi + 1], make_float2(X.z, X.w),
+                                                make_float2(Y.z, Y.w), make_float2(Z.z, Z.w), nhi, nrm[qi + 1]);
+                    cm[qi] = fmin3(cm[qi], a0.x, a0.y);
+                    cm[qi] = fmin3(cm[qi], e0.x, e0.y);
+                    cm[qi + 1] = fmin3(cm[qi + 1], a1.x, a1.y);
+                    cm[qi + 1] = fmin3(cm[qi + 1], e1.x, e1.y);
+                    cacc[t + 0] = fmin3(cacc[t + 0], a0.x, a1.x);
+                    cacc[t + 1] = fmin3(cacc[t + 1], a0.y, a1.y);
+                    cacc[t + 2] = fmin3(cacc[t + 2], e0.x, e1.x);
+                    cacc[t + 3] = fmin3(cacc[t + 3], e0.y, e1.y);
+                }
+#else
 #pragma unroll
                 for (int qi = 0; qi < QT; qi += 2) {
                     const float2 a0 = sqdist_ref_x2(nqx[qi], nqy[qi], nqz[qi], make_float2(X.x, X.y),
@@ -168,6 +216,7 @@ __device__ __forceinline__ void nn_sym_item(float (*s)[SYM_SPAN_MAX], const floa
                     cacc[t + 2] = fmin3(cacc[t + 2], e0.x, e1.x);
                     cacc[t + 3] = fmin3(cacc[t + 3], e0.y, e1.y);
                 }
+#endif
             }
 #pragma unroll
             for (int qi = 0; qi < QT; ++qi) {
