@@ -66,6 +66,7 @@ _SIGNATURES = {
                                     _vp]),
     "genpc_unproject": (_int, [_vp, _vp, _int, _vp, _vp, _int, _int, _int, _vp, _vp, _vp, _vp]),
     "genpc_emd_workspace_bytes": (_sz, [_int]),
+    "genpc_emd_workspace_bytes_n": (_sz, [_int, _int]),
     "genpc_emd_forward": (_int, [_vp] * 12 + [_int, _int, _int, _flt, _int, _vp, _sz, _vp]),
     "genpc_emd_backward": (_int, [_vp, _vp, _vp, _vp, _vp, _int, _int, _vp]),
     "genpc_register_workspace_bytes": (_sz, [_int, _int, _int]),

@@ -42,6 +42,9 @@ struct EmdArgs {
     int two_level_div;     // two-level pre-filter while U * two_level_div >= n (0: never)
     int getmax_lowest;     // GetMax race resolved as lowest (1) or highest (0, default) bidder index
     int direct_p;          // items with at most this many bidders read the targets from global memory (no staging)
+    // pruned Bid (r02): targets re-ordered along a Morton curve by emd_sort_kernel, (x, y, z, original index) per target,
+    // and the bounding box (lo, hi) of every EMD_BLOCK consecutive sorted targets
+    const float4 *tsort, *boxes;
 };
 
 struct BidState {
@@ -310,16 +313,140 @@ __device__ __noinline__ void emd_getmax_assign(const int *__restrict__ uidx, con
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(EMD_THREADS, 5) emd_auction_kernel(const EmdArgs a) {
+// ---- pruned Bid (r02) ------------------------------------------------------------------------------------------------
+// A candidate target only matters to a bidder if its value reaches the bidder's second-best value, i.e. if
+// sqrt(s) <= (3 - price) - better; every price is >= pmin0 (prices only rise), so with the targets grouped into spatially
+// compact blocks a whole block is rejected by ONE test of the squared distance between the bidder and the block's bounding
+// box against the same target-independent cap s_cap the two-level filter uses.  The test rejects a subset of what the
+// per-target filter rejects, so the result is bit-identical to the exhaustive scan whatever the order and the grouping
+// are (best / second-best with multiplicity and the (reference_thread(k), k) tie key do not depend on the visiting order).
+// On the bench's inputs 5-7 % of the blocks survive in every iteration (tools/emd_prune_stats.py).
+constexpr int EMD_BLOCK = 64;            // targets per block: one target PAIR per lane of the scanning warp
+constexpr int EMD_PRUNE_MAX_N = 32768;   // boxes of a cloud fit the kernel's shared memory, the sort fits one CTA's
+constexpr int EMD_SORT_THREADS = 1024;
+constexpr int EMD_PBATCH = 4;            // surviving blocks whose loads are in flight together
+constexpr int EMD_BOXR = 4;              // box distances of the first EMD_BOXR * 32 blocks stay in registers (n <= 8192: all)
+
+// One CTA per cloud: Morton keys of the targets (cell << idxbits | original index), bitonic sort in shared memory, sorted
+// (x, y, z, index) records and per-block bounding boxes (all lower corners, then all upper corners).  The ORDER only affects how well the blocks prune, never a result.
+__global__ void __launch_bounds__(EMD_SORT_THREADS) emd_sort_kernel(const float *__restrict__ xyz2, float4 *__restrict__ tsort,
+                                                                    float4 *__restrict__ boxes, int n, int np2, int idxbits,
+                                                                    int mbits) {
+    extern __shared__ unsigned skeys[];
+    __shared__ float sred[6][EMD_SORT_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float *p2 = xyz2 + (size_t)blockIdx.x * n * 3;
+    float4 *ts = tsort + (size_t)blockIdx.x * n;
+    float4 *bx = boxes + (size_t)blockIdx.x * (n / EMD_BLOCK) * 2;
+    const float inf = __int_as_float(0x7f800000);
+    float lo[3] = {inf, inf, inf}, hi[3] = {-inf, -inf, -inf};
+    for (int k = tid; k < n; k += EMD_SORT_THREADS) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float v = __ldg(p2 + k * 3 + c);
+            if (fabsf(v) < inf) lo[c] = fminf(lo[c], v), hi[c] = fmaxf(hi[c], v);   // NaN / Inf do not stretch the grid
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[c] = fminf(lo[c], __shfl_xor_sync(0xffffffffu, lo[c], o));
+            hi[c] = fmaxf(hi[c], __shfl_xor_sync(0xffffffffu, hi[c], o));
+        }
+        if (lane == 0) sred[c][warp] = lo[c], sred[3 + c][warp] = hi[c];
+    }
+    __syncthreads();
+    float scale[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        float l = inf, h = -inf;
+        for (int w = 0; w < EMD_SORT_THREADS / 32; ++w) l = fminf(l, sred[c][w]), h = fmaxf(h, sred[3 + c][w]);
+        lo[c] = l;
+        const float ext = h - l;
+        scale[c] = (ext > 0.f && ext < inf) ? (float)(1 << mbits) / ext : 0.f;
+    }
+    const int cmax = (1 << mbits) - 1;
+    for (int k = tid; k < np2; k += EMD_SORT_THREADS) {
+        unsigned key = 0xffffffffu;
+        if (k < n) {
+            unsigned code = 0;
+            int cell[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float f = (__ldg(p2 + k * 3 + c) - lo[c]) * scale[c];
+                cell[c] = f >= 0.f ? min((int)fminf(f, 2e9f), cmax) : 0;   // NaN -> 0
+            }
+            for (int bit = 0; bit < mbits; ++bit)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) code |= (unsigned)((cell[c] >> bit) & 1) << (3 * bit + c);
+            key = (code << idxbits) | (unsigned)k;
+        }
+        skeys[k] = key;
+    }
+    for (int size = 2; size <= np2; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            __syncthreads();
+            for (int t = tid; t < (np2 >> 1); t += EMD_SORT_THREADS) {
+                const int i = 2 * t - (t & (stride - 1));
+                const unsigned u = skeys[i], v = skeys[i + stride];
+                const bool up = (i & size) == 0;
+                if ((u > v) == up) skeys[i] = v, skeys[i + stride] = u;
+            }
+        }
+    }
+    __syncthreads();
+    const unsigned imask = (1u << idxbits) - 1u;
+    for (int k = tid; k < n; k += EMD_SORT_THREADS) {
+        const int o = (int)(skeys[k] & imask);
+        ts[k] = make_float4(__ldg(p2 + o * 3), __ldg(p2 + o * 3 + 1), __ldg(p2 + o * 3 + 2), __int_as_float(o));
+    }
+    for (int blk = warp; blk < n / EMD_BLOCK; blk += EMD_SORT_THREADS / 32) {
+        float l[3] = {inf, inf, inf}, h[3] = {-inf, -inf, -inf};
+#pragma unroll
+        for (int e = 0; e < EMD_BLOCK / 32; ++e) {
+            const int o = (int)(skeys[blk * EMD_BLOCK + e * 32 + lane] & imask);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float v = __ldg(p2 + o * 3 + c);
+                l[c] = fminf(l[c], v), h[c] = fmaxf(h[c], v);   // NaN coordinates are ignored: such targets never matter
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                l[c] = fminf(l[c], __shfl_xor_sync(0xffffffffu, l[c], o));
+                h[c] = fmaxf(h[c], __shfl_xor_sync(0xffffffffu, h[c], o));
+            }
+        if (lane == 0) bx[blk] = make_float4(l[0], l[1], l[2], 0.f), bx[n / EMD_BLOCK + blk] = make_float4(h[0], h[1], h[2], 0.f);
+    }
+}
+
+// monotone float <-> int map (REDUX works on integers; values may be negative)
+__device__ __forceinline__ int f2ord(float f) {
+    const int i = __float_as_int(f);
+    return i ^ ((i >> 31) & 0x7fffffff);
+}
+__device__ __forceinline__ float ord2f(int i) { return __int_as_float(i ^ ((i >> 31) & 0x7fffffff)); }
+
+template <bool PRUNE, int MINB>
+__global__ void __launch_bounds__(EMD_THREADS, MINB) emd_auction_kernel(const EmdArgs a) {
     // targets + prices of one chunk, two float4 planes per target PAIR p: stg[p] = (x0, x1, y0, y1), stg[EMD_CHUNK/2 + p] =
     // (z0, z1, price0, price1) -- one address register (second plane at a constant offset) and two LDS.128 per step of the
     // Bid scan (r02; four separate SoA arrays cost four LEA, four LDS.64 and six uniform address instructions per step:
     // 31 -> 21 instructions per target pair on the reject path).  Consecutive pairs are 16 B apart inside a plane, so the
     // lanes of a bidder hit distinct banks (a first r02 layout interleaved the two float4 of a pair: 32-byte lane stride,
     // 2-way conflict on every load -- 930 M of 2000 M wavefronts).
-    __shared__ __align__(16) float4 stg[EMD_CHUNK];
+    // (PRUNE: the same array holds the cloud's block boxes instead: nblk lower corners, then nblk upper corners -- 16-byte
+    // lane stride on both loads of the box test)
+    __shared__ __align__(16) float4 stg[PRUNE ? 2 * (EMD_PRUNE_MAX_N / EMD_BLOCK) : EMD_CHUNK];
     constexpr unsigned STG_PLANE = (EMD_CHUNK / 2) * 16;
-    __shared__ BidState smerge[EMD_THREADS];
+    __shared__ BidState smerge[PRUNE ? 1 : EMD_THREADS];
+    // PRUNE: per warp, the list of blocks that survive the box test and the queue of (original index, s) candidates
+    __shared__ unsigned short s_blist[PRUNE ? EMD_THREADS / 32 : 1][PRUNE ? EMD_PRUNE_MAX_N / EMD_BLOCK : 1];
+    __shared__ float s_slist[PRUNE ? EMD_THREADS / 32 : 1][PRUNE ? EMD_PRUNE_MAX_N / EMD_BLOCK : 1];   // their box distances
+    __shared__ float2 s_queue[PRUNE ? EMD_THREADS / 32 : 1][PRUNE ? 96 : 1];
     __shared__ int sscan[EMD_THREADS / 32];
     __shared__ int s_last;
     const int tid = threadIdx.x;
@@ -363,6 +490,13 @@ __global__ void __launch_bounds__(EMD_THREADS, 5) emd_auction_kernel(const EmdAr
             }
         }
 
+        if constexpr (PRUNE) {
+            __syncthreads();   // the previous cloud's boxes are no longer read
+            const float4 *bx = a.boxes + (size_t)b * (n / EMD_BLOCK) * 2;
+            for (int k = tid; k < 2 * (n / EMD_BLOCK); k += EMD_THREADS) stg[k] = __ldg(bx + k);
+            __syncthreads();
+        }
+
         bool complete = false;  // every point assigned: the remaining iterations change nothing (reference: empty launches)
         for (int it = 0; it < a.iters; ++it) {
             const bool last = (it == a.iters - 1);
@@ -378,7 +512,230 @@ __global__ void __launch_bounds__(EMD_THREADS, 5) emd_auction_kernel(const EmdAr
             const float c_max = __fsub_rn(3.0f, __ldcg(a.pmin + b));
             const bool two_level = (a.two_level_div > 0) && ((long long)U * a.two_level_div >= n);
             // ---- Bid (emd_cuda.cu:95-179) ----
-            if (U > 0) {
+            if constexpr (PRUNE) {
+                const int upb_ref = (U + block_cnt - 1) / block_cnt;
+                const int tpu_ref = 256 / upb_ref;
+                const int lane = tid & 31, wid = tid >> 5;
+                const unsigned lt = (1u << lane) - 1u;
+                const int nblk = n / EMD_BLOCK;
+                const float4 *ts = a.tsort + (size_t)b * n + 2 * lane;   // lane l: sorted targets blk*64 + 2l, 2l+1
+                const float inf = __int_as_float(0x7f800000);
+                unsigned short *blist = s_blist[wid];
+                float *slist = s_slist[wid];
+                float2 *queue = s_queue[wid];
+                // One WARP per bidder.  Everything that touches L2 is issued in batches, because a bidder is otherwise a chain
+                // of dependent L2 round trips (a first version that scanned the surviving blocks one after the other, each
+                // with its own price gather, spent 30 us per bidder):
+                //   1. box tests (shared memory) -> nearest block = seed; its 64 targets are evaluated exactly -> threshold
+                //   2. box tests against the threshold -> list of surviving blocks, the EMD_PBATCH nearest moved to the front
+                //   3. surviving blocks in batches of EMD_PBATCH (all loads of a batch in flight together); targets inside the
+                //      target-independent cap s_cap are queued as (original index, s)
+                //   4. the queue is drained 32 entries at a time: price gather, per-target filter, exact value; after the
+                //      first (nearest) batch the threshold is final for most bidders and the list is re-filtered with it
+                for (int u = rank * (EMD_THREADS / 32) + wid; u < U; u += a.group * (EMD_THREADS / 32)) {
+                    const int j = __ldcg(uidx + u);
+                    const float x1 = __ldg(p1 + j * 3), y1 = __ldg(p1 + j * 3 + 1), z1 = __ldg(p1 + j * 3 + 2);
+                    BidState st;
+                    st.best = -1e9f, st.better = -1e9f, st.bi = -1;
+                    float bm = -2e9f;     // (lower bound of the bidder's final second-best value) - margin
+                    float s_cap = inf;    // ((3 - pmin0) - bm)^2: no target beyond it can matter, whatever its price
+                    auto raise_threshold = [&](float better) {
+                        const float nb = __fsub_rn(better, __fmul_rn(1e-4f, fmaxf(1.f, fabsf(better))));
+                        if (nb > bm) {
+                            bm = nb;
+                            const float tq0 = __fsub_rn(c_max, bm);
+                            s_cap = tq0 > 0.f ? __fmul_rn(tq0, tq0) : -1.f;
+                        }
+                    };
+                    auto consider = [&](int k, float s, float pk) {   // the reference's arithmetic and tie rule
+                        const float d = (float)((3.0 - (double)__fsqrt_rn(s)) - (double)pk);
+                        if (d > st.best) {
+                            st.better = st.best;
+                            st.best = d;
+                            st.bi = k;
+                        } else {
+                            st.better = fmaxf(st.better, d);
+                            if (d == st.best && ref_visit_key(k, n, tpu_ref) < ref_visit_key(st.bi, n, tpu_ref)) st.bi = k;
+                        }
+                        raise_threshold(st.better);
+                    };
+                    // per-target filter (as in the exhaustive scan) + exact evaluation
+                    auto candidate = [&](int k, float s, float pk) {
+                        const float tq = __fsub_rn(__fsub_rn(3.0f, pk), bm);
+                        if (tq > 0.f && s <= __fmul_rn(tq, tq)) consider(k, s, pk);
+                    };
+                    // squared distance to the block's box, scaled DOWN by 1e-5: the reference's rounded s of a target inside
+                    // the box is never below it (each difference and the fma chain are within a few 2^-24 of exact)
+                    auto box_s = [&](int blk) {
+                        const float4 lo = stg[blk], hi = stg[nblk + blk];
+                        const float dx = fmaxf(fmaxf(lo.x - x1, x1 - hi.x), 0.f);
+                        const float dy = fmaxf(fmaxf(lo.y - y1, y1 - hi.y), 0.f);
+                        const float dz = fmaxf(fmaxf(lo.z - z1, z1 - hi.z), 0.f);
+                        return __fmul_rn(__fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy))), 0.99999f);
+                    };
+                    // the warp-wide second-best value so far bounds every lane's filter: the second largest `best` of two
+                    // different lanes, or the largest `better` of any lane.  Leaves bm / s_cap identical in all lanes.
+                    auto share_threshold = [&]() {
+                        const int ob = f2ord(st.best);
+                        const int m1 = __reduce_max_sync(0xffffffffu, ob);
+                        const int first = __ffs(__ballot_sync(0xffffffffu, ob == m1)) - 1;
+                        const int m2 = __reduce_max_sync(0xffffffffu, lane == first ? (int)0x80000000 : ob);
+                        const int mb = __reduce_max_sync(0xffffffffu, f2ord(st.better));
+                        raise_threshold(ord2f(max(m2, mb)));
+                    };
+                    const float2 nx = make_float2(-x1, -x1), ny = make_float2(-y1, -y1), nz = make_float2(-z1, -z1);
+                    // ---- 1. box distances (kept in registers for the first EMD_BOXR * 32 blocks) and the seed ----
+                    float sl[EMD_BOXR];
+                    unsigned skey = 0xffffffffu;   // (distance bits, block id): any near block makes a good seed
+#pragma unroll
+                    for (int r = 0; r < EMD_BOXR; ++r) {
+                        const int blk = r * 32 + lane;
+                        sl[r] = blk < nblk ? box_s(blk) : inf;
+                        skey = min(skey, (__float_as_uint(sl[r]) & 0xfffffe00u) | (unsigned)blk);
+                    }
+                    for (int r0 = EMD_BOXR * 32; r0 < nblk; r0 += 32) {
+                        const int blk = r0 + lane;
+                        if (blk < nblk) skey = min(skey, (__float_as_uint(box_s(blk)) & 0xfffffe00u) | (unsigned)blk);
+                    }
+                    const int sb = (int)(__reduce_min_sync(0xffffffffu, skey) & 0x1ffu) % nblk;   // (NaN bidder: block 0)
+                    {
+                        const float4 t0 = __ldg(ts + sb * EMD_BLOCK), t1 = __ldg(ts + sb * EMD_BLOCK + 1);
+                        const int k0 = __float_as_int(t0.w), k1 = __float_as_int(t1.w);
+                        const float pk0 = __ldcg(pr + k0), pk1 = __ldcg(pr + k1);
+                        const float2 s2 = sqdist_ref_x2(nx, ny, nz, make_float2(t0.x, t1.x), make_float2(t0.y, t1.y),
+                                                        make_float2(t0.z, t1.z));
+                        candidate(k0, s2.x, pk0);
+                        candidate(k1, s2.y, pk1);
+                    }
+                    share_threshold();
+                    // ---- 2. surviving blocks ----
+                    int nlist = 0;
+#pragma unroll
+                    for (int r = 0; r < EMD_BOXR; ++r) {
+                        const int blk = r * 32 + lane;
+                        const bool pass = sl[r] <= s_cap && blk != sb;
+                        const unsigned mask = __ballot_sync(0xffffffffu, pass);
+                        if (pass) blist[nlist + __popc(mask & lt)] = (unsigned short)blk, slist[nlist + __popc(mask & lt)] = sl[r];
+                        nlist += __popc(mask);
+                    }
+                    for (int r0 = EMD_BOXR * 32; r0 < nblk; r0 += 32) {
+                        const int blk = r0 + lane;
+                        const float sv = blk < nblk ? box_s(blk) : inf;
+                        const bool pass = sv <= s_cap && blk != sb;
+                        const unsigned mask = __ballot_sync(0xffffffffu, pass);
+                        if (pass) blist[nlist + __popc(mask & lt)] = (unsigned short)blk, slist[nlist + __popc(mask & lt)] = sv;
+                        nlist += __popc(mask);
+                    }
+                    __syncwarp();
+                    // the EMD_PBATCH nearest blocks to the front: they settle the threshold
+                    if (nlist > EMD_PBATCH) {
+#pragma unroll 1
+                        for (int q = 0; q < EMD_PBATCH; ++q) {
+                            unsigned key = 0xffffffffu;
+                            for (int e = q + lane; e < nlist; e += 32) key = min(key, (__float_as_uint(slist[e]) & 0xfffffe00u) | (unsigned)e);
+                            const int e = (int)(__reduce_min_sync(0xffffffffu, key) & 0x1ffu);
+                            __syncwarp();
+                            if (lane == 0 && e != q) {
+                                const unsigned short tb = blist[q];
+                                const float tsv = slist[q];
+                                blist[q] = blist[e], slist[q] = slist[e];
+                                blist[e] = tb, slist[e] = tsv;
+                            }
+                            __syncwarp();
+                        }
+                    }
+                    // ---- 3. / 4. ----
+                    int nq = 0;
+                    auto drain = [&]() {   // the last min(nq, 32) entries of the queue
+                        const int e = nq - 1 - lane;
+                        if (e >= 0) {
+                            const float2 qe = queue[e];
+                            const int k = __float_as_int(qe.x);
+                            candidate(k, qe.y, __ldcg(pr + k));
+                        }
+                        nq = max(nq - 32, 0);
+                        __syncwarp();
+                        share_threshold();
+                    };
+                    for (int i0 = 0; i0 < nlist; i0 += EMD_PBATCH) {
+                        float4 t[EMD_PBATCH][2];
+#pragma unroll
+                        for (int q = 0; q < EMD_PBATCH; ++q) {
+                            if (i0 + q < nlist) {
+                                const int blk = blist[i0 + q];
+                                t[q][0] = __ldg(ts + blk * EMD_BLOCK), t[q][1] = __ldg(ts + blk * EMD_BLOCK + 1);
+                            }
+                        }
+#pragma unroll
+                        for (int q = 0; q < EMD_PBATCH; ++q) {
+                            if (i0 + q < nlist) {
+                                const float2 s2 = sqdist_ref_x2(nx, ny, nz, make_float2(t[q][0].x, t[q][1].x),
+                                                                make_float2(t[q][0].y, t[q][1].y), make_float2(t[q][0].z, t[q][1].z));
+                                const bool f0 = s2.x <= s_cap, f1 = s2.y <= s_cap;
+                                if (__any_sync(0xffffffffu, f0 || f1)) {
+                                    const unsigned m0 = __ballot_sync(0xffffffffu, f0), m1 = __ballot_sync(0xffffffffu, f1);
+                                    if (f0) queue[nq + __popc(m0 & lt)] = make_float2(t[q][0].w, s2.x);
+                                    nq += __popc(m0);
+                                    if (f1) queue[nq + __popc(m1 & lt)] = make_float2(t[q][1].w, s2.y);
+                                    nq += __popc(m1);
+                                    __syncwarp();
+                                    while (nq >= 32) drain();   // keeps nq < 32 before the next block adds at most 64
+                                }
+                            }
+                        }
+                        if (i0 == 0 && nlist > EMD_PBATCH) {
+                            // the nearest blocks are in: settle the threshold and drop the blocks it now excludes
+                            if (nq > 0) drain();
+                            int keep = EMD_PBATCH;
+                            for (int r0 = EMD_PBATCH; r0 < nlist; r0 += 32) {
+                                const int e = r0 + lane;
+                                unsigned short bk = 0;
+                                float sv = inf;
+                                if (e < nlist) bk = blist[e], sv = slist[e];
+                                const bool pass = sv <= s_cap;
+                                const unsigned mask = __ballot_sync(0xffffffffu, pass);
+                                __syncwarp();
+                                if (pass) blist[keep + __popc(mask & lt)] = bk;   // keep + rank <= e: in place
+                                keep += __popc(mask);
+                            }
+                            nlist = keep;
+                            __syncwarp();
+                        }
+                    }
+                    if (nq > 0) drain();
+                    // ---- merge the 32 lane states (order-independent: ties go by the reference's visit key) ----
+                    {
+                        const int ob = f2ord(st.best);
+                        const int m1 = __reduce_max_sync(0xffffffffu, ob);
+                        const unsigned tie = __ballot_sync(0xffffffffu, ob == m1);
+                        if (__popc(tie) == 1) {
+                            // one lane holds the best value: second-best = the larger of the other lanes' best and anybody's better
+                            const int src = __ffs(tie) - 1;
+                            const int m2 = __reduce_max_sync(0xffffffffu, lane == src ? (int)0x80000000 : ob);
+                            const int mb = __reduce_max_sync(0xffffffffu, f2ord(st.better));
+                            st.bi = __shfl_sync(0xffffffffu, st.bi, src);
+                            st.best = ord2f(m1);
+                            st.better = ord2f(max(m2, mb));
+                        } else {
+#pragma unroll 1
+                            for (int o = 16; o > 0; o >>= 1) {
+                                BidState ot;
+                                ot.best = __shfl_down_sync(0xffffffffu, st.best, o);
+                                ot.better = __shfl_down_sync(0xffffffffu, st.better, o);
+                                ot.bi = __shfl_down_sync(0xffffffffu, st.bi, o);
+                                bid_merge(st, ot, n, tpu_ref);
+                            }
+                        }
+                    }
+                    if (lane == 0) {
+                        const float inc = __fadd_rn(__fsub_rn(st.best, st.better), a.eps);
+                        bd[j] = st.bi;
+                        binc[j] = inc;
+                        atomicMax(reinterpret_cast<int *>(minc + st.bi), __float_as_int(inc));  // inc > 0
+                    }
+                    __syncwarp();   // the next bidder reuses the warp's list and queue
+                }
+            } else if (U > 0) {
                 const int upb_ref = (U + block_cnt - 1) / block_cnt;
                 const int tpu_ref = 256 / upb_ref;
                 // points per item: spread the U bidders over the group; every item re-stages the whole target cloud, so
@@ -565,6 +922,17 @@ using namespace genpc;
 
 extern "C" size_t genpc_emd_workspace_bytes(int B) { return B < 0 ? 0 : (size_t)B * 3 * sizeof(int); }
 
+static size_t emd_ctl_bytes(int B) { return (genpc_emd_workspace_bytes(B) + 255) & ~(size_t)255; }
+
+// the pruned Bid needs the sorted targets (16 B each) and the block boxes behind the control words
+static bool emd_prune_feasible(int n) { return n >= EMD_BLOCK && n % EMD_BLOCK == 0 && n <= EMD_PRUNE_MAX_N; }
+
+extern "C" size_t genpc_emd_workspace_bytes_n(int B, int n) {
+    if (B < 0 || n < 0) return 0;
+    if (!emd_prune_feasible(n)) return genpc_emd_workspace_bytes(B);
+    return emd_ctl_bytes(B) + (size_t)B * n * sizeof(float4) + (size_t)B * (n / EMD_BLOCK) * 2 * sizeof(float4);
+}
+
 extern "C" int genpc_emd_forward(const float *xyz1, const float *xyz2, float *dist, int *assignment, float *price,
                                  int *assignment_inv, int *bid, float *bid_increments, float *max_increments,
                                  int *unass_idx, int *unass_cnt, int *max_idx, int B, int n, int m, float eps, int iters,
@@ -580,10 +948,20 @@ extern "C" int genpc_emd_forward(const float *xyz1, const float *xyz2, float *di
     if (workspace == nullptr || workspace_bytes < genpc_emd_workspace_bytes(B)) return GENPC_ERR_WORKSPACE;
     cudaError_t e = cudaMemsetAsync(workspace, 0, genpc_emd_workspace_bytes(B), stream);
     if (e != cudaSuccess) return (int)e;
+    // pruned Bid: default whenever the caller's workspace holds the sorted copy (genpc_emd_workspace_bytes_n) and the cloud is
+    // large enough for the sort to pay; GENPC_EMD_PRUNE=0 forces the exhaustive scan, =1 the pruned one wherever feasible
+    const char *pt = tunable("GENPC_EMD_PRUNE");
+    const int prune_knob = pt != nullptr ? atoi(pt) : -1;
+    bool prune = emd_prune_feasible(n) && workspace_bytes >= genpc_emd_workspace_bytes_n(B, n) &&
+                 (reinterpret_cast<size_t>(workspace) & 15) == 0;
+    if (prune_knob == 0 || (prune_knob < 0 && n < 1024)) prune = false;
     int dev = 0, sms = 0, per_sm = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, emd_auction_kernel, EMD_THREADS, 0);
+    const char *pmb = tunable("GENPC_EMD_PRUNE_MINB");  // experiments only
+    void *kernel = prune ? ((pmb != nullptr && atoi(pmb) == 3) ? (void *)emd_auction_kernel<true, 3> : (void *)emd_auction_kernel<true, 4>)
+                         : (void *)emd_auction_kernel<false, 5>;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, EMD_THREADS, 0);
     if (e != cudaSuccess) return (int)e;
     const int resident = sms * per_sm;
     if (resident <= 0) return (int)cudaErrorLaunchOutOfResources;
@@ -615,8 +993,26 @@ extern "C" int genpc_emd_forward(const float *xyz1, const float *xyz2, float *di
     const char *dp = tunable("GENPC_EMD_DIRECT_P");  // experiments only
     if (dp != nullptr) a.direct_p = atoi(dp);
     if ((reinterpret_cast<size_t>(xyz2) & 7) != 0 || (reinterpret_cast<size_t>(price) & 7) != 0) a.direct_p = 0;  // LDG.64
+    if (prune) {
+        float4 *tsort = reinterpret_cast<float4 *>(static_cast<char *>(workspace) + emd_ctl_bytes(B));
+        float4 *boxes = tsort + (size_t)B * n;
+        int np2 = 1, idxbits = 0;
+        while (np2 < n) np2 <<= 1, ++idxbits;
+        int mbits = (31 - idxbits) / 3;   // cell << idxbits | index stays below the 0xffffffff padding key
+        if (mbits > 10) mbits = 10;
+        const size_t smem = (size_t)np2 * sizeof(unsigned);
+        static bool attr_set[64] = {};
+        if (smem > 48 * 1024 && !(dev < 64 && attr_set[dev])) {
+            e = cudaFuncSetAttribute(emd_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+            if (e != cudaSuccess) return (int)e;
+            if (dev < 64) attr_set[dev] = true;
+        }
+        emd_sort_kernel<<<B, EMD_SORT_THREADS, smem, stream>>>(xyz2, tsort, boxes, n, np2, idxbits, mbits);
+        GENPC_CHECK_LAUNCH();
+        a.tsort = tsort, a.boxes = boxes;
+    }
     void *kargs[] = {(void *)&a};
-    e = cudaLaunchCooperativeKernel((void *)emd_auction_kernel, dim3(grid), dim3(EMD_THREADS), kargs, 0, stream);
+    e = cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(EMD_THREADS), kargs, 0, stream);
     if (e != cudaSuccess) return (int)e;
     return GENPC_OK;
 }

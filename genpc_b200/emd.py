@@ -32,8 +32,8 @@ def forward(xyz1, xyz2, dist, assignment, price, assignment_inv, bid, bid_increm
         raise _lib.GenpcError("unass_cnt must hold at least B ints")
     L = _lib.lib()
     with torch.cuda.device(xyz1.device):
-        nbytes = L.genpc_emd_workspace_bytes(B)
-        ws = torch.empty(max(nbytes, 8), dtype=torch.uint8, device=xyz1.device)
+        nbytes = L.genpc_emd_workspace_bytes_n(B, n)
+        ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=xyz1.device)
         rc = L.genpc_emd_forward(_lib.ptr(xyz1), _lib.ptr(xyz2), _lib.ptr(dist), _lib.ptr(assignment), _lib.ptr(price),
                                  _lib.ptr(assignment_inv), _lib.ptr(bid), _lib.ptr(bid_increments),
                                  _lib.ptr(max_increments), _lib.ptr(unass_idx), _lib.ptr(unass_cnt), _lib.ptr(max_idx),

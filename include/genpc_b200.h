@@ -248,8 +248,12 @@ int genpc_unproject(const float *cams, const float *bounds, int rescale, const u
  * reference itself is deterministic (its GetMax store race is resolved as "highest bidder index"; the knob
  * GENPC_EMD_GETMAX=lowest -- environment at load time or genpc_set_tunable -- selects the other outcome the reference is
  * seen to produce).
- * workspace: genpc_emd_workspace_bytes(B). */
+ * workspace: genpc_emd_workspace_bytes_n(B, n) -- control words plus a spatially sorted copy of the targets (16 B per
+ * target) and the boxes of its 64-target blocks, which let the Bid scan skip every block that cannot reach a bidder's
+ * second-best value (bit-identical to the exhaustive scan; 64 <= n <= 32768).  A workspace of only
+ * genpc_emd_workspace_bytes(B) bytes (the r01 size) is still accepted and selects the exhaustive scan. */
 size_t genpc_emd_workspace_bytes(int B);
+size_t genpc_emd_workspace_bytes_n(int B, int n);
 int genpc_emd_forward(const float *xyz1, const float *xyz2, float *dist, int *assignment, float *price,
                       int *assignment_inv, int *bid, float *bid_increments, float *max_increments,
                       int *unass_idx, int *unass_cnt, int *max_idx, int B, int n, int m, float eps, int iters,

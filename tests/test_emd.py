@@ -45,12 +45,59 @@ def run_ours(x1, x2, eps, iters, dev):
                                            (1, 2304, 0.005, 50), (32, 1024, 0.005, 50), (1, 8192, 0.005, 50), (1, 16384, 0.005, 50),
                                            (2, 2048, 0.05, 400)])
 def test_emd_gpu_bit_exact_vs_oracle(cuda, B, n, eps, iters):
+    from genpc_b200 import _lib
+
     rng = np.random.default_rng(n + B)
     x1, x2 = rng.random((B, n, 3), dtype=np.float32), rng.random((B, n, 3), dtype=np.float32)
-    d, a = run_ours(x1, x2, eps, iters, cuda)
     ed, ea = oracle.emd_forward(x1, x2, eps, iters)
-    assert np.array_equal(a, ea), f"{(a != ea).sum()} assignments differ"
-    assert np.array_equal(d.view(np.int32), ed.view(np.int32))
+    # default (block-pruned Bid from n = 1024 up), pruned forced, exhaustive scan forced: one answer
+    for knob in (None, "1", "0"):
+        with _lib.tunable(GENPC_EMD_PRUNE=knob):
+            d, a = run_ours(x1, x2, eps, iters, cuda)
+        assert np.array_equal(a, ea), f"prune={knob}: {(a != ea).sum()} assignments differ"
+        assert np.array_equal(d.view(np.int32), ed.view(np.int32)), f"prune={knob}"
+
+
+def _adversarial_emd_inputs():
+    rng = np.random.default_rng(11)
+    g = np.stack(np.meshgrid(*[np.arange(16, dtype=np.float32) / 16] * 3, indexing="ij"), -1).reshape(-1, 3)     # 4096 lattice points
+    yield "lattice_ties", g[rng.permutation(4096)][None], g[rng.permutation(4096)][None], 0.005, 60
+    x = rng.random((2, 2048, 3), dtype=np.float32)
+    yield "identical_clouds", x, x.copy(), 0.005, 50
+    d = rng.random((1, 1024, 3), dtype=np.float32)
+    yield "duplicated_targets", rng.random((1, 2048, 3), dtype=np.float32), np.concatenate([d, d], 1), 0.005, 50
+    c = (rng.random((1, 4096, 3), dtype=np.float32) * 1e-3 + 0.5).astype(np.float32)
+    yield "tiny_extent", c, (rng.random((1, 4096, 3), dtype=np.float32) * 1e-3 + 0.5).astype(np.float32), 0.005, 50
+    yield "two_far_clusters", np.concatenate([rng.random((1, 1024, 3)), rng.random((1, 1024, 3)) + 40], 1).astype(np.float32), \
+        np.concatenate([rng.random((1, 512, 3)), rng.random((1, 1536, 3)) + 40], 1).astype(np.float32), 0.01, 100
+    yield "offset_scene", (rng.random((1, 2048, 3)) * 3 - 100).astype(np.float32), (rng.random((1, 2048, 3)) * 3 - 100).astype(np.float32), 0.005, 50
+    yield "planar", np.concatenate([rng.random((1, 2048, 2)), np.zeros((1, 2048, 1))], 2).astype(np.float32), \
+        np.concatenate([rng.random((1, 2048, 2)), np.zeros((1, 2048, 1))], 2).astype(np.float32), 0.005, 50
+    yield "five_blocks", rng.random((3, 320 * 4, 3), dtype=np.float32)[:, :1280], rng.random((3, 1280, 3), dtype=np.float32), 0.005, 50
+    yield "largest_pruned_n", rng.random((1, 32768, 3), dtype=np.float32), rng.random((1, 32768, 3), dtype=np.float32), 0.005, 20
+    yield "more_clouds_than_ctas_per_group", rng.random((40, 1024, 3), dtype=np.float32), rng.random((40, 1024, 3), dtype=np.float32), 0.005, 50
+    yield "large_eps", rng.random((1, 2048, 3), dtype=np.float32), rng.random((1, 2048, 3), dtype=np.float32), 0.5, 30
+
+
+@pytest.mark.gpu
+def test_emd_pruned_bid_equals_exhaustive_bid_on_adversarial_inputs(cuda):
+    """The block-pruned Bid (Morton-sorted targets, box test per 64-target block) only skips targets the per-target filter
+    rejects, so it must reproduce the exhaustive scan bit for bit on any input: exact ties (lattice, duplicates, identical
+    clouds), degenerate boxes (planar, tiny extent), loose bounds (far clusters, large eps), shapes (5 blocks, n = 32768,
+    B = 40).  The small cases are also checked against the oracle."""
+    from genpc_b200 import _lib
+
+    for name, x1, x2, eps, iters in _adversarial_emd_inputs():
+        x1, x2 = np.ascontiguousarray(x1, np.float32), np.ascontiguousarray(x2, np.float32)
+        with _lib.tunable(GENPC_EMD_PRUNE="1"):
+            d1, a1 = run_ours(x1, x2, eps, iters, cuda)
+        with _lib.tunable(GENPC_EMD_PRUNE="0"):
+            d0, a0 = run_ours(x1, x2, eps, iters, cuda)
+        assert np.array_equal(a1, a0), f"{name}: {(a1 != a0).sum()} assignments differ"
+        assert np.array_equal(d1.view(np.int32), d0.view(np.int32)), name
+        if x1.shape[0] * x1.shape[1] <= 4096:
+            ed, ea = oracle.emd_forward(x1, x2, eps, iters)
+            assert np.array_equal(a1, ea) and np.array_equal(d1.view(np.int32), ed.view(np.int32)), name
 
 
 @pytest.mark.gpu

@@ -1,15 +1,18 @@
-"""EMD cost per auction iteration: time of genpc_emd_forward for iters = 1..50 (ours), final unassigned count."""
+"""EMD cost per auction iteration: time of genpc_emd_forward for iters = 1..50 (ours), final unassigned count.
+args: BxN shapes; EMD_ITERS=1,2,50 picks the iteration counts; GENPC_EMD_PRUNE=0/1 selects the Bid form."""
 import json, os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from genpc_b200 import emd as ours
+SHAPES = [(1, 8192), (32, 8192)] if len(sys.argv) < 2 else [tuple(int(v) for v in a.split("x")) for a in sys.argv[1:]]
+ITERS = (1, 2, 3, 4, 6, 8, 12, 16, 24, 32, 50) if not os.environ.get("EMD_ITERS") else tuple(int(v) for v in os.environ["EMD_ITERS"].split(","))
 dev = torch.device("cuda:0")
 out = {}
-for (B, n) in [(1, 8192), (32, 8192)]:
+for (B, n) in SHAPES:
     g = torch.Generator().manual_seed(0)
     x1, x2 = torch.rand(B, n, 3, generator=g).to(dev), torch.rand(B, n, 3, generator=g).to(dev)
     res = {}
-    for iters in (1, 2, 3, 4, 6, 8, 12, 16, 24, 32, 50):
+    for iters in ITERS:
         ts = []
         for rep in range(3):
             dist = torch.zeros(B, n, device=dev); asg = torch.zeros(B, n, device=dev, dtype=torch.int32) - 1
