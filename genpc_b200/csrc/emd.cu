@@ -325,7 +325,6 @@ constexpr int EMD_BLOCK = 64;            // targets per block: one target PAIR p
 constexpr int EMD_PRUNE_MAX_N = 32768;   // boxes of a cloud fit the kernel's shared memory, the sort fits one CTA's
 constexpr int EMD_SORT_THREADS = 1024;
 constexpr int EMD_PBATCH = 4;            // surviving blocks whose loads are in flight together
-constexpr int EMD_BOXR = 4;              // box distances of the first EMD_BOXR * 32 blocks stay in registers (n <= 8192: all)
 
 // One CTA per cloud: Morton keys of the targets (cell << idxbits | original index), bitonic sort in shared memory, sorted
 // (x, y, z, index) records and per-block bounding boxes (all lower corners, then all upper corners).  The ORDER only affects how well the blocks prune, never a result.
@@ -430,8 +429,10 @@ __device__ __forceinline__ int f2ord(float f) {
 }
 __device__ __forceinline__ float ord2f(int i) { return __int_as_float(i ^ ((i >> 31) & 0x7fffffff)); }
 
-template <bool PRUNE, int MINB>
+// BOXR = 0: exhaustive Bid; BOXR > 0: pruned Bid for clouds of up to BOXR * 32 blocks (box distances in BOXR registers per lane)
+template <int BOXR, int MINB>
 __global__ void __launch_bounds__(EMD_THREADS, MINB) emd_auction_kernel(const EmdArgs a) {
+    constexpr bool PRUNE = BOXR > 0;
     // targets + prices of one chunk, two float4 planes per target PAIR p: stg[p] = (x0, x1, y0, y1), stg[EMD_CHUNK/2 + p] =
     // (z0, z1, price0, price1) -- one address register (second plane at a constant offset) and two LDS.128 per step of the
     // Bid scan (r02; four separate SoA arrays cost four LEA, four LDS.64 and six uniform address instructions per step:
@@ -440,12 +441,11 @@ __global__ void __launch_bounds__(EMD_THREADS, MINB) emd_auction_kernel(const Em
     // 2-way conflict on every load -- 930 M of 2000 M wavefronts).
     // (PRUNE: the same array holds the cloud's block boxes instead: nblk lower corners, then nblk upper corners -- 16-byte
     // lane stride on both loads of the box test)
-    __shared__ __align__(16) float4 stg[PRUNE ? 2 * (EMD_PRUNE_MAX_N / EMD_BLOCK) : EMD_CHUNK];
+    __shared__ __align__(16) float4 stg[PRUNE ? 2 * BOXR * 32 : EMD_CHUNK];
     constexpr unsigned STG_PLANE = (EMD_CHUNK / 2) * 16;
     __shared__ BidState smerge[PRUNE ? 1 : EMD_THREADS];
     // PRUNE: per warp, the list of blocks that survive the box test and the queue of (original index, s) candidates
-    __shared__ unsigned short s_blist[PRUNE ? EMD_THREADS / 32 : 1][PRUNE ? EMD_PRUNE_MAX_N / EMD_BLOCK : 1];
-    __shared__ float s_slist[PRUNE ? EMD_THREADS / 32 : 1][PRUNE ? EMD_PRUNE_MAX_N / EMD_BLOCK : 1];   // their box distances
+    __shared__ unsigned short s_blist[PRUNE ? EMD_THREADS / 32 : 1][PRUNE ? BOXR * 32 + EMD_PBATCH : 1];
     __shared__ float2 s_queue[PRUNE ? EMD_THREADS / 32 : 1][PRUNE ? 96 : 1];
     __shared__ int sscan[EMD_THREADS / 32];
     __shared__ int s_last;
@@ -493,7 +493,8 @@ __global__ void __launch_bounds__(EMD_THREADS, MINB) emd_auction_kernel(const Em
         if constexpr (PRUNE) {
             __syncthreads();   // the previous cloud's boxes are no longer read
             const float4 *bx = a.boxes + (size_t)b * (n / EMD_BLOCK) * 2;
-            for (int k = tid; k < 2 * (n / EMD_BLOCK); k += EMD_THREADS) stg[k] = __ldg(bx + k);
+            for (int k = tid; k < 2 * (n / EMD_BLOCK); k += EMD_THREADS)
+                stg[k < n / EMD_BLOCK ? k : BOXR * 32 + (k - n / EMD_BLOCK)] = __ldg(bx + k);
             __syncthreads();
         }
 
@@ -521,20 +522,32 @@ __global__ void __launch_bounds__(EMD_THREADS, MINB) emd_auction_kernel(const Em
                 const float4 *ts = a.tsort + (size_t)b * n + 2 * lane;   // lane l: sorted targets blk*64 + 2l, 2l+1
                 const float inf = __int_as_float(0x7f800000);
                 unsigned short *blist = s_blist[wid];
-                float *slist = s_slist[wid];
                 float2 *queue = s_queue[wid];
                 // One WARP per bidder.  Everything that touches L2 is issued in batches, because a bidder is otherwise a chain
                 // of dependent L2 round trips (a first version that scanned the surviving blocks one after the other, each
                 // with its own price gather, spent 30 us per bidder):
-                //   1. box tests (shared memory) -> nearest block = seed; its 64 targets are evaluated exactly -> threshold
-                //   2. box tests against the threshold -> list of surviving blocks, the EMD_PBATCH nearest moved to the front
-                //   3. surviving blocks in batches of EMD_PBATCH (all loads of a batch in flight together); targets inside the
-                //      target-independent cap s_cap are queued as (original index, s)
-                //   4. the queue is drained 32 entries at a time: price gather, per-target filter, exact value; after the
-                //      first (nearest) batch the threshold is final for most bidders and the list is re-filtered with it
-                for (int u = rank * (EMD_THREADS / 32) + wid; u < U; u += a.group * (EMD_THREADS / 32)) {
-                    const int j = __ldcg(uidx + u);
-                    const float x1 = __ldg(p1 + j * 3), y1 = __ldg(p1 + j * 3 + 1), z1 = __ldg(p1 + j * 3 + 2);
+                //   1. box distances of all blocks (shared memory -> BOXR registers per lane)
+                //   2. the nearest block (seed) is evaluated exactly -> first threshold
+                //   3. the EMD_PBATCH next nearest blocks, loads in flight together; targets inside the target-independent cap
+                //      s_cap are queued as (original index, s); the queue is drained 32 entries at a time (price gather,
+                //      per-target filter, exact value) -> the threshold is final for most bidders
+                //   4. the blocks that still pass the box test (usually 0-3) are listed and handled like 3.
+                // The next bidder's index and coordinates are fetched while the current one is processed.
+                const int wstride = a.group * (EMD_THREADS / 32);
+                int u = rank * (EMD_THREADS / 32) + wid;
+                int jn = 0;
+                float xn = 0.f, yn = 0.f, zn = 0.f;
+                if (u < U) {
+                    jn = __ldcg(uidx + u);
+                    xn = __ldg(p1 + jn * 3), yn = __ldg(p1 + jn * 3 + 1), zn = __ldg(p1 + jn * 3 + 2);
+                }
+                for (; u < U; u += wstride) {
+                    const int j = jn;
+                    const float x1 = xn, y1 = yn, z1 = zn;
+                    if (u + wstride < U) {
+                        jn = __ldcg(uidx + u + wstride);
+                        xn = __ldg(p1 + jn * 3), yn = __ldg(p1 + jn * 3 + 1), zn = __ldg(p1 + jn * 3 + 2);
+                    }
                     BidState st;
                     st.best = -1e9f, st.better = -1e9f, st.bi = -1;
                     float bm = -2e9f;     // (lower bound of the bidder's final second-best value) - margin
@@ -564,15 +577,6 @@ __global__ void __launch_bounds__(EMD_THREADS, MINB) emd_auction_kernel(const Em
                         const float tq = __fsub_rn(__fsub_rn(3.0f, pk), bm);
                         if (tq > 0.f && s <= __fmul_rn(tq, tq)) consider(k, s, pk);
                     };
-                    // squared distance to the block's box, scaled DOWN by 1e-5: the reference's rounded s of a target inside
-                    // the box is never below it (each difference and the fma chain are within a few 2^-24 of exact)
-                    auto box_s = [&](int blk) {
-                        const float4 lo = stg[blk], hi = stg[nblk + blk];
-                        const float dx = fmaxf(fmaxf(lo.x - x1, x1 - hi.x), 0.f);
-                        const float dy = fmaxf(fmaxf(lo.y - y1, y1 - hi.y), 0.f);
-                        const float dz = fmaxf(fmaxf(lo.z - z1, z1 - hi.z), 0.f);
-                        return __fmul_rn(__fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy))), 0.99999f);
-                    };
                     // the warp-wide second-best value so far bounds every lane's filter: the second largest `best` of two
                     // different lanes, or the largest `better` of any lane.  Leaves bm / s_cap identical in all lanes.
                     auto share_threshold = [&]() {
@@ -584,21 +588,38 @@ __global__ void __launch_bounds__(EMD_THREADS, MINB) emd_auction_kernel(const Em
                         raise_threshold(ord2f(max(m2, mb)));
                     };
                     const float2 nx = make_float2(-x1, -x1), ny = make_float2(-y1, -y1), nz = make_float2(-z1, -z1);
-                    // ---- 1. box distances (kept in registers for the first EMD_BOXR * 32 blocks) and the seed ----
-                    float sl[EMD_BOXR];
-                    unsigned skey = 0xffffffffu;   // (distance bits, block id): any near block makes a good seed
+                    // ---- 1. squared distance to every block's box, scaled DOWN by 1e-5: the reference's rounded s of a target
+                    // inside the box is never below it (each difference and the fma chain are within a few 2^-24 of exact)
+                    float sl[BOXR];
 #pragma unroll
-                    for (int r = 0; r < EMD_BOXR; ++r) {
+                    for (int r = 0; r < BOXR; ++r) {
                         const int blk = r * 32 + lane;
-                        sl[r] = blk < nblk ? box_s(blk) : inf;
-                        skey = min(skey, (__float_as_uint(sl[r]) & 0xfffffe00u) | (unsigned)blk);
+                        sl[r] = inf;
+                        if (blk < nblk) {
+                            const float4 lo = stg[blk], hi = stg[BOXR * 32 + blk];
+                            const float dx = fmaxf(fmaxf(lo.x - x1, x1 - hi.x), 0.f);
+                            const float dy = fmaxf(fmaxf(lo.y - y1, y1 - hi.y), 0.f);
+                            const float dz = fmaxf(fmaxf(lo.z - z1, z1 - hi.z), 0.f);
+                            sl[r] = __fmul_rn(__fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy))), 0.99999f);
+                        }
                     }
-                    for (int r0 = EMD_BOXR * 32; r0 < nblk; r0 += 32) {
-                        const int blk = r0 + lane;
-                        if (blk < nblk) skey = min(skey, (__float_as_uint(box_s(blk)) & 0xfffffe00u) | (unsigned)blk);
-                    }
-                    const int sb = (int)(__reduce_min_sync(0xffffffffu, skey) & 0x1ffu) % nblk;   // (NaN bidder: block 0)
+                    // nearest remaining block as (distance bits without the low 9, block id): any near block will do; the block
+                    // is removed from sl
+                    auto take_nearest = [&]() {
+                        unsigned key = 0xffffffffu;
+#pragma unroll
+                        for (int r = 0; r < BOXR; ++r) key = min(key, (__float_as_uint(sl[r]) & 0xfffffe00u) | (unsigned)(r * 32 + lane));
+                        key = __reduce_min_sync(0xffffffffu, key);
+                        const int blk = (int)(key & 0x1ffu);
+#pragma unroll
+                        for (int r = 0; r < BOXR; ++r)
+                            if (r * 32 + lane == blk) sl[r] = inf;
+                        return key;   // >= 0x7f800000: only +inf (taken / out of range) or NaN distances were left
+                    };
+                    // ---- 2. seed ----
                     {
+                        const unsigned skey = take_nearest();
+                        const int sb = skey < 0x7f800000u ? (int)(skey & 0x1ffu) : 0;   // NaN bidder: nothing will ever qualify
                         const float4 t0 = __ldg(ts + sb * EMD_BLOCK), t1 = __ldg(ts + sb * EMD_BLOCK + 1);
                         const int k0 = __float_as_int(t0.w), k1 = __float_as_int(t1.w);
                         const float pk0 = __ldcg(pr + k0), pk1 = __ldcg(pr + k1);
@@ -608,42 +629,6 @@ __global__ void __launch_bounds__(EMD_THREADS, MINB) emd_auction_kernel(const Em
                         candidate(k1, s2.y, pk1);
                     }
                     share_threshold();
-                    // ---- 2. surviving blocks ----
-                    int nlist = 0;
-#pragma unroll
-                    for (int r = 0; r < EMD_BOXR; ++r) {
-                        const int blk = r * 32 + lane;
-                        const bool pass = sl[r] <= s_cap && blk != sb;
-                        const unsigned mask = __ballot_sync(0xffffffffu, pass);
-                        if (pass) blist[nlist + __popc(mask & lt)] = (unsigned short)blk, slist[nlist + __popc(mask & lt)] = sl[r];
-                        nlist += __popc(mask);
-                    }
-                    for (int r0 = EMD_BOXR * 32; r0 < nblk; r0 += 32) {
-                        const int blk = r0 + lane;
-                        const float sv = blk < nblk ? box_s(blk) : inf;
-                        const bool pass = sv <= s_cap && blk != sb;
-                        const unsigned mask = __ballot_sync(0xffffffffu, pass);
-                        if (pass) blist[nlist + __popc(mask & lt)] = (unsigned short)blk, slist[nlist + __popc(mask & lt)] = sv;
-                        nlist += __popc(mask);
-                    }
-                    __syncwarp();
-                    // the EMD_PBATCH nearest blocks to the front: they settle the threshold
-                    if (nlist > EMD_PBATCH) {
-#pragma unroll 1
-                        for (int q = 0; q < EMD_PBATCH; ++q) {
-                            unsigned key = 0xffffffffu;
-                            for (int e = q + lane; e < nlist; e += 32) key = min(key, (__float_as_uint(slist[e]) & 0xfffffe00u) | (unsigned)e);
-                            const int e = (int)(__reduce_min_sync(0xffffffffu, key) & 0x1ffu);
-                            __syncwarp();
-                            if (lane == 0 && e != q) {
-                                const unsigned short tb = blist[q];
-                                const float tsv = slist[q];
-                                blist[q] = blist[e], slist[q] = slist[e];
-                                blist[e] = tb, slist[e] = tsv;
-                            }
-                            __syncwarp();
-                        }
-                    }
                     // ---- 3. / 4. ----
                     int nq = 0;
                     auto drain = [&]() {   // the last min(nq, 32) entries of the queue
@@ -657,18 +642,28 @@ __global__ void __launch_bounds__(EMD_THREADS, MINB) emd_auction_kernel(const Em
                         __syncwarp();
                         share_threshold();
                     };
+                    // the EMD_PBATCH nearest blocks inside the cap open the list; the others join it once these are in
+                    int nlist = EMD_PBATCH;
+#pragma unroll
+                    for (int q = 0; q < EMD_PBATCH; ++q) {
+                        const unsigned key = take_nearest();
+                        // a block beyond the cap is not needed (the truncated distance errs on the near side)
+                        const bool in = key < 0x7f800000u && __uint_as_float(key & 0xfffffe00u) <= s_cap;
+                        if (lane == 0) blist[q] = (unsigned short)(in ? (key & 0x1ffu) : nblk);
+                    }
+                    __syncwarp();
+#pragma unroll 1
                     for (int i0 = 0; i0 < nlist; i0 += EMD_PBATCH) {
+                        int bk[EMD_PBATCH];   // block ids, nblk = none; warp-uniform
                         float4 t[EMD_PBATCH][2];
 #pragma unroll
                         for (int q = 0; q < EMD_PBATCH; ++q) {
-                            if (i0 + q < nlist) {
-                                const int blk = blist[i0 + q];
-                                t[q][0] = __ldg(ts + blk * EMD_BLOCK), t[q][1] = __ldg(ts + blk * EMD_BLOCK + 1);
-                            }
+                            bk[q] = i0 + q < nlist ? (int)blist[i0 + q] : nblk;
+                            if (bk[q] < nblk) t[q][0] = __ldg(ts + bk[q] * EMD_BLOCK), t[q][1] = __ldg(ts + bk[q] * EMD_BLOCK + 1);
                         }
 #pragma unroll
                         for (int q = 0; q < EMD_PBATCH; ++q) {
-                            if (i0 + q < nlist) {
+                            if (bk[q] < nblk) {
                                 const float2 s2 = sqdist_ref_x2(nx, ny, nz, make_float2(t[q][0].x, t[q][1].x),
                                                                 make_float2(t[q][0].y, t[q][1].y), make_float2(t[q][0].z, t[q][1].z));
                                 const bool f0 = s2.x <= s_cap, f1 = s2.y <= s_cap;
@@ -683,22 +678,16 @@ __global__ void __launch_bounds__(EMD_THREADS, MINB) emd_auction_kernel(const Em
                                 }
                             }
                         }
-                        if (i0 == 0 && nlist > EMD_PBATCH) {
-                            // the nearest blocks are in: settle the threshold and drop the blocks it now excludes
+                        if (i0 == 0) {
+                            // the nearest blocks are in: settle the threshold, then list what still passes the box test
                             if (nq > 0) drain();
-                            int keep = EMD_PBATCH;
-                            for (int r0 = EMD_PBATCH; r0 < nlist; r0 += 32) {
-                                const int e = r0 + lane;
-                                unsigned short bk = 0;
-                                float sv = inf;
-                                if (e < nlist) bk = blist[e], sv = slist[e];
-                                const bool pass = sv <= s_cap;
+#pragma unroll
+                            for (int r = 0; r < BOXR; ++r) {
+                                const bool pass = sl[r] <= s_cap;   // taken blocks are +inf
                                 const unsigned mask = __ballot_sync(0xffffffffu, pass);
-                                __syncwarp();
-                                if (pass) blist[keep + __popc(mask & lt)] = bk;   // keep + rank <= e: in place
-                                keep += __popc(mask);
+                                if (pass) blist[nlist + __popc(mask & lt)] = (unsigned short)(r * 32 + lane);
+                                nlist += __popc(mask);
                             }
-                            nlist = keep;
                             __syncwarp();
                         }
                     }
@@ -959,8 +948,14 @@ extern "C" int genpc_emd_forward(const float *xyz1, const float *xyz2, float *di
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const char *pmb = tunable("GENPC_EMD_PRUNE_MINB");  // experiments only
-    void *kernel = prune ? ((pmb != nullptr && atoi(pmb) == 3) ? (void *)emd_auction_kernel<true, 3> : (void *)emd_auction_kernel<true, 4>)
-                         : (void *)emd_auction_kernel<false, 5>;
+    const bool mb4 = pmb != nullptr && atoi(pmb) == 4;
+    void *kernel = (void *)emd_auction_kernel<0, 5>;
+    if (prune) {
+        const int nblk = n / EMD_BLOCK;
+        if (nblk <= 128) kernel = mb4 ? (void *)emd_auction_kernel<4, 4> : (void *)emd_auction_kernel<4, 3>;
+        else if (nblk <= 256) kernel = mb4 ? (void *)emd_auction_kernel<8, 4> : (void *)emd_auction_kernel<8, 3>;
+        else kernel = mb4 ? (void *)emd_auction_kernel<16, 4> : (void *)emd_auction_kernel<16, 3>;
+    }
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, EMD_THREADS, 0);
     if (e != cudaSuccess) return (int)e;
     const int resident = sms * per_sm;
