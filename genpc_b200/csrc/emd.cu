@@ -4,11 +4,15 @@
 // calc_unass_cnt, calc_unass_cnt_sum, calc_unass_idx, Bid, GetMax, Assign) + CalcDist = 351 launches at
 // iters = 50, launch-latency bound, and every Bid block re-stages the whole target cloud for <= 256 bidders.
 // Here a group of CTAs owns each batch entry for the whole run:
-//   * Bid is spread over the group: an item = P unassigned points x all targets, T = 256/P threads per point
-//     (P adapts so the items fill the group); targets + prices staged as float4 chunks in shared memory;
-//   * the last CTA of the group to finish an iteration's items (atomic ticket) runs the O(n) tail on its own:
+//   * Bid, pruned form (r02, 64 <= n <= 32768): emd_sort_kernel orders the targets along a Morton curve once per call;
+//     one WARP per bidder tests the bounding boxes of the 64-target blocks against the bidder's second-best bound and
+//     scans only the blocks that can matter (5-7 % on the bench's inputs) -- see "pruned Bid" below;
+//   * Bid, exhaustive form (other n, GENPC_EMD_PRUNE=0): an item = P unassigned points x all targets, T = 256/P threads
+//     per point (P adapts so the items fill the group); targets + prices staged as float4 chunks in shared memory;
+//   * the last CTA of the group to finish an iteration's bids (atomic ticket) runs the O(n) tail on its own:
 //     GetMax -> Assign -> reset -> ascending compaction of the still-unassigned points, then releases a
-//     per-batch flag the group spins on.  No grid-wide barrier, no host round trip.
+//     per-batch flag the group spins on (the first iterations, thousands of bidders, spread GetMax / Assign over the
+//     group between two counter barriers instead).  No grid-wide barrier, no host round trip.
 // Arithmetic and tie rules are the reference's, bit for bit (oracle_emd_forward has the derivation):
 //   value = (float)((3.0 - (double)sqrtf(fma(dz,dz,fma(dx,dx,dy*dy)))) - (double)price)   (emd_cuda.cu:146)
 //   best / second-best with multiplicity; among equal best values the winner is the target with the smallest
@@ -34,7 +38,7 @@ struct EmdArgs {
     int *assignment_inv, *bid;
     float *bid_increments, *max_increments;
     int *unass_idx, *unass_cnt, *max_idx;
-    int *flags, *tickets;  // workspace [B] each, zeroed by the host
+    int *flags, *tickets, *bars;  // workspace [B] each, zeroed by the host
     float *pmin;           // workspace [B]: lowest price of the cloud at the start of the run (prices only rise)
     int B, n;
     float eps;
@@ -42,6 +46,7 @@ struct EmdArgs {
     int two_level_div;     // two-level pre-filter while U * two_level_div >= n (0: never)
     int getmax_lowest;     // GetMax race resolved as lowest (1) or highest (0, default) bidder index
     int direct_p;          // items with at most this many bidders read the targets from global memory (no staging)
+    int tail_spread_u;     // GetMax / Assign are spread over the group from this many bidders up
     // pruned Bid (r02): targets re-ordered along a Morton curve by emd_sort_kernel, (x, y, z, original index) per target,
     // and the bounding box (lo, hi) of every EMD_BLOCK consecutive sorted targets
     const float4 *tsort, *boxes;
@@ -246,16 +251,16 @@ __device__ __noinline__ int compact_unassigned(const int *__restrict__ asg, int 
 // the order in which they are processed does not matter.
 constexpr int EMD_TAIL_R = 2;
 
-__device__ __noinline__ void emd_getmax_assign(const int *__restrict__ uidx, const int *__restrict__ bd,
-                                               const float *__restrict__ binc, float *minc, int *midx, int *asg, int *asg_inv,
-                                               float *pr, int U, bool last, bool lowest) {
-    const int tid = threadIdx.x;
-    for (int u0 = 0; u0 < U; u0 += EMD_THREADS * EMD_TAIL_R) {
+// Both phases take the bidders u = first, first + stride, ... (first = tid, stride = EMD_THREADS when one CTA runs the tail;
+// a slice per CTA when the group shares it).
+__device__ __noinline__ void emd_getmax(const int *__restrict__ uidx, const int *__restrict__ bd, const float *__restrict__ binc,
+                                        const float *minc, int *midx, int U, bool lowest, int first, int stride) {
+    for (int u0 = first; u0 < U; u0 += stride * EMD_TAIL_R) {
         int j[EMD_TAIL_R], bid[EMD_TAIL_R];
         float inc[EMD_TAIL_R], mx[EMD_TAIL_R];
 #pragma unroll
         for (int r = 0; r < EMD_TAIL_R; ++r) {
-            const int u = u0 + r * EMD_THREADS + tid;
+            const int u = u0 + r * stride;
             j[r] = (u < U) ? __ldcg(uidx + u) : -1;
         }
 #pragma unroll
@@ -272,13 +277,17 @@ __device__ __noinline__ void emd_getmax_assign(const int *__restrict__ uidx, con
                 else atomicMax(midx + bid[r], j[r]);
             }
     }
-    __syncthreads();
-    for (int u0 = 0; u0 < U; u0 += EMD_THREADS * EMD_TAIL_R) {
+}
+
+__device__ __noinline__ void emd_assign(const int *__restrict__ uidx, const int *__restrict__ bd, const float *__restrict__ binc,
+                                        float *minc, const int *midx, int *asg, int *asg_inv, float *pr, int U, bool last,
+                                        int first, int stride) {
+    for (int u0 = first; u0 < U; u0 += stride * EMD_TAIL_R) {
         int j[EMD_TAIL_R], bid[EMD_TAIL_R], win[EMD_TAIL_R], inv[EMD_TAIL_R];
         float inc[EMD_TAIL_R], p[EMD_TAIL_R];
 #pragma unroll
         for (int r = 0; r < EMD_TAIL_R; ++r) {
-            const int u = u0 + r * EMD_THREADS + tid;
+            const int u = u0 + r * stride;
             j[r] = (u < U) ? __ldcg(uidx + u) : -1;
         }
 #pragma unroll
@@ -310,7 +319,6 @@ __device__ __noinline__ void emd_getmax_assign(const int *__restrict__ uidx, con
                 minc[bid[r]] = -1e9f;
             }
     }
-    __syncthreads();
 }
 
 // ---- pruned Bid (r02) ------------------------------------------------------------------------------------------------
@@ -429,6 +437,20 @@ __device__ __forceinline__ int f2ord(float f) {
 }
 __device__ __forceinline__ float ord2f(int i) { return __int_as_float(i ^ ((i >> 31) & 0x7fffffff)); }
 
+#ifdef GENPC_EMD_TRACE
+// profiling build only (tools/emd_trace.py): phase timestamps of cloud 0, eight per iteration (0-3 phases of the
+// iteration, 4-7 inside the first bidder of CTA 0 / warp 0)
+__device__ unsigned long long g_emd_trace[8 * 1024];
+__device__ __forceinline__ void emd_trace(int it, int k) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    if (it < 1024) g_emd_trace[it * 8 + k] = t;
+}
+#define EMD_TRACE(cond, it, k) do { if ((cond) && threadIdx.x == 0) emd_trace(it, k); } while (0)
+#else
+#define EMD_TRACE(cond, it, k) do { } while (0)
+#endif
+
 // BOXR = 0: exhaustive Bid; BOXR > 0: pruned Bid for clouds of up to BOXR * 32 blocks (box distances in BOXR registers per lane)
 template <int BOXR, int MINB>
 __global__ void __launch_bounds__(EMD_THREADS, MINB) emd_auction_kernel(const EmdArgs a) {
@@ -467,7 +489,8 @@ __global__ void __launch_bounds__(EMD_THREADS, MINB) emd_auction_kernel(const Em
         float *minc = a.max_increments + (size_t)b * n;
         int *uidx = a.unass_idx + (size_t)b * n;
         int *midx = a.max_idx + (size_t)b * n;
-        int *flag = a.flags + b, *ticket = a.tickets + b;
+        int *flag = a.flags + b, *ticket = a.tickets + b, *bar = a.bars + b;
+        int tix_target = 0, bar_target = 0;   // arrivals expected so far (same sequence of decisions in every CTA of the group)
 
         if (rank == 0) {  // initial compaction (calc_unass_cnt / calc_unass_idx of iteration 0)
             const int U0 = compact_unassigned(asg, uidx, midx, n, sscan);
@@ -510,6 +533,7 @@ __global__ void __launch_bounds__(EMD_THREADS, MINB) emd_auction_kernel(const Em
                 complete = true;
                 break;
             }
+            EMD_TRACE(b == 0 && rank == 0, it, 0);   // Bid starts
             const float c_max = __fsub_rn(3.0f, __ldcg(a.pmin + b));
             const bool two_level = (a.two_level_div > 0) && ((long long)U * a.two_level_div >= n);
             // ---- Bid (emd_cuda.cu:95-179) ----
@@ -527,10 +551,11 @@ __global__ void __launch_bounds__(EMD_THREADS, MINB) emd_auction_kernel(const Em
                 // of dependent L2 round trips (a first version that scanned the surviving blocks one after the other, each
                 // with its own price gather, spent 30 us per bidder):
                 //   1. box distances of all blocks (shared memory -> BOXR registers per lane)
-                //   2. the nearest block (seed) is evaluated exactly -> first threshold
-                //   3. the EMD_PBATCH next nearest blocks, loads in flight together; targets inside the target-independent cap
-                //      s_cap are queued as (original index, s); the queue is drained 32 entries at a time (price gather,
-                //      per-target filter, exact value) -> the threshold is final for most bidders
+                //   2. the EMD_PBATCH nearest blocks, loads in flight together; every lane evaluates its nearest target of the
+                //      batch exactly (one price gather) -> first threshold
+                //   3. the batch's other targets inside the target-independent cap s_cap are queued as (original index, s);
+                //      the queue is drained 32 entries at a time (price gather, per-target filter, exact value) -> the
+                //      threshold is final for most bidders
                 //   4. the blocks that still pass the box test (usually 0-3) are listed and handled like 3.
                 // The next bidder's index and coordinates are fetched while the current one is processed.
                 const int wstride = a.group * (EMD_THREADS / 32);
@@ -541,9 +566,14 @@ __global__ void __launch_bounds__(EMD_THREADS, MINB) emd_auction_kernel(const Em
                     jn = __ldcg(uidx + u);
                     xn = __ldg(p1 + jn * 3), yn = __ldg(p1 + jn * 3 + 1), zn = __ldg(p1 + jn * 3 + 2);
                 }
+                EMD_TRACE(b == 0 && rank == 0 && U > 0, it, 4);   // U, pmin known; first bidder's loads issued
                 for (; u < U; u += wstride) {
                     const int j = jn;
                     const float x1 = xn, y1 = yn, z1 = zn;
+#ifdef GENPC_EMD_TRACE
+                    if (x1 == 123456.f) continue;   // make the timestamp below wait for the coordinates
+                    EMD_TRACE(b == 0 && rank == 0 && u == 0, it, 5);
+#endif
                     if (u + wstride < U) {
                         jn = __ldcg(uidx + u + wstride);
                         xn = __ldg(p1 + jn * 3), yn = __ldg(p1 + jn * 3 + 1), zn = __ldg(p1 + jn * 3 + 2);
@@ -616,20 +646,7 @@ __global__ void __launch_bounds__(EMD_THREADS, MINB) emd_auction_kernel(const Em
                             if (r * 32 + lane == blk) sl[r] = inf;
                         return key;   // >= 0x7f800000: only +inf (taken / out of range) or NaN distances were left
                     };
-                    // ---- 2. seed ----
-                    {
-                        const unsigned skey = take_nearest();
-                        const int sb = skey < 0x7f800000u ? (int)(skey & 0x1ffu) : 0;   // NaN bidder: nothing will ever qualify
-                        const float4 t0 = __ldg(ts + sb * EMD_BLOCK), t1 = __ldg(ts + sb * EMD_BLOCK + 1);
-                        const int k0 = __float_as_int(t0.w), k1 = __float_as_int(t1.w);
-                        const float pk0 = __ldcg(pr + k0), pk1 = __ldcg(pr + k1);
-                        const float2 s2 = sqdist_ref_x2(nx, ny, nz, make_float2(t0.x, t1.x), make_float2(t0.y, t1.y),
-                                                        make_float2(t0.z, t1.z));
-                        candidate(k0, s2.x, pk0);
-                        candidate(k1, s2.y, pk1);
-                    }
-                    share_threshold();
-                    // ---- 3. / 4. ----
+                    // ---- 2. / 3. / 4. ----
                     int nq = 0;
                     auto drain = [&]() {   // the last min(nq, 32) entries of the queue
                         const int e = nq - 1 - lane;
@@ -642,14 +659,12 @@ __global__ void __launch_bounds__(EMD_THREADS, MINB) emd_auction_kernel(const Em
                         __syncwarp();
                         share_threshold();
                     };
-                    // the EMD_PBATCH nearest blocks inside the cap open the list; the others join it once these are in
+                    // the EMD_PBATCH nearest blocks open the list; the others join it once these have settled the threshold
                     int nlist = EMD_PBATCH;
 #pragma unroll
                     for (int q = 0; q < EMD_PBATCH; ++q) {
                         const unsigned key = take_nearest();
-                        // a block beyond the cap is not needed (the truncated distance errs on the near side)
-                        const bool in = key < 0x7f800000u && __uint_as_float(key & 0xfffffe00u) <= s_cap;
-                        if (lane == 0) blist[q] = (unsigned short)(in ? (key & 0x1ffu) : nblk);
+                        if (lane == 0) blist[q] = (unsigned short)(key < 0x7f800000u ? (key & 0x1ffu) : nblk);
                     }
                     __syncwarp();
 #pragma unroll 1
@@ -661,12 +676,45 @@ __global__ void __launch_bounds__(EMD_THREADS, MINB) emd_auction_kernel(const Em
                             bk[q] = i0 + q < nlist ? (int)blist[i0 + q] : nblk;
                             if (bk[q] < nblk) t[q][0] = __ldg(ts + bk[q] * EMD_BLOCK), t[q][1] = __ldg(ts + bk[q] * EMD_BLOCK + 1);
                         }
+                        float2 sq[EMD_PBATCH];
+#pragma unroll
+                        for (int q = 0; q < EMD_PBATCH; ++q)
+                            sq[q] = sqdist_ref_x2(nx, ny, nz, make_float2(t[q][0].x, t[q][1].x), make_float2(t[q][0].y, t[q][1].y),
+                                                  make_float2(t[q][0].z, t[q][1].z));
+                        int ev = -1;   // the target this lane has already evaluated exactly (2 * q + half)
+                        if (i0 == 0) {
+                            // no threshold yet: every lane evaluates its NEAREST target of the batch exactly (one price gather
+                            // for the warp) -- 32 candidates that contain the bidder's nearest targets -- and the warp-wide
+                            // second-best of those is the threshold for everything else
+                            float smin = inf;
+#pragma unroll
+                            for (int q = 0; q < EMD_PBATCH; ++q) {
+                                if (bk[q] < nblk) {
+                                    if (sq[q].x < smin) smin = sq[q].x, ev = 2 * q;
+                                    if (sq[q].y < smin) smin = sq[q].y, ev = 2 * q + 1;
+                                }
+                            }
+                            float kw = 0.f;
+#pragma unroll
+                            for (int q = 0; q < EMD_PBATCH; ++q) {
+                                if (ev == 2 * q) kw = t[q][0].w;
+                                if (ev == 2 * q + 1) kw = t[q][1].w;
+                            }
+                            if (ev >= 0) {
+                                const int k = __float_as_int(kw);
+                                candidate(k, smin, __ldcg(pr + k));
+                            }
+                            share_threshold();
+#ifdef GENPC_EMD_TRACE
+                            if (s_cap == 123456.f) continue;
+                            EMD_TRACE(b == 0 && rank == 0 && u == 0, it, 6);   // first threshold
+#endif
+                        }
 #pragma unroll
                         for (int q = 0; q < EMD_PBATCH; ++q) {
                             if (bk[q] < nblk) {
-                                const float2 s2 = sqdist_ref_x2(nx, ny, nz, make_float2(t[q][0].x, t[q][1].x),
-                                                                make_float2(t[q][0].y, t[q][1].y), make_float2(t[q][0].z, t[q][1].z));
-                                const bool f0 = s2.x <= s_cap, f1 = s2.y <= s_cap;
+                                const float2 s2 = sq[q];
+                                const bool f0 = s2.x <= s_cap && ev != 2 * q, f1 = s2.y <= s_cap && ev != 2 * q + 1;
                                 if (__any_sync(0xffffffffu, f0 || f1)) {
                                     const unsigned m0 = __ballot_sync(0xffffffffu, f0), m1 = __ballot_sync(0xffffffffu, f1);
                                     if (f0) queue[nq + __popc(m0 & lt)] = make_float2(t[q][0].w, s2.x);
@@ -723,6 +771,7 @@ __global__ void __launch_bounds__(EMD_THREADS, MINB) emd_auction_kernel(const Em
                         atomicMax(reinterpret_cast<int *>(minc + st.bi), __float_as_int(inc));  // inc > 0
                     }
                     __syncwarp();   // the next bidder reuses the warp's list and queue
+                    EMD_TRACE(b == 0 && rank == 0 && u == 0, it, 7);   // first bidder done
                 }
             } else if (U > 0) {
                 const int upb_ref = (U + block_cnt - 1) / block_cnt;
@@ -856,14 +905,49 @@ __global__ void __launch_bounds__(EMD_THREADS, MINB) emd_auction_kernel(const Em
                     }
                 }
             }
-            // ---- ticket: the last CTA of the group runs the O(n) tail of this iteration ----
-            __threadfence();
-            __syncthreads();
-            if (tid == 0) s_last = (a.group == 1) || (atomicAdd(ticket, 1) == (it + 1) * a.group - 1);
-            __syncthreads();
-            if (s_last) {
+            // ---- tail of the iteration: GetMax -> Assign -> compaction ----
+            // Few bidders (the common case): the last CTA that bid (atomic ticket; CTAs without a bidder do not take part in
+            // the pruned form) runs all three on its own -- no group-wide barrier.  Many bidders (the first iterations; one
+            // CTA would spend up to 90 us on them at n = 16384): GetMax and Assign are spread over the group between two
+            // counter barriers, the last CTA to finish Assign compacts.
+            const int work_ctas = (PRUNE && a.group > 1) ? min(a.group, (U + EMD_THREADS / 32 - 1) / (EMD_THREADS / 32)) : a.group;
+            const bool spread = a.group > 1 && U >= a.tail_spread_u;
+            auto group_barrier = [&]() {
                 __threadfence();
-                emd_getmax_assign(uidx, bd, binc, minc, midx, asg, asg_inv, pr, U, last, a.getmax_lowest != 0);
+                __syncthreads();
+                bar_target += a.group;
+                if (tid == 0) {
+                    atomicAdd(bar, 1);
+                    while (ld_acquire(bar) < bar_target) {
+                    }
+                }
+                __syncthreads();
+            };
+            if (spread) {
+                group_barrier();   // every bid of the cloud is in
+                emd_getmax(uidx, bd, binc, minc, midx, U, a.getmax_lowest != 0, rank * EMD_THREADS + tid, a.group * EMD_THREADS);
+                group_barrier();
+                emd_assign(uidx, bd, binc, minc, midx, asg, asg_inv, pr, U, last, rank * EMD_THREADS + tid, a.group * EMD_THREADS);
+            }
+            const bool takes_ticket = spread || rank < work_ctas;
+            const int arrivals = spread ? a.group : work_ctas;
+            if (takes_ticket) {
+                __threadfence();
+                __syncthreads();
+                if (tid == 0) s_last = (a.group == 1) || (atomicAdd(ticket, 1) == tix_target + arrivals - 1);
+                __syncthreads();
+            }
+            tix_target += arrivals;
+            if (takes_ticket && s_last) {
+                EMD_TRACE(b == 0, it, 1);   // every CTA of the group has bid
+                __threadfence();
+                if (!spread) {
+                    emd_getmax(uidx, bd, binc, minc, midx, U, a.getmax_lowest != 0, tid, EMD_THREADS);
+                    __syncthreads();
+                    emd_assign(uidx, bd, binc, minc, midx, asg, asg_inv, pr, U, last, tid, EMD_THREADS);
+                    __syncthreads();
+                }
+                EMD_TRACE(b == 0, it, 2);
                 const int U2 = compact_unassigned(asg, uidx, midx, n, sscan);
                 __threadfence();
                 __syncthreads();
@@ -872,6 +956,7 @@ __global__ void __launch_bounds__(EMD_THREADS, MINB) emd_auction_kernel(const Em
                     __threadfence();
                     st_release(flag, it + 2);
                 }
+                EMD_TRACE(b == 0, it, 3);   // released
             }
         }
         // ---- CalcDist (:217-226), split over the group ----
@@ -909,7 +994,13 @@ __global__ void emd_grad_kernel(const float *__restrict__ xyz1, const float *__r
 
 using namespace genpc;
 
-extern "C" size_t genpc_emd_workspace_bytes(int B) { return B < 0 ? 0 : (size_t)B * 3 * sizeof(int); }
+#ifdef GENPC_EMD_TRACE
+extern "C" int genpc_emd_trace_read(unsigned long long *host, int count) {
+    return (int)cudaMemcpyFromSymbol(host, g_emd_trace, sizeof(unsigned long long) * count);
+}
+#endif
+
+extern "C" size_t genpc_emd_workspace_bytes(int B) { return B < 0 ? 0 : (size_t)B * 4 * sizeof(int); }
 
 static size_t emd_ctl_bytes(int B) { return (genpc_emd_workspace_bytes(B) + 255) & ~(size_t)255; }
 
@@ -948,7 +1039,9 @@ extern "C" int genpc_emd_forward(const float *xyz1, const float *xyz2, float *di
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const char *pmb = tunable("GENPC_EMD_PRUNE_MINB");  // experiments only
-    const bool mb4 = pmb != nullptr && atoi(pmb) == 4;
+    // four CTAs per SM (64 registers, some spills) win once the bidders saturate the GPU; three (80 registers) when the
+    // iteration's serial tail dominates (profiles/r02k_emd_prune.txt)
+    const bool mb4 = pmb != nullptr ? atoi(pmb) == 4 : (long long)B * n >= 131072;
     void *kernel = (void *)emd_auction_kernel<0, 5>;
     if (prune) {
         const int nblk = n / EMD_BLOCK;
@@ -965,6 +1058,7 @@ extern "C" int genpc_emd_forward(const float *xyz1, const float *xyz2, float *di
     a.assignment_inv = assignment_inv, a.bid = bid, a.bid_increments = bid_increments;
     a.max_increments = max_increments, a.unass_idx = unass_idx, a.unass_cnt = unass_cnt, a.max_idx = max_idx;
     a.flags = (int *)workspace, a.tickets = (int *)workspace + B, a.pmin = (float *)workspace + 2 * (size_t)B;
+    a.bars = (int *)workspace + 3 * (size_t)B;
     a.B = B, a.n = n, a.eps = eps, a.iters = iters;
     int grid;
     if (B >= resident) {
@@ -980,6 +1074,9 @@ extern "C" int genpc_emd_forward(const float *xyz1, const float *xyz2, float *di
     }
     // measured on B200 (profiles/r01j_emd_direct.txt)
     a.direct_p = 8;
+    a.tail_spread_u = 2048;
+    const char *tsu = tunable("GENPC_EMD_TAIL_SPREAD");  // experiments only
+    if (tsu != nullptr) a.tail_spread_u = atoi(tsu);
     a.two_level_div = 8;
     const char *gm = tunable("GENPC_EMD_GETMAX");  // "lowest": the other legitimate outcome of the reference's race
     a.getmax_lowest = (gm != nullptr && strcmp(gm, "lowest") == 0) ? 1 : 0;
