@@ -1039,9 +1039,9 @@ extern "C" int genpc_emd_forward(const float *xyz1, const float *xyz2, float *di
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const char *pmb = tunable("GENPC_EMD_PRUNE_MINB");  // experiments only
-    // four CTAs per SM (64 registers, some spills) win once the bidders saturate the GPU; three (80 registers) when the
-    // iteration's serial tail dominates (profiles/r02k_emd_prune.txt)
-    const bool mb4 = pmb != nullptr ? atoi(pmb) == 4 : (long long)B * n >= 131072;
+    // three CTAs per SM (80 registers) beat four (64 registers, spills) on every shape of a same-box A/B
+    // (profiles/r02k_emd_prune.txt)
+    const bool mb4 = pmb != nullptr && atoi(pmb) == 4;
     void *kernel = (void *)emd_auction_kernel<0, 5>;
     if (prune) {
         const int nblk = n / EMD_BLOCK;

@@ -3,6 +3,9 @@ args: BxN shapes; EMD_ITERS=1,2,50 picks the iteration counts; GENPC_EMD_PRUNE=0
 import json, os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from genpc_b200 import _lib
+if os.environ.get("GENPC_LIB"):   # A/B of two builds on the same box
+    _lib.LIB_PATH = os.path.abspath(os.environ["GENPC_LIB"])
 from genpc_b200 import emd as ours
 SHAPES = [(1, 8192), (32, 8192)] if len(sys.argv) < 2 else [tuple(int(v) for v in a.split("x")) for a in sys.argv[1:]]
 ITERS = (1, 2, 3, 4, 6, 8, 12, 16, 24, 32, 50) if not os.environ.get("EMD_ITERS") else tuple(int(v) for v in os.environ["EMD_ITERS"].split(","))
