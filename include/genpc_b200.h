@@ -251,7 +251,7 @@ int genpc_unproject(const float *cams, const float *bounds, int rescale, const u
  * workspace: genpc_emd_workspace_bytes_n(B, n) -- control words plus a spatially sorted copy of the targets (16 B per
  * target) and the boxes of its 64-target blocks, which let the Bid scan skip every block that cannot reach a bidder's
  * second-best value (bit-identical to the exhaustive scan; 64 <= n <= 32768).  A workspace of only
- * genpc_emd_workspace_bytes(B) bytes (the r01 size) is still accepted and selects the exhaustive scan. */
+ * genpc_emd_workspace_bytes(B) bytes (control words only) is accepted and selects the exhaustive scan. */
 size_t genpc_emd_workspace_bytes(int B);
 size_t genpc_emd_workspace_bytes_n(int B, int n);
 int genpc_emd_forward(const float *xyz1, const float *xyz2, float *dist, int *assignment, float *price,
