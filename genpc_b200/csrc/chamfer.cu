@@ -20,6 +20,7 @@
 #include "nn_core.cuh"
 #include "nn_sym.cuh"
 #include "nn_tc.cuh"
+#include "nn_prune.cuh"
 
 #ifndef GENPC_DEFAULT_SYM
 #define GENPC_DEFAULT_SYM true
@@ -219,13 +220,45 @@ static bool tc_eligible(int B, int nr, int nc) {
     return nr >= TC_RBLK && nc >= 1;
 }
 
+// Spatially pruned exact scan (nn_prune.cuh), r02 experiment: GENPC_CHAMFER_PRUNE=1 selects it for device-resident clouds of
+// 64 .. 32768 points each.  MEASURED (profiles/r02m_chamfer_prune.txt): bit-identical, visits 16 % of the (query group, target
+// block) pairs on C2, and takes 0.70 ms against 0.27 ms of the exhaustive symmetric scan -- one query per lane has none of the
+// register reuse that lets nn_sym evaluate a pair in a tenth of an issue slot, and its dependent uniform loads leave the SM at
+// 1.1 instructions per cycle.  OFF by default; kept with its tests as the record of that measurement.
+static bool prune_shape_ok(int nr, int nc) { return nr >= PR_BLOCK && nc >= PR_BLOCK && nr <= PR_MAX_N && nc <= PR_MAX_N; }
+static bool prune_eligible(int nr, int nc) {
+    const char *k = tunable("GENPC_CHAMFER_PRUNE");
+    return k != nullptr && atoi(k) == 1 && prune_shape_ok(nr, nc);
+}
+static size_t prune_extra_bytes(int B, int N, int M) {
+    if (!prune_eligible(N, M)) return 0;   // the knob is read when the workspace is sized: no growth for anybody else
+    return 256 + (size_t)B * ((size_t)pr_npad(N) + pr_npad(M)) * sizeof(float4) +
+           (size_t)B * 2 * ((size_t)pr_nblk(N) + pr_nblk(M)) * sizeof(float4);
+}
+static unsigned *g_prune_stats = nullptr;   // diagnostics (genpc_chamfer_prune_stats), nullptr in production
+
+template <int BOXR>
+static void launch_prune_t(const PruneParams &q, cudaStream_t stream) {
+    const int groups = (q.nq + PR_GROUP - 1) / PR_GROUP;
+    const int ctas = (groups + PR_THREADS / 32 - 1) / (PR_THREADS / 32);
+    nn_prune_kernel<BOXR><<<(unsigned)(q.B * ctas), PR_THREADS, 0, stream>>>(q);
+}
+static void launch_prune(const PruneParams &q, cudaStream_t stream) {
+    const int nblk = pr_nblk(q.nt);
+    if (nblk <= 32) launch_prune_t<1>(q, stream);
+    else if (nblk <= 64) launch_prune_t<2>(q, stream);
+    else if (nblk <= 128) launch_prune_t<4>(q, stream);
+    else if (nblk <= 256) launch_prune_t<8>(q, stream);
+    else launch_prune_t<16>(q, stream);
+}
+
 // Symmetric path: rows = the larger cloud (registers), cols = the smaller one (shared-memory sweep).
 // gate != nullptr: host-fed launch (nn_sym_gated_kernel), see genpc_chamfer_forward_host.
 static int chamfer_forward_sym(const float *xyz1, const float *xyz2, float *dist1, float *dist2, int *idx1, int *idx2,
                                int B, int N, int M, unsigned long long *packed, int *counter, cudaStream_t stream,
                                const unsigned *gate = nullptr, unsigned gate_gen = 0, int gate_pairs = 1,
                                const genpc_chamfer_fuse_t *fuse = nullptr, double *fuse_partial = nullptr,
-                               unsigned *fuse_ticket = nullptr) {
+                               unsigned *fuse_ticket = nullptr, void *prune_extra = nullptr) {
     const bool swap = M > N;
     SymParams p = {};
     p.rows = swap ? xyz2 : xyz1, p.cols = swap ? xyz1 : xyz2;
@@ -239,7 +272,29 @@ static int chamfer_forward_sym(const float *xyz1, const float *xyz2, float *dist
     // ---- tensor-core filter (nn_tc.cuh): both launches are queued, a device-side flag written by the precheck decides which
     // one does the work (coordinates at unit scale -> nn_tc_kernel, anything else -> the FP32 kernel below) ----
     int *ctl = counter;   // [0] persistent work counter, [1] selection flag, [2] precheck accumulator, [3] precheck ticket
-    const bool use_tc = ctl != nullptr && tc_eligible(B, p.nr, p.nc);
+    // ---- spatially pruned scan (nn_prune.cuh): the sort doubles as the range check and sets the same selection flag ----
+    const bool use_prune = ctl != nullptr && gate == nullptr && prune_extra != nullptr && prune_eligible(p.nr, p.nc);
+    if (use_prune) {
+        char *w = reinterpret_cast<char *>((reinterpret_cast<size_t>(prune_extra) + 255) & ~(size_t)255);
+        PruneSortParams sp = {};
+        sp.xyz[0] = p.rows, sp.xyz[1] = p.cols, sp.n[0] = p.nr, sp.n[1] = p.nc, sp.B = B, sp.limit = 1e15f, sp.ctl = ctl;
+        sp.sorted[0] = reinterpret_cast<float4 *>(w);
+        sp.sorted[1] = sp.sorted[0] + (size_t)B * pr_npad(p.nr);
+        sp.boxes[0] = sp.sorted[1] + (size_t)B * pr_npad(p.nc);
+        sp.boxes[1] = sp.boxes[0] + (size_t)B * 2 * pr_nblk(p.nr);
+        nn_bin_sort_kernel<<<2 * B, PR_SORT_THREADS, 0, stream>>>(sp);
+        GENPC_CHECK_LAUNCH();
+        p.select = ctl + 1;
+        PruneParams q = {};
+        q.B = B, q.select = ctl + 1, q.stats = g_prune_stats;
+        q.q = sp.sorted[0], q.t = sp.sorted[1], q.tbox = sp.boxes[1], q.out = p.prow, q.nq = p.nr, q.nt = p.nc;
+        launch_prune(q, stream);
+        GENPC_CHECK_LAUNCH();
+        q.q = sp.sorted[1], q.t = sp.sorted[0], q.tbox = sp.boxes[0], q.out = p.pcol, q.nq = p.nc, q.nt = p.nr;
+        launch_prune(q, stream);
+        GENPC_CHECK_LAUNCH();
+    }
+    const bool use_tc = !use_prune && ctl != nullptr && tc_eligible(B, p.nr, p.nc);
     if (use_tc) {
         static bool attr_done = false;   // opt in to 166 KB of dynamic shared memory once per process
         if (!attr_done) {
@@ -327,7 +382,7 @@ static int chamfer_forward_sym(const float *xyz1, const float *xyz2, float *dist
     memset(&f, 0, sizeof(f));
     // column words are exact iff the filter did the work: ctl[1] == 0 after the precheck; a gated launch has no precheck and
     // points at ctl[2], which is zero between launches
-    f.select = use_tc ? (gate == nullptr ? ctl + 1 : ctl + 2) : nullptr;
+    f.select = use_tc ? (gate == nullptr ? ctl + 1 : ctl + 2) : (use_prune ? ctl + 1 : nullptr);
     if (fuse == nullptr) {
         nn_sym_epilogue_kernel<false><<<fix_blocks + unpack_blocks, 256, 0, stream>>>(
             p.rows, p.cols, p.prow, p.pcol, B, p.nr, p.nc, 32 * QT, fix_blocks, dist_r, idx_r, dist_c, idx_c, f);
@@ -358,9 +413,13 @@ static size_t sym_epilogue_ctas(int B, int N, int M) {
 
 using namespace genpc;
 
+// packed words + work-item counter / selection words
+static size_t chamfer_base_bytes(int B, int N, int M) { return ((size_t)B * N + (size_t)B * M) * sizeof(unsigned long long) + 16; }
+
 extern "C" size_t genpc_chamfer_workspace_bytes(int B, int N, int M) {
     if (B < 0 || N < 0 || M < 0) return 0;
-    return ((size_t)B * N + (size_t)B * M) * sizeof(unsigned long long) + 16;  // packed words + work-item counter
+    // (+ the sorted copies and block boxes of the pruned scan while GENPC_CHAMFER_PRUNE=1)
+    return chamfer_base_bytes(B, N, M) + prune_extra_bytes(B, N, M);
 }
 
 static bool takes_sym_path(int N, int M) {
@@ -425,7 +484,7 @@ extern "C" int genpc_chamfer_forward_fused(const float *xyz1, const float *xyz2,
         GENPC_CHECK_LAUNCH();
         return fuse ? fuse_tail_unfused(fuse, dist1, dist2, B, N, M, stream) : GENPC_OK;
     }
-    if (workspace == nullptr || workspace_bytes < genpc_chamfer_workspace_bytes(B, N, M)) return GENPC_ERR_WORKSPACE;
+    if (workspace == nullptr || workspace_bytes < chamfer_base_bytes(B, N, M)) return GENPC_ERR_WORKSPACE;
     unsigned long long *packed = (unsigned long long *)workspace;
     cudaError_t e;
     const bool sym = takes_sym_path(N, M);
@@ -443,8 +502,12 @@ extern "C" int genpc_chamfer_forward_fused(const float *xyz1, const float *xyz2,
         }
         double *partial = fuse ? (double *)fuse->loss_workspace : nullptr;
         unsigned *ticket = partial ? (unsigned *)(partial + sym_epilogue_ctas(B, N, M)) : nullptr;
+        // (a workspace sized while the knob was off stays on the exhaustive kernels)
+        const size_t base_bytes = chamfer_base_bytes(B, N, M);
+        void *extra = (prune_extra_bytes(B, N, M) != 0 && workspace_bytes >= base_bytes + prune_extra_bytes(B, N, M))
+                          ? (void *)((char *)(packed + n1 + n2) + 16) : nullptr;
         return chamfer_forward_sym(xyz1, xyz2, dist1, dist2, idx1, idx2, B, N, M, packed, counter, stream, nullptr, 0, 1, fuse,
-                                   partial, ticket);
+                                   partial, ticket, extra);
     }
 
     const int QT = nn_pick_qt(N < M ? N : M);
@@ -495,6 +558,12 @@ extern "C" int genpc_chamfer_backward(const float *xyz1, const float *xyz2, cons
 
 // Diagnostics of the tensor-core filter: while `stats4` (device, 4 x u32, zeroed by the caller) is set, every filter launch
 // adds {runner-up chunk re-evaluations, whole-tile exact scans, degenerate items, items} to it.  nullptr switches it off.
+// diagnostics of the pruned scan: stats4 = device pointer to 4 counters (blocks scanned, groups that took the tie pass, groups, -)
+extern "C" int genpc_chamfer_prune_stats(unsigned *stats4) {
+    g_prune_stats = stats4;
+    return GENPC_OK;
+}
+
 extern "C" int genpc_chamfer_tc_stats(unsigned *stats4) {
     g_tc_stats = stats4;
     return GENPC_OK;
@@ -588,7 +657,7 @@ extern "C" int genpc_chamfer_forward_host_fused(genpc_host_feed_t *f, const floa
         if (n2) FEED_CHECK(cudaMemcpyAsync(xyz2, h_xyz2, n2 * 12, cudaMemcpyHostToDevice, stream));
         return genpc_chamfer_forward_fused(xyz1, xyz2, dist1, dist2, idx1, idx2, B, N, M, workspace, workspace_bytes, fuse, stream_);
     }
-    if (workspace == nullptr || workspace_bytes < genpc_chamfer_workspace_bytes(B, N, M)) return GENPC_ERR_WORKSPACE;
+    if (workspace == nullptr || workspace_bytes < chamfer_base_bytes(B, N, M)) return GENPC_ERR_WORKSPACE;
     std::lock_guard<std::mutex> guard(f->lock);   // host threads sharing the handle take turns
     if (chunks > GATE_MAX_CHUNKS) chunks = GATE_MAX_CHUNKS;
     if (chunks > B) chunks = B;

@@ -1,0 +1,312 @@
+// nn_prune.cuh -- exact nearest neighbours with spatial pruning (r02 experiment, GENPC_CHAMFER_PRUNE=1).
+//
+// The symmetric scan (nn_sym.cuh) evaluates every (row, column) distance of a cloud pair: at its issue limit that is
+// 7.9e12 pairs/s and nothing in its instruction stream is left to remove.  What is left is not to evaluate most pairs:
+//   1. nn_bin_sort_kernel orders every cloud along a Morton curve (counting sort over 8^m grid cells in shared memory,
+//      one CTA per cloud) into (x, y, z, original index) records and stores the bounding box of every PR_BLOCK
+//      consecutive ones;
+//   2. nn_prune_kernel: one warp owns PR_GROUP consecutive sorted queries (one per lane -- neighbours in space).  It
+//      computes the squared distance between the group's box and every target block's box, visits the blocks nearest
+//      first (REDUX picks them) and stops at the first block farther than the group's worst running minimum: no target
+//      in it, or in any later block, can improve (or tie) any lane.  Inside a block all lanes walk the same 64 targets
+//      (uniform loads) with the packed FP32 distance of the exhaustive kernels: the same bits.
+// Exactness: the minimum of a set does not depend on the visiting order; the reported index is the LOWEST original index
+// among the targets at the minimum, as in the exhaustive kernels (the winner's 8-target chunk is re-evaluated; a lane
+// that saw the same minimum in two chunks takes a second pass over the surviving blocks).  The box distance is scaled
+// down by 1e-5, far more than the rounding of the reference's arithmetic, and compared with <= so that ties are kept.
+// The sort kernel doubles as the range check (NaN / Inf / |x| > 1e15 -> the exhaustive kernel runs instead, selected on
+// the device through the same flag as the tensor-core filter).
+#pragma once
+#include "common.cuh"
+
+namespace genpc {
+
+constexpr int PR_BLOCK = 64;
+constexpr int PR_GROUP = 32;
+constexpr int PR_MAX_N = 32768;       // 512 blocks: the block id fits the 9 low bits of the selection key
+constexpr int PR_SORT_THREADS = 1024;
+constexpr int PR_MAX_CELLS = 4096;
+constexpr int PR_THREADS = 256;
+
+__host__ __device__ inline int pr_nblk(int n) { return (n + PR_BLOCK - 1) / PR_BLOCK; }
+__host__ __device__ inline int pr_npad(int n) { return pr_nblk(n) * PR_BLOCK; }
+
+struct PruneSortParams {
+    const float *xyz[2];   // [B][n][3]
+    float4 *sorted[2];     // [B][npad]   (x, y, z, original index); NaN records pad the last block
+    float4 *boxes[2];      // [B][2][nblk] lower corners, then upper corners
+    int n[2];
+    int B;
+    float limit;
+    int *ctl;              // [1] selection flag (0: pruned kernels run), [2] accumulator, [3] ticket -- as nn_tc_precheck_kernel
+};
+
+// grid = 2 * B CTAs: blockIdx.x = side * B + b
+__global__ void __launch_bounds__(PR_SORT_THREADS) nn_bin_sort_kernel(const PruneSortParams p) {
+    __shared__ int hist[PR_MAX_CELLS];
+    __shared__ float sred[6][PR_SORT_THREADS / 32];
+    __shared__ int swarp[PR_SORT_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int side = (int)blockIdx.x / p.B, b = (int)blockIdx.x % p.B;
+    const int n = p.n[side], nblk = pr_nblk(n), npad = nblk * PR_BLOCK;
+    const float *src = p.xyz[side] + (size_t)b * n * 3;
+    float4 *dst = p.sorted[side] + (size_t)b * npad;
+    float4 *bx = p.boxes[side] + (size_t)b * 2 * nblk;
+    const float inf = __int_as_float(0x7f800000);
+    // ---- bounding box + range check ----
+    float lo[3] = {inf, inf, inf}, hi[3] = {-inf, -inf, -inf};
+    bool bad = false;
+    for (int k = tid; k < n; k += PR_SORT_THREADS) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float v = __ldg(src + k * 3 + c);
+            bad |= !(fabsf(v) <= p.limit);
+            lo[c] = fminf(lo[c], v), hi[c] = fmaxf(hi[c], v);
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[c] = fminf(lo[c], __shfl_xor_sync(0xffffffffu, lo[c], o));
+            hi[c] = fmaxf(hi[c], __shfl_xor_sync(0xffffffffu, hi[c], o));
+        }
+        if (lane == 0) sred[c][warp] = lo[c], sred[3 + c][warp] = hi[c];
+    }
+    int mbits = n >= 8192 ? 4 : (n >= 1024 ? 3 : (n >= 128 ? 2 : 1));
+    const int ncell = 1 << (3 * mbits);
+    for (int k = tid; k < ncell; k += PR_SORT_THREADS) hist[k] = 0;
+    const int anybad = __syncthreads_or(bad ? 1 : 0);
+    float scale[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        float l = inf, h = -inf;
+        for (int w = 0; w < PR_SORT_THREADS / 32; ++w) l = fminf(l, sred[c][w]), h = fmaxf(h, sred[3 + c][w]);
+        lo[c] = l;
+        const float ext = h - l;
+        scale[c] = (ext > 0.f && ext < inf) ? (float)(1 << mbits) / ext : 0.f;
+    }
+    const int cmax = (1 << mbits) - 1;
+    auto cell_of = [&](int k, float &x, float &y, float &z) {
+        x = __ldg(src + k * 3), y = __ldg(src + k * 3 + 1), z = __ldg(src + k * 3 + 2);
+        const float v[3] = {x, y, z};
+        unsigned code = 0;
+        int cc[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float f = (v[c] - lo[c]) * scale[c];
+            cc[c] = f >= 0.f ? min((int)fminf(f, 2e9f), cmax) : 0;
+        }
+        for (int bit = 0; bit < mbits; ++bit)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) code |= (unsigned)((cc[c] >> bit) & 1) << (3 * bit + c);
+        return (int)code;
+    };
+    // ---- histogram ----
+    for (int k = tid; k < n; k += PR_SORT_THREADS) {
+        float x, y, z;
+        atomicAdd(&hist[cell_of(k, x, y, z)], 1);
+    }
+    __syncthreads();
+    // ---- exclusive scan of the histogram (4 entries per thread) ----
+    {
+        const int per = PR_MAX_CELLS / PR_SORT_THREADS;
+        int v[per], s = 0;
+#pragma unroll
+        for (int i = 0; i < per; ++i) {
+            const int e = tid * per + i;
+            v[i] = e < ncell ? hist[e] : 0;
+            s += v[i];
+        }
+        int incl = s;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) swarp[warp] = incl;
+        __syncthreads();
+        int base = 0;
+        for (int w = 0; w < warp; ++w) base += swarp[w];
+        int run = base + incl - s;
+#pragma unroll
+        for (int i = 0; i < per; ++i) {
+            const int e = tid * per + i;
+            if (e < ncell) hist[e] = run;
+            run += v[i];
+        }
+    }
+    __syncthreads();
+    // ---- scatter (the order inside a cell is whatever the atomics give: it only shapes the blocks, never a result) ----
+    for (int k = tid; k < n; k += PR_SORT_THREADS) {
+        float x, y, z;
+        const int cell = cell_of(k, x, y, z);
+        const int pos = atomicAdd(&hist[cell], 1);
+        dst[pos] = make_float4(x, y, z, __int_as_float(k));
+    }
+    const float qnan = __int_as_float(0x7fc00000);
+    for (int k = n + tid; k < npad; k += PR_SORT_THREADS) dst[k] = make_float4(qnan, qnan, qnan, __int_as_float(0));
+    __syncthreads();   // the CTA's own global writes are visible to it after the barrier
+    // ---- block boxes ----
+    for (int blk = warp; blk < nblk; blk += PR_SORT_THREADS / 32) {
+        float l[3] = {inf, inf, inf}, h[3] = {-inf, -inf, -inf};
+#pragma unroll
+        for (int e = 0; e < PR_BLOCK / 32; ++e) {
+            const float4 t = dst[blk * PR_BLOCK + e * 32 + lane];
+            l[0] = fminf(l[0], t.x), h[0] = fmaxf(h[0], t.x);   // NaN padding is ignored
+            l[1] = fminf(l[1], t.y), h[1] = fmaxf(h[1], t.y);
+            l[2] = fminf(l[2], t.z), h[2] = fmaxf(h[2], t.z);
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                l[c] = fminf(l[c], __shfl_xor_sync(0xffffffffu, l[c], o));
+                h[c] = fmaxf(h[c], __shfl_xor_sync(0xffffffffu, h[c], o));
+            }
+        if (lane == 0) bx[blk] = make_float4(l[0], l[1], l[2], 0.f), bx[nblk + blk] = make_float4(h[0], h[1], h[2], 0.f);
+    }
+    // ---- selection flag: last CTA publishes "any cloud out of range" ----
+    if (tid == 0) {
+        if (anybad) atomicOr(p.ctl + 2, 1);
+        __threadfence();
+        if (atomicAdd(p.ctl + 3, 1) == (int)gridDim.x - 1) {
+            __threadfence();
+            p.ctl[1] = atomicExch(p.ctl + 2, 0);
+            p.ctl[3] = 0;
+        }
+    }
+}
+
+struct PruneParams {
+    const float4 *q, *t;      // sorted queries [B][npad_q], sorted targets [B][npad_t]
+    const float4 *tbox;       // [B][2][nblk_t]
+    unsigned long long *out;  // [B][nq] packed (dist, original target index), addressed by the query's original index
+    int nq, nt, B;
+    const int *select;        // run only when *select == 0
+    unsigned *stats;          // optional [4]: blocks scanned, tie passes, groups, -
+};
+
+__device__ __forceinline__ int pr_f2ord(float f) {
+    const int i = __float_as_int(f);
+    return i ^ ((i >> 31) & 0x7fffffff);
+}
+__device__ __forceinline__ float pr_ord2f(int i) { return __int_as_float(i ^ ((i >> 31) & 0x7fffffff)); }
+
+// grid = B * ceil(groups / 8) CTAs of 8 warps; BOXR * 32 >= nblk_t
+template <int BOXR>
+__global__ void __launch_bounds__(PR_THREADS) nn_prune_kernel(const PruneParams p) {
+    if (p.select != nullptr && *p.select != 0) return;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int groups = (p.nq + PR_GROUP - 1) / PR_GROUP;
+    const int ctas_per_cloud = (groups + PR_THREADS / 32 - 1) / (PR_THREADS / 32);
+    const int b = (int)blockIdx.x / ctas_per_cloud;
+    const int g = ((int)blockIdx.x % ctas_per_cloud) * (PR_THREADS / 32) + wid;
+    if (g >= groups) return;
+    const int nblk = pr_nblk(p.nt);
+    const float4 *T = p.t + (size_t)b * pr_npad(p.nt);
+    const float4 *BL = p.tbox + (size_t)b * 2 * nblk, *BH = BL + nblk;
+    const float inf = __int_as_float(0x7f800000);
+    const int qi = g * PR_GROUP + lane;
+    const bool valid = qi < p.nq;
+    const float4 q = p.q[(size_t)b * pr_npad(p.nq) + qi];   // the padding records are NaN: they never win, nothing is stored
+    // ---- the group's box ----
+    float glo[3], ghi[3];
+    {
+        const float v[3] = {q.x, q.y, q.z};
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            // NaN (padding) must not take part: +inf / -inf are neutral
+            const float a = valid ? v[c] : inf, z = valid ? v[c] : -inf;
+            glo[c] = pr_ord2f(__reduce_min_sync(0xffffffffu, pr_f2ord(a)));
+            ghi[c] = pr_ord2f(__reduce_max_sync(0xffffffffu, pr_f2ord(z)));
+        }
+    }
+    // ---- squared box-to-box distances, scaled down (see the header) ----
+    float bd[BOXR];
+#pragma unroll
+    for (int r = 0; r < BOXR; ++r) {
+        const int blk = r * 32 + lane;
+        bd[r] = inf;
+        if (blk < nblk) {
+            const float4 lo = __ldg(BL + blk), hi = __ldg(BH + blk);
+            const float dx = fmaxf(fmaxf(lo.x - ghi[0], glo[0] - hi.x), 0.f);
+            const float dy = fmaxf(fmaxf(lo.y - ghi[1], glo[1] - hi.y), 0.f);
+            const float dz = fmaxf(fmaxf(lo.z - ghi[2], glo[2] - hi.z), 0.f);
+            bd[r] = __fmul_rn(__fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy))), 0.99999f);
+        }
+    }
+    const float2 nx = make_float2(-q.x, -q.x), ny = make_float2(-q.y, -q.y), nz = make_float2(-q.z, -q.z);
+    float best = inf;
+    int bchunk = 0;
+    bool tie = false;
+    float thr = inf;   // the largest running minimum of the group's lanes
+    unsigned scanned = 0;
+    for (;;) {
+        // nearest remaining block: (distance bits without the low 9, block id); the truncation errs on the near side
+        unsigned key = 0xffffffffu;
+#pragma unroll
+        for (int r = 0; r < BOXR; ++r) key = min(key, (__float_as_uint(bd[r]) & 0xfffffe00u) | (unsigned)(r * 32 + lane));
+        key = __reduce_min_sync(0xffffffffu, key);
+        if (key >= 0x7f800000u || !(__uint_as_float(key & 0xfffffe00u) <= thr)) break;
+        const int blk = (int)(key & 0x1ffu);
+#pragma unroll
+        for (int r = 0; r < BOXR; ++r)
+            if (r * 32 + lane == blk) bd[r] = inf;
+        const float4 *tb = T + blk * PR_BLOCK;
+#pragma unroll 2
+        for (int c = 0; c < PR_BLOCK / 8; ++c) {
+            float cm = inf;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float4 t0 = __ldg(tb + c * 8 + 2 * i), t1 = __ldg(tb + c * 8 + 2 * i + 1);
+                const float2 s2 = sqdist_ref_x2(nx, ny, nz, make_float2(t0.x, t1.x), make_float2(t0.y, t1.y), make_float2(t0.z, t1.z));
+                cm = fmin3(cm, s2.x, s2.y);
+            }
+            if (cm < best) {
+                best = cm, bchunk = blk * (PR_BLOCK / 8) + c, tie = false;
+            } else if (cm == best && cm < inf) {
+                tie = true;
+            }
+        }
+        ++scanned;
+        thr = pr_ord2f(__reduce_max_sync(0xffffffffu, valid ? pr_f2ord(best) : (int)0x80000000));
+    }
+    // ---- the lowest original index at the minimum: inside the winning chunk ... ----
+    int bidx = 0x7fffffff;
+    {
+        const float4 *tc = T + bchunk * 8;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float4 t = __ldg(tc + i);
+            const float d = sqdist_ref(q.x, q.y, q.z, t.x, t.y, t.z);
+            if (d == best) bidx = min(bidx, __float_as_int(t.w));
+        }
+    }
+    // ---- ... and, for a lane that met its minimum in two chunks, over every block that could hold it ----
+    const unsigned ties = __ballot_sync(0xffffffffu, tie && valid);
+    if (ties != 0u) {
+        for (int blk = 0; blk < nblk; ++blk) {
+            const float4 lo = __ldg(BL + blk), hi = __ldg(BH + blk);
+            const float dx = fmaxf(fmaxf(lo.x - ghi[0], glo[0] - hi.x), 0.f);
+            const float dy = fmaxf(fmaxf(lo.y - ghi[1], glo[1] - hi.y), 0.f);
+            const float dz = fmaxf(fmaxf(lo.z - ghi[2], glo[2] - hi.z), 0.f);
+            const float s = __fmul_rn(__fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy))), 0.99999f);
+            if (!(s <= thr)) continue;   // warp-uniform
+            const float4 *tb = T + blk * PR_BLOCK;
+            for (int i = 0; i < PR_BLOCK; ++i) {
+                const float4 t = __ldg(tb + i);
+                const float d = sqdist_ref(q.x, q.y, q.z, t.x, t.y, t.z);
+                if (tie && d == best) bidx = min(bidx, __float_as_int(t.w));
+            }
+        }
+    }
+    if (valid) p.out[(size_t)b * p.nq + __float_as_int(q.w)] = pack_dist_idx(best, bidx);
+    if (p.stats != nullptr && lane == 0) {
+        atomicAdd(p.stats + 0, scanned);
+        if (ties != 0u) atomicAdd(p.stats + 1, 1u);
+        atomicAdd(p.stats + 2, 1u);
+    }
+}
+
+}  // namespace genpc

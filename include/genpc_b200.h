@@ -58,6 +58,9 @@ int genpc_chamfer_forward(const float *xyz1, const float *xyz2, float *dist1, fl
  * items} to a caller-zeroed device array (NULL: off); genpc_tc_probe dumps e(x,y) of one 128 x 256 tile as computed by the
  * tensor pipe, for the error-margin test. */
 int genpc_chamfer_tc_stats(unsigned *stats4);
+/* Diagnostics of the spatially pruned scan (GENPC_CHAMFER_PRUNE=1, csrc/nn_prune.cuh): launches add {target blocks scanned,
+ * query groups that needed the tie pass, query groups, -} to the four device counters; NULL switches it off. */
+int genpc_chamfer_prune_stats(unsigned *stats4);
 int genpc_tc_probe(const float *rows128, const float *cols256, float *e_out, genpc_stream_t stream);
 
 /* Host-fed forward: the same result as genpc_chamfer_forward, but the clouds start in HOST memory
