@@ -42,7 +42,7 @@ struct PruneSortParams {
 };
 
 // grid = 2 * B CTAs: blockIdx.x = side * B + b
-__global__ void __launch_bounds__(PR_SORT_THREADS) nn_bin_sort_kernel(const PruneSortParams p) {
+static __global__ void __launch_bounds__(PR_SORT_THREADS) nn_bin_sort_kernel(const PruneSortParams p) {
     __shared__ int hist[PR_MAX_CELLS];
     __shared__ float sred[6][PR_SORT_THREADS / 32];
     __shared__ int swarp[PR_SORT_THREADS / 32];

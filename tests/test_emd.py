@@ -89,8 +89,8 @@ def test_emd_pruned_bid_equals_exhaustive_bid_on_adversarial_inputs(cuda):
 
     for name, x1, x2, eps, iters in _adversarial_emd_inputs():
         x1, x2 = np.ascontiguousarray(x1, np.float32), np.ascontiguousarray(x2, np.float32)
-        with _lib.tunable(GENPC_EMD_PRUNE="1"):
-            d1, a1 = run_ours(x1, x2, eps, iters, cuda)
+        with _lib.tunable(GENPC_EMD_PRUNE="1", GENPC_EMD_SORT="bitonic" if name in ("lattice_ties", "planar", "largest_pruned_n") else None):
+            d1, a1 = run_ours(x1, x2, eps, iters, cuda)   # (both target sorts: counting sort by default, bitonic on request)
         with _lib.tunable(GENPC_EMD_PRUNE="0"):
             d0, a0 = run_ours(x1, x2, eps, iters, cuda)
         assert np.array_equal(a1, a0), f"{name}: {(a1 != a0).sum()} assignments differ"
