@@ -21,6 +21,7 @@
 #include "nn_sym.cuh"
 #include "nn_tc.cuh"
 #include "nn_prune.cuh"
+#include "nn_grid.cuh"
 
 #ifndef GENPC_DEFAULT_SYM
 #define GENPC_DEFAULT_SYM true
@@ -230,7 +231,51 @@ static bool prune_eligible(int nr, int nc) {
     const char *k = tunable("GENPC_CHAMFER_PRUNE");
     return k != nullptr && atoi(k) == 1 && prune_shape_ok(nr, nc);
 }
+// Large clouds (nn_grid.cuh): multi-CTA sort + two-level pruned scan.  GENPC_CHAMFER_PRUNE=2 forces it for any shape it can
+// take, =0 switches it off; by default it takes the shapes whose exhaustive scan is at least 2^30 distance evaluations with
+// more than 32768 points on one side (BASELINE C1: 71 372 x 16 384, C5: 1M x 1M).
+static bool grid_shape_ok(int nr, int nc) { return nr >= PR_BLOCK && nc >= PR_BLOCK && nr <= GR_MAX_N && nc <= GR_MAX_N; }
+static bool grid_eligible(int nr, int nc) {
+    if (!grid_shape_ok(nr, nc)) return false;
+    const char *k = tunable("GENPC_CHAMFER_PRUNE");
+    if (k != nullptr) return atoi(k) == 2;
+    return (long long)nr * nc >= (1LL << 30) && (nr > PR_MAX_N || nc > PR_MAX_N);
+}
+static size_t grid_sort_temp_bytes(int nmax) {
+    size_t t = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, t, (const unsigned *)nullptr, (unsigned *)nullptr, (const int *)nullptr, (int *)nullptr,
+                                    nmax, 0, 30);
+    return (t + 255) & ~(size_t)255;
+}
+static size_t grid_extra_bytes(int B, int N, int M) {
+    if (!grid_eligible(N, M)) return 0;
+    size_t s = 256;
+    const int n[2] = {N, M};
+    for (int i = 0; i < 2; ++i) {
+        s += (size_t)B * pr_npad(n[i]) * sizeof(float4);                                   // sorted records
+        s += (size_t)B * 2 * ((size_t)pr_nblk(n[i]) + gr_nsb(n[i])) * sizeof(float4);      // block + superblock boxes
+        s += (size_t)B * 8 * sizeof(int);                                                  // bounding box words
+    }
+    const int nmax = N > M ? N : M;
+    s += 4 * (((size_t)nmax * 4 + 255) & ~(size_t)255) + grid_sort_temp_bytes(nmax);       // keys / values in and out, cub's scratch
+    return s;
+}
+template <int SBR>
+static void launch_prune2_t(const Prune2Params &q, cudaStream_t stream) {
+    const int groups = (q.nq + PR_GROUP - 1) / PR_GROUP;
+    nn_prune2_kernel<SBR><<<dim3((unsigned)((groups + PR_THREADS / 32 - 1) / (PR_THREADS / 32)), (unsigned)q.B), PR_THREADS, 0, stream>>>(q);
+}
+static void launch_prune2(const Prune2Params &q, cudaStream_t stream) {
+    const int nsb = gr_nsb(q.nt);
+    if (nsb <= 32) launch_prune2_t<1>(q, stream);
+    else if (nsb <= 64) launch_prune2_t<2>(q, stream);
+    else if (nsb <= 128) launch_prune2_t<4>(q, stream);
+    else if (nsb <= 256) launch_prune2_t<8>(q, stream);
+    else launch_prune2_t<16>(q, stream);
+}
+
 static size_t prune_extra_bytes(int B, int N, int M) {
+    if (grid_eligible(N, M)) return grid_extra_bytes(B, N, M);
     if (!prune_eligible(N, M)) return 0;   // the knob is read when the workspace is sized: no growth for anybody else
     return 256 + (size_t)B * ((size_t)pr_npad(N) + pr_npad(M)) * sizeof(float4) +
            (size_t)B * 2 * ((size_t)pr_nblk(N) + pr_nblk(M)) * sizeof(float4);
@@ -273,8 +318,55 @@ static int chamfer_forward_sym(const float *xyz1, const float *xyz2, float *dist
     // one does the work (coordinates at unit scale -> nn_tc_kernel, anything else -> the FP32 kernel below) ----
     int *ctl = counter;   // [0] persistent work counter, [1] selection flag, [2] precheck accumulator, [3] precheck ticket
     // ---- spatially pruned scan (nn_prune.cuh): the sort doubles as the range check and sets the same selection flag ----
-    const bool use_prune = ctl != nullptr && gate == nullptr && prune_extra != nullptr && prune_eligible(p.nr, p.nc);
-    if (use_prune) {
+    const bool use_grid = ctl != nullptr && gate == nullptr && prune_extra != nullptr && B <= 8 && grid_eligible(p.nr, p.nc);   // one sort per cloud: small batches only
+    const bool use_prune = use_grid || (ctl != nullptr && gate == nullptr && prune_extra != nullptr && prune_eligible(p.nr, p.nc));
+    if (use_grid) {
+        char *w = reinterpret_cast<char *>((reinterpret_cast<size_t>(prune_extra) + 255) & ~(size_t)255);
+        GridParams gp = {};
+        gp.B = B, gp.limit = 1e15f, gp.ctl = ctl;
+        gp.xyz[0] = p.rows, gp.xyz[1] = p.cols, gp.n[0] = p.nr, gp.n[1] = p.nc;
+        for (int i = 0; i < 2; ++i) {
+            gp.sorted[i] = reinterpret_cast<float4 *>(w), w += (size_t)B * pr_npad(gp.n[i]) * sizeof(float4);
+            gp.boxes[i] = reinterpret_cast<float4 *>(w), w += (size_t)B * 2 * pr_nblk(gp.n[i]) * sizeof(float4);
+            gp.sboxes[i] = reinterpret_cast<float4 *>(w), w += (size_t)B * 2 * gr_nsb(gp.n[i]) * sizeof(float4);
+        }
+        for (int i = 0; i < 2; ++i) gp.bb[i] = reinterpret_cast<int *>(w), w += (size_t)B * 8 * sizeof(int);
+        w = reinterpret_cast<char *>((reinterpret_cast<size_t>(w) + 255) & ~(size_t)255);
+        const int nmax = p.nr > p.nc ? p.nr : p.nc;
+        const size_t arr = ((size_t)nmax * 4 + 255) & ~(size_t)255;
+        unsigned *keys_in = reinterpret_cast<unsigned *>(w), *keys_out = reinterpret_cast<unsigned *>(w + arr);
+        int *vals_in = reinterpret_cast<int *>(w + 2 * arr), *vals_out = reinterpret_cast<int *>(w + 3 * arr);
+        void *cub_tmp = w + 4 * arr;
+        size_t cub_bytes = grid_sort_temp_bytes(nmax);
+        gp.keys = keys_in, gp.vals = vals_in, gp.order = vals_out;
+        int ctas = (nmax + 4095) / 4096;
+        if (ctas > 4 * GENPC_NUM_SMS) ctas = 4 * GENPC_NUM_SMS;
+        if (ctas < 1) ctas = 1;
+        grid_init_kernel<<<1, 256, 0, stream>>>(gp);
+        grid_bbox_kernel<<<dim3(ctas, B, 2), GR_THREADS, 0, stream>>>(gp);
+        GENPC_CHECK_LAUNCH();
+        for (int side = 0; side < 2; ++side)
+            for (int b = 0; b < B; ++b) {   // (large clouds come in small batches)
+                grid_key_kernel<<<ctas, GR_THREADS, 0, stream>>>(gp, side, b);
+                cudaError_t es = cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, (const unsigned *)keys_in, keys_out,
+                                                                 (const int *)vals_in, vals_out, gp.n[side], 0, 30, stream);
+                if (es != cudaSuccess) return (int)es;
+                grid_gather_kernel<<<ctas, GR_THREADS, 0, stream>>>(gp, side, b, side == 0 && b == 0);
+            }
+        GENPC_CHECK_LAUNCH();
+        const int nblk_max = pr_nblk(nmax), nsb_max = gr_nsb(nmax);
+        grid_boxes_kernel<false><<<dim3((nblk_max + 7) / 8, B, 2), GR_THREADS, 0, stream>>>(gp);
+        grid_boxes_kernel<true><<<dim3((nsb_max + 7) / 8, B, 2), GR_THREADS, 0, stream>>>(gp);
+        GENPC_CHECK_LAUNCH();
+        p.select = ctl + 1;
+        Prune2Params q = {};
+        q.B = B, q.select = ctl + 1, q.stats = g_prune_stats;
+        q.q = gp.sorted[0], q.t = gp.sorted[1], q.tbox = gp.boxes[1], q.tsbox = gp.sboxes[1], q.out = p.prow, q.nq = p.nr, q.nt = p.nc;
+        launch_prune2(q, stream);
+        q.q = gp.sorted[1], q.t = gp.sorted[0], q.tbox = gp.boxes[0], q.tsbox = gp.sboxes[0], q.out = p.pcol, q.nq = p.nc, q.nt = p.nr;
+        launch_prune2(q, stream);
+        GENPC_CHECK_LAUNCH();
+    } else if (use_prune) {
         char *w = reinterpret_cast<char *>((reinterpret_cast<size_t>(prune_extra) + 255) & ~(size_t)255);
         PruneSortParams sp = {};
         sp.xyz[0] = p.rows, sp.xyz[1] = p.cols, sp.n[0] = p.nr, sp.n[1] = p.nc, sp.B = B, sp.limit = 1e15f, sp.ctl = ctl;
@@ -343,7 +435,9 @@ static int chamfer_forward_sym(const float *xyz1, const float *xyz2, float *dist
     // CTAs drift out of phase, so staging / publishing of one overlaps the scan of the other)
     const char *bm = tunable("GENPC_SYM_BALANCED");
     const bool few_items = (long long)B * p.rtiles * ((p.nc + SYM_SPAN_MAX - 1) / SYM_SPAN_MAX) < 4LL * GENPC_NUM_SMS;
-    const bool balanced = (bm == nullptr) ? (GENPC_DEFAULT_BALANCED && few_items) : (atoi(bm) != 0);
+    // (the pruned grid scan queues this launch only as the device-selected fall-back: a fixed-size grid returns at once,
+    // one CTA per work item of a 1M x 1M pair spent 0.8 ms launching CTAs that do nothing)
+    const bool balanced = (bm == nullptr) ? ((GENPC_DEFAULT_BALANCED && few_items) || use_grid) : (atoi(bm) != 0);
     if (!fp32_needed) {
         // nothing: nn_tc_kernel<true> does the whole scan
     } else if (gate != nullptr) {

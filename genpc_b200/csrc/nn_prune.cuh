@@ -31,6 +31,41 @@ constexpr int PR_THREADS = 256;
 __host__ __device__ inline int pr_nblk(int n) { return (n + PR_BLOCK - 1) / PR_BLOCK; }
 __host__ __device__ inline int pr_npad(int n) { return pr_nblk(n) * PR_BLOCK; }
 
+// 3 * BITS-bit Hilbert index of a grid cell (Skilling, "Programming the Hilbert curve", 2004: axes -> transpose -> interleave).
+// Consecutive indices are always neighbouring cells, so ANY run of consecutive sorted points is spatially connected; a
+// Morton (Z-order) run that crosses a high-level cell boundary joins two far-apart regions in one bounding box, and every
+// query group inside that box has to open it (the first r02 form: 59 instead of ~10 block visits per group on the LiDAR scene).
+template <int BITS>
+__device__ __forceinline__ unsigned hilbert_key(unsigned x, unsigned y, unsigned z) {
+    unsigned X[3] = {x, y, z};
+    constexpr unsigned M = 1u << (BITS - 1);
+#pragma unroll
+    for (unsigned Q = M; Q > 1; Q >>= 1) {
+        const unsigned P = Q - 1;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            if (X[i] & Q) {
+                X[0] ^= P;
+            } else {
+                const unsigned t = (X[0] ^ X[i]) & P;
+                X[0] ^= t, X[i] ^= t;
+            }
+        }
+    }
+    X[1] ^= X[0], X[2] ^= X[1];
+    unsigned t = 0;
+#pragma unroll
+    for (unsigned Q = M; Q > 1; Q >>= 1)
+        if (X[2] & Q) t ^= Q - 1;
+    X[0] ^= t, X[1] ^= t, X[2] ^= t;
+    unsigned key = 0;
+#pragma unroll
+    for (int j = BITS - 1; j >= 0; --j)
+#pragma unroll
+        for (int i = 0; i < 3; ++i) key = (key << 1) | ((X[i] >> j) & 1u);
+    return key;
+}
+
 struct PruneSortParams {
     const float *xyz[2];   // [B][n][3]
     float4 *sorted[2];     // [B][npad]   (x, y, z, original index); NaN records pad the last block
@@ -196,6 +231,7 @@ __device__ __forceinline__ float pr_ord2f(int i) { return __int_as_float(i ^ ((i
 // grid = B * ceil(groups / 8) CTAs of 8 warps; BOXR * 32 >= nblk_t
 template <int BOXR>
 __global__ void __launch_bounds__(PR_THREADS) nn_prune_kernel(const PruneParams p) {
+    __shared__ __align__(16) float4 stage[PR_THREADS / 32][PR_BLOCK];
     if (p.select != nullptr && *p.select != 0) return;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int groups = (p.nq + PR_GROUP - 1) / PR_GROUP;
@@ -253,13 +289,20 @@ __global__ void __launch_bounds__(PR_THREADS) nn_prune_kernel(const PruneParams 
 #pragma unroll
         for (int r = 0; r < BOXR; ++r)
             if (r * 32 + lane == blk) bd[r] = inf;
-        const float4 *tb = T + blk * PR_BLOCK;
+        {   // one coalesced 1 KB read per block, walked in shared memory (see nn_prune2_kernel)
+            const float4 *tg = T + blk * PR_BLOCK;
+            const float4 u0 = __ldg(tg + lane), u1 = __ldg(tg + 32 + lane);
+            __syncwarp();
+            stage[wid][lane] = u0, stage[wid][32 + lane] = u1;
+            __syncwarp();
+        }
+        const float4 *tb = stage[wid];
 #pragma unroll 2
         for (int c = 0; c < PR_BLOCK / 8; ++c) {
             float cm = inf;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const float4 t0 = __ldg(tb + c * 8 + 2 * i), t1 = __ldg(tb + c * 8 + 2 * i + 1);
+                const float4 t0 = tb[c * 8 + 2 * i], t1 = tb[c * 8 + 2 * i + 1];
                 const float2 s2 = sqdist_ref_x2(nx, ny, nz, make_float2(t0.x, t1.x), make_float2(t0.y, t1.y), make_float2(t0.z, t1.z));
                 cm = fmin3(cm, s2.x, s2.y);
             }

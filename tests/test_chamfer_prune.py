@@ -13,14 +13,17 @@ pytestmark = pytest.mark.gpu
 
 
 def run(a, b, dev, prune=True):
+    """prune: True / "1" = one-CTA sort + single-level scan (nn_prune.cuh), "2" = multi-CTA sort + two-level scan
+    (nn_grid.cuh), "0" = exhaustive kernels even where the large-cloud default would prune, False = library default."""
     from genpc_b200 import _lib
     from genpc_b200.loss_functions import chamfer_3DDist
 
     stats = torch.zeros(4, dtype=torch.int32, device=dev)
     L = _lib.lib()
     L.genpc_chamfer_prune_stats(_lib.ptr(stats))
+    knob = "1" if prune is True else (None if prune is False else prune)
     try:
-        with _lib.tunable(GENPC_CHAMFER_PRUNE="1" if prune else None):
+        with _lib.tunable(GENPC_CHAMFER_PRUNE=knob):
             d1, d2, i1, i2 = chamfer_3DDist()(torch.from_numpy(a).to(dev), torch.from_numpy(b).to(dev))
             torch.cuda.synchronize()
     finally:
@@ -121,3 +124,59 @@ def test_fused_loss_step_with_the_pruned_scan(cuda):
     for (l0, ga0, gb0), (l1, ga1, gb1) in zip(res[False], res[True]):
         assert l0 == l1                                          # deterministic reduction of identical distances
         assert np.allclose(ga0, ga1, rtol=1e-5, atol=1e-9) and np.allclose(gb0, gb1, rtol=1e-5, atol=1e-9)   # float atomics
+
+
+# ---- large-cloud form (nn_grid.cuh) ----
+
+@pytest.mark.parametrize("B,N,M", [(1, 64, 512), (2, 100, 777), (3, 2049, 2047), (2, 700, 4100), (4, 2048, 16384), (1, 5000, 40000),
+                                   (1, 71372, 16384)])
+def test_grid_scan_bit_exact(cuda, B, N, M):
+    a, b = shape_cloud(B * 5 + N, B, N), shape_cloud(M + 3, B, M)
+    got, st = run(a, b, cuda, prune="2")
+    if B * N * M <= 6e7:
+        same(got, oracle.chamfer_forward(a, b), f"{B}x{N}x{M} vs oracle")
+    ref, st0 = run(a, b, cuda, prune="0")
+    same(got, ref, f"{B}x{N}x{M} vs exhaustive")
+    assert st[2] > 0 and st0[2] == 0, (st, st0)
+
+
+def test_grid_scan_ties_degenerate_and_out_of_range(cuda):
+    rng = np.random.default_rng(15)
+    cases = {
+        "lattice": (lattice_cloud(1, 1, 8192, 16), lattice_cloud(2, 1, 4096, 16)),
+        "identical": (rand_cloud(3, 1, 9000), rand_cloud(3, 1, 9000)),
+        "planar": (np.concatenate([rng.random((1, 6000, 2)), np.zeros((1, 6000, 1))], 2).astype(np.float32),
+                   np.concatenate([rng.random((1, 5000, 2)), np.zeros((1, 5000, 1))], 2).astype(np.float32)),
+        "far_apart": (rand_cloud(7, 1, 5000), (rand_cloud(8, 1, 5000) + 1000).astype(np.float32)),
+        "two_clusters": (np.concatenate([rng.random((1, 3000, 3)), rng.random((1, 3000, 3)) + 40], 1).astype(np.float32),
+                         np.concatenate([rng.random((1, 500, 3)), rng.random((1, 6000, 3)) + 40], 1).astype(np.float32)),
+        "all_points_equal": (np.full((1, 4500, 3), 0.5, np.float32), np.full((1, 4200, 3), 0.5, np.float32)),
+    }
+    for name, (a, b) in cases.items():
+        a, b = np.ascontiguousarray(a, np.float32), np.ascontiguousarray(b, np.float32)
+        got, st = run(a, b, cuda, prune="2")
+        same(got, oracle.chamfer_forward(a, b), name)
+        assert st[2] > 0, name
+    a, b = rand_cloud(9, 1, 6000), rand_cloud(10, 1, 7000)
+    a2 = a.copy()
+    a2[0, 4321, 2] = np.nan
+    got, st = run(a2, b, cuda, prune="2")
+    ref, _ = run(a2, b, cuda, prune="0")
+    same(got, ref, "nan")
+    assert st[2] == 0
+
+
+def test_large_clouds_take_the_grid_scan_by_default(cuda):
+    """300 000 x 250 000 LiDAR-like scene pair (the C5 generator): the library default is the pruned scan, bit-identical to the
+    exhaustive kernels (forced with the knob), visiting a small fraction of the blocks."""
+    from genpc_b200.synthetic import lidar_scene_pair
+
+    a, b = lidar_scene_pair(300000, 0)
+    a, b = a.numpy()[None, :300000], b.numpy()[None, :250000]
+    got, st = run(np.ascontiguousarray(a), np.ascontiguousarray(b), cuda, prune=False)
+    ref, st0 = run(np.ascontiguousarray(a), np.ascontiguousarray(b), cuda, prune="0")
+    same(got, ref, "300k x 250k")
+    tot = blocks_total(1, 300000, 250000)
+    print("grid scan: %d of %d (group, block) pairs visited = %.3f %%, %d superblocks opened by %d groups" %
+          (st[0], tot, 100.0 * st[0] / tot, st[3], st[2]))
+    assert st[2] > 0 and st0[2] == 0 and st[0] < 0.02 * tot
