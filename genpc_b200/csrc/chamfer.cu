@@ -232,14 +232,14 @@ static bool prune_eligible(int nr, int nc) {
     return k != nullptr && atoi(k) == 1 && prune_shape_ok(nr, nc);
 }
 // Large clouds (nn_grid.cuh): multi-CTA sort + two-level pruned scan.  GENPC_CHAMFER_PRUNE=2 forces it for any shape it can
-// take, =0 switches it off; by default it takes the shapes whose exhaustive scan is at least 2^30 distance evaluations with
-// more than 32768 points on one side (BASELINE C1: 71 372 x 16 384, C5: 1M x 1M).
+// take (and skips the probe below), =0 switches it off; by default it takes the shapes whose exhaustive scan is at least 2^32
+// distance evaluations (>= 1 ms) with more than 32768 points on one side (BASELINE C5: 1M x 1M; not C1: 71 372 x 16 384).
 static bool grid_shape_ok(int nr, int nc) { return nr >= PR_BLOCK && nc >= PR_BLOCK && nr <= GR_MAX_N && nc <= GR_MAX_N; }
 static bool grid_eligible(int nr, int nc) {
     if (!grid_shape_ok(nr, nc)) return false;
     const char *k = tunable("GENPC_CHAMFER_PRUNE");
     if (k != nullptr) return atoi(k) == 2;
-    return (long long)nr * nc >= (1LL << 30) && (nr > PR_MAX_N || nc > PR_MAX_N);
+    return (long long)nr * nc >= (1LL << 32) && (nr > PR_MAX_N || nc > PR_MAX_N);
 }
 static size_t grid_sort_temp_bytes(int nmax) {
     size_t t = 0;
@@ -261,18 +261,22 @@ static size_t grid_extra_bytes(int B, int N, int M) {
     return s;
 }
 template <int SBR>
-static void launch_prune2_t(const Prune2Params &q, cudaStream_t stream) {
+static void launch_prune2_t(const Prune2Params &q, cudaStream_t stream, bool probe) {
     const int groups = (q.nq + PR_GROUP - 1) / PR_GROUP;
-    nn_prune2_kernel<SBR><<<dim3((unsigned)((groups + PR_THREADS / 32 - 1) / (PR_THREADS / 32)), (unsigned)q.B), PR_THREADS, 0, stream>>>(q);
+    const int work = probe ? (groups + q.probe_stride - 1) / q.probe_stride : groups;
+    const dim3 grid((unsigned)((work + PR_THREADS / 32 - 1) / (PR_THREADS / 32)), (unsigned)q.B);
+    if (probe) nn_prune2_kernel<SBR, true><<<grid, PR_THREADS, 0, stream>>>(q);
+    else nn_prune2_kernel<SBR, false><<<grid, PR_THREADS, 0, stream>>>(q);
 }
-static void launch_prune2(const Prune2Params &q, cudaStream_t stream) {
+static void launch_prune2(const Prune2Params &q, cudaStream_t stream, bool probe = false) {
     const int nsb = gr_nsb(q.nt);
-    if (nsb <= 32) launch_prune2_t<1>(q, stream);
-    else if (nsb <= 64) launch_prune2_t<2>(q, stream);
-    else if (nsb <= 128) launch_prune2_t<4>(q, stream);
-    else if (nsb <= 256) launch_prune2_t<8>(q, stream);
-    else launch_prune2_t<16>(q, stream);
+    if (nsb <= 32) launch_prune2_t<1>(q, stream, probe);
+    else if (nsb <= 64) launch_prune2_t<2>(q, stream, probe);
+    else if (nsb <= 128) launch_prune2_t<4>(q, stream, probe);
+    else if (nsb <= 256) launch_prune2_t<8>(q, stream, probe);
+    else launch_prune2_t<16>(q, stream, probe);
 }
+constexpr int GR_PROBE_GROUPS = 128;   // sampled query groups per direction and cloud
 
 static size_t prune_extra_bytes(int B, int N, int M) {
     if (grid_eligible(N, M)) return grid_extra_bytes(B, N, M);
@@ -361,10 +365,27 @@ static int chamfer_forward_sym(const float *xyz1, const float *xyz2, float *dist
         p.select = ctl + 1;
         Prune2Params q = {};
         q.B = B, q.select = ctl + 1, q.stats = g_prune_stats;
-        q.q = gp.sorted[0], q.t = gp.sorted[1], q.tbox = gp.boxes[1], q.tsbox = gp.sboxes[1], q.out = p.prow, q.nq = p.nr, q.nt = p.nc;
-        launch_prune2(q, stream);
-        q.q = gp.sorted[1], q.t = gp.sorted[0], q.tbox = gp.boxes[0], q.tsbox = gp.sboxes[0], q.out = p.pcol, q.nq = p.nc, q.nt = p.nr;
-        launch_prune2(q, stream);
+        // data-dependent guard: a sample of the query groups runs first and counts its block visits; when a group needs more
+        // than a tenth of the target blocks on average (clouds that do not overlap, e.g. BASELINE C1's scan against an
+        // unrelated shape) the exhaustive kernels are faster and take over through the selection flag
+        const char *pk = tunable("GENPC_CHAMFER_PRUNE");
+        const bool forced = pk != nullptr && atoi(pk) == 2;
+        for (int pass = forced ? 1 : 0; pass < 2; ++pass) {
+            const bool probe = pass == 0;
+            long long limit = 0;
+            for (int dir = 0; dir < 2; ++dir) {
+                q.q = gp.sorted[dir], q.t = gp.sorted[1 - dir], q.tbox = gp.boxes[1 - dir], q.tsbox = gp.sboxes[1 - dir];
+                q.out = dir == 0 ? p.prow : p.pcol, q.nq = gp.n[dir], q.nt = gp.n[1 - dir];
+                const int groups = (q.nq + PR_GROUP - 1) / PR_GROUP, nblk = pr_nblk(q.nt);
+                q.probe_stride = groups > GR_PROBE_GROUPS ? groups / GR_PROBE_GROUPS : 1;
+                q.probe_cap = nblk / 5 > 64 ? nblk / 5 : 64;
+                q.probe_acc = ctl + 2;
+                const long long sampled = (long long)B * ((groups + q.probe_stride - 1) / q.probe_stride);
+                limit += sampled * (nblk / 10 > 16 ? nblk / 10 : 16);
+                launch_prune2(q, stream, probe);
+            }
+            if (probe) grid_decide_kernel<<<1, 1, 0, stream>>>(ctl, (int)(limit > 0x7fffffffLL ? 0x7fffffffLL : limit));
+        }
         GENPC_CHECK_LAUNCH();
     } else if (use_prune) {
         char *w = reinterpret_cast<char *>((reinterpret_cast<size_t>(prune_extra) + 255) & ~(size_t)255);

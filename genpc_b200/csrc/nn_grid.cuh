@@ -172,7 +172,19 @@ struct Prune2Params {
     int nq, nt, B;
     const int *select;
     unsigned *stats;           // optional [4]: blocks scanned, tie passes, groups, superblocks opened
+    // probe launch (PROBE = true): only every probe_stride-th group runs, gives up after probe_cap block visits and adds its
+    // visits to *probe_acc -- grid_decide_kernel turns the sum into the selection flag before the real launches
+    int probe_stride, probe_cap;
+    int *probe_acc;
 };
+
+// <<<1, 1>>>: the pruned scan only pays while a query group visits a small share of the target blocks; the probe measured it
+// on a sample.  ctl[1] |= 1 (exhaustive kernels) when the sampled groups visited more than `limit` blocks in all; the
+// accumulator ctl[2] is left zero.
+static __global__ void grid_decide_kernel(int *ctl, int limit) {
+    const int v = atomicExch(ctl + 2, 0);
+    if (v > limit) ctl[1] = 1;
+}
 
 __device__ __forceinline__ float gr_box_dist(const float4 &lo, const float4 &hi, const float (&glo)[3], const float (&ghi)[3]) {
     const float dx = fmaxf(fmaxf(lo.x - ghi[0], glo[0] - hi.x), 0.f);
@@ -182,14 +194,14 @@ __device__ __forceinline__ float gr_box_dist(const float4 &lo, const float4 &hi,
 }
 
 // grid (ceil(groups / 8), B); SBR * 32 >= number of superblocks of the target cloud
-template <int SBR>
+template <int SBR, bool PROBE = false>
 __global__ void __launch_bounds__(PR_THREADS) nn_prune2_kernel(const Prune2Params p) {
     __shared__ __align__(16) float4 stage[PR_THREADS / 32][PR_BLOCK];
     if (p.select != nullptr && *p.select != 0) return;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int groups = (p.nq + PR_GROUP - 1) / PR_GROUP;
     const int b = blockIdx.y;
-    const int g = (int)blockIdx.x * (PR_THREADS / 32) + wid;
+    const int g = ((int)blockIdx.x * (PR_THREADS / 32) + wid) * (PROBE ? p.probe_stride : 1);
     if (g >= groups) return;
     const int nblk = pr_nblk(p.nt), nsb = gr_nsb(p.nt);
     const float4 *T = p.t + (size_t)b * pr_npad(p.nt);
@@ -278,7 +290,13 @@ __global__ void __launch_bounds__(PR_THREADS) nn_prune2_kernel(const Prune2Param
             }
             ++scanned;
             thr = pr_ord2f(__reduce_max_sync(0xffffffffu, valid ? pr_f2ord(best) : (int)0x80000000));
+            if (PROBE && scanned >= (unsigned)p.probe_cap) break;
         }
+        if (PROBE && scanned >= (unsigned)p.probe_cap) break;
+    }
+    if (PROBE) {
+        if (lane == 0) atomicAdd(p.probe_acc, (int)scanned);
+        return;
     }
     // lowest original index at the minimum: inside the winning chunk ...
     int bidx = 0x7fffffff;

@@ -180,3 +180,19 @@ def test_large_clouds_take_the_grid_scan_by_default(cuda):
     print("grid scan: %d of %d (group, block) pairs visited = %.3f %%, %d superblocks opened by %d groups" %
           (st[0], tot, 100.0 * st[0] / tot, st[3], st[2]))
     assert st[2] > 0 and st0[2] == 0 and st[0] < 0.02 * tot
+
+
+def test_probe_hands_non_overlapping_large_clouds_to_the_exhaustive_kernels(cuda):
+    """Default path at 70 000 x 70 000 (>= 2^32 evaluations): overlapping clouds take the pruned scan; clouds that do not
+    overlap would make every query group open every block -- the sampled probe sees that and the exhaustive kernels run."""
+    a = rand_cloud(21, 1, 70000)
+    b_near = (a[:, ::-1] + 0.003 * rand_cloud(22, 1, 70000)).astype(np.float32).copy()
+    b_far = (rand_cloud(23, 1, 70000) * np.array([1, 1, 0.01], np.float32) + np.array([0, 0, 5], np.float32)).astype(np.float32)
+    got, st = run(a, b_near, cuda, prune=False)
+    ref, _ = run(a, b_near, cuda, prune="0")
+    same(got, ref, "overlapping")
+    assert st[2] > 0, st
+    got, st = run(a, b_far, cuda, prune=False)
+    ref, _ = run(a, b_far, cuda, prune="0")
+    same(got, ref, "apart")
+    assert st[2] == 0, st
