@@ -391,6 +391,7 @@ static int chamfer_forward_sym(const float *xyz1, const float *xyz2, float *dist
         char *w = reinterpret_cast<char *>((reinterpret_cast<size_t>(prune_extra) + 255) & ~(size_t)255);
         PruneSortParams sp = {};
         sp.xyz[0] = p.rows, sp.xyz[1] = p.cols, sp.n[0] = p.nr, sp.n[1] = p.nc, sp.B = B, sp.limit = 1e15f, sp.ctl = ctl;
+        sp.hilbert = 1;
         sp.sorted[0] = reinterpret_cast<float4 *>(w);
         sp.sorted[1] = sp.sorted[0] + (size_t)B * pr_npad(p.nr);
         sp.boxes[0] = sp.sorted[1] + (size_t)B * pr_npad(p.nc);

@@ -74,6 +74,7 @@ struct PruneSortParams {
     int B;
     float limit;
     int *ctl;              // [1] selection flag (0: pruned kernels run), [2] accumulator, [3] ticket -- as nn_tc_precheck_kernel
+    int hilbert;           // cell order: Hilbert curve (1) or Z-order (0)
 };
 
 // grid = 2 * B CTAs: blockIdx.x = side * B + b
@@ -122,15 +123,21 @@ static __global__ void __launch_bounds__(PR_SORT_THREADS) nn_bin_sort_kernel(con
         scale[c] = (ext > 0.f && ext < inf) ? (float)(1 << mbits) / ext : 0.f;
     }
     const int cmax = (1 << mbits) - 1;
+    const bool hilbert = p.hilbert != 0;
     auto cell_of = [&](int k, float &x, float &y, float &z) {
         x = __ldg(src + k * 3), y = __ldg(src + k * 3 + 1), z = __ldg(src + k * 3 + 2);
         const float v[3] = {x, y, z};
         unsigned code = 0;
-        int cc[3];
+        unsigned cc[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             const float f = (v[c] - lo[c]) * scale[c];
-            cc[c] = f >= 0.f ? min((int)fminf(f, 2e9f), cmax) : 0;
+            cc[c] = f >= 0.f ? (unsigned)min((int)fminf(f, 2e9f), cmax) : 0u;
+        }
+        if (hilbert) {   // connected runs: tighter block boxes than the Z-order below
+            code = mbits == 4 ? hilbert_key<4>(cc[0], cc[1], cc[2]) : mbits == 3 ? hilbert_key<3>(cc[0], cc[1], cc[2])
+                 : mbits == 2 ? hilbert_key<2>(cc[0], cc[1], cc[2]) : hilbert_key<1>(cc[0], cc[1], cc[2]);
+            return (int)code;
         }
         for (int bit = 0; bit < mbits; ++bit)
 #pragma unroll
