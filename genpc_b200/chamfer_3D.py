@@ -54,6 +54,9 @@ _step_ws = {}
 def step_workspace(device, B, N, M):
     key = (device.index, torch.cuda.current_stream(device).cuda_stream, B, N, M)
     ws = _step_ws.get(key)
+    if ws is not None and ws.packed_bytes != _lib.lib().genpc_chamfer_workspace_bytes(B, N, M):
+        ws = None   # the size depends on the scan the library would pick now (a knob was flipped): start over, unarmed
+        _step_ws.pop(key)
     if ws is None:
         if len(_step_ws) >= 16:   # a few live shapes at most: drop the oldest
             _step_ws.pop(next(iter(_step_ws)))

@@ -64,7 +64,7 @@ def test_c2_full_batch_pruned(cuda):
     tot = blocks_total(32, 2048, 16384)
     print("C2 pruned scan: %d of %d (group, block) pairs visited = %.1f %%, %d of %d groups took the tie pass" %
           (st[0], tot, 100.0 * st[0] / tot, st[1], st[2]))
-    assert st[0] < 0.5 * tot
+    assert st[2] == 32 * (2048 // 32 + 16384 // 32) and st[0] < 0.5 * tot
 
 
 def test_exact_ties_and_degenerate_geometry(cuda):

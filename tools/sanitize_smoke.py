@@ -59,4 +59,19 @@ d1, d2, i1, i2 = chamfer_3DDist()(a.to(dev).requires_grad_(True), torch.rand(2, 
 (d1[:, 10:].mean() + d2.mean()).backward()
 step = GraphedLossStep(cl, torch.rand(2, 600, 3, generator=g).to(dev), torch.rand(2, 1500, 3, generator=g).to(dev))
 step(); step()
+# ---- r02 (late): pruned EMD Bid (both target sorts, spread tail at n = 4096), pruned Chamfer scans (one-CTA sort / grid sort
+# with probe and forced), out-of-range hand-over
+for n_, it_ in ((1024, 6), (4096, 3)):
+    emdModule()(torch.rand(2, n_, 3, generator=g).to(dev), torch.rand(2, n_, 3, generator=g).to(dev), 0.005, it_)
+with _lib.tunable(GENPC_EMD_SORT="bitonic"):
+    emdModule()(torch.rand(1, 1280, 3, generator=g).to(dev), torch.rand(1, 1280, 3, generator=g).to(dev), 0.005, 4)
+with _lib.tunable(GENPC_EMD_PRUNE="0"):
+    emdModule()(torch.rand(1, 1024, 3, generator=g).to(dev), torch.rand(1, 1024, 3, generator=g).to(dev), 0.005, 4)
+for knob in ("1", "2"):
+    with _lib.tunable(GENPC_CHAMFER_PRUNE=knob):
+        for (B, N, M) in [(2, 700, 1300), (1, 3000, 999), (1, 64, 513)]:
+            chamfer_3DDist()(torch.rand(B, N, 3, generator=g).to(dev), torch.rand(B, M, 3, generator=g).to(dev))
+        bad = torch.rand(1, 900, 3, generator=g); bad[0, 7, 1] = float("inf")
+        chamfer_3DDist()(bad.to(dev), torch.rand(1, 700, 3, generator=g).to(dev))
+chamfer_3DDist()(torch.rand(1, 70000, 3, generator=g).to(dev), torch.rand(1, 66000, 3, generator=g).to(dev))   # default: probe + grid scan
 torch.cuda.synchronize(); print("sanitize smoke done")
