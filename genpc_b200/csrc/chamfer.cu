@@ -221,15 +221,20 @@ static bool tc_eligible(int B, int nr, int nc) {
     return nr >= TC_RBLK && nc >= 1;
 }
 
-// Spatially pruned exact scan (nn_prune.cuh), r02 experiment: GENPC_CHAMFER_PRUNE=1 selects it for device-resident clouds of
-// 64 .. 32768 points each.  MEASURED (profiles/r02m_chamfer_prune.txt): bit-identical, visits 16 % of the (query group, target
-// block) pairs on C2, and takes 0.70 ms against 0.27 ms of the exhaustive symmetric scan -- one query per lane has none of the
-// register reuse that lets nn_sym evaluate a pair in a tenth of an issue slot, and its dependent uniform loads leave the SM at
-// 1.1 instructions per cycle.  OFF by default; kept with its tests as the record of that measurement.
+// Spatially pruned exact scan (nn_prune.cuh, r02): Hilbert-ordered clouds, one warp per 32 queries, blocks visited nearest first.
+// GENPC_CHAMFER_PRUNE=1 forces it for any shape it can take (64 .. 32768 points per cloud), =0 forbids it; by default it takes
+// device-resident batches whose exhaustive scan is at least 2^30 distance evaluations with >= 1024 points per cloud -- BASELINE C2
+// (32 x 2048 x 16384: forward 0.271 -> 0.196 ms), 32 x 8192 x 8192 (0.539 -> 0.292 ms); below that the fixed cost of the sort
+// and of a group's dependent block chain (0.1 ms) loses (8 x 8192 x 8192: 0.155 vs 0.200 ms; profiles/r02m_chamfer_prune.txt).
+// The first form (Z-order cells, a uniform global load per target) took 0.70 ms on C2.
 static bool prune_shape_ok(int nr, int nc) { return nr >= PR_BLOCK && nc >= PR_BLOCK && nr <= PR_MAX_N && nc <= PR_MAX_N; }
-static bool prune_eligible(int nr, int nc) {
+static bool prune_eligible(int B, int nr, int nc) {
+    if (!prune_shape_ok(nr, nc)) return false;
     const char *k = tunable("GENPC_CHAMFER_PRUNE");
-    return k != nullptr && atoi(k) == 1 && prune_shape_ok(nr, nc);
+    if (k != nullptr) return atoi(k) == 1;
+    const char *tc = tunable("GENPC_CHAMFER_TC");
+    if (tc != nullptr && atoi(tc) == 1) return false;   // an explicit request for the tensor-core filter wins over the default
+    return nr >= 1024 && nc >= 1024 && (long long)B * nr * nc >= (1LL << 30);
 }
 // Large clouds (nn_grid.cuh): multi-CTA sort + two-level pruned scan.  GENPC_CHAMFER_PRUNE=2 forces it for any shape it can
 // take (and skips the probe below), =0 switches it off; by default it takes the shapes whose exhaustive scan is at least 2^32
@@ -279,26 +284,30 @@ static void launch_prune2(const Prune2Params &q, cudaStream_t stream, bool probe
 constexpr int GR_PROBE_GROUPS = 128;   // sampled query groups per direction and cloud
 
 static size_t prune_extra_bytes(int B, int N, int M) {
-    if (grid_eligible(N, M)) return grid_extra_bytes(B, N, M);
-    if (!prune_eligible(N, M)) return 0;   // the knob is read when the workspace is sized: no growth for anybody else
+    if (B <= 8 && grid_eligible(N, M)) return grid_extra_bytes(B, N, M);
+    if (!prune_eligible(B, N, M)) return 0;   // (the knob is read when the workspace is sized)
     return 256 + (size_t)B * ((size_t)pr_npad(N) + pr_npad(M)) * sizeof(float4) +
-           (size_t)B * 2 * ((size_t)pr_nblk(N) + pr_nblk(M)) * sizeof(float4);
+           (size_t)B * 2 * ((size_t)pr_nblk(N) + pr_nblk(M)) * sizeof(float4) + (size_t)B * 2 * 8 * sizeof(float);
 }
 static unsigned *g_prune_stats = nullptr;   // diagnostics (genpc_chamfer_prune_stats), nullptr in production
 
-template <int BOXR>
-static void launch_prune_t(const PruneParams &q, cudaStream_t stream) {
+static int prune_ctas(const PruneParams &q) {
     const int groups = (q.nq + PR_GROUP - 1) / PR_GROUP;
-    const int ctas = (groups + PR_THREADS / 32 - 1) / (PR_THREADS / 32);
-    nn_prune_kernel<BOXR><<<(unsigned)(q.B * ctas), PR_THREADS, 0, stream>>>(q);
+    return q.B * ((groups + PR_THREADS / 32 - 1) / (PR_THREADS / 32));
 }
-static void launch_prune(const PruneParams &q, cudaStream_t stream) {
-    const int nblk = pr_nblk(q.nt);
-    if (nblk <= 32) launch_prune_t<1>(q, stream);
-    else if (nblk <= 64) launch_prune_t<2>(q, stream);
-    else if (nblk <= 128) launch_prune_t<4>(q, stream);
-    else if (nblk <= 256) launch_prune_t<8>(q, stream);
-    else launch_prune_t<16>(q, stream);
+// both directions in one launch; the direction with fewer queries (longer chains per group: more target blocks) goes first
+static void launch_prune(const PruneParams &a, const PruneParams &b, cudaStream_t stream) {
+    PrunePair pp;
+    const bool a_first = a.nq <= b.nq;
+    pp.d[0] = a_first ? a : b, pp.d[1] = a_first ? b : a;
+    pp.ctas0 = prune_ctas(pp.d[0]);
+    const unsigned grid = (unsigned)(pp.ctas0 + prune_ctas(pp.d[1]));
+    const int nblk = pr_nblk(a.nt > b.nt ? a.nt : b.nt);
+    if (nblk <= 32) nn_prune_kernel<1><<<grid, PR_THREADS, 0, stream>>>(pp);
+    else if (nblk <= 64) nn_prune_kernel<2><<<grid, PR_THREADS, 0, stream>>>(pp);
+    else if (nblk <= 128) nn_prune_kernel<4><<<grid, PR_THREADS, 0, stream>>>(pp);
+    else if (nblk <= 256) nn_prune_kernel<8><<<grid, PR_THREADS, 0, stream>>>(pp);
+    else nn_prune_kernel<16><<<grid, PR_THREADS, 0, stream>>>(pp);
 }
 
 // Symmetric path: rows = the larger cloud (registers), cols = the smaller one (shared-memory sweep).
@@ -323,7 +332,7 @@ static int chamfer_forward_sym(const float *xyz1, const float *xyz2, float *dist
     int *ctl = counter;   // [0] persistent work counter, [1] selection flag, [2] precheck accumulator, [3] precheck ticket
     // ---- spatially pruned scan (nn_prune.cuh): the sort doubles as the range check and sets the same selection flag ----
     const bool use_grid = ctl != nullptr && gate == nullptr && prune_extra != nullptr && B <= 8 && grid_eligible(p.nr, p.nc);   // one sort per cloud: small batches only
-    const bool use_prune = use_grid || (ctl != nullptr && gate == nullptr && prune_extra != nullptr && prune_eligible(p.nr, p.nc));
+    const bool use_prune = use_grid || (ctl != nullptr && gate == nullptr && prune_extra != nullptr && prune_eligible(B, p.nr, p.nc));
     if (use_grid) {
         char *w = reinterpret_cast<char *>((reinterpret_cast<size_t>(prune_extra) + 255) & ~(size_t)255);
         GridParams gp = {};
@@ -396,16 +405,16 @@ static int chamfer_forward_sym(const float *xyz1, const float *xyz2, float *dist
         sp.sorted[1] = sp.sorted[0] + (size_t)B * pr_npad(p.nr);
         sp.boxes[0] = sp.sorted[1] + (size_t)B * pr_npad(p.nc);
         sp.boxes[1] = sp.boxes[0] + (size_t)B * 2 * pr_nblk(p.nr);
+        sp.bbx = reinterpret_cast<float *>(sp.boxes[1] + (size_t)B * 2 * pr_nblk(p.nc));
         nn_bin_sort_kernel<<<2 * B, PR_SORT_THREADS, 0, stream>>>(sp);
         GENPC_CHECK_LAUNCH();
         p.select = ctl + 1;
         PruneParams q = {};
         q.B = B, q.select = ctl + 1, q.stats = g_prune_stats;
         q.q = sp.sorted[0], q.t = sp.sorted[1], q.tbox = sp.boxes[1], q.out = p.prow, q.nq = p.nr, q.nt = p.nc;
-        launch_prune(q, stream);
-        GENPC_CHECK_LAUNCH();
-        q.q = sp.sorted[1], q.t = sp.sorted[0], q.tbox = sp.boxes[0], q.out = p.pcol, q.nq = p.nc, q.nt = p.nr;
-        launch_prune(q, stream);
+        PruneParams q2 = q;
+        q2.q = sp.sorted[1], q2.t = sp.sorted[0], q2.tbox = sp.boxes[0], q2.out = p.pcol, q2.nq = p.nc, q2.nt = p.nr;
+        launch_prune(q, q2, stream);
         GENPC_CHECK_LAUNCH();
     }
     const bool use_tc = !use_prune && ctl != nullptr && tc_eligible(B, p.nr, p.nc);

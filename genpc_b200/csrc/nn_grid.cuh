@@ -196,7 +196,7 @@ __device__ __forceinline__ float gr_box_dist(const float4 &lo, const float4 &hi,
 // grid (ceil(groups / 8), B); SBR * 32 >= number of superblocks of the target cloud
 template <int SBR, bool PROBE = false>
 __global__ void __launch_bounds__(PR_THREADS) nn_prune2_kernel(const Prune2Params p) {
-    __shared__ __align__(16) float4 stage[PR_THREADS / 32][PR_BLOCK];
+    __shared__ __align__(16) float stage[PR_THREADS / 32][3][PR_BLOCK];   // the block being walked, SoA: x[64] y[64] z[64]
     if (p.select != nullptr && *p.select != 0) return;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int groups = (p.nq + PR_GROUP - 1) / PR_GROUP;
@@ -269,18 +269,24 @@ __global__ void __launch_bounds__(PR_THREADS) nn_prune2_kernel(const Prune2Param
                 const float4 *tg = T + (size_t)blk * PR_BLOCK;
                 const float4 u0 = __ldg(tg + lane), u1 = __ldg(tg + 32 + lane);
                 __syncwarp();
-                stage[wid][lane] = u0, stage[wid][32 + lane] = u1;
+                stage[wid][0][lane] = u0.x, stage[wid][1][lane] = u0.y, stage[wid][2][lane] = u0.z;
+                stage[wid][0][32 + lane] = u1.x, stage[wid][1][32 + lane] = u1.y, stage[wid][2][32 + lane] = u1.z;
                 __syncwarp();
             }
-            const float4 *tb = stage[wid];
+            // SoA: one LDS.128 per coordinate brings four targets as two register pairs the packed FP32 instructions take as they
+            // are (the AoS form spent 6 of its 15 instructions per target pair moving registers into pairs)
+            const float4 *sx4 = reinterpret_cast<const float4 *>(stage[wid][0]), *sy4 = reinterpret_cast<const float4 *>(stage[wid][1]),
+                         *sz4 = reinterpret_cast<const float4 *>(stage[wid][2]);
 #pragma unroll 2
             for (int c = 0; c < PR_BLOCK / 8; ++c) {
                 float cm = inf;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float4 t0 = tb[c * 8 + 2 * i], t1 = tb[c * 8 + 2 * i + 1];
-                    const float2 s2 = sqdist_ref_x2(nx, ny, nz, make_float2(t0.x, t1.x), make_float2(t0.y, t1.y), make_float2(t0.z, t1.z));
-                    cm = fmin3(cm, s2.x, s2.y);
+                for (int i = 0; i < 2; ++i) {
+                    const float4 X = sx4[c * 2 + i], Y = sy4[c * 2 + i], Z = sz4[c * 2 + i];
+                    const float2 a2 = sqdist_ref_x2(nx, ny, nz, make_float2(X.x, X.y), make_float2(Y.x, Y.y), make_float2(Z.x, Z.y));
+                    const float2 b2 = sqdist_ref_x2(nx, ny, nz, make_float2(X.z, X.w), make_float2(Y.z, Y.w), make_float2(Z.z, Z.w));
+                    cm = fmin3(cm, a2.x, a2.y);
+                    cm = fmin3(cm, b2.x, b2.y);
                 }
                 if (cm < best) {
                     best = cm, bchunk = blk * (PR_BLOCK / 8) + c, tie = false;

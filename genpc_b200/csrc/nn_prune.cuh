@@ -75,6 +75,7 @@ struct PruneSortParams {
     float limit;
     int *ctl;              // [1] selection flag (0: pruned kernels run), [2] accumulator, [3] ticket -- as nn_tc_precheck_kernel
     int hilbert;           // cell order: Hilbert curve (1) or Z-order (0)
+    float *bbx;            // optional [2][B][8]: every cloud's bounding box, for the overlap test below (nullptr: none)
 };
 
 // grid = 2 * B CTAs: blockIdx.x = side * B + b
@@ -208,13 +209,35 @@ static __global__ void __launch_bounds__(PR_SORT_THREADS) nn_bin_sort_kernel(con
             }
         if (lane == 0) bx[blk] = make_float4(l[0], l[1], l[2], 0.f), bx[nblk + blk] = make_float4(h[0], h[1], h[2], 0.f);
     }
-    // ---- selection flag: last CTA publishes "any cloud out of range" ----
+    // ---- selection flag: the last CTA publishes "any cloud out of range, or a pair of clouds that does not overlap" (pruning
+    // needs neighbours to be near: when the two boxes of a pair are further apart than a quarter of the smaller one's diagonal
+    // every query group would open every block, 2.8x the cost of the exhaustive scan) ----
     if (tid == 0) {
+        if (p.bbx != nullptr) {
+            float *o = p.bbx + ((size_t)side * p.B + b) * 8;
+            for (int c = 0; c < 3; ++c) {
+                float l = inf, h = -inf;
+                for (int w = 0; w < PR_SORT_THREADS / 32; ++w) l = fminf(l, sred[c][w]), h = fmaxf(h, sred[3 + c][w]);
+                o[c] = l, o[3 + c] = h;
+            }
+        }
         if (anybad) atomicOr(p.ctl + 2, 1);
         __threadfence();
         if (atomicAdd(p.ctl + 3, 1) == (int)gridDim.x - 1) {
             __threadfence();
-            p.ctl[1] = atomicExch(p.ctl + 2, 0);
+            int apart = 0;
+            if (p.bbx != nullptr && (int)gridDim.x == 2 * p.B) {
+                for (int i = 0; i < p.B; ++i) {
+                    const volatile float *u = p.bbx + (size_t)i * 8, *v = p.bbx + ((size_t)p.B + i) * 8;
+                    float gap2 = 0.f, du = 0.f, dv = 0.f;
+                    for (int c = 0; c < 3; ++c) {
+                        const float g = fmaxf(fmaxf(u[c] - v[3 + c], v[c] - u[3 + c]), 0.f);
+                        gap2 += g * g, du += (u[3 + c] - u[c]) * (u[3 + c] - u[c]), dv += (v[3 + c] - v[c]) * (v[3 + c] - v[c]);
+                    }
+                    if (gap2 > 0.0625f * fminf(du, dv)) apart = 1;
+                }
+            }
+            p.ctl[1] = atomicExch(p.ctl + 2, 0) | apart;
             p.ctl[3] = 0;
         }
     }
@@ -235,16 +258,26 @@ __device__ __forceinline__ int pr_f2ord(float f) {
 }
 __device__ __forceinline__ float pr_ord2f(int i) { return __int_as_float(i ^ ((i >> 31) & 0x7fffffff)); }
 
-// grid = B * ceil(groups / 8) CTAs of 8 warps; BOXR * 32 >= nblk_t
+// Both directions of a cloud pair in ONE launch: the first ctas0 CTAs take direction d[0] (put the direction with the longer
+// per-group chains there: it is scheduled first), the rest d[1].
+struct PrunePair {
+    PruneParams d[2];
+    int ctas0;
+};
+
+// grid = sum over the two directions of B * ceil(groups / 8) CTAs of 8 warps; BOXR * 32 >= nblk of either target cloud
 template <int BOXR>
-__global__ void __launch_bounds__(PR_THREADS) nn_prune_kernel(const PruneParams p) {
-    __shared__ __align__(16) float4 stage[PR_THREADS / 32][PR_BLOCK];
+__global__ void __launch_bounds__(PR_THREADS) nn_prune_kernel(const PrunePair pp) {
+    __shared__ __align__(16) float stage[PR_THREADS / 32][3][PR_BLOCK];   // the block being walked, SoA: x[64] y[64] z[64]
+    const int dir = (int)blockIdx.x >= pp.ctas0 ? 1 : 0;
+    const PruneParams &p = pp.d[dir];
     if (p.select != nullptr && *p.select != 0) return;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int groups = (p.nq + PR_GROUP - 1) / PR_GROUP;
     const int ctas_per_cloud = (groups + PR_THREADS / 32 - 1) / (PR_THREADS / 32);
-    const int b = (int)blockIdx.x / ctas_per_cloud;
-    const int g = ((int)blockIdx.x % ctas_per_cloud) * (PR_THREADS / 32) + wid;
+    const int bx = (int)blockIdx.x - dir * pp.ctas0;
+    const int b = bx / ctas_per_cloud;
+    const int g = (bx % ctas_per_cloud) * (PR_THREADS / 32) + wid;
     if (g >= groups) return;
     const int nblk = pr_nblk(p.nt);
     const float4 *T = p.t + (size_t)b * pr_npad(p.nt);
@@ -300,18 +333,24 @@ __global__ void __launch_bounds__(PR_THREADS) nn_prune_kernel(const PruneParams 
             const float4 *tg = T + blk * PR_BLOCK;
             const float4 u0 = __ldg(tg + lane), u1 = __ldg(tg + 32 + lane);
             __syncwarp();
-            stage[wid][lane] = u0, stage[wid][32 + lane] = u1;
+            stage[wid][0][lane] = u0.x, stage[wid][1][lane] = u0.y, stage[wid][2][lane] = u0.z;
+            stage[wid][0][32 + lane] = u1.x, stage[wid][1][32 + lane] = u1.y, stage[wid][2][32 + lane] = u1.z;
             __syncwarp();
         }
-        const float4 *tb = stage[wid];
+        // SoA: one LDS.128 per coordinate brings four targets as two register pairs the packed FP32 instructions take as they
+        // are (the AoS form spent 6 of its 15 instructions per target pair moving registers into pairs)
+        const float4 *sx4 = reinterpret_cast<const float4 *>(stage[wid][0]), *sy4 = reinterpret_cast<const float4 *>(stage[wid][1]),
+                     *sz4 = reinterpret_cast<const float4 *>(stage[wid][2]);
 #pragma unroll 2
         for (int c = 0; c < PR_BLOCK / 8; ++c) {
             float cm = inf;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float4 t0 = tb[c * 8 + 2 * i], t1 = tb[c * 8 + 2 * i + 1];
-                const float2 s2 = sqdist_ref_x2(nx, ny, nz, make_float2(t0.x, t1.x), make_float2(t0.y, t1.y), make_float2(t0.z, t1.z));
-                cm = fmin3(cm, s2.x, s2.y);
+            for (int i = 0; i < 2; ++i) {
+                const float4 X = sx4[c * 2 + i], Y = sy4[c * 2 + i], Z = sz4[c * 2 + i];
+                const float2 a2 = sqdist_ref_x2(nx, ny, nz, make_float2(X.x, X.y), make_float2(Y.x, Y.y), make_float2(Z.x, Z.y));
+                const float2 b2 = sqdist_ref_x2(nx, ny, nz, make_float2(X.z, X.w), make_float2(Y.z, Y.w), make_float2(Z.z, Z.w));
+                cm = fmin3(cm, a2.x, a2.y);
+                cm = fmin3(cm, b2.x, b2.y);
             }
             if (cm < best) {
                 best = cm, bchunk = blk * (PR_BLOCK / 8) + c, tie = false;

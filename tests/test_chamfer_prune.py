@@ -86,7 +86,20 @@ def test_exact_ties_and_degenerate_geometry(cuda):
         a, b = np.ascontiguousarray(a, np.float32), np.ascontiguousarray(b, np.float32)
         got, st = run(a, b, cuda)
         same(got, oracle.chamfer_forward(a, b), name)
-        assert st[2] > 0, name
+        # clouds whose bounding boxes are far apart cannot be pruned (every group would open every block): the sort kernel's
+        # overlap test hands them to the exhaustive kernels
+        assert (st[2] > 0) == (name != "far_apart"), (name, st)
+
+
+def test_default_takes_the_pruned_scan_from_2_30_evaluations(cuda):
+    """Library default (no knob): 16 x 8192 x 8192 = 2^30 evaluations is pruned, 8 x 8192 x 8192 is not; both bit-identical to the
+    exhaustive kernels."""
+    for B, expect in ((16, True), (8, False)):
+        a, b = shape_cloud(31 + B, B, 8192), shape_cloud(77 + B, B, 8192)
+        got, st = run(a, b, cuda, prune=False)
+        ref, st0 = run(a, b, cuda, prune="0")
+        same(got, ref, f"B={B}")
+        assert (st[2] > 0) == expect and st0[2] == 0, (B, st, st0)
 
 
 def test_out_of_range_inputs_go_to_the_exhaustive_kernels(cuda):

@@ -30,7 +30,7 @@ for (B, N, M) in shapes:
     a, b = pcn_batch(0, B, N, M)
     ta, tb = torch.from_numpy(a).to(dev), torch.from_numpy(b).to(dev)
     row = {}
-    for prune in (None, "1"):
+    for prune in ("0", "1"):
         with _lib.tunable(GENPC_CHAMFER_PRUNE=prune):
             cd = chamfer_3DDist()
             fwd = timed(lambda: cd(ta, tb))
@@ -45,7 +45,7 @@ for (B, N, M) in shapes:
             _lib.lib().genpc_chamfer_prune_stats(_lib.ptr(stats))
             cd(ta, tb); torch.cuda.synchronize()
             _lib.lib().genpc_chamfer_prune_stats(None)
-            row["pruned" if prune else "exhaustive"] = {"forward": fwd, "loss_step": st, "stats_blocks_ties_groups": stats.cpu().tolist()[:3]}
+            row["pruned" if prune == "1" else "exhaustive"] = {"forward": fwd, "loss_step": st, "stats_blocks_ties_groups": stats.cpu().tolist()[:3]}
     g = lambda n: (n + 31) // 32
     k = lambda n: (n + 63) // 64
     row["group_block_pairs_total"] = B * (g(N) * k(M) + g(M) * k(N))
