@@ -76,7 +76,15 @@ struct PruneSortParams {
     int *ctl;              // [1] selection flag (0: pruned kernels run), [2] accumulator, [3] ticket -- as nn_tc_precheck_kernel
     int hilbert;           // cell order: Hilbert curve (1) or Z-order (0)
     float *bbx;            // optional [2][B][8]: every cloud's bounding box, for the overlap test below (nullptr: none)
+    int accumulate;        // 1: OR the verdict into ctl[1] (a later chunk of the same batch), 0: overwrite it
 };
+
+// <<<ctas, 256>>>: all-ones into the packed words when the selection flag asks for the exhaustive kernels AFTER pruned launches
+// have already stored exact (dist, index) words (chunked host-fed batches: a later chunk may be the one out of range)
+static __global__ void prune_rearm_kernel(unsigned long long *words, size_t n, const int *select) {
+    if (*select == 0) return;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) words[i] = ~0ull;
+}
 
 // grid = 2 * B CTAs: blockIdx.x = side * B + b
 static __global__ void __launch_bounds__(PR_SORT_THREADS) nn_bin_sort_kernel(const PruneSortParams p) {
@@ -237,7 +245,8 @@ static __global__ void __launch_bounds__(PR_SORT_THREADS) nn_bin_sort_kernel(con
                     if (gap2 > 0.0625f * fminf(du, dv)) apart = 1;
                 }
             }
-            p.ctl[1] = atomicExch(p.ctl + 2, 0) | apart;
+            const int verdict = atomicExch(p.ctl + 2, 0) | apart;
+            p.ctl[1] = p.accumulate ? (p.ctl[1] | verdict) : verdict;
             p.ctl[3] = 0;
         }
     }

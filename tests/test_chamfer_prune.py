@@ -209,3 +209,36 @@ def test_probe_hands_non_overlapping_large_clouds_to_the_exhaustive_kernels(cuda
     ref, _ = run(a, b_far, cuda, prune="0")
     same(got, ref, "apart")
     assert st[2] == 0, st
+
+
+def test_host_fed_chunks_take_the_pruned_scan_and_a_late_bad_chunk_starts_over(cuda):
+    """Host-fed C2 batch (forward_from_host, 6 chunks): sort + pruned scan are queued per chunk behind the chunk's copy event.
+    A NaN in the LAST chunk is only seen after earlier chunks have stored exact words: the words are re-armed and the
+    exhaustive kernels redo the batch -- same outputs as the device-resident exhaustive call."""
+    from genpc_b200 import _lib
+    from genpc_b200.loss_functions import chamfer_3DDist
+
+    a, b = shape_cloud(41, 32, 2048), shape_cloud(42, 32, 16384)
+
+    def host(x, y):
+        stats = torch.zeros(4, dtype=torch.int32, device=cuda)
+        _lib.lib().genpc_chamfer_prune_stats(_lib.ptr(stats))
+        try:
+            with _lib.tunable(GENPC_HOST_PRUNE="1"):   # opt-in: slower than the gated exhaustive launch (DESIGN.md section 4.1b)
+                out = chamfer_3DDist().forward_from_host(torch.from_numpy(x).pin_memory(), torch.from_numpy(y).pin_memory(), device=cuda, chunks=6)
+                torch.cuda.synchronize()
+        finally:
+            _lib.lib().genpc_chamfer_prune_stats(None)
+        return tuple(t.detach().cpu().numpy() for t in out[:4]), stats.cpu().numpy()
+
+    got, st = host(a, b)
+    same(got, oracle.chamfer_forward(a, b), "host-fed C2")
+    assert st[2] == 32 * (2048 // 32 + 16384 // 32), st
+    a2 = a.copy()
+    a2[31, 100, 0] = np.nan
+    got, st = host(a2, b)
+    ref, _ = run(a2, b, cuda, prune="0")
+    same(got, ref, "host-fed, NaN in the last chunk")
+    got, st = host(a, b)                                     # the flag does not stick
+    same(got, oracle.chamfer_forward(a, b), "host-fed C2 again")
+    assert st[2] > 0
