@@ -312,7 +312,8 @@ static void launch_prune(const PruneParams &a, const PruneParams &b, cudaStream_
 
 // Sort + pruned scan of the cloud pairs [b0, b0 + nb) of a batch (rows / cols / prow / pcol: the batch's arrays).
 static int launch_prune_subbatch(const float *rows, const float *cols, int nr, int nc, unsigned long long *prow, unsigned long long *pcol,
-                                 int B, int b0, int nb, int *ctl, void *prune_extra, bool accumulate, cudaStream_t stream) {
+                                 int B, int b0, int nb, int *ctl, void *prune_extra, bool accumulate, cudaStream_t stream,
+                                 int *chunk_ctl = nullptr) {
     char *w = reinterpret_cast<char *>((reinterpret_cast<size_t>(prune_extra) + 255) & ~(size_t)255);
     float4 *sorted0 = reinterpret_cast<float4 *>(w);
     float4 *sorted1 = sorted0 + (size_t)B * pr_npad(nr);
@@ -321,7 +322,8 @@ static int launch_prune_subbatch(const float *rows, const float *cols, int nr, i
     float *bbx = reinterpret_cast<float *>(boxes1 + (size_t)B * 2 * pr_nblk(nc));
     PruneSortParams sp = {};
     sp.xyz[0] = rows + (size_t)b0 * nr * 3, sp.xyz[1] = cols + (size_t)b0 * nc * 3, sp.n[0] = nr, sp.n[1] = nc, sp.B = nb;
-    sp.limit = 1e15f, sp.ctl = ctl, sp.hilbert = 1, sp.accumulate = accumulate ? 1 : 0;
+    sp.limit = 1e15f, sp.ctl = chunk_ctl != nullptr ? chunk_ctl : ctl, sp.hilbert = 1, sp.accumulate = accumulate ? 1 : 0;
+    sp.flag = chunk_ctl != nullptr ? ctl + 1 : nullptr;
     sp.sorted[0] = sorted0 + (size_t)b0 * pr_npad(nr), sp.sorted[1] = sorted1 + (size_t)b0 * pr_npad(nc);
     sp.boxes[0] = boxes0 + (size_t)b0 * 2 * pr_nblk(nr), sp.boxes[1] = boxes1 + (size_t)b0 * 2 * pr_nblk(nc);
     sp.bbx = bbx + (size_t)b0 * 16;
@@ -734,6 +736,10 @@ struct genpc_host_feed {
     cudaStream_t copy_stream;
     cudaEvent_t ready, copied;
     cudaEvent_t chunk_ev[GATE_MAX_CHUNKS];   // chunked pruned path: chunk c's copies have landed
+    cudaEvent_t done_ev[GATE_MAX_CHUNKS];    //   ... its sort + scan have finished
+    cudaEvent_t fork;
+    cudaStream_t cstream[GATE_MAX_CHUNKS];   //   ... the stream they run on (chunks overlap each other and the copies)
+    int *cctl;                               //   ... per-chunk accumulator / ticket words of the sort kernel (device, zero between launches)
     unsigned *gate;    // device: GATE_MAX_CHUNKS generation words + the error word
     unsigned *h_ring;  // pinned: source words of the gate writes
     unsigned gen;
@@ -747,9 +753,16 @@ extern "C" int genpc_host_feed_create(genpc_host_feed_t **out) {
     genpc_host_feed *f = new (std::nothrow) genpc_host_feed();
     if (f == nullptr) return (int)cudaErrorMemoryAllocation;
     f->copy_stream = nullptr, f->ready = nullptr, f->copied = nullptr, f->gate = nullptr, f->h_ring = nullptr, f->gen = 0;
-    for (int c = 0; c < GATE_MAX_CHUNKS; ++c) f->chunk_ev[c] = nullptr;
+    for (int c = 0; c < GATE_MAX_CHUNKS; ++c) f->chunk_ev[c] = nullptr, f->done_ev[c] = nullptr, f->cstream[c] = nullptr;
+    f->fork = nullptr, f->cctl = nullptr;
     cudaError_t e = cudaGetDevice(&f->device);
-    for (int c = 0; c < GATE_MAX_CHUNKS && e == cudaSuccess; ++c) e = cudaEventCreateWithFlags(&f->chunk_ev[c], cudaEventDisableTiming);
+    for (int c = 0; c < GATE_MAX_CHUNKS && e == cudaSuccess; ++c) {
+        e = cudaEventCreateWithFlags(&f->chunk_ev[c], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&f->done_ev[c], cudaEventDisableTiming);
+    }
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&f->fork, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&f->cctl, GATE_MAX_CHUNKS * 4 * sizeof(int));
+    if (e == cudaSuccess) e = cudaMemset(f->cctl, 0, GATE_MAX_CHUNKS * 4 * sizeof(int));
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&f->copy_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&f->ready, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&f->copied, cudaEventDisableTiming);
@@ -769,8 +782,13 @@ extern "C" int genpc_host_feed_destroy(genpc_host_feed_t *f) {
     if (f->copy_stream) cudaStreamSynchronize(f->copy_stream), cudaStreamDestroy(f->copy_stream);
     if (f->ready) cudaEventDestroy(f->ready);
     if (f->copied) cudaEventDestroy(f->copied);
-    for (int c = 0; c < GATE_MAX_CHUNKS; ++c)
+    for (int c = 0; c < GATE_MAX_CHUNKS; ++c) {
         if (f->chunk_ev[c]) cudaEventDestroy(f->chunk_ev[c]);
+        if (f->done_ev[c]) cudaEventDestroy(f->done_ev[c]);
+        if (f->cstream[c]) cudaStreamSynchronize(f->cstream[c]), cudaStreamDestroy(f->cstream[c]);
+    }
+    if (f->fork) cudaEventDestroy(f->fork);
+    if (f->cctl) cudaFree(f->cctl);
     if (f->gate) cudaFree(f->gate);
     if (f->h_ring) cudaFreeHost(f->h_ring);
     delete f;
@@ -814,9 +832,11 @@ extern "C" int genpc_chamfer_forward_host_fused(genpc_host_feed_t *f, const floa
     // ---- pruned scan (the default for batches of this size): sort + scan are queued per chunk behind an event of the chunk's
     // copies -- no kernel waits on a gate, the last chunk's sort + scan (a few tens of us) is all that follows the last copy ----
     const int nr_ = M > N ? M : N, nc_ = M > N ? N : M;
-    const char *hp = tunable("GENPC_HOST_PRUNE");   // measured r02: 0.81 ms per C2 step against 0.36 ms of the gated exhaustive launch
-                                                    // (six chunks x (sort + scan), each bound by its own latency, one after the other
-                                                    // on the stream) -- off unless GENPC_HOST_PRUNE=1
+    // MEASURED r02 (C2 step from pinned memory, fwd + bwd + loss to host): gated exhaustive launch 0.361 ms; this path with all
+    // chunks on the caller's stream 0.81 ms (six x (sort + scan), each bound by its own latency, one after the other), with one
+    // stream per chunk 0.371 ms, the same captured in a CUDA graph 0.337-0.368 ms (3-6 chunks).  The step is bound by the
+    // copies (12 small H2D copies: 0.23 ms), not by the scan -- so the pruned scan buys nothing here: opt-in, GENPC_HOST_PRUNE=1.
+    const char *hp = tunable("GENPC_HOST_PRUNE");
     if (hp != nullptr && atoi(hp) == 1 && prune_eligible(B, nr_, nc_) && !(B <= 8 && grid_eligible(nr_, nc_)) &&
         workspace_bytes >= chamfer_base_bytes(B, N, M) + prune_extra_bytes(B, N, M)) {
         unsigned long long *packed = (unsigned long long *)workspace;
@@ -828,18 +848,26 @@ extern "C" int genpc_chamfer_forward_host_fused(genpc_host_feed_t *f, const floa
         if (!(fuse != nullptr && fuse->workspace_armed)) {
             FEED_CHECK(cudaMemsetAsync(packed, 0xff, (n1 + n2) * 8, stream));
             FEED_CHECK(cudaMemsetAsync(ctl, 0, 16, stream));
+        } else {
+            FEED_CHECK(cudaMemsetAsync(ctl + 1, 0, 4, stream));   // the chunks OR their verdicts into the selection flag
         }
+        FEED_CHECK(cudaEventRecord(f->fork, stream));
         for (int c = 0; c < chunks; ++c) {
             const int b0 = c * pairs, nb = (B - b0 < pairs) ? B - b0 : pairs;
+            if (f->cstream[c] == nullptr) FEED_CHECK(cudaStreamCreateWithFlags(&f->cstream[c], cudaStreamNonBlocking));
             FEED_CHECK(cudaMemcpyAsync(xyz1 + (size_t)b0 * N * 3, h_xyz1 + (size_t)b0 * N * 3, (size_t)nb * N * 12,
                                        cudaMemcpyHostToDevice, f->copy_stream));
             FEED_CHECK(cudaMemcpyAsync(xyz2 + (size_t)b0 * M * 3, h_xyz2 + (size_t)b0 * M * 3, (size_t)nb * M * 12,
                                        cudaMemcpyHostToDevice, f->copy_stream));
             FEED_CHECK(cudaEventRecord(f->chunk_ev[c], f->copy_stream));
-            FEED_CHECK(cudaStreamWaitEvent(stream, f->chunk_ev[c], 0));
-            const int rcs = launch_prune_subbatch(rows, cols, nr_, nc_, packed, packed + (size_t)B * nr_, B, b0, nb, ctl, extra, c > 0, stream);
+            FEED_CHECK(cudaStreamWaitEvent(f->cstream[c], f->fork, 0));
+            FEED_CHECK(cudaStreamWaitEvent(f->cstream[c], f->chunk_ev[c], 0));
+            const int rcs = launch_prune_subbatch(rows, cols, nr_, nc_, packed, packed + (size_t)B * nr_, B, b0, nb, ctl, extra, true,
+                                                  f->cstream[c], f->cctl + 4 * c);
             if (rcs != GENPC_OK) return rcs;
+            FEED_CHECK(cudaEventRecord(f->done_ev[c], f->cstream[c]));
         }
+        for (int c = 0; c < chunks; ++c) FEED_CHECK(cudaStreamWaitEvent(stream, f->done_ev[c], 0));
         double *partial = fuse ? (double *)fuse->loss_workspace : nullptr;
         unsigned *ticket = partial ? (unsigned *)(partial + sym_epilogue_ctas(B, N, M)) : nullptr;
         const int marker = chunks;

@@ -77,6 +77,8 @@ struct PruneSortParams {
     int hilbert;           // cell order: Hilbert curve (1) or Z-order (0)
     float *bbx;            // optional [2][B][8]: every cloud's bounding box, for the overlap test below (nullptr: none)
     int accumulate;        // 1: OR the verdict into ctl[1] (a later chunk of the same batch), 0: overwrite it
+    int *flag;             // optional: atomicOr the verdict here instead (chunks sorted concurrently on several streams; ctl then
+                           // only provides the chunk's own accumulator / ticket words)
 };
 
 // <<<ctas, 256>>>: all-ones into the packed words when the selection flag asks for the exhaustive kernels AFTER pruned launches
@@ -246,7 +248,11 @@ static __global__ void __launch_bounds__(PR_SORT_THREADS) nn_bin_sort_kernel(con
                 }
             }
             const int verdict = atomicExch(p.ctl + 2, 0) | apart;
-            p.ctl[1] = p.accumulate ? (p.ctl[1] | verdict) : verdict;
+            if (p.flag != nullptr) {
+                if (verdict) atomicOr(p.flag, 1);
+            } else {
+                p.ctl[1] = p.accumulate ? (p.ctl[1] | verdict) : verdict;
+            }
             p.ctl[3] = 0;
         }
     }
