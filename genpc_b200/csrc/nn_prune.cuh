@@ -18,6 +18,7 @@
 // the device through the same flag as the tensor-core filter).
 #pragma once
 #include "common.cuh"
+#include "nn_core.cuh"   // Similarity / apply_similarity (registration: the moving cloud is sorted in its current pose)
 
 namespace genpc {
 
@@ -79,6 +80,11 @@ struct PruneSortParams {
     int accumulate;        // 1: OR the verdict into ctl[1] (a later chunk of the same batch), 0: overwrite it
     int *flag;             // optional: atomicOr the verdict here instead (chunks sorted concurrently on several streams; ctl then
                            // only provides the chunk's own accumulator / ticket words)
+    // registration: only one side is sorted per launch (side0 = its index, grid = B), its points taken from cloud b / src_div
+    // and moved by the similarity sim[b] while they are read (the same rounding as the exhaustive scan's staging)
+    int side0, single_side;
+    int src_div[2];
+    const Similarity *sim[2];
 };
 
 // <<<ctas, 256>>>: all-ones into the packed words when the selection flag asks for the exhaustive kernels AFTER pruned launches
@@ -94,9 +100,17 @@ static __global__ void __launch_bounds__(PR_SORT_THREADS) nn_bin_sort_kernel(con
     __shared__ float sred[6][PR_SORT_THREADS / 32];
     __shared__ int swarp[PR_SORT_THREADS / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int side = (int)blockIdx.x / p.B, b = (int)blockIdx.x % p.B;
+    const int side = p.single_side ? p.side0 : (int)blockIdx.x / p.B, b = (int)blockIdx.x % p.B;
     const int n = p.n[side], nblk = pr_nblk(n), npad = nblk * PR_BLOCK;
-    const float *src = p.xyz[side] + (size_t)b * n * 3;
+    const float *src = p.xyz[side] + (size_t)(p.src_div[side] > 1 ? b / p.src_div[side] : b) * n * 3;
+    __shared__ Similarity sT;
+    const bool moved = p.sim[side] != nullptr;
+    if (moved && tid == 0) sT = p.sim[side][b];
+    if (moved) __syncthreads();
+    auto load_point = [&](int k, float &x, float &y, float &z) {
+        x = __ldg(src + k * 3), y = __ldg(src + k * 3 + 1), z = __ldg(src + k * 3 + 2);
+        if (moved) apply_similarity(sT, x, y, z);
+    };
     float4 *dst = p.sorted[side] + (size_t)b * npad;
     float4 *bx = p.boxes[side] + (size_t)b * 2 * nblk;
     const float inf = __int_as_float(0x7f800000);
@@ -104,11 +118,12 @@ static __global__ void __launch_bounds__(PR_SORT_THREADS) nn_bin_sort_kernel(con
     float lo[3] = {inf, inf, inf}, hi[3] = {-inf, -inf, -inf};
     bool bad = false;
     for (int k = tid; k < n; k += PR_SORT_THREADS) {
+        float v[3];
+        load_point(k, v[0], v[1], v[2]);
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            const float v = __ldg(src + k * 3 + c);
-            bad |= !(fabsf(v) <= p.limit);
-            lo[c] = fminf(lo[c], v), hi[c] = fmaxf(hi[c], v);
+            bad |= !(fabsf(v[c]) <= p.limit);
+            lo[c] = fminf(lo[c], v[c]), hi[c] = fmaxf(hi[c], v[c]);
         }
     }
 #pragma unroll
@@ -136,7 +151,7 @@ static __global__ void __launch_bounds__(PR_SORT_THREADS) nn_bin_sort_kernel(con
     const int cmax = (1 << mbits) - 1;
     const bool hilbert = p.hilbert != 0;
     auto cell_of = [&](int k, float &x, float &y, float &z) {
-        x = __ldg(src + k * 3), y = __ldg(src + k * 3 + 1), z = __ldg(src + k * 3 + 2);
+        load_point(k, x, y, z);
         const float v[3] = {x, y, z};
         unsigned code = 0;
         unsigned cc[3];
@@ -236,7 +251,7 @@ static __global__ void __launch_bounds__(PR_SORT_THREADS) nn_bin_sort_kernel(con
         if (atomicAdd(p.ctl + 3, 1) == (int)gridDim.x - 1) {
             __threadfence();
             int apart = 0;
-            if (p.bbx != nullptr && (int)gridDim.x == 2 * p.B) {
+            if (p.bbx != nullptr && !p.single_side && (int)gridDim.x == 2 * p.B) {
                 for (int i = 0; i < p.B; ++i) {
                     const volatile float *u = p.bbx + (size_t)i * 8, *v = p.bbx + ((size_t)p.B + i) * 8;
                     float gap2 = 0.f, du = 0.f, dv = 0.f;
@@ -265,6 +280,8 @@ struct PruneParams {
     int nq, nt, B;
     const int *select;        // run only when *select == 0
     unsigned *stats;          // optional [4]: blocks scanned, tie passes, groups, -
+    int qdiv, tdiv;           // batch entry b reads queries / targets of cloud b / qdiv, b / tdiv (0 or 1: its own; registration: the
+                              // starts of one scan share the fixed cloud's sorted copy)
 };
 
 __device__ __forceinline__ int pr_f2ord(float f) {
@@ -278,6 +295,7 @@ __device__ __forceinline__ float pr_ord2f(int i) { return __int_as_float(i ^ ((i
 struct PrunePair {
     PruneParams d[2];
     int ctas0;
+    int ctas1_unused;   // (host-side bookkeeping of the registration loop)
 };
 
 // grid = sum over the two directions of B * ceil(groups / 8) CTAs of 8 warps; BOXR * 32 >= nblk of either target cloud
@@ -295,12 +313,13 @@ __global__ void __launch_bounds__(PR_THREADS) nn_prune_kernel(const PrunePair pp
     const int g = (bx % ctas_per_cloud) * (PR_THREADS / 32) + wid;
     if (g >= groups) return;
     const int nblk = pr_nblk(p.nt);
-    const float4 *T = p.t + (size_t)b * pr_npad(p.nt);
-    const float4 *BL = p.tbox + (size_t)b * 2 * nblk, *BH = BL + nblk;
+    const int bt = p.tdiv > 1 ? b / p.tdiv : b, bq = p.qdiv > 1 ? b / p.qdiv : b;
+    const float4 *T = p.t + (size_t)bt * pr_npad(p.nt);
+    const float4 *BL = p.tbox + (size_t)bt * 2 * nblk, *BH = BL + nblk;
     const float inf = __int_as_float(0x7f800000);
     const int qi = g * PR_GROUP + lane;
     const bool valid = qi < p.nq;
-    const float4 q = p.q[(size_t)b * pr_npad(p.nq) + qi];   // the padding records are NaN: they never win, nothing is stored
+    const float4 q = p.q[(size_t)bq * pr_npad(p.nq) + qi];   // the padding records are NaN: they never win, nothing is stored
     // ---- the group's box ----
     float glo[3], ghi[3];
     {

@@ -23,6 +23,7 @@
 
 #include "nn_core.cuh"
 #include "nn_sym.cuh"
+#include "nn_prune.cuh"
 
 namespace genpc {
 
@@ -46,6 +47,9 @@ struct RegArgs {
     float step_size[3];     // lr_g / (1 - beta1^t) for the rot / trans / log_scale groups
     float w_fwd, w_inv, cd_weight;
     float omb1, beta2, omb2, eps, bc2_sqrt;  // 1-beta1, beta2, 1-beta2 (rounded from double like torch's scalars)
+    // pruned scan (nn_prune.cuh): *select == 0 -> the packed words of both directions already hold exact indices (the symmetric
+    // scan kernel returns at once, the finish kernel skips its fix-up); nullptr: exhaustive path only
+    const int *select;
 };
 
 __device__ __forceinline__ void load_similarity(const float *par, const float *center, Similarity &T) {
@@ -354,6 +358,7 @@ template <int QT>
 __global__ void __launch_bounds__(SYM_THREADS, GENPC_SYM_MINB(QT)) register_sym_scan_kernel(const RegArgs a) {
     __shared__ __align__(16) float s[3][SYM_SPAN_MAX];
     __shared__ Similarity T;
+    if (a.select != nullptr && *a.select == 0) return;   // the pruned scan did the work
     const int per_scan = a.rtiles * a.cspans;
     const int scan = blockIdx.x / per_scan;
     const int item = blockIdx.x - scan * per_scan;
@@ -399,7 +404,8 @@ __global__ void __launch_bounds__(FIX_THREADS, 2) register_finish_kernel(const R
     unsigned long long *pA = a.packedA + (size_t)scan * a.Nc;
     unsigned long long *pB = a.packedB + (size_t)scan * a.Nr;
     const int c_lo = part * FIX_COLS_PER_CTA, c_hi = min(a.Nc, c_lo + FIX_COLS_PER_CTA);
-    {
+    const bool words_exact = a.select != nullptr && *a.select == 0;
+    if (!words_exact) {
         // a warp resolves FIX_COLS_PER_WARP columns (c_lo + warp + k * warps): lane k fetches the word and the transformed
         // point of column k up front (ONE exposed L2 latency for all of them instead of one per column), the columns
         // are then handed round by shuffles and their row-block loads are independent, so they overlap as well
@@ -420,6 +426,7 @@ __global__ void __launch_bounds__(FIX_THREADS, 2) register_finish_kernel(const R
             const unsigned long long w = __shfl_sync(0xffffffffu, my_w, k);
             const float x = __shfl_sync(0xffffffffu, mx, k), y = __shfl_sync(0xffffffffu, my, k), z = __shfl_sync(0xffffffffu, mz, k);
             const float d = __uint_as_float((unsigned)(w >> 32));
+            if (words_exact) continue;   // warp-uniform
             const int found = sym_fix_column(Rf, a.Nr, a.rows_per_block, x, y, z, d, (int)(unsigned)(w & 0xffffffffu), lane);
             if (lane == 0) pA[c] = pack_dist_idx(d, found);
         }
@@ -480,9 +487,31 @@ __global__ void __launch_bounds__(FIX_THREADS, 2) register_finish_kernel(const R
     if (threadIdx.x == 0) pose_update(a, scan, T, tot, adam_step_from_args(a));
 }
 
+// current similarity of every scan, for the sort of the moving clouds (pruned path)
+__global__ void register_sims_kernel(const RegArgs a, Similarity *sims) {
+    const int scan = blockIdx.x * blockDim.x + threadIdx.x;
+    if (scan < a.S) load_similarity(a.params + (size_t)scan * REG_NPAR, a.center + (size_t)(scan / a.n_starts) * 3, sims[scan]);
+}
+
 }  // namespace genpc
 
 using namespace genpc;
+
+// Pruned scan for the symmetric path (nn_prune.cuh): the fixed clouds are sorted once per call, the moving
+// clouds every iteration in their current pose; default from S * Nc * Nr >= 2^30 evaluations, GENPC_REGISTER_PRUNE=0 / 1 forbids /
+// forces it.  Results are those of the exhaustive path bit for bit (same distances, lowest index at the minimum).
+static bool register_prune_eligible(int S, int Nc, int Nr) {
+    if (Nc < PR_BLOCK || Nr < PR_BLOCK || Nc > PR_MAX_N || Nr > PR_MAX_N) return false;
+    const char *k = tunable("GENPC_REGISTER_PRUNE");
+    if (k != nullptr) return atoi(k) == 1;
+    return Nc >= 1024 && Nr >= 1024 && (double)S * (double)Nc * (double)Nr >= (double)(1LL << 30);
+}
+static size_t register_prune_bytes(int S, int n_starts, int Nc, int Nr) {
+    if (!register_prune_eligible(S, Nc, Nr)) return 0;
+    const size_t C = (size_t)S / (n_starts > 0 ? n_starts : 1);
+    return 512 + (size_t)S * sizeof(Similarity) + ((size_t)S * pr_npad(Nc) + C * pr_npad(Nr)) * sizeof(float4) +
+           2 * ((size_t)S * pr_nblk(Nc) + C * pr_nblk(Nr)) * sizeof(float4);
+}
 
 // symmetric path (default for big problems): rows = fixed cloud, cols = moving cloud; the one-scan-per-direction kernel
 // stays for tiny fixed clouds and for A/B runs (GENPC_REGISTER_MODE=scan).  Measured on B200
@@ -503,16 +532,23 @@ static size_t register_partial_slots(int Nc, int Nr) {
     return fix_ctas > items ? fix_ctas : items;
 }
 
-extern "C" size_t genpc_register_workspace_bytes(int S, int Nc, int Nr) {
-    if (S < 0 || Nc < 0 || Nr < 0) return 0;
+static size_t register_base_bytes(int S, int Nc, int Nr) {
     return ((size_t)S * Nc + (size_t)S * Nr) * 8 + (size_t)S * register_partial_slots(Nc, Nr) * 14 * sizeof(double) +
            3 * (size_t)S * sizeof(int);   // tickets, iter_done, arrivals
+}
+
+extern "C" size_t genpc_register_workspace_bytes(int S, int Nc, int Nr) {
+    if (S < 0 || Nc < 0 || Nr < 0) return 0;
+    // (+ the pruned scan's copies, sized for one start per cloud -- the largest case; genpc_register_run checks what it needs)
+    return register_base_bytes(S, Nc, Nr) + register_prune_bytes(S, 1, Nc, Nr);
 }
 
 // Kernel launches one Adam iteration costs at this problem size (1: single-launch path, 2: symmetric scan + finish).
 extern "C" int genpc_register_launches_per_iter(int S, int Nc, int Nr) {
     if (S <= 0 || Nc <= 0 || Nr <= 0) return GENPC_ERR_SHAPE;
-    return register_takes_sym_path(S, Nc, Nr) ? 2 : 1;   // (small problems: ONE launch for all iterations of a run call)
+    if (!register_takes_sym_path(S, Nc, Nr)) return 1;   // (small problems: ONE launch for all iterations of a run call)
+    // pruned: similarities, sort of the moving clouds, pruned scan, (de-selected) symmetric scan, finish
+    return register_prune_eligible(S, Nc, Nr) ? 5 : 2;
 }
 
 extern "C" int genpc_register_run(const float *complete, const float *center, const float *ref, float *params,
@@ -523,7 +559,7 @@ extern "C" int genpc_register_run(const float *complete, const float *center, co
     cudaStream_t stream = (cudaStream_t)stream_;
     if (S <= 0 || n_starts <= 0 || S % n_starts != 0 || Nc <= 0 || Nr <= 0 || iters < 0 || t_start < 0) return GENPC_ERR_SHAPE;
     if (loss_hist != nullptr && t_start + iters > T) return GENPC_ERR_SHAPE;
-    if (workspace == nullptr || workspace_bytes < genpc_register_workspace_bytes(S, Nc, Nr)) return GENPC_ERR_WORKSPACE;
+    if (workspace == nullptr || workspace_bytes < register_base_bytes(S, Nc, Nr)) return GENPC_ERR_WORKSPACE;
     RegArgs a = {};
     a.complete = complete, a.center = center, a.ref = ref, a.params = params, a.adam_m = adam_m, a.adam_v = adam_v;
     a.packedA = (unsigned long long *)workspace;
@@ -607,6 +643,46 @@ extern "C" int genpc_register_run(const float *complete, const float *center, co
             return GENPC_OK;
         }
     }
+    // ---- pruned scan set-up: control words, similarities, sorted copies behind the base workspace ----
+    const bool prune = sym && register_prune_eligible(S, Nc, Nr) &&
+                       workspace_bytes >= register_base_bytes(S, Nc, Nr) + register_prune_bytes(S, n_starts, Nc, Nr);
+    PruneSortParams sp = {};
+    PrunePair pp = {};
+    Similarity *sims = nullptr;
+    if (prune) {
+        const int C = S / n_starts;
+        char *w = (char *)workspace + register_base_bytes(S, Nc, Nr);
+        w = (char *)(((size_t)w + 255) & ~(size_t)255);
+        int *ctl = (int *)w;
+        w += 256;
+        sims = (Similarity *)w, w += (((size_t)S * sizeof(Similarity)) + 15) & ~(size_t)15;
+        float4 *sortedM = (float4 *)w; w += (size_t)S * pr_npad(Nc) * sizeof(float4);     // moving clouds, current pose, per scan
+        float4 *sortedF = (float4 *)w; w += (size_t)C * pr_npad(Nr) * sizeof(float4);     // fixed clouds, per cloud
+        float4 *boxesM = (float4 *)w; w += (size_t)S * 2 * pr_nblk(Nc) * sizeof(float4);
+        float4 *boxesF = (float4 *)w;
+        cudaError_t e = cudaMemsetAsync(ctl, 0, 16, stream);
+        if (e != cudaSuccess) return (int)e;
+        sp.xyz[0] = ref, sp.xyz[1] = complete, sp.n[0] = Nr, sp.n[1] = Nc, sp.limit = 1e15f, sp.ctl = ctl, sp.hilbert = 1;
+        sp.sorted[0] = sortedF, sp.sorted[1] = sortedM, sp.boxes[0] = boxesF, sp.boxes[1] = boxesM;
+        sp.single_side = 1, sp.accumulate = 1;
+        // the fixed clouds once per call (their verdict opens the flag), the moving clouds every iteration (OR-ed in)
+        sp.side0 = 0, sp.B = C, sp.accumulate = 0;
+        nn_bin_sort_kernel<<<C, PR_SORT_THREADS, 0, stream>>>(sp);
+        GENPC_CHECK_LAUNCH();
+        sp.side0 = 1, sp.B = S, sp.accumulate = 1, sp.src_div[1] = n_starts, sp.sim[1] = sims;
+        a.select = ctl + 1;
+        PruneParams qa = {}, qb = {};
+        qa.B = S, qa.select = ctl + 1;
+        qb = qa;
+        // direction A: moving point -> nearest fixed point (packedA); direction B: fixed point -> nearest moving point (packedB)
+        qa.q = sortedM, qa.t = sortedF, qa.tbox = boxesF, qa.out = a.packedA, qa.nq = Nc, qa.nt = Nr, qa.qdiv = 1, qa.tdiv = n_starts;
+        qb.q = sortedF, qb.t = sortedM, qb.tbox = boxesM, qb.out = a.packedB, qb.nq = Nr, qb.nt = Nc, qb.qdiv = n_starts, qb.tdiv = 1;
+        const bool a_first = qa.nq <= qb.nq;
+        pp.d[0] = a_first ? qa : qb, pp.d[1] = a_first ? qb : qa;
+        const int g0 = (pp.d[0].nq + PR_GROUP - 1) / PR_GROUP, g1 = (pp.d[1].nq + PR_GROUP - 1) / PR_GROUP;
+        pp.ctas0 = S * ((g0 + PR_THREADS / 32 - 1) / (PR_THREADS / 32));
+        pp.ctas1_unused = S * ((g1 + PR_THREADS / 32 - 1) / (PR_THREADS / 32));
+    }
     for (int it = 0; it < iters; ++it) {
         const int t = t_start + it;
         a.t_index = t;
@@ -614,6 +690,18 @@ extern "C" int genpc_register_run(const float *complete, const float *center, co
         a.step_size[0] = (float)(lr_rot / bc1), a.step_size[1] = (float)(lr_trans / bc1), a.step_size[2] = (float)(lr_scale / bc1);
         a.bc2_sqrt = (float)sqrt(1.0 - pow(0.999, (double)(t + 1)));
         if (sym) {
+            if (prune) {
+                register_sims_kernel<<<(S + 127) / 128, 128, 0, stream>>>(a, sims);
+                nn_bin_sort_kernel<<<S, PR_SORT_THREADS, 0, stream>>>(sp);
+                const unsigned pgrid = (unsigned)(pp.ctas0 + pp.ctas1_unused);
+                const int nblk = pr_nblk(Nc > Nr ? Nc : Nr);
+                if (nblk <= 32) nn_prune_kernel<1><<<pgrid, PR_THREADS, 0, stream>>>(pp);
+                else if (nblk <= 64) nn_prune_kernel<2><<<pgrid, PR_THREADS, 0, stream>>>(pp);
+                else if (nblk <= 128) nn_prune_kernel<4><<<pgrid, PR_THREADS, 0, stream>>>(pp);
+                else if (nblk <= 256) nn_prune_kernel<8><<<pgrid, PR_THREADS, 0, stream>>>(pp);
+                else nn_prune_kernel<16><<<pgrid, PR_THREADS, 0, stream>>>(pp);
+                GENPC_CHECK_LAUNCH();
+            }
             if (SQT == 4) register_sym_scan_kernel<4><<<(unsigned)sgrid, SYM_THREADS, 0, stream>>>(a);
             else register_sym_scan_kernel<2><<<(unsigned)sgrid, SYM_THREADS, 0, stream>>>(a);
             GENPC_CHECK_LAUNCH();
