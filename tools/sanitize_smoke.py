@@ -74,4 +74,11 @@ for knob in ("1", "2"):
         bad = torch.rand(1, 900, 3, generator=g); bad[0, 7, 1] = float("inf")
         chamfer_3DDist()(bad.to(dev), torch.rand(1, 700, 3, generator=g).to(dev))
 chamfer_3DDist()(torch.rand(1, 70000, 3, generator=g).to(dev), torch.rand(1, 66000, 3, generator=g).to(dev))   # default: probe + grid scan
+# pruned scan inside the registration loop (forced on a small symmetric-path problem), host-fed batch through the chunked pruned path
+with _lib.tunable(GENPC_REGISTER_PRUNE="1", GENPC_REGISTER_MODE="sym"):
+    rb = RegistrationBatch(torch.rand(2, 3000, 3, generator=g).to(dev) - 0.5, torch.rand(2, 2100, 3, generator=g).to(dev) - 0.5, n_starts=2)
+    rb.run(2); rb.run(1)
+with _lib.tunable(GENPC_HOST_PRUNE="1", GENPC_CHAMFER_PRUNE="1"):
+    ha2, hb2 = torch.rand(6, 700, 3, generator=g).pin_memory(), torch.rand(6, 1500, 3, generator=g).pin_memory()
+    loss, da, db = Completionloss("cd_l2").get_loss_from_host(ha2, hb2, device=dev, chunks=3); loss.backward()
 torch.cuda.synchronize(); print("sanitize smoke done")
