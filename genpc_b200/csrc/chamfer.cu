@@ -291,6 +291,30 @@ static size_t prune_extra_bytes(int B, int N, int M) {
 }
 static unsigned *g_prune_stats = nullptr;   // diagnostics (genpc_chamfer_prune_stats), nullptr in production
 
+// side stream + fork / join events for the cooperative kernel, one set per (device, caller stream): created on first use, kept
+// for the life of the process (fork / join is also what a CUDA-graph capture of the step records)
+struct PruneSide {
+    cudaStream_t stream;
+    cudaEvent_t fork, join;
+};
+static PruneSide *prune_side_stream(cudaStream_t caller) {
+    static std::mutex mtx;
+    static struct { int dev; cudaStream_t caller; PruneSide s; } tab[64];
+    static int used = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> guard(mtx);
+    for (int i = 0; i < used; ++i)
+        if (tab[i].dev == dev && tab[i].caller == caller) return &tab[i].s;
+    if (used == 64) return nullptr;   // (more caller streams than slots: the single-launch form)
+    PruneSide s;
+    if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    tab[used].dev = dev, tab[used].caller = caller, tab[used].s = s;
+    return &tab[used++].s;
+}
+
 static int prune_ctas(const PruneParams &q) {
     const int groups = (q.nq + PR_GROUP - 1) / PR_GROUP;
     return q.B * ((groups + PR_THREADS / 32 - 1) / (PR_THREADS / 32));
@@ -301,13 +325,33 @@ static void launch_prune(const PruneParams &a, const PruneParams &b, cudaStream_
     const bool a_first = a.nq <= b.nq;
     pp.d[0] = a_first ? a : b, pp.d[1] = a_first ? b : a;
     pp.ctas0 = prune_ctas(pp.d[0]);
+    // few query groups against many target blocks (C2's partial -> complete direction): a CTA per group, eight warps sharing
+    // its chain (nn_prune_coop_kernel) on a side stream, next to the other direction; GENPC_PRUNE_COOP=0 / 1 forbids / forces it
+    const long long groups0 = (long long)pp.d[0].B * ((pp.d[0].nq + PR_GROUP - 1) / PR_GROUP);
+    const char *ck = tunable("GENPC_PRUNE_COOP");
+    const bool coop = ck != nullptr ? atoi(ck) != 0 : (groups0 <= 4096 && 4LL * pp.d[0].nq <= pp.d[1].nq);
+    PruneSide *side = coop ? prune_side_stream(stream) : nullptr;
+    if (side != nullptr) {
+        cudaEventRecord(side->fork, stream);
+        cudaStreamWaitEvent(side->stream, side->fork, 0);
+        const int nb0 = pr_nblk(pp.d[0].nt);
+        const unsigned g0 = (unsigned)groups0;
+        if (nb0 <= 32) nn_prune_coop_kernel<1><<<g0, PR_THREADS, 0, side->stream>>>(pp.d[0]);
+        else if (nb0 <= 64) nn_prune_coop_kernel<2><<<g0, PR_THREADS, 0, side->stream>>>(pp.d[0]);
+        else if (nb0 <= 128) nn_prune_coop_kernel<4><<<g0, PR_THREADS, 0, side->stream>>>(pp.d[0]);
+        else if (nb0 <= 256) nn_prune_coop_kernel<8><<<g0, PR_THREADS, 0, side->stream>>>(pp.d[0]);
+        else nn_prune_coop_kernel<16><<<g0, PR_THREADS, 0, side->stream>>>(pp.d[0]);
+        cudaEventRecord(side->join, side->stream);
+        pp.ctas0 = 0;   // the launch below: direction d[1] only
+    }
     const unsigned grid = (unsigned)(pp.ctas0 + prune_ctas(pp.d[1]));
-    const int nblk = pr_nblk(a.nt > b.nt ? a.nt : b.nt);
+    const int nblk = pr_nblk(side != nullptr ? pp.d[1].nt : (a.nt > b.nt ? a.nt : b.nt));
     if (nblk <= 32) nn_prune_kernel<1><<<grid, PR_THREADS, 0, stream>>>(pp);
     else if (nblk <= 64) nn_prune_kernel<2><<<grid, PR_THREADS, 0, stream>>>(pp);
     else if (nblk <= 128) nn_prune_kernel<4><<<grid, PR_THREADS, 0, stream>>>(pp);
     else if (nblk <= 256) nn_prune_kernel<8><<<grid, PR_THREADS, 0, stream>>>(pp);
     else nn_prune_kernel<16><<<grid, PR_THREADS, 0, stream>>>(pp);
+    if (side != nullptr) cudaStreamWaitEvent(stream, side->join, 0);
 }
 
 // Sort + pruned scan of the cloud pairs [b0, b0 + nb) of a batch (rows / cols / prow / pcol: the batch's arrays).

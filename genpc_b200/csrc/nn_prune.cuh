@@ -432,4 +432,168 @@ __global__ void __launch_bounds__(PR_THREADS) nn_prune_kernel(const PrunePair pp
     }
 }
 
+// Cooperative form for a direction with FEW query groups and many target blocks (C2: 2048 groups against 256 blocks each): one
+// CTA per group, each of its eight warps walks an eighth of the blocks nearest first; the running minima are shared through
+// shared-memory atomics, so every warp stops where a single warp would (its bound is never below the final one: no block that
+// matters is skipped), and warp 0 merges the eight partial results.  A group's dependent chain -- up to 256
+// block visits of 0.35 us in one warp, which set the duration of the whole launch (118 us on one batch of the bench's generator,
+// 167 us on others with the same instruction count) -- becomes an eighth as long.  Launched on a side stream next to the other
+// direction's nn_prune_kernel.
+template <int BOXR>
+__global__ void __launch_bounds__(PR_THREADS) nn_prune_coop_kernel(const PruneParams p) {
+    __shared__ __align__(16) float stage[PR_THREADS / 32][3][PR_BLOCK];
+    __shared__ unsigned s_best[PR_GROUP];                       // running minimum per query over all warps (float bits, >= 0)
+    __shared__ float m_best[PR_THREADS / 32][PR_GROUP];
+    __shared__ int m_chunk[PR_THREADS / 32][PR_GROUP], m_tie[PR_THREADS / 32][PR_GROUP];
+    if (p.select != nullptr && *p.select != 0) return;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int groups = (p.nq + PR_GROUP - 1) / PR_GROUP;
+    const int b = (int)blockIdx.x / groups;
+    const int g = (int)blockIdx.x % groups;
+    if (wid == 0) s_best[lane] = 0x7f800000u;
+    __syncthreads();
+    const int nblk = pr_nblk(p.nt);
+    const int bt = p.tdiv > 1 ? b / p.tdiv : b, bq = p.qdiv > 1 ? b / p.qdiv : b;
+    const float4 *T = p.t + (size_t)bt * pr_npad(p.nt);
+    const float4 *BL = p.tbox + (size_t)bt * 2 * nblk, *BH = BL + nblk;
+    const float inf = __int_as_float(0x7f800000);
+    const int qi = g * PR_GROUP + lane;
+    const bool valid = qi < p.nq;
+    const float4 q = p.q[(size_t)bq * pr_npad(p.nq) + qi];   // the padding records are NaN: they never win, nothing is stored
+    // ---- the group's box ----
+    float glo[3], ghi[3];
+    {
+        const float v[3] = {q.x, q.y, q.z};
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            // NaN (padding) must not take part: +inf / -inf are neutral
+            const float a = valid ? v[c] : inf, z = valid ? v[c] : -inf;
+            glo[c] = pr_ord2f(__reduce_min_sync(0xffffffffu, pr_f2ord(a)));
+            ghi[c] = pr_ord2f(__reduce_max_sync(0xffffffffu, pr_f2ord(z)));
+        }
+    }
+    // ---- squared box-to-box distances, scaled down (see the header) ----
+    // warp w owns the blocks w, w + 8, w + 16, ... (consecutive Hilbert blocks are neighbours: every warp gets an even sample
+    // of the cloud) and runs the nearest-first walk over ITS blocks only -- no selection work is repeated
+    constexpr int WARPS = PR_THREADS / 32;
+    constexpr int CBOXR = (BOXR + WARPS - 1) / WARPS;
+    float bd[CBOXR];
+#pragma unroll
+    for (int r = 0; r < CBOXR; ++r) {
+        const int blk = wid + WARPS * (r * 32 + lane);
+        bd[r] = inf;
+        if (blk < nblk) {
+            const float4 lo = __ldg(BL + blk), hi = __ldg(BH + blk);
+            const float dx = fmaxf(fmaxf(lo.x - ghi[0], glo[0] - hi.x), 0.f);
+            const float dy = fmaxf(fmaxf(lo.y - ghi[1], glo[1] - hi.y), 0.f);
+            const float dz = fmaxf(fmaxf(lo.z - ghi[2], glo[2] - hi.z), 0.f);
+            bd[r] = __fmul_rn(__fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy))), 0.99999f);
+        }
+    }
+    const float2 nx = make_float2(-q.x, -q.x), ny = make_float2(-q.y, -q.y), nz = make_float2(-q.z, -q.z);
+    float best = inf;
+    int bchunk = 0;
+    bool tie = false;
+    float thr = inf;   // the largest running minimum of the group's lanes
+    unsigned scanned = 0;
+    for (;;) {
+        unsigned key = 0xffffffffu;   // (distance bits without the low 9, slot = r * 32 + lane of the owned block)
+#pragma unroll
+        for (int r = 0; r < CBOXR; ++r) key = min(key, (__float_as_uint(bd[r]) & 0xfffffe00u) | (unsigned)(r * 32 + lane));
+        key = __reduce_min_sync(0xffffffffu, key);
+        // the bound uses what ANY warp has found so far for each query
+        thr = pr_ord2f(__reduce_max_sync(0xffffffffu, valid ? pr_f2ord(fminf(best, __uint_as_float(*(volatile unsigned *)&s_best[lane])))
+                                                            : (int)0x80000000));
+        if (key >= 0x7f800000u || !(__uint_as_float(key & 0xfffffe00u) <= thr)) break;
+        const int slot = (int)(key & 0x1ffu);
+#pragma unroll
+        for (int r = 0; r < CBOXR; ++r)
+            if (r * 32 + lane == slot) bd[r] = inf;
+        const int blk = wid + WARPS * slot;
+        {   // one coalesced 1 KB read per block, walked in shared memory (see nn_prune2_kernel)
+            const float4 *tg = T + blk * PR_BLOCK;
+            const float4 u0 = __ldg(tg + lane), u1 = __ldg(tg + 32 + lane);
+            __syncwarp();
+            stage[wid][0][lane] = u0.x, stage[wid][1][lane] = u0.y, stage[wid][2][lane] = u0.z;
+            stage[wid][0][32 + lane] = u1.x, stage[wid][1][32 + lane] = u1.y, stage[wid][2][32 + lane] = u1.z;
+            __syncwarp();
+        }
+        // SoA: one LDS.128 per coordinate brings four targets as two register pairs the packed FP32 instructions take as they
+        // are (the AoS form spent 6 of its 15 instructions per target pair moving registers into pairs)
+        const float4 *sx4 = reinterpret_cast<const float4 *>(stage[wid][0]), *sy4 = reinterpret_cast<const float4 *>(stage[wid][1]),
+                     *sz4 = reinterpret_cast<const float4 *>(stage[wid][2]);
+#pragma unroll 2
+        for (int c = 0; c < PR_BLOCK / 8; ++c) {
+            float cm = inf;
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const float4 X = sx4[c * 2 + i], Y = sy4[c * 2 + i], Z = sz4[c * 2 + i];
+                const float2 a2 = sqdist_ref_x2(nx, ny, nz, make_float2(X.x, X.y), make_float2(Y.x, Y.y), make_float2(Z.x, Z.y));
+                const float2 b2 = sqdist_ref_x2(nx, ny, nz, make_float2(X.z, X.w), make_float2(Y.z, Y.w), make_float2(Z.z, Z.w));
+                cm = fmin3(cm, a2.x, a2.y);
+                cm = fmin3(cm, b2.x, b2.y);
+            }
+            if (cm < best) {
+                best = cm, bchunk = blk * (PR_BLOCK / 8) + c, tie = false;
+            } else if (cm == best && cm < inf) {
+                tie = true;
+            }
+        }
+        ++scanned;
+        if (valid) atomicMin(&s_best[lane], __float_as_uint(best));
+    }
+    // ---- merge the eight warps' results (warp 0 finishes the group) ----
+    m_best[wid][lane] = best, m_chunk[wid][lane] = bchunk, m_tie[wid][lane] = tie ? 1 : 0;
+    if (p.stats != nullptr && lane == 0 && wid != 0) atomicAdd(p.stats + 0, scanned);
+    __syncthreads();
+    if (wid != 0) return;
+#pragma unroll
+    for (int w = 1; w < PR_THREADS / 32; ++w) {
+        const float mb = m_best[w][lane];
+        const int mc = m_chunk[w][lane];
+        const bool mt = m_tie[w][lane] != 0;
+        if (mb < best) {
+            best = mb, bchunk = mc, tie = mt;
+        } else if (mb == best && mb < inf) {
+            tie = tie || mt || mc != bchunk;
+        }
+    }
+    thr = pr_ord2f(__reduce_max_sync(0xffffffffu, valid ? pr_f2ord(best) : (int)0x80000000));
+    // ---- the lowest original index at the minimum: inside the winning chunk ... ----
+    int bidx = 0x7fffffff;
+    {
+        const float4 *tc = T + bchunk * 8;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float4 t = __ldg(tc + i);
+            const float d = sqdist_ref(q.x, q.y, q.z, t.x, t.y, t.z);
+            if (d == best) bidx = min(bidx, __float_as_int(t.w));
+        }
+    }
+    // ---- ... and, for a lane that met its minimum in two chunks, over every block that could hold it ----
+    const unsigned ties = __ballot_sync(0xffffffffu, tie && valid);
+    if (ties != 0u) {
+        for (int blk = 0; blk < nblk; ++blk) {
+            const float4 lo = __ldg(BL + blk), hi = __ldg(BH + blk);
+            const float dx = fmaxf(fmaxf(lo.x - ghi[0], glo[0] - hi.x), 0.f);
+            const float dy = fmaxf(fmaxf(lo.y - ghi[1], glo[1] - hi.y), 0.f);
+            const float dz = fmaxf(fmaxf(lo.z - ghi[2], glo[2] - hi.z), 0.f);
+            const float s = __fmul_rn(__fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy))), 0.99999f);
+            if (!(s <= thr)) continue;   // warp-uniform
+            const float4 *tb = T + blk * PR_BLOCK;
+            for (int i = 0; i < PR_BLOCK; ++i) {
+                const float4 t = __ldg(tb + i);
+                const float d = sqdist_ref(q.x, q.y, q.z, t.x, t.y, t.z);
+                if (tie && d == best) bidx = min(bidx, __float_as_int(t.w));
+            }
+        }
+    }
+    if (valid) p.out[(size_t)b * p.nq + __float_as_int(q.w)] = pack_dist_idx(best, bidx);
+    if (p.stats != nullptr && lane == 0) {
+        atomicAdd(p.stats + 0, scanned);
+        if (ties != 0u) atomicAdd(p.stats + 1, 1u);
+        atomicAdd(p.stats + 2, 1u);
+    }
+}
+
 }  // namespace genpc

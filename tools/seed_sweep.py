@@ -12,7 +12,7 @@ for seed0 in (0, 1000, 2000, 3000, 4000, 5000, 6000, 7000):       # bench.py: ra
     a, b = pcn_batch(seed0, 32, 2048, 16384)
     ta, tb = torch.from_numpy(a).to(dev), torch.from_numpy(b).to(dev)
     row = {}
-    for name, knobs in (("pruned", {}), ("exhaustive", {"GENPC_CHAMFER_PRUNE": "0"})):
+    for name, knobs in (("pruned", {}), ("pruned_one_launch", {"GENPC_PRUNE_COOP": "0"}), ("exhaustive", {"GENPC_CHAMFER_PRUNE": "0"})):
         with _lib.tunable(**knobs):
             st = GraphedLossStep(cl, ta, tb)
             ts = []
