@@ -360,9 +360,15 @@ def run_gpu_arm(args, loss_fn, rank, world, dev, part, comp, tag, host_loss_fn=N
         "clocks": clocks,
     }
     if graphed_factory is not None:
-        res["api_value"] = "GraphedLossStep(Completionloss('cd_l2'), gen, gt)(): the fused step replayed as one CUDA graph"
+        graph_api = "GraphedLossStep(Completionloss('cd_l2'), gen, gt)(): the fused step replayed as one CUDA graph"
+        eager_api = "Completionloss('cd_l2').get_loss(gen, gt); loss.backward()  (Python + autograd per step)"
+        res["api_value"] = graph_api
         res["eager"] = {"value": pairs_per_step * args.steps / (ms_eager * 1e-3), "unit": "pairs/s", "ms_per_step": ms_eager / args.steps,
-                        "api": "Completionloss('cd_l2').get_loss(gen, gt); loss.backward()  (Python + autograd per step)"}
+                        "api": eager_api}
+        if ms_eager < ms_res:
+            # both are public calls on the same device-resident inputs; `value` is the faster one, the other stays beside it
+            res["graphed"] = {"value": res["value"], "unit": "pairs/s", "ms_per_step": res["ms_per_step"], "api": graph_api}
+            res["value"], res["ms_per_step"], res["api_value"] = res["eager"]["value"], res["eager"]["ms_per_step"], eager_api
     if host_loss_fn is not None:
         res["e2e"]["api"] = ("Completionloss('cd_l2').get_loss_from_host(gen_pinned, gt_pinned); loss.backward(); loss -> host "
                              "(genpc_chamfer_forward_host: H2D copy in 6 chunks overlapped with the one scan launch)")
@@ -748,9 +754,10 @@ def main():
                                      host_loss_fn=lambda ha, hb: ours_loss.get_loss_from_host(ha, hb, device=dev),
                                      graphed_factory=lambda ga, gb: GraphedLossStep(ours_loss, ga, gb))
     line.update(res)
-    # per step: nn_bin_sort_kernel, nn_prune_kernel (both directions), nn_sym_kernel (device-deselected fall-back: returns at
-    # once), nn_sym_epilogue_kernel<fused> (unpack + loss + zero-fill), chamfer_grad_kernel<.., LOSS>
-    line["gpu_launches"] = 5 * args.steps
+    # per step: nn_bin_sort_kernel, nn_prune_coop_kernel (partial -> complete direction, side stream), nn_prune_kernel (the other
+    # direction), nn_sym_kernel (device-deselected fall-back: returns at once), nn_sym_epilogue_kernel<fused> (unpack + loss +
+    # zero-fill), chamfer_grad_kernel<.., LOSS>
+    line["gpu_launches"] = 6 * args.steps
     line["api"] = "genpc_b200.utils.loss_util.Completionloss('cd_l2').get_loss(gen, gt); loss.backward()"
     # ---- the other BASELINE configs ride in the same line (outside the C2 timed region) ----
     cfgs = {}
