@@ -321,7 +321,7 @@ static int prune_ctas(const PruneParams &q) {
 }
 // both directions in one launch; the direction with fewer queries (longer chains per group: more target blocks) goes first
 static void launch_prune(const PruneParams &a, const PruneParams &b, cudaStream_t stream) {
-    PrunePair pp;
+    PrunePair pp = {};
     const bool a_first = a.nq <= b.nq;
     pp.d[0] = a_first ? a : b, pp.d[1] = a_first ? b : a;
     pp.ctas0 = prune_ctas(pp.d[0]);
