@@ -747,6 +747,17 @@ extern "C" int genpc_chamfer_backward(const float *xyz1, const float *xyz2, cons
 
 // Diagnostics of the tensor-core filter: while `stats4` (device, 4 x u32, zeroed by the caller) is set, every filter launch
 // adds {runner-up chunk re-evaluations, whole-tile exact scans, degenerate items, items} to it.  nullptr switches it off.
+// Which scan genpc_chamfer_forward would queue for this shape with the current knobs (host logic only, no device call):
+// 0 = exhaustive (symmetric or per-direction), 1 = Hilbert-sorted pruned scan (nn_prune.cuh), 2 = two-level pruned scan for large
+// clouds (nn_grid.cuh).  The device may still hand a pruned launch back to the exhaustive kernels (range / overlap / probe).
+extern "C" int genpc_chamfer_scan_kind(int B, int N, int M) {
+    if (B <= 0 || N <= 0 || M <= 0) return GENPC_ERR_SHAPE;
+    if (!takes_sym_path(N, M)) return 0;
+    const int nr = N > M ? N : M, nc = N > M ? M : N;
+    if (B <= 8 && grid_eligible(nr, nc)) return 2;
+    return prune_eligible(B, nr, nc) ? 1 : 0;
+}
+
 // diagnostics of the pruned scan: stats4 = device pointer to 4 counters (blocks scanned, groups that took the tie pass, groups, -)
 extern "C" int genpc_chamfer_prune_stats(unsigned *stats4) {
     g_prune_stats = stats4;

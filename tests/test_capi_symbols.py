@@ -46,3 +46,30 @@ def test_no_cpu_fallback():
 
     with pytest.raises(_lib.GenpcError):
         chamfer_3DDist()(torch.rand(1, 4, 3), torch.rand(1, 5, 3))
+
+
+def test_scan_selection_host_logic():
+    """Which Chamfer scan the library would queue (host logic, no device): exhaustive for small batches, the Hilbert-sorted pruned
+    scan from 2^30 evaluations, the two-level pruned scan for large clouds; the knob overrides; workspace sizes follow."""
+    from genpc_b200 import _lib
+
+    L = _lib.lib()
+    kind = L.genpc_chamfer_scan_kind
+    assert kind(32, 2048, 16384) == 1 and kind(32, 16384, 2048) == 1          # BASELINE C2: 2^30 evaluations
+    assert kind(8, 8192, 8192) == 0 and kind(16, 8192, 8192) == 1
+    assert kind(1, 71372, 16384) == 0                                         # C1: below 2^32 evaluations
+    assert kind(1, 1000000, 1000000) == 2 and kind(9, 1000000, 1000000) == 0  # C5; the grid path sorts cloud by cloud (B <= 8)
+    assert kind(32, 512, 4096) == 0 and kind(4, 100, 37) == 0
+    assert kind(0, 5, 5) < 0
+    base = lambda B, N, M: (B * N + B * M) * 8 + 16                           # noqa: E731
+    assert L.genpc_chamfer_workspace_bytes(8, 8192, 8192) == base(8, 8192, 8192)
+    assert L.genpc_chamfer_workspace_bytes(32, 2048, 16384) > base(32, 2048, 16384) + 32 * (2048 + 16384) * 16
+    with _lib.tunable(GENPC_CHAMFER_PRUNE="0"):
+        assert kind(32, 2048, 16384) == 0 and kind(1, 1000000, 1000000) == 0
+        assert L.genpc_chamfer_workspace_bytes(32, 2048, 16384) == base(32, 2048, 16384)
+    with _lib.tunable(GENPC_CHAMFER_PRUNE="1"):
+        assert kind(2, 700, 1300) == 1 and kind(2, 40, 1300) == 0
+    with _lib.tunable(GENPC_CHAMFER_PRUNE="2"):
+        assert kind(2, 700, 1300) == 2
+    assert L.genpc_emd_workspace_bytes_n(32, 8192) > L.genpc_emd_workspace_bytes(32) + 32 * 8192 * 16
+    assert L.genpc_emd_workspace_bytes_n(1, 65536) == L.genpc_emd_workspace_bytes(1)   # beyond the pruned Bid's range
