@@ -235,8 +235,9 @@ static __global__ void __launch_bounds__(PR_SORT_THREADS) nn_bin_sort_kernel(con
         if (lane == 0) bx[blk] = make_float4(l[0], l[1], l[2], 0.f), bx[nblk + blk] = make_float4(h[0], h[1], h[2], 0.f);
     }
     // ---- selection flag: the last CTA publishes "any cloud out of range, or a pair of clouds that does not overlap" (pruning
-    // needs neighbours to be near: when the two boxes of a pair are further apart than a quarter of the smaller one's diagonal
-    // every query group would open every block, 2.8x the cost of the exhaustive scan) ----
+    // needs neighbours to be near: when the two boxes of a pair are further apart than a quarter of the smaller one's diagonal,
+    // or one box is less than a quarter of the other across, every query group would open every block, 2.8x the cost of the
+    // exhaustive scan) ----
     if (tid == 0) {
         if (p.bbx != nullptr) {
             float *o = p.bbx + ((size_t)side * p.B + b) * 8;
@@ -260,6 +261,9 @@ static __global__ void __launch_bounds__(PR_SORT_THREADS) nn_bin_sort_kernel(con
                         gap2 += g * g, du += (u[3 + c] - u[c]) * (u[3 + c] - u[c]), dv += (v[3 + c] - v[c]) * (v[3 + c] - v[c]);
                     }
                     if (gap2 > 0.0625f * fminf(du, dv)) apart = 1;
+                    // ... and a cloud collapsed to a blob next to a spread-out one (an untrained generator's output against its
+                    // target): every group of the large cloud finds all blocks of the blob equally near and opens them all
+                    if (fminf(du, dv) < 0.0625f * fmaxf(du, dv)) apart = 1;
                 }
             }
             const int verdict = atomicExch(p.ctl + 2, 0) | apart;

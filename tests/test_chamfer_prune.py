@@ -88,7 +88,7 @@ def test_exact_ties_and_degenerate_geometry(cuda):
         same(got, oracle.chamfer_forward(a, b), name)
         # clouds whose bounding boxes are far apart cannot be pruned (every group would open every block): the sort kernel's
         # overlap test hands them to the exhaustive kernels
-        assert (st[2] > 0) == (name != "far_apart"), (name, st)
+        assert (st[2] > 0) == (name not in ("far_apart", "one_point_cloud_repeated")), (name, st)   # (a blob against a spread-out cloud, too)
 
 
 def test_default_takes_the_pruned_scan_from_2_30_evaluations(cuda):
