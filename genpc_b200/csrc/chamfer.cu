@@ -223,7 +223,7 @@ static bool tc_eligible(int B, int nr, int nc) {
 
 // Spatially pruned exact scan (nn_prune.cuh, r02): Hilbert-ordered clouds, one warp per 32 queries, blocks visited nearest first.
 // GENPC_CHAMFER_PRUNE=1 forces it for any shape it can take (64 .. 32768 points per cloud), =0 forbids it; by default it takes
-// device-resident batches whose exhaustive scan is at least 2^30 distance evaluations with >= 1024 points per cloud -- BASELINE C2
+// device-resident batches whose exhaustive scan is at least 2^30 distance evaluations with >= 2048 points per cloud -- BASELINE C2
 // (32 x 2048 x 16384: forward 0.271 -> 0.196 ms), 32 x 8192 x 8192 (0.539 -> 0.292 ms); below that the fixed cost of the sort
 // and of a group's dependent block chain (0.1 ms) loses (8 x 8192 x 8192: 0.155 vs 0.200 ms; profiles/r02m_chamfer_prune.txt).
 // The first form (Z-order cells, a uniform global load per target) took 0.70 ms on C2.
@@ -234,7 +234,9 @@ static bool prune_eligible(int B, int nr, int nc) {
     if (k != nullptr) return atoi(k) == 1;
     const char *tc = tunable("GENPC_CHAMFER_TC");
     if (tc != nullptr && atoi(tc) == 1) return false;   // an explicit request for the tensor-core filter wins over the default
-    return nr >= 1024 && nc >= 1024 && (long long)B * nr * nc >= (1LL << 30);
+    // (>= 2048 points per cloud: a thousand 1.8 K-point clouds -- the ICP scale search -- pay one sort CTA per cloud for next to
+    // nothing: 72.6 vs 66.2 ms per search)
+    return nr >= 2048 && nc >= 2048 && (long long)B * nr * nc >= (1LL << 30);
 }
 // Large clouds (nn_grid.cuh): multi-CTA sort + two-level pruned scan.  GENPC_CHAMFER_PRUNE=2 forces it for any shape it can
 // take (and skips the probe below), =0 switches it off; by default it takes the shapes whose exhaustive scan is at least 2^32

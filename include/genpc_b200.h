@@ -65,7 +65,7 @@ int genpc_chamfer_tc_stats(unsigned *stats4);
  * query groups that needed the tie pass, query groups, -} to the four device counters; NULL switches it off. */
 int genpc_chamfer_prune_stats(unsigned *stats4);
 /* Which scan genpc_chamfer_forward would queue for this shape with the current knobs (host logic only): 0 = exhaustive,
- * 1 = Hilbert-sorted pruned exact scan (batches of >= 2^30 evaluations, 1024 .. 32768 points per cloud), 2 = two-level pruned
+ * 1 = Hilbert-sorted pruned exact scan (batches of >= 2^30 evaluations, 2048 .. 32768 points per cloud), 2 = two-level pruned
  * exact scan for large clouds (>= 2^32 evaluations, more than 32768 points on a side, B <= 8).  Same outputs in every case. */
 int genpc_chamfer_scan_kind(int B, int N, int M);
 int genpc_tc_probe(const float *rows128, const float *cols256, float *e_out, genpc_stream_t stream);

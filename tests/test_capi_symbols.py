@@ -60,6 +60,7 @@ def test_scan_selection_host_logic():
     assert kind(1, 71372, 16384) == 0                                         # C1: below 2^32 evaluations
     assert kind(1, 1000000, 1000000) == 2 and kind(9, 1000000, 1000000) == 0  # C5; the grid path sorts cloud by cloud (B <= 8)
     assert kind(32, 512, 4096) == 0 and kind(4, 100, 37) == 0
+    assert kind(1000, 1791, 1755) == 0                                        # the ICP scale search: clouds too small for the sort to pay
     assert kind(0, 5, 5) < 0
     base = lambda B, N, M: (B * N + B * M) * 8 + 16                           # noqa: E731
     assert L.genpc_chamfer_workspace_bytes(8, 8192, 8192) == base(8, 8192, 8192)
