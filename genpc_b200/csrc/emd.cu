@@ -1035,7 +1035,9 @@ extern "C" int genpc_emd_forward(const float *xyz1, const float *xyz2, float *di
     const int prune_knob = pt != nullptr ? atoi(pt) : -1;
     bool prune = emd_prune_feasible(n) && workspace_bytes >= genpc_emd_workspace_bytes_n(B, n) &&
                  (reinterpret_cast<size_t>(workspace) & 15) == 0;
-    if (prune_knob == 0 || (prune_knob < 0 && n < 1024)) prune = false;
+    // measured (ms, exhaustive / pruned): 1 x 1024: 0.63 / 0.71, 32 x 1024: 1.06 / 0.88, 1 x 2048: 0.77 / 0.75, 8 x 4096: 2.00 / 1.01,
+    // 2 x 32768: 10.6 / 2.44
+    if (prune_knob == 0 || (prune_knob < 0 && (n < 1024 || (n < 2048 && (long long)B * n < 16384)))) prune = false;
     int dev = 0, sms = 0, per_sm = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
