@@ -170,10 +170,27 @@ static __global__ void __launch_bounds__(PR_SORT_THREADS) nn_bin_sort_kernel(con
             for (int c = 0; c < 3; ++c) code |= (unsigned)((cc[c] >> bit) & 1) << (3 * bit + c);
         return (int)code;
     };
-    // ---- histogram ----
-    for (int k = tid; k < n; k += PR_SORT_THREADS) {
-        float x, y, z;
-        atomicAdd(&hist[cell_of(k, x, y, z)], 1);
+    // ---- histogram; clouds of up to 16384 points keep each point's cell in registers for the scatter pass (the Hilbert key is
+    // a third of this kernel's instructions when it is computed in both passes) ----
+    constexpr int KEEP = 16;
+    const bool keep = n <= KEEP * PR_SORT_THREADS;
+    unsigned short cells[KEEP];
+    if (keep) {
+#pragma unroll
+        for (int i = 0; i < KEEP; ++i) {
+            const int k = tid + i * PR_SORT_THREADS;
+            cells[i] = 0;
+            if (k < n) {
+                float x, y, z;
+                cells[i] = (unsigned short)cell_of(k, x, y, z);
+                atomicAdd(&hist[cells[i]], 1);
+            }
+        }
+    } else {
+        for (int k = tid; k < n; k += PR_SORT_THREADS) {
+            float x, y, z;
+            atomicAdd(&hist[cell_of(k, x, y, z)], 1);
+        }
     }
     __syncthreads();
     // ---- exclusive scan of the histogram (4 entries per thread) ----
@@ -206,11 +223,24 @@ static __global__ void __launch_bounds__(PR_SORT_THREADS) nn_bin_sort_kernel(con
     }
     __syncthreads();
     // ---- scatter (the order inside a cell is whatever the atomics give: it only shapes the blocks, never a result) ----
-    for (int k = tid; k < n; k += PR_SORT_THREADS) {
-        float x, y, z;
-        const int cell = cell_of(k, x, y, z);
-        const int pos = atomicAdd(&hist[cell], 1);
-        dst[pos] = make_float4(x, y, z, __int_as_float(k));
+    if (keep) {
+#pragma unroll
+        for (int i = 0; i < KEEP; ++i) {
+            const int k = tid + i * PR_SORT_THREADS;
+            if (k < n) {
+                float x, y, z;
+                load_point(k, x, y, z);
+                const int pos = atomicAdd(&hist[cells[i]], 1);
+                dst[pos] = make_float4(x, y, z, __int_as_float(k));
+            }
+        }
+    } else {
+        for (int k = tid; k < n; k += PR_SORT_THREADS) {
+            float x, y, z;
+            const int cell = cell_of(k, x, y, z);
+            const int pos = atomicAdd(&hist[cell], 1);
+            dst[pos] = make_float4(x, y, z, __int_as_float(k));
+        }
     }
     const float qnan = __int_as_float(0x7fc00000);
     for (int k = n + tid; k < npad; k += PR_SORT_THREADS) dst[k] = make_float4(qnan, qnan, qnan, __int_as_float(0));
