@@ -333,7 +333,14 @@ __device__ __noinline__ void emd_assign(const int *__restrict__ uidx, const int 
 constexpr int EMD_BLOCK = 64;            // targets per block: one target PAIR per lane of the scanning warp
 constexpr int EMD_PRUNE_MAX_N = 32768;   // boxes of a cloud fit the kernel's shared memory, the sort fits one CTA's
 constexpr int EMD_SORT_THREADS = 1024;
-constexpr int EMD_PBATCH = 4;            // surviving blocks whose loads are in flight together
+// surviving blocks whose loads are in flight together.  Same-box sweep with the final structure (ms: B1 n8192 | B32 n8192 | B1
+// n16384 | B20 n2048): 1: 1.32 | 2.99 | 1.65 | 1.07;  2: 1.10 | 2.50 | 1.36 | 0.89;  3: 1.10 | 2.60 | 1.41 | 0.92;
+// 4: 1.17 | 2.88 | 1.47 | 0.97;  5: 1.22 | 3.12 | 1.57 | 1.01;  6: 1.36 | 3.56 | 1.67 | 1.10 (more blocks fetched before the first
+// threshold exists = more targets evaluated for nothing; with the first structure, which had a separate seed block, 2 lost to 4)
+#ifndef GENPC_EMD_PBATCH
+#define GENPC_EMD_PBATCH 2
+#endif
+constexpr int EMD_PBATCH = GENPC_EMD_PBATCH;
 
 // One CTA per cloud: Morton keys of the targets (cell << idxbits | original index), bitonic sort in shared memory, sorted
 // (x, y, z, index) records and per-block bounding boxes (all lower corners, then all upper corners).  The ORDER only affects how well the blocks prune, never a result.
