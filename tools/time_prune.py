@@ -5,6 +5,8 @@ import numpy as np
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from genpc_b200 import _lib
+if os.environ.get("GENPC_LIB"):   # A/B of two builds on the same box
+    _lib.LIB_PATH = os.path.abspath(os.environ["GENPC_LIB"])
 from genpc_b200.loss_functions import chamfer_3DDist
 from genpc_b200.synthetic import pcn_batch
 from genpc_b200.utils.loss_util import Completionloss
