@@ -11,7 +11,7 @@
 //     per point (P adapts so the items fill the group); targets + prices staged as float4 chunks in shared memory;
 //   * the last CTA of the group to finish an iteration's bids (atomic ticket) runs the O(n) tail on its own:
 //     GetMax -> Assign -> reset -> ascending compaction of the still-unassigned points, then releases a
-//     per-batch flag the group spins on (the first iterations, thousands of bidders, spread GetMax / Assign over the
+//     per-batch flag the group spins on (iterations with 512 or more bidders spread GetMax / Assign over the
 //     group between two counter barriers instead).  No grid-wide barrier, no host round trip.
 // Arithmetic and tie rules are the reference's, bit for bit (oracle_emd_forward has the derivation):
 //   value = (float)((3.0 - (double)sqrtf(fma(dz,dz,fma(dx,dx,dy*dy)))) - (double)price)   (emd_cuda.cu:146)
@@ -1084,7 +1084,9 @@ extern "C" int genpc_emd_forward(const float *xyz1, const float *xyz2, float *di
     }
     // measured on B200 (profiles/r01j_emd_direct.txt)
     a.direct_p = 8;
-    a.tail_spread_u = 2048;
+    // same-box sweep (ms: B1 n8192 | B32 n8192 | B1 n16384 | B20 n2048): 64: 1.10 | 2.48 | 1.24 | 0.99;  256: 1.08 | 2.47 | 1.24 | 0.91;
+    // 512: 1.04 | 2.45 | 1.23 | 0.90;  1024: 1.08 | 2.48 | 1.31 | 0.90;  2048: 1.10 | 2.51 | 1.38 | 0.89;  4096: 1.12 | 2.53 | 1.43 | 0.90
+    a.tail_spread_u = 512;
     const char *tsu = tunable("GENPC_EMD_TAIL_SPREAD");  // experiments only
     if (tsu != nullptr) a.tail_spread_u = atoi(tsu);
     a.two_level_div = 8;
