@@ -193,7 +193,10 @@ def test_nccl_two_ranks_sharded_chamfer_and_batch_sharded_emd(cuda):
     worker = os.path.join(os.path.dirname(os.path.abspath(__file__)), "nccl_sharded_worker.py")
     p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
                         "127.0.0.1", "--master-port", str(port), worker], capture_output=True, text=True, timeout=600)
-    lines = [ln for ln in p.stdout.splitlines() if ln.startswith("RANK")]
+    import re
+
+    # (the two ranks share one pipe: their lines may arrive glued together, so look for the records, not for line starts)
+    lines = re.findall(r"RANK\d+ \{[^{}]*\}", p.stdout)
     assert p.returncode == 0 and len(lines) == 2, p.stdout[-2000:] + p.stderr[-2000:]
     for ln in lines:
         assert '"all_ranks_ok": true' in ln, ln
