@@ -6,7 +6,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgenpc_b200.so")
+# GENPC_LIB: an alternative build of the same library (same-box A/B runs of compile-time variants, tools/); default: in-tree
+LIB_PATH = os.path.abspath(os.environ["GENPC_LIB"]) if os.environ.get("GENPC_LIB") else os.path.join(_HERE, "libgenpc_b200.so")
 _lib = None
 
 _vp = ctypes.c_void_p

@@ -76,17 +76,19 @@ __device__ __forceinline__ void rot6d_to_matrix(const float *d6, float *R) {
 // j0 = first query of the tile, t0 = first target of the span, idx_base = value added to the reported index
 // (0 for plain Chamfer; the shard offset for target-sharded clouds).  qT / tT: optional similarity applied to
 // the queries / targets on the fly (nullptr = identity).  out = packed words of this cloud's queries.
-template <int QT>
-__device__ __forceinline__ void nn_scan_item(float (*s)[NN_SPAN], const float *__restrict__ q, int nq, int j0,
+// SPAN (a multiple of NN_CHUNK): targets per item -- NN_SPAN everywhere except the persistent small-registration kernel, which
+// uses shorter spans to spread a scan over more CTAs (the packed atomicMin merge makes the result independent of the split)
+template <int QT, int SPAN = NN_SPAN>
+__device__ __forceinline__ void nn_scan_item(float (*s)[SPAN], const float *__restrict__ q, int nq, int j0,
                                              const float *__restrict__ t, int mt, int t0, int idx_base,
                                              const Similarity *qT, const Similarity *tT,
                                              unsigned long long *__restrict__ out) {
     const int tid = threadIdx.x;
-    const int cnt = min(NN_SPAN, mt - t0);
+    const int cnt = min(SPAN, mt - t0);
     // ---- stage targets: AoS global -> SoA shared ----
     {
         const float qnan = __int_as_float(0x7fc00000);
-        for (int k = tid; k < NN_SPAN; k += NN_THREADS) {
+        for (int k = tid; k < SPAN; k += NN_THREADS) {
             float x = qnan, y = qnan, z = qnan;
             if (k < cnt) {
                 const float *tp = t + (size_t)(t0 + k) * 3;

@@ -50,6 +50,7 @@ struct RegArgs {
     // pruned scan (nn_prune.cuh): *select == 0 -> the packed words of both directions already hold exact indices (the symmetric
     // scan kernel returns at once, the finish kernel skips its fix-up); nullptr: exhaustive path only
     const int *select;
+    int nn_span;   // targets per work item of the single-launch / persistent kernels (256, 512 or NN_SPAN)
 };
 
 __device__ __forceinline__ void load_similarity(const float *par, const float *center, Similarity &T) {
@@ -237,11 +238,11 @@ __global__ void __launch_bounds__(NN_THREADS, NN_MINBLOCKS) register_step_kernel
 //                                                                           | releases `iter_done[scan] = k + 1`
 // Scans never wait for each other.  Adam's per-iteration scalars are computed on the device from t (same double formulas
 // as the host loop).
-template <int QT>
+template <int QT, int SPAN = NN_SPAN>
 __global__ void __launch_bounds__(NN_THREADS, NN_MINBLOCKS) register_persistent_kernel(RegArgs a, int iters, int t_start, double lr_rot,
                                                                                        double lr_trans, double lr_scale, int *iter_done,
                                                                                        int *arrivals) {
-    __shared__ __align__(16) float s[3][NN_SPAN];
+    __shared__ __align__(16) float s[3][SPAN];
     __shared__ Similarity T;
     __shared__ int is_last;
     __shared__ double shp[NN_THREADS / 32][14];
@@ -275,11 +276,11 @@ __global__ void __launch_bounds__(NN_THREADS, NN_MINBLOCKS) register_persistent_
         int item = item0;
         if (item < a.itemsA) {
             const int ts = item % a.tsplitsA, qt = item / a.tsplitsA;
-            nn_scan_item<QT>(s, V, a.Nc, qt * (NN_THREADS * QT), Rf, a.Nr, ts * NN_SPAN, 0, &T, nullptr, pA);
+            nn_scan_item<QT, SPAN>(s, V, a.Nc, qt * (NN_THREADS * QT), Rf, a.Nr, ts * SPAN, 0, &T, nullptr, pA);
         } else {
             item -= a.itemsA;
             const int ts = item % a.tsplitsB, qt = item / a.tsplitsB;
-            nn_scan_item<QT>(s, Rf, a.Nr, qt * (NN_THREADS * QT), V, a.Nc, ts * NN_SPAN, 0, nullptr, &T, pB);
+            nn_scan_item<QT, SPAN>(s, Rf, a.Nr, qt * (NN_THREADS * QT), V, a.Nc, ts * SPAN, 0, nullptr, &T, pB);
         }
         // ---- per-scan barrier: every item of the scan has published its minima ----
         __threadfence();
@@ -527,12 +528,14 @@ static bool register_takes_sym_path(int S, int Nc, int Nr) {
     return (mode == nullptr ? big : strcmp(mode, "sym") == 0) && Nr >= 512;
 }
 
+constexpr int REG_SPAN_MIN = 256;   // shortest target span of the persistent kernel's work items
+
 // per-scan slots of 14-double partial sums: one per finish CTA (symmetric path, finest granularity 128 columns) or one per
 // work item of the persistent small path (at its finest, one query per thread)
 static size_t register_partial_slots(int Nc, int Nr) {
     const size_t fix_ctas = ((size_t)Nc + 128 - 1) / 128;
-    const size_t items = (size_t)((Nc + NN_THREADS - 1) / NN_THREADS) * ((Nr + NN_SPAN - 1) / NN_SPAN) +
-                         (size_t)((Nr + NN_THREADS - 1) / NN_THREADS) * ((Nc + NN_SPAN - 1) / NN_SPAN);
+    const size_t items = (size_t)((Nc + NN_THREADS - 1) / NN_THREADS) * ((Nr + REG_SPAN_MIN - 1) / REG_SPAN_MIN) +
+                         (size_t)((Nr + NN_THREADS - 1) / NN_THREADS) * ((Nc + REG_SPAN_MIN - 1) / REG_SPAN_MIN);
     return fix_ctas > items ? fix_ctas : items;
 }
 
@@ -586,14 +589,19 @@ extern "C" int genpc_register_run(const float *complete, const float *center, co
             QT >>= 1;
         }
     }
-    a.qtilesA = (Nc + NN_THREADS * QT - 1) / (NN_THREADS * QT);
-    a.tsplitsA = (Nr + NN_SPAN - 1) / NN_SPAN;
-    a.itemsA = a.qtilesA * a.tsplitsA;
-    a.qtilesB = (Nr + NN_THREADS * QT - 1) / (NN_THREADS * QT);
-    a.tsplitsB = (Nc + NN_SPAN - 1) / NN_SPAN;
-    a.items_per_scan = a.itemsA + a.qtilesB * a.tsplitsB;
-    a.ticket_total = a.items_per_scan;
-    const long long grid = (long long)S * a.items_per_scan;
+    // work items of the single-launch kernels for a given target span (NN_SPAN unless the persistent kernel picks a shorter one)
+    auto set_span = [&](int span) {
+        a.nn_span = span;
+        a.qtilesA = (Nc + NN_THREADS * QT - 1) / (NN_THREADS * QT);
+        a.tsplitsA = (Nr + span - 1) / span;
+        a.itemsA = a.qtilesA * a.tsplitsA;
+        a.qtilesB = (Nr + NN_THREADS * QT - 1) / (NN_THREADS * QT);
+        a.tsplitsB = (Nc + span - 1) / span;
+        a.items_per_scan = a.itemsA + a.qtilesB * a.tsplitsB;
+        a.ticket_total = a.items_per_scan;
+        return (long long)S * a.items_per_scan;
+    };
+    long long grid = set_span(NN_SPAN);
     if (grid > 0x7fffffffLL) return GENPC_ERR_RANGE;
     const bool sym = register_takes_sym_path(S, Nc, Nr);
     const int SQT = Nr >= 1024 ? 4 : 2;
@@ -633,6 +641,18 @@ extern "C" int genpc_register_run(const float *complete, const float *center, co
             case 2: eo = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, register_persistent_kernel<2>, NN_THREADS, 0); break;
             default: eo = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, register_persistent_kernel<1>, NN_THREADS, 0); break;
         }
+        // shorter target spans spread a scan over more CTAs (the scan phase is the longest link of an iteration's chain): the
+        // shortest of 256 / 512 / NN_SPAN whose grid is still co-resident, when the fixed cloud fits one full span (the real
+        // pipeline's 1 K-point scans).  Same-box A/B (us per iteration, 4 starts): 1200 x 800 25.2 -> 19.8, 2500 x 1000 25.8 ->
+        // 23.7; with a larger fixed cloud the extra merges cost more than the shorter scans save (924 x 2500: 25.4 -> 27.1), so
+        // those keep full spans.  The results do not depend on the split (packed atomicMin merge).
+        if (eo == cudaSuccess && (pk == nullptr || atoi(pk) != 0) && QT == 1 && Nr <= NN_SPAN) {
+            for (int span = REG_SPAN_MIN; span < NN_SPAN; span <<= 1) {
+                if (set_span(span) <= (long long)sms * per_sm) break;
+                set_span(NN_SPAN);
+            }
+            grid = (long long)S * a.items_per_scan;
+        }
         if (eo == cudaSuccess && (pk == nullptr || atoi(pk) != 0) && grid <= (long long)sms * per_sm) {
             int *iter_done = a.counters + S, *arrivals = a.counters + 2 * S;
             cudaError_t e = cudaMemsetAsync(iter_done, 0, 2 * (size_t)S * sizeof(int), stream);
@@ -641,11 +661,15 @@ extern "C" int genpc_register_run(const float *complete, const float *center, co
             void *kargs[] = {(void *)&a, (void *)&it_n, (void *)&t0, (void *)&lr_rot, (void *)&lr_trans, (void *)&lr_scale, (void *)&iter_done,
                              (void *)&arrivals};
             const void *fn = QT == 4 ? (const void *)register_persistent_kernel<4>
-                                     : (QT == 2 ? (const void *)register_persistent_kernel<2> : (const void *)register_persistent_kernel<1>);
+                                     : (QT == 2 ? (const void *)register_persistent_kernel<2>
+                                                : (a.nn_span == 256 ? (const void *)register_persistent_kernel<1, 256>
+                                                                    : (a.nn_span == 512 ? (const void *)register_persistent_kernel<1, 512>
+                                                                                        : (const void *)register_persistent_kernel<1>)));
             e = cudaLaunchCooperativeKernel(fn, dim3((unsigned)grid), dim3(NN_THREADS), kargs, 0, stream);
             if (e != cudaSuccess) return (int)e;
             return GENPC_OK;
         }
+        grid = set_span(NN_SPAN);   // not co-resident: one launch per iteration with full spans
     }
     // ---- pruned scan set-up: control words, similarities, sorted copies behind the base workspace ----
     const bool prune = sym && register_prune_eligible(S, Nc, Nr) &&
