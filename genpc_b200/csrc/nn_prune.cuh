@@ -1,15 +1,19 @@
-// nn_prune.cuh -- exact nearest neighbours with spatial pruning (r02 experiment, GENPC_CHAMFER_PRUNE=1).
+// nn_prune.cuh -- exact nearest neighbours with spatial pruning (r02).  The default Chamfer scan for device-resident batches of
+// >= 2^30 distance evaluations (BASELINE C2) and inside the registration loop from ~20 scans up; the sort kernel also serves the
+// EMD auction's pruned Bid.  GENPC_CHAMFER_PRUNE / GENPC_REGISTER_PRUNE = 0 / 1 forbid / force it.
 //
 // The symmetric scan (nn_sym.cuh) evaluates every (row, column) distance of a cloud pair: at its issue limit that is
 // 7.9e12 pairs/s and nothing in its instruction stream is left to remove.  What is left is not to evaluate most pairs:
-//   1. nn_bin_sort_kernel orders every cloud along a Morton curve (counting sort over 8^m grid cells in shared memory,
+//   1. nn_bin_sort_kernel orders every cloud along a Hilbert curve (counting sort over 8^m grid cells in shared memory,
 //      one CTA per cloud) into (x, y, z, original index) records and stores the bounding box of every PR_BLOCK
 //      consecutive ones;
 //   2. nn_prune_kernel: one warp owns PR_GROUP consecutive sorted queries (one per lane -- neighbours in space).  It
 //      computes the squared distance between the group's box and every target block's box, visits the blocks nearest
 //      first (REDUX picks them) and stops at the first block farther than the group's worst running minimum: no target
-//      in it, or in any later block, can improve (or tie) any lane.  Inside a block all lanes walk the same 64 targets
-//      (uniform loads) with the packed FP32 distance of the exhaustive kernels: the same bits.
+//      in it, or in any later block, can improve (or tie) any lane.  A block is fetched with one coalesced read into the
+//      warp's shared-memory slice (SoA) and walked there with the packed FP32 distance of the exhaustive kernels: the
+//      same bits.  nn_prune_coop_kernel is the form for a direction with few query groups and many target blocks: a CTA
+//      per group, the blocks partitioned over its eight warps, running minima shared through shared memory.
 // Exactness: the minimum of a set does not depend on the visiting order; the reported index is the LOWEST original index
 // among the targets at the minimum, as in the exhaustive kernels (the winner's 8-target chunk is re-evaluated; a lane
 // that saw the same minimum in two chunks takes a second pass over the surviving blocks).  The box distance is scaled
