@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(PR_THREADS) nn_prune2_kernel(const Prune2Param
             // are (the AoS form spent 6 of its 15 instructions per target pair moving registers into pairs)
             const float4 *sx4 = reinterpret_cast<const float4 *>(stage[wid][0]), *sy4 = reinterpret_cast<const float4 *>(stage[wid][1]),
                          *sz4 = reinterpret_cast<const float4 *>(stage[wid][2]);
-#pragma unroll 2
+#pragma unroll PR_UNROLL
             for (int c = 0; c < PR_BLOCK / 8; ++c) {
                 float cm = inf;
 #pragma unroll

@@ -24,8 +24,13 @@
 #include "common.cuh"
 #include "nn_core.cuh"   // Similarity / apply_similarity (registration: the moving cloud is sorted in its current pose)
 
+#ifndef GENPC_PR_UNROLL
+#define GENPC_PR_UNROLL 4   // 8-target chunks per unrolled step of a block walk (sweep 1/2/4/8: profiles/r02w_unroll_sweep.txt)
+#endif
+
 namespace genpc {
 
+constexpr int PR_UNROLL = GENPC_PR_UNROLL;
 constexpr int PR_BLOCK = 64;
 constexpr int PR_GROUP = 32;
 constexpr int PR_MAX_N = 32768;       // 512 blocks: the block id fits the 9 low bits of the selection key
@@ -416,7 +421,7 @@ __global__ void __launch_bounds__(PR_THREADS) nn_prune_kernel(const PrunePair pp
         // are (the AoS form spent 6 of its 15 instructions per target pair moving registers into pairs)
         const float4 *sx4 = reinterpret_cast<const float4 *>(stage[wid][0]), *sy4 = reinterpret_cast<const float4 *>(stage[wid][1]),
                      *sz4 = reinterpret_cast<const float4 *>(stage[wid][2]);
-#pragma unroll 2
+#pragma unroll PR_UNROLL
         for (int c = 0; c < PR_BLOCK / 8; ++c) {
             float cm = inf;
 #pragma unroll
@@ -563,7 +568,7 @@ __global__ void __launch_bounds__(PR_THREADS) nn_prune_coop_kernel(const PrunePa
         // are (the AoS form spent 6 of its 15 instructions per target pair moving registers into pairs)
         const float4 *sx4 = reinterpret_cast<const float4 *>(stage[wid][0]), *sy4 = reinterpret_cast<const float4 *>(stage[wid][1]),
                      *sz4 = reinterpret_cast<const float4 *>(stage[wid][2]);
-#pragma unroll 2
+#pragma unroll PR_UNROLL
         for (int c = 0; c < PR_BLOCK / 8; ++c) {
             float cm = inf;
 #pragma unroll
