@@ -356,6 +356,51 @@ static void launch_prune(const PruneParams &a, const PruneParams &b, cudaStream_
     if (side != nullptr) cudaStreamWaitEvent(stream, side->join, 0);
 }
 
+// The sort of `clouds` clouds: one CTA per cloud, or a thread-block cluster of CS CTAs per cloud when one CTA per cloud would leave
+// most SMs idle behind a few long CTAs (C2: 64 clouds, the 32 of 16384 points take 55 us in one CTA each).  GENPC_SORT_CLUSTER =
+// 1 / 2 / 4 / 8 forces the cluster size.
+template <int CS>
+static void launch_bin_sort_cs(PruneSortParams sp, int ctas, cudaStream_t stream) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)((ctas + CS - 1) / CS * CS));
+    cfg.blockDim = dim3(PR_SORT_THREADS);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CS, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr, cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, nn_bin_sort_kernel<CS>, sp);
+}
+
+// both sides of nb cloud pairs
+static void launch_bin_sort(PruneSortParams sp, int nb, cudaStream_t stream) {
+    const int nmax = sp.n[0] > sp.n[1] ? sp.n[0] : sp.n[1], nmin = sp.n[0] > sp.n[1] ? sp.n[1] : sp.n[0];
+    int cs = 1, mixed = 0;
+    const char *k = tunable("GENPC_SORT_CLUSTER");   // "2" / "3" / "4" / "8": every cloud a cluster; "m2" / "m3" / "m4": mixed layout
+    if (k != nullptr) {
+        mixed = k[0] == 'm' ? 1 : 0;
+        cs = atoi(k + mixed);
+    } else if (nmax >= 8192) {
+        // as many CTAs per cloud as keep the grid inside one wave (one 1024-thread CTA per SM); when one side is much smaller, its
+        // clouds take one CTA each and leave the SMs to the clusters of the larger side (C2: 32 x 3 + 33 CTAs)
+        const int sms = num_sms();
+        if (nmin * 4 <= nmax && nmin <= 4096) {
+            mixed = 1;
+            cs = nb * 4 + (nb + 3) / 4 * 4 <= sms ? 4 : nb * 3 + (nb + 2) / 3 * 3 <= sms ? 3 : nb * 2 + (nb + 1) / 2 * 2 <= sms ? 2 : 1;
+        } else {
+            cs = nb * 16 <= sms ? 8 : nb * 8 <= sms ? 4 : nb * 4 <= sms ? 2 : 1;
+        }
+    }
+    if (cs < 2) mixed = 0;
+    sp.mixed = mixed;
+    const int ctas = mixed ? nb * cs + nb : 2 * nb * cs;
+    if (cs >= 8) launch_bin_sort_cs<8>(sp, ctas, stream);
+    else if (cs >= 4) launch_bin_sort_cs<4>(sp, ctas, stream);
+    else if (cs == 3) launch_bin_sort_cs<3>(sp, ctas, stream);
+    else if (cs == 2) launch_bin_sort_cs<2>(sp, ctas, stream);
+    else nn_bin_sort_kernel<1><<<2 * nb, PR_SORT_THREADS, 0, stream>>>(sp);
+}
+
 // Sort + pruned scan of the cloud pairs [b0, b0 + nb) of a batch (rows / cols / prow / pcol: the batch's arrays).
 static int launch_prune_subbatch(const float *rows, const float *cols, int nr, int nc, unsigned long long *prow, unsigned long long *pcol,
                                  int B, int b0, int nb, int *ctl, void *prune_extra, bool accumulate, cudaStream_t stream,
@@ -373,7 +418,7 @@ static int launch_prune_subbatch(const float *rows, const float *cols, int nr, i
     sp.sorted[0] = sorted0 + (size_t)b0 * pr_npad(nr), sp.sorted[1] = sorted1 + (size_t)b0 * pr_npad(nc);
     sp.boxes[0] = boxes0 + (size_t)b0 * 2 * pr_nblk(nr), sp.boxes[1] = boxes1 + (size_t)b0 * 2 * pr_nblk(nc);
     sp.bbx = bbx + (size_t)b0 * 16;
-    nn_bin_sort_kernel<<<2 * nb, PR_SORT_THREADS, 0, stream>>>(sp);
+    launch_bin_sort(sp, nb, stream);
     GENPC_CHECK_LAUNCH();
     PruneParams q = {};
     q.B = nb, q.select = ctl + 1, q.stats = g_prune_stats;

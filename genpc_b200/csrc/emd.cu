@@ -1121,7 +1121,7 @@ extern "C" int genpc_emd_forward(const float *xyz1, const float *xyz2, float *di
             sp.sorted[0] = tsort, sp.sorted[1] = tsort, sp.boxes[0] = boxes, sp.boxes[1] = boxes;
             sp.ctl = (int *)workspace + 4 * (size_t)B;   // scratch words of the range check (unused here)
             sp.hilbert = (sk == nullptr || strcmp(sk, "morton") != 0) ? 1 : 0;
-            nn_bin_sort_kernel<<<B, PR_SORT_THREADS, 0, stream>>>(sp);   // grid = B: side 0 only
+            nn_bin_sort_kernel<1><<<B, PR_SORT_THREADS, 0, stream>>>(sp);   // grid = B: side 0 only
         } else {
             emd_sort_kernel<<<B, EMD_SORT_THREADS, smem, stream>>>(xyz2, tsort, boxes, n, np2, idxbits, mbits);
         }

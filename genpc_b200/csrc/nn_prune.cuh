@@ -21,6 +21,8 @@
 // The sort kernel doubles as the range check (NaN / Inf / |x| > 1e15 -> the exhaustive kernel runs instead, selected on
 // the device through the same flag as the tensor-core filter).
 #pragma once
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 #include "nn_core.cuh"   // Similarity / apply_similarity (registration: the moving cloud is sorted in its current pose)
 
@@ -92,6 +94,7 @@ struct PruneSortParams {
     // registration: only one side is sorted per launch (side0 = its index, grid = B), its points taken from cloud b / src_div
     // and moved by the similarity sim[b] while they are read (the same rounding as the exhaustive scan's staging)
     int side0, single_side;
+    int mixed;             // cluster launches only: the larger side's clouds take a whole cluster each, the other side's one CTA each
     int src_div[2];
     const Similarity *sim[2];
 };
@@ -103,14 +106,42 @@ static __global__ void prune_rearm_kernel(unsigned long long *words, size_t n, c
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) words[i] = ~0ull;
 }
 
-// grid = 2 * B CTAs: blockIdx.x = side * B + b
+// grid = 2 * B * CS CTAs: cloud = blockIdx.x / CS = side * B + b (or the mixed layout below).  CS > 1 (launched as thread-block clusters of CS CTAs): the CTAs of
+// a cluster share one cloud -- every CTA takes each CS-th slab of 1024 points, keeps its own histogram, and reads its siblings'
+// bounding boxes and histograms through distributed shared memory (a point's slot = cells before it + the same cell's counts in
+// the lower-ranked CTAs + the CTA's own atomic counter); the block boxes are split between the CTAs after the last cluster
+// barrier.  One CTA per 16384-point cloud was 55 us of C2's 170 us forward with 84 of the 148 SMs idle.
+template <int CS>
 static __global__ void __launch_bounds__(PR_SORT_THREADS) nn_bin_sort_kernel(const PruneSortParams p) {
-    __shared__ int hist[PR_MAX_CELLS];
+    __shared__ __align__(16) int hist[PR_MAX_CELLS];
+    __shared__ __align__(16) int slot[CS > 1 ? PR_MAX_CELLS : 4];   // CS > 1: next free slot per cell (hist stays readable for the siblings)
     __shared__ float sred[6][PR_SORT_THREADS / 32];
+    __shared__ float cbox[8];
     __shared__ int swarp[PR_SORT_THREADS / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int side = p.single_side ? p.side0 : (int)blockIdx.x / p.B, b = (int)blockIdx.x % p.B;
-    const int n = p.n[side], nblk = pr_nblk(n), npad = nblk * PR_BLOCK;
+    // cr = rank of this CTA among the `ceff` CTAs that share its cloud, r0 = cluster rank of the first of them
+    int cr = 0, r0 = 0, ceff = 1, cloud = (int)blockIdx.x;
+    bool idle = false;
+    if constexpr (CS > 1) {
+        const int rank = (int)cooperative_groups::this_cluster().block_rank();
+        if (p.mixed) {
+            // clusters [0, B): one cloud of the LARGER side each; the CTAs behind them: one cloud of the other side each, on their
+            // own (they only keep the cluster barriers company); CTAs that round the grid up to whole clusters idle
+            const int big = p.n[1] > p.n[0] ? 1 : 0;
+            if ((int)blockIdx.x < p.B * CS) {
+                cloud = big * p.B + (int)blockIdx.x / CS, cr = rank, ceff = CS;
+            } else {
+                const int j = (int)blockIdx.x - p.B * CS;
+                idle = j >= p.B;
+                cloud = (1 - big) * p.B + (idle ? 0 : j), r0 = rank;
+            }
+        } else {
+            cloud = (int)blockIdx.x / CS, cr = rank, ceff = CS;
+        }
+    }
+    const int side = p.single_side ? p.side0 : cloud / p.B, b = cloud % p.B;
+    const int STRIDE = ceff * PR_SORT_THREADS;
+    const int n = idle ? 0 : p.n[side], nblk = pr_nblk(n), npad = nblk * PR_BLOCK;
     const float *src = p.xyz[side] + (size_t)(p.src_div[side] > 1 ? b / p.src_div[side] : b) * n * 3;
     __shared__ Similarity sT;
     const bool moved = p.sim[side] != nullptr;
@@ -126,7 +157,7 @@ static __global__ void __launch_bounds__(PR_SORT_THREADS) nn_bin_sort_kernel(con
     // ---- bounding box + range check ----
     float lo[3] = {inf, inf, inf}, hi[3] = {-inf, -inf, -inf};
     bool bad = false;
-    for (int k = tid; k < n; k += PR_SORT_THREADS) {
+    for (int k = cr * PR_SORT_THREADS + tid; k < n; k += STRIDE) {
         float v[3];
         load_point(k, v[0], v[1], v[2]);
 #pragma unroll
@@ -152,12 +183,38 @@ static __global__ void __launch_bounds__(PR_SORT_THREADS) nn_bin_sort_kernel(con
     for (int k = tid; k < ncell; k += PR_SORT_THREADS) hist[k] = 0;
     const int anybad = __syncthreads_or(bad ? 1 : 0);
     float scale[3];
+    if constexpr (CS > 1) {   // the cloud's box = the union of the CTAs' boxes
+        if (tid < 6) {
+            float r = tid < 3 ? inf : -inf;
+            for (int w = 0; w < PR_SORT_THREADS / 32; ++w) r = tid < 3 ? fminf(r, sred[tid][w]) : fmaxf(r, sred[tid][w]);
+            cbox[tid] = r;
+        }
+        cooperative_groups::cluster_group cluster = cooperative_groups::this_cluster();
+        cluster.sync();
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float l = inf, h = -inf;
+            for (int r = r0; r < r0 + ceff; ++r) {
+                const float *o = cluster.map_shared_rank(cbox, r);
+                l = fminf(l, o[c]), h = fmaxf(h, o[3 + c]);
+            }
+            lo[c] = l, hi[c] = h;
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float l = inf, h = -inf;
+            for (int w = 0; w < PR_SORT_THREADS / 32; ++w) l = fminf(l, sred[c][w]), h = fmaxf(h, sred[3 + c][w]);
+            lo[c] = l, hi[c] = h;
+        }
+    }
+    if (tid == 0 && cr == 0 && !idle && p.bbx != nullptr) {   // read by the last CTA of the grid, behind its ticket (below)
+        float *o = p.bbx + ((size_t)side * p.B + b) * 8;
+        for (int c = 0; c < 3; ++c) o[c] = lo[c], o[3 + c] = hi[c];
+    }
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-        float l = inf, h = -inf;
-        for (int w = 0; w < PR_SORT_THREADS / 32; ++w) l = fminf(l, sred[c][w]), h = fmaxf(h, sred[3 + c][w]);
-        lo[c] = l;
-        const float ext = h - l;
+        const float ext = hi[c] - lo[c];
         scale[c] = (ext > 0.f && ext < inf) ? (float)(1 << mbits) / ext : 0.f;
     }
     const int cmax = (1 << mbits) - 1;
@@ -184,13 +241,13 @@ static __global__ void __launch_bounds__(PR_SORT_THREADS) nn_bin_sort_kernel(con
     };
     // ---- histogram; clouds of up to 16384 points keep each point's cell in registers for the scatter pass (the Hilbert key is
     // a third of this kernel's instructions when it is computed in both passes) ----
-    constexpr int KEEP = 16;
-    const bool keep = n <= KEEP * PR_SORT_THREADS;
+    constexpr int KEEP = CS == 1 ? 16 : (PR_MAX_N + CS * PR_SORT_THREADS - 1) / (CS * PR_SORT_THREADS);   // CS > 1: every size up to PR_MAX_N
+    const bool keep = n <= KEEP * STRIDE;
     unsigned short cells[KEEP];
     if (keep) {
 #pragma unroll
         for (int i = 0; i < KEEP; ++i) {
-            const int k = tid + i * PR_SORT_THREADS;
+            const int k = cr * PR_SORT_THREADS + tid + i * STRIDE;
             cells[i] = 0;
             if (k < n) {
                 float x, y, z;
@@ -199,22 +256,40 @@ static __global__ void __launch_bounds__(PR_SORT_THREADS) nn_bin_sort_kernel(con
             }
         }
     } else {
-        for (int k = tid; k < n; k += PR_SORT_THREADS) {
+        for (int k = cr * PR_SORT_THREADS + tid; k < n; k += STRIDE) {
             float x, y, z;
             atomicAdd(&hist[cell_of(k, x, y, z)], 1);
         }
     }
-    __syncthreads();
-    // ---- exclusive scan of the histogram (4 entries per thread) ----
+    if constexpr (CS > 1) cooperative_groups::this_cluster().sync();   // every sibling's histogram is complete
+    else __syncthreads();
+    // ---- exclusive scan of the histogram (4 entries per thread; CS > 1: of the sum of the CS histograms) ----
+    int *next = CS > 1 ? slot : hist;
     {
-        const int per = PR_MAX_CELLS / PR_SORT_THREADS;
-        int v[per], s = 0;
+        constexpr int per = PR_MAX_CELLS / PR_SORT_THREADS;
+        static_assert(per == 4, "one int4 of cells per thread");
+        int v[per], below[per], s = 0;
 #pragma unroll
-        for (int i = 0; i < per; ++i) {
-            const int e = tid * per + i;
-            v[i] = e < ncell ? hist[e] : 0;
-            s += v[i];
+        for (int i = 0; i < per; ++i) v[i] = below[i] = 0;
+        if (tid * per < ncell) {   // ncell is 8, 64, 512 or 4096: a thread's four cells are all inside or all outside
+            if constexpr (CS > 1) {
+                cooperative_groups::cluster_group cluster = cooperative_groups::this_cluster();
+                for (int r = r0; r < r0 + ceff; ++r) {
+                    const int4 t = *reinterpret_cast<const int4 *>(cluster.map_shared_rank(hist, r) + tid * per);
+                    const int tv[per] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+                    for (int i = 0; i < per; ++i) {
+                        v[i] += tv[i];
+                        if (r < r0 + cr) below[i] += tv[i];
+                    }
+                }
+            } else {
+                const int4 t = *reinterpret_cast<const int4 *>(hist + tid * per);
+                v[0] = t.x, v[1] = t.y, v[2] = t.z, v[3] = t.w;
+            }
         }
+#pragma unroll
+        for (int i = 0; i < per; ++i) s += v[i];
         int incl = s;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -229,7 +304,7 @@ static __global__ void __launch_bounds__(PR_SORT_THREADS) nn_bin_sort_kernel(con
 #pragma unroll
         for (int i = 0; i < per; ++i) {
             const int e = tid * per + i;
-            if (e < ncell) hist[e] = run;
+            if (e < ncell) next[e] = run + below[i];
             run += v[i];
         }
     }
@@ -238,31 +313,39 @@ static __global__ void __launch_bounds__(PR_SORT_THREADS) nn_bin_sort_kernel(con
     if (keep) {
 #pragma unroll
         for (int i = 0; i < KEEP; ++i) {
-            const int k = tid + i * PR_SORT_THREADS;
+            const int k = cr * PR_SORT_THREADS + tid + i * STRIDE;
             if (k < n) {
                 float x, y, z;
                 load_point(k, x, y, z);
-                const int pos = atomicAdd(&hist[cells[i]], 1);
+                const int pos = atomicAdd(&next[cells[i]], 1);
                 dst[pos] = make_float4(x, y, z, __int_as_float(k));
             }
         }
     } else {
-        for (int k = tid; k < n; k += PR_SORT_THREADS) {
+        for (int k = cr * PR_SORT_THREADS + tid; k < n; k += STRIDE) {
             float x, y, z;
             const int cell = cell_of(k, x, y, z);
-            const int pos = atomicAdd(&hist[cell], 1);
+            const int pos = atomicAdd(&next[cell], 1);
             dst[pos] = make_float4(x, y, z, __int_as_float(k));
         }
     }
     const float qnan = __int_as_float(0x7fc00000);
-    for (int k = n + tid; k < npad; k += PR_SORT_THREADS) dst[k] = make_float4(qnan, qnan, qnan, __int_as_float(0));
-    __syncthreads();   // the CTA's own global writes are visible to it after the barrier
+    if (cr == 0)
+        for (int k = n + tid; k < npad; k += PR_SORT_THREADS) dst[k] = make_float4(qnan, qnan, qnan, __int_as_float(0));
+    if constexpr (CS > 1) {
+        // the siblings' records are read below: fence + cluster barrier, and the loads bypass L1 (__ldcg).  The barrier also is
+        // the last point at which a sibling reads this CTA's shared memory: nobody exits before it
+        __threadfence();
+        cooperative_groups::this_cluster().sync();
+    } else {
+        __syncthreads();   // the CTA's own global writes are visible to it after the barrier
+    }
     // ---- block boxes ----
-    for (int blk = warp; blk < nblk; blk += PR_SORT_THREADS / 32) {
+    for (int blk = cr * (PR_SORT_THREADS / 32) + warp; blk < nblk; blk += ceff * (PR_SORT_THREADS / 32)) {
         float l[3] = {inf, inf, inf}, h[3] = {-inf, -inf, -inf};
 #pragma unroll
         for (int e = 0; e < PR_BLOCK / 32; ++e) {
-            const float4 t = dst[blk * PR_BLOCK + e * 32 + lane];
+            const float4 t = CS > 1 ? __ldcg(dst + blk * PR_BLOCK + e * 32 + lane) : dst[blk * PR_BLOCK + e * 32 + lane];
             l[0] = fminf(l[0], t.x), h[0] = fmaxf(h[0], t.x);   // NaN padding is ignored
             l[1] = fminf(l[1], t.y), h[1] = fmaxf(h[1], t.y);
             l[2] = fminf(l[2], t.z), h[2] = fmaxf(h[2], t.z);
@@ -281,20 +364,12 @@ static __global__ void __launch_bounds__(PR_SORT_THREADS) nn_bin_sort_kernel(con
     // or one box is less than a quarter of the other across, every query group would open every block, 2.8x the cost of the
     // exhaustive scan) ----
     if (tid == 0) {
-        if (p.bbx != nullptr) {
-            float *o = p.bbx + ((size_t)side * p.B + b) * 8;
-            for (int c = 0; c < 3; ++c) {
-                float l = inf, h = -inf;
-                for (int w = 0; w < PR_SORT_THREADS / 32; ++w) l = fminf(l, sred[c][w]), h = fmaxf(h, sred[3 + c][w]);
-                o[c] = l, o[3 + c] = h;
-            }
-        }
         if (anybad) atomicOr(p.ctl + 2, 1);
         __threadfence();
         if (atomicAdd(p.ctl + 3, 1) == (int)gridDim.x - 1) {
             __threadfence();
             int apart = 0;
-            if (p.bbx != nullptr && !p.single_side && (int)gridDim.x == 2 * p.B) {
+            if (p.bbx != nullptr && !p.single_side) {
                 for (int i = 0; i < p.B; ++i) {
                     const volatile float *u = p.bbx + (size_t)i * 8, *v = p.bbx + ((size_t)p.B + i) * 8;
                     float gap2 = 0.f, du = 0.f, dv = 0.f;

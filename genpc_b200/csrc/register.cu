@@ -695,7 +695,7 @@ extern "C" int genpc_register_run(const float *complete, const float *center, co
         sp.single_side = 1, sp.accumulate = 1;
         // the fixed clouds once per call (their verdict opens the flag), the moving clouds every iteration (OR-ed in)
         sp.side0 = 0, sp.B = C, sp.accumulate = 0;
-        nn_bin_sort_kernel<<<C, PR_SORT_THREADS, 0, stream>>>(sp);
+        nn_bin_sort_kernel<1><<<C, PR_SORT_THREADS, 0, stream>>>(sp);
         GENPC_CHECK_LAUNCH();
         sp.side0 = 1, sp.B = S, sp.accumulate = 1, sp.src_div[1] = n_starts, sp.sim[1] = sims;
         a.select = ctl + 1;
@@ -720,7 +720,7 @@ extern "C" int genpc_register_run(const float *complete, const float *center, co
         if (sym) {
             if (prune) {
                 register_sims_kernel<<<(S + 127) / 128, 128, 0, stream>>>(a, sims);
-                nn_bin_sort_kernel<<<S, PR_SORT_THREADS, 0, stream>>>(sp);
+                nn_bin_sort_kernel<1><<<S, PR_SORT_THREADS, 0, stream>>>(sp);
                 const unsigned pgrid = (unsigned)(pp.ctas0 + pp.ctas1_unused);
                 const int nblk = pr_nblk(Nc > Nr ? Nc : Nr);
                 if (nblk <= 32) nn_prune_kernel<1><<<pgrid, PR_THREADS, 0, stream>>>(pp);

@@ -28,6 +28,7 @@ static Knob g_knobs[] = {
     {"GENPC_EMD_TAIL_SPREAD", "", false}, {"GENPC_CHAMFER_PRUNE", "", false},
     {"GENPC_EMD_SORT", "", false},       {"GENPC_HOST_PRUNE", "", false},
     {"GENPC_REGISTER_PRUNE", "", false}, {"GENPC_PRUNE_COOP", "", false},
+    {"GENPC_SORT_CLUSTER", "", false},
 };
 constexpr int N_KNOBS = sizeof(g_knobs) / sizeof(g_knobs[0]);
 
