@@ -934,12 +934,13 @@ extern "C" int genpc_chamfer_forward_host_fused(genpc_host_feed_t *f, const floa
     // ---- pruned scan (the default for batches of this size): sort + scan are queued per chunk behind an event of the chunk's
     // copies -- no kernel waits on a gate, the last chunk's sort + scan (a few tens of us) is all that follows the last copy ----
     const int nr_ = M > N ? M : N, nc_ = M > N ? N : M;
-    // MEASURED r02 (C2 step from pinned memory, fwd + bwd + loss to host): gated exhaustive launch 0.361 ms; this path with all
-    // chunks on the caller's stream 0.81 ms (six x (sort + scan), each bound by its own latency, one after the other), with one
-    // stream per chunk 0.371 ms, the same captured in a CUDA graph 0.337-0.368 ms (3-6 chunks).  The step is bound by the
-    // copies (12 small H2D copies: 0.23 ms), not by the scan -- so the pruned scan buys nothing here: opt-in, GENPC_HOST_PRUNE=1.
+    // MEASURED r02 (C2 forward from pinned memory, same box, tools/time_hostfeed.py -> profiles/r02w_time_hostfeed.json): gated
+    // exhaustive launch 0.326-0.334 ms (6 / 8 chunks), this path 0.260-0.270 ms (2-6 chunks, one stream per chunk; all chunks on the
+    // caller's stream: 0.81 ms, each chunk's sort + scan bound by its own latency).  Before the sort kernel spread a cloud over a
+    // cluster a chunk of five clouds was five 55-us CTAs and the two paths tied (0.371 vs 0.361 ms per step) -- default since then;
+    // GENPC_HOST_PRUNE=0 keeps the gated launch.
     const char *hp = tunable("GENPC_HOST_PRUNE");
-    if (hp != nullptr && atoi(hp) == 1 && prune_eligible(B, nr_, nc_) && !(B <= 8 && grid_eligible(nr_, nc_)) &&
+    if ((hp == nullptr || atoi(hp) == 1) && prune_eligible(B, nr_, nc_) && !(B <= 8 && grid_eligible(nr_, nc_)) &&
         workspace_bytes >= chamfer_base_bytes(B, N, M) + prune_extra_bytes(B, N, M)) {
         unsigned long long *packed = (unsigned long long *)workspace;
         int *ctl = (int *)(packed + n1 + n2);

@@ -224,7 +224,7 @@ def test_host_fed_chunks_take_the_pruned_scan_and_a_late_bad_chunk_starts_over(c
         stats = torch.zeros(4, dtype=torch.int32, device=cuda)
         _lib.lib().genpc_chamfer_prune_stats(_lib.ptr(stats))
         try:
-            with _lib.tunable(GENPC_HOST_PRUNE="1"):   # opt-in: slower than the gated exhaustive launch
+            with _lib.tunable(GENPC_HOST_PRUNE="1"):   # the default for a batch of this size; forced here
                 out = chamfer_3DDist().forward_from_host(torch.from_numpy(x).pin_memory(), torch.from_numpy(y).pin_memory(), device=cuda, chunks=6)
                 torch.cuda.synchronize()
         finally:

@@ -42,4 +42,8 @@ out["resident_forward"] = timed(lambda: chamfer_3D.forward(xa, xb, d1, d2, i1, i
 out["copy_then_forward"] = timed(plain)
 for chunks in (2, 3, 4, 6, 8, 16):
     out[f"host_fed_chunks{chunks}"] = timed(lambda: chamfer_3D.forward_host(ha, hb, xa, xb, d1, d2, i1, i2, chunks))
+from genpc_b200 import _lib  # noqa: E402
+with _lib.tunable(GENPC_HOST_PRUNE="1"):   # sort + pruned scan per chunk behind the chunk's copy, one stream per chunk
+    for chunks in (2, 3, 4, 6, 8):
+        out[f"host_fed_pruned_chunks{chunks}"] = timed(lambda: chamfer_3D.forward_host(ha, hb, xa, xb, d1, d2, i1, i2, chunks))
 print(json.dumps(out, indent=1))
