@@ -955,6 +955,12 @@ extern "C" int genpc_chamfer_forward_host_fused(genpc_host_feed_t *f, const floa
             FEED_CHECK(cudaMemsetAsync(ctl + 1, 0, 4, stream));   // the chunks OR their verdicts into the selection flag
         }
         FEED_CHECK(cudaEventRecord(f->fork, stream));
+        // TWO chunks whatever the caller asked for: a chunk costs ~15 driver calls (copies, events, sort, fork / join of the side
+        // stream, scan) and two more streams.  Six chunks were ~90 calls per 0.3-ms step -- as fast as two on a quiet box (0.270 vs
+        // 0.260 ms) but 0.69 ms on one of three 2-GPU runs (host-launch bound; 14 streams on 8 hardware queues)
+        if (chunks > 2) chunks = 2;
+        const int pairs = (B + chunks - 1) / chunks;
+        chunks = (B + pairs - 1) / pairs;
         for (int c = 0; c < chunks; ++c) {
             const int b0 = c * pairs, nb = (B - b0 < pairs) ? B - b0 : pairs;
             if (f->cstream[c] == nullptr) FEED_CHECK(cudaStreamCreateWithFlags(&f->cstream[c], cudaStreamNonBlocking));
