@@ -369,7 +369,12 @@ static void launch_bin_sort_cs(PruneSortParams sp, int ctas, cudaStream_t stream
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CS, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr, cfg.numAttrs = 1;
-    cudaLaunchKernelEx(&cfg, nn_bin_sort_kernel<CS>, sp);
+    if (cudaLaunchKernelEx(&cfg, nn_bin_sort_kernel<CS>, sp) != cudaSuccess) {
+        // a part whose GPCs cannot co-schedule CS 1024-thread CTAs (MIG slices, harvested parts): one CTA per cloud
+        (void)cudaGetLastError();
+        sp.mixed = 0;
+        nn_bin_sort_kernel<1><<<2 * sp.B, PR_SORT_THREADS, 0, stream>>>(sp);
+    }
 }
 
 // both sides of nb cloud pairs

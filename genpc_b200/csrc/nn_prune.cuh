@@ -496,7 +496,10 @@ __global__ void __launch_bounds__(PR_THREADS) nn_prune_kernel(const PrunePair pp
         // are (the AoS form spent 6 of its 15 instructions per target pair moving registers into pairs)
         const float4 *sx4 = reinterpret_cast<const float4 *>(stage[wid][0]), *sy4 = reinterpret_cast<const float4 *>(stage[wid][1]),
                      *sz4 = reinterpret_cast<const float4 *>(stage[wid][2]);
-#pragma unroll PR_UNROLL
+        // 256 target blocks and more (C3: 16384^2 inside the registration loop) keep the 2x form: 4x cost C3 9 % on the same box
+        // (26 100 vs 28 600 scan-iters/s) while the 32- and 128-block instantiations gained 1-4 % (profiles/r02w_unroll_sweep.txt)
+        constexpr int UNR = BOXR >= 8 ? 2 : PR_UNROLL;
+#pragma unroll UNR
         for (int c = 0; c < PR_BLOCK / 8; ++c) {
             float cm = inf;
 #pragma unroll

@@ -54,6 +54,25 @@ def test_pruned_scan_bit_exact_on_awkward_shapes(cuda, B, N, M):
     assert st[2] > 0 and st0[2] == 0, (st, st0)           # the pruned kernels ran (query groups counted), and only on request
 
 
+@pytest.mark.parametrize("layout", ["1", "2", "3", "4", "8", "m2", "m3", "m4"])
+def test_sort_cluster_layouts_bit_exact(cuda, layout):
+    """nn_bin_sort_kernel<CS>: a cloud sorted by a thread-block cluster of CS CTAs (sibling histograms and boxes through distributed
+    shared memory), every CS and the mixed layout ("m": the smaller side's clouds take one CTA each, CTAs that round the grid up to
+    whole clusters idle) -- the order inside a cell changes, the nearest neighbours must not.  Ragged sizes: slabs that only some
+    CTAs of a cluster own, clouds smaller than one slab, 5 clouds (a mixed grid that is not a multiple of the cluster size)."""
+    from genpc_b200 import _lib
+
+    for (B, N, M) in [(5, 2048, 16384), (3, 1500, 9000), (2, 5000, 4100), (1, 32768, 777), (7, 200, 2300)]:
+        a, b = shape_cloud(B + N, B, N), shape_cloud(M + 3, B, M)
+        with _lib.tunable(GENPC_SORT_CLUSTER=layout):
+            got, st = run(a, b, cuda)
+        ref, _ = run(a, b, cuda, prune="0")
+        same(got, ref, f"layout {layout}, {B}x{N}x{M} vs exhaustive")
+        if B * N * M <= 6e7:
+            same(got, oracle.chamfer_forward(a, b), f"layout {layout}, {B}x{N}x{M} vs oracle")
+        assert st[2] > 0, st
+
+
 def test_c2_full_batch_pruned(cuda):
     """BASELINE C2 (B=32, 2048 x 16384, the bench's batch): bit-exact against the oracle, and most blocks are never visited."""
     from genpc_b200.synthetic import pcn_batch
