@@ -69,3 +69,14 @@ def test_other_kernels_use_the_instructions_claimed(sass):
     emd = _one(sass, "emd_auction_kernel")
     assert "FFMA2" in emd and "DADD" in emd or "DFMA" in emd or "F2F.F64.F32" in emd   # packed scan + FP64 exact value
     assert "ATOMG.E.MIN.64" in _one(sass, "zsplat") or "REDG.E.MIN.64" in _one(sass, "zsplat")  # packed z-buffer atomicMin
+
+
+def test_cluster_sort_uses_cluster_barriers_and_dsmem(sass):
+    """nn_bin_sort_kernel<3> (C2's layout): three cluster barriers, the siblings' histograms read as 128-bit generic loads through
+    distributed shared memory, shared-memory atomics for the histogram and the slots; the one-CTA form has none of the cluster ops."""
+    k = _one(sass, "nn_bin_sort_kernelILi3E")
+    assert len(re.findall(r"\bUCGABAR_ARV\b", k)) == 3 and len(re.findall(r"\bUCGABAR_WAIT\b", k)) == 3
+    assert re.search(r"\bLD\.E\.128\b", k) and "ATOMS" in k
+    assert "LDG.E.128.STRONG.GPU" in k                                                 # sorted records of the siblings bypass L1
+    k1 = _one(sass, "nn_bin_sort_kernelILi1E")
+    assert "UCGABAR" not in k1
