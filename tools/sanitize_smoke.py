@@ -81,4 +81,10 @@ with _lib.tunable(GENPC_REGISTER_PRUNE="1", GENPC_REGISTER_MODE="sym"):
 with _lib.tunable(GENPC_HOST_PRUNE="1", GENPC_CHAMFER_PRUNE="1"):
     ha2, hb2 = torch.rand(6, 700, 3, generator=g).pin_memory(), torch.rand(6, 1500, 3, generator=g).pin_memory()
     loss, da, db = Completionloss("cd_l2").get_loss_from_host(ha2, hb2, device=dev, chunks=3); loss.backward()
+# r02w: the sort kernel as thread-block clusters (sibling histograms / boxes through distributed shared memory, cross-CTA reads of the
+# sorted records), every layout, ragged sizes
+for layout in ("2", "3", "4", "8", "m2", "m3", "m4"):
+    with _lib.tunable(GENPC_CHAMFER_PRUNE="1", GENPC_SORT_CLUSTER=layout):
+        for (B, N, M) in [(3, 700, 5300), (2, 2048, 9000), (1, 64, 513)]:
+            chamfer_3DDist()(torch.rand(B, N, 3, generator=g).to(dev), torch.rand(B, M, 3, generator=g).to(dev))
 torch.cuda.synchronize(); print("sanitize smoke done")
