@@ -1,12 +1,13 @@
-// nn_prune.cuh -- exact nearest neighbours with spatial pruning (r02).  The default Chamfer scan for device-resident batches of
-// >= 2^30 distance evaluations (BASELINE C2) and inside the registration loop from ~20 scans up; the sort kernel also serves the
+// nn_prune.cuh -- exact nearest neighbours with spatial pruning (r02).  The default Chamfer scan for batches (device-resident or
+// host-fed) of >= 2^30 distance evaluations (BASELINE C2) and inside the registration loop from ~20 scans up; the sort kernel also serves the
 // EMD auction's pruned Bid.  GENPC_CHAMFER_PRUNE / GENPC_REGISTER_PRUNE = 0 / 1 forbid / force it.
 //
 // The symmetric scan (nn_sym.cuh) evaluates every (row, column) distance of a cloud pair: at its issue limit that is
 // 7.9e12 pairs/s and nothing in its instruction stream is left to remove.  What is left is not to evaluate most pairs:
-//   1. nn_bin_sort_kernel orders every cloud along a Hilbert curve (counting sort over 8^m grid cells in shared memory,
-//      one CTA per cloud) into (x, y, z, original index) records and stores the bounding box of every PR_BLOCK
-//      consecutive ones;
+//   1. nn_bin_sort_kernel<CS> orders every cloud along a Hilbert curve (counting sort over 8^m grid cells in shared memory;
+//      one CTA per cloud, or a thread-block cluster of CS CTAs that read each other's histograms through distributed shared
+//      memory when one CTA per cloud would leave most SMs idle) into (x, y, z, original index) records and stores the
+//      bounding box of every PR_BLOCK consecutive ones;
 //   2. nn_prune_kernel: one warp owns PR_GROUP consecutive sorted queries (one per lane -- neighbours in space).  It
 //      computes the squared distance between the group's box and every target block's box, visits the blocks nearest
 //      first (REDUX picks them) and stops at the first block farther than the group's worst running minimum: no target

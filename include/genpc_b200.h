@@ -77,7 +77,10 @@ int genpc_tc_probe(const float *rows128, const float *cols256, float *e_out, gen
  * scan launch on `stream` consumes each group as soon as its copy has landed.  This is the reference's stock flow
  * `xyz.cuda()` + chamfer_3D.forward (dist_chamfer_3D.py:33-47) with the 7 MB PCIe transfer of a PCN batch hidden
  * behind 0.27 ms of compute.  On return, all work is queued; `stream` is ordered after the copies, so xyz1 / xyz2 can
- * be used by later work on `stream` (e.g. genpc_chamfer_backward).  A handle serves one call at a time (host threads
+ * be used by later work on `stream` (e.g. genpc_chamfer_backward).  Batches large enough for the pruned exact scan (>= 2^30
+ * distance evaluations, >= 2048 points per cloud) are cut in TWO chunks whatever `chunks` says, and each chunk's sort + scan
+ * is queued on a stream of its own behind the chunk's copies instead of the one gated launch (same results; C2 forward from
+ * pinned memory 0.33 -> 0.26 ms; GENPC_HOST_PRUNE=0 keeps the gated launch).  A handle serves one call at a time (host threads
  * sharing it are serialised by a lock inside the handle).  A gated launch that waits more than ~2 s for its data gives
  * up and raises the handle's error word: the fused form then returns loss = NaN, so the failure is seen at the first
  * natural synchronisation point; genpc_host_feed_error reports (synchronising `stream`) whether that happened since it
