@@ -358,26 +358,7 @@ static void launch_prune(const PruneParams &a, const PruneParams &b, cudaStream_
 
 // The sort of `clouds` clouds: one CTA per cloud, or a thread-block cluster of CS CTAs per cloud when one CTA per cloud would leave
 // most SMs idle behind a few long CTAs (C2: 64 clouds, the 32 of 16384 points take 55 us in one CTA each).  GENPC_SORT_CLUSTER =
-// 1 / 2 / 4 / 8 forces the cluster size.
-template <int CS>
-static void launch_bin_sort_cs(PruneSortParams sp, int ctas, cudaStream_t stream) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)((ctas + CS - 1) / CS * CS));
-    cfg.blockDim = dim3(PR_SORT_THREADS);
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CS, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr, cfg.numAttrs = 1;
-    if (cudaLaunchKernelEx(&cfg, nn_bin_sort_kernel<CS>, sp) != cudaSuccess) {
-        // a part whose GPCs cannot co-schedule CS 1024-thread CTAs (MIG slices, harvested parts): one CTA per cloud
-        (void)cudaGetLastError();
-        sp.mixed = 0;
-        nn_bin_sort_kernel<1><<<2 * sp.B, PR_SORT_THREADS, 0, stream>>>(sp);
-    }
-}
-
-// both sides of nb cloud pairs
+// 1 / 2 / 3 / 4 / 8 / m2 / m3 / m4 forces the layout (launch_bin_sort_cs: nn_prune.cuh).  Both sides of nb cloud pairs:
 static void launch_bin_sort(PruneSortParams sp, int nb, cudaStream_t stream) {
     const int nmax = sp.n[0] > sp.n[1] ? sp.n[0] : sp.n[1], nmin = sp.n[0] > sp.n[1] ? sp.n[1] : sp.n[0];
     int cs = 1, mixed = 0;

@@ -395,6 +395,26 @@ static __global__ void __launch_bounds__(PR_SORT_THREADS) nn_bin_sort_kernel(con
     }
 }
 
+// `ctas` CTAs (rounded up to whole clusters) as thread-block clusters of CS
+template <int CS>
+static void launch_bin_sort_cs(PruneSortParams sp, int ctas, cudaStream_t stream) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)((ctas + CS - 1) / CS * CS));
+    cfg.blockDim = dim3(PR_SORT_THREADS);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CS, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr, cfg.numAttrs = 1;
+    if (cudaLaunchKernelEx(&cfg, nn_bin_sort_kernel<CS>, sp) != cudaSuccess) {
+        // a part whose GPCs cannot co-schedule CS 1024-thread CTAs (MIG slices, harvested parts): one CTA per cloud
+        (void)cudaGetLastError();
+        sp.mixed = 0;
+        nn_bin_sort_kernel<1><<<(sp.single_side ? 1 : 2) * sp.B, PR_SORT_THREADS, 0, stream>>>(sp);
+    }
+}
+
+
 struct PruneParams {
     const float4 *q, *t;      // sorted queries [B][npad_q], sorted targets [B][npad_t]
     const float4 *tbox;       // [B][2][nblk_t]
