@@ -668,6 +668,57 @@ def c1_metric(dev):
     return res
 
 
+def c2_16k_metric(dev, Bk=16, n=16384):
+    """The north_star's roofline target shape: batched Chamfer fwd+bwd at 16384 x 16384 points per pair (Bk pairs: 8.6e9 directed
+    pairs per step), through Completionloss('cd_l2'): the library default (pruned exact scan) and, beside it, the exhaustive
+    symmetric scan (GENPC_CHAMFER_PRUNE=0), each as a fraction of the nominal FP32 peak on ALGORITHMIC flops (8 per directed
+    pair); L2 flushed before every timed step; the two paths' outputs compared bit for bit."""
+    from genpc_b200 import _lib
+    from genpc_b200.loss_functions import chamfer_3DDist
+    from genpc_b200.synthetic import pcn_batch
+    from genpc_b200.utils.loss_util import Completionloss
+
+    part, comp = pcn_batch(100, Bk, n, n)
+    a = torch.from_numpy(part).to(dev).requires_grad_(True)
+    b = torch.from_numpy(comp).to(dev).requires_grad_(True)
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+    crit = Completionloss("cd_l2")
+
+    def step():
+        a.grad = None
+        b.grad = None
+        crit.get_loss(a, b).backward()
+
+    def timed(reps=10, warm=3):
+        ts = []
+        for r in range(reps + warm):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            step()
+            e1.record()
+            torch.cuda.synchronize()
+            if r >= warm:
+                ts.append(e0.elapsed_time(e1))
+        return float(np.median(ts))
+
+    pairs = 2.0 * Bk * n * n
+    out = {"workload": f"batched Chamfer fwd+bwd, B={Bk}, {n} x {n} pts, loss = chamfer_l2 (north_star roofline target shape)",
+           "pairs_per_step": pairs}
+    res = {}
+    for name, knob in (("default_pruned_exact", None), ("exhaustive", "0")):
+        with _lib.tunable(GENPC_CHAMFER_PRUNE=knob):
+            ms = timed()
+            res[name] = tuple(x.cpu().numpy() for x in chamfer_3DDist()(a.detach(), b.detach()))
+        tf = pairs * FLOP_PER_PAIR / (ms * 1e-3) / 1e12
+        out[name] = {"ms_fwd_bwd": ms, "pairs_per_s": pairs / (ms * 1e-3), "algorithmic_tflops": tf,
+                     "frac_of_fp32_peak": tf / FP32_NOMINAL_TFLOPS}
+    same = all(np.array_equal(x.view(np.int32), y.view(np.int32)) for x, y in zip(res["default_pruned_exact"], res["exhaustive"]))
+    out["identical_outputs"] = bool(same)
+    assert same, "16K x 16K: the pruned scan differs from the exhaustive scan"
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -880,7 +931,8 @@ def main():
                 assert ok, "C2: the timed kernels differ from the oracle"
                 line["cpu_baseline"] = cb
             if not args.no_extras:
-                for key, fn in (("C1_real_scan", c1_metric), ("C4_depth_fps", c4_metric), ("C5_emd", emd_c5_metric)):
+                for key, fn in (("C1_real_scan", c1_metric), ("C2_16k_batched", c2_16k_metric), ("C4_depth_fps", c4_metric),
+                                ("C5_emd", emd_c5_metric)):
                     try:
                         cfgs[key] = fn(dev)
                     except AssertionError:
