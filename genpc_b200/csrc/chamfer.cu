@@ -359,17 +359,19 @@ static void launch_prune(const PruneParams &a, const PruneParams &b, cudaStream_
 // The sort of `clouds` clouds: one CTA per cloud, or a thread-block cluster of CS CTAs per cloud when one CTA per cloud would leave
 // most SMs idle behind a few long CTAs (C2: 64 clouds, the 32 of 16384 points take 55 us in one CTA each).  GENPC_SORT_CLUSTER =
 // 1 / 2 / 3 / 4 / 8 / m2 / m3 / m4 forces the layout (launch_bin_sort_cs: nn_prune.cuh).  Both sides of nb cloud pairs:
-static void launch_bin_sort(PruneSortParams sp, int nb, cudaStream_t stream) {
-    const int nmax = sp.n[0] > sp.n[1] ? sp.n[0] : sp.n[1], nmin = sp.n[0] > sp.n[1] ? sp.n[1] : sp.n[0];
+// The layout rule (host logic only; genpc_chamfer_sort_layout exposes it to the CPU tests): -> CTAs per cloud of the larger side,
+// *mixed = 1 when the smaller side's clouds take one CTA each, *grid = CTAs launched.
+static int sort_layout(int nb, int n0, int n1, int sms, int *mixed_out, int *grid_out) {
+    const int nmax = n0 > n1 ? n0 : n1, nmin = n0 > n1 ? n1 : n0;
     int cs = 1, mixed = 0;
     const char *k = tunable("GENPC_SORT_CLUSTER");   // "2" / "3" / "4" / "8": every cloud a cluster; "m2" / "m3" / "m4": mixed layout
     if (k != nullptr) {
         mixed = k[0] == 'm' ? 1 : 0;
         cs = atoi(k + mixed);
+        cs = cs >= 8 ? 8 : cs >= 4 ? 4 : cs == 3 ? 3 : cs == 2 ? 2 : 1;
     } else if (nmax >= 8192) {
         // as many CTAs per cloud as keep the grid inside one wave (one 1024-thread CTA per SM); when one side is much smaller, its
         // clouds take one CTA each and leave the SMs to the clusters of the larger side (C2: 32 x 3 + 33 CTAs)
-        const int sms = num_sms();
         if (nmin * 4 <= nmax && nmin <= 4096) {
             mixed = 1;
             cs = nb * 4 + (nb + 3) / 4 * 4 <= sms ? 4 : nb * 3 + (nb + 2) / 3 * 3 <= sms ? 3 : nb * 2 + (nb + 1) / 2 * 2 <= sms ? 2 : 1;
@@ -378,10 +380,19 @@ static void launch_bin_sort(PruneSortParams sp, int nb, cudaStream_t stream) {
         }
     }
     if (cs < 2) mixed = 0;
+    const int ctas = mixed ? nb * cs + nb : 2 * nb * cs;
+    *mixed_out = mixed;
+    *grid_out = (ctas + cs - 1) / cs * cs;
+    return cs;
+}
+
+static void launch_bin_sort(PruneSortParams sp, int nb, cudaStream_t stream) {
+    int mixed = 0, grid = 0;
+    const int cs = sort_layout(nb, sp.n[0], sp.n[1], num_sms(), &mixed, &grid);
     sp.mixed = mixed;
     const int ctas = mixed ? nb * cs + nb : 2 * nb * cs;
-    if (cs >= 8) launch_bin_sort_cs<8>(sp, ctas, stream);
-    else if (cs >= 4) launch_bin_sort_cs<4>(sp, ctas, stream);
+    if (cs == 8) launch_bin_sort_cs<8>(sp, ctas, stream);
+    else if (cs == 4) launch_bin_sort_cs<4>(sp, ctas, stream);
     else if (cs == 3) launch_bin_sort_cs<3>(sp, ctas, stream);
     else if (cs == 2) launch_bin_sort_cs<2>(sp, ctas, stream);
     else nn_bin_sort_kernel<1><<<2 * nb, PR_SORT_THREADS, 0, stream>>>(sp);
@@ -783,6 +794,11 @@ extern "C" int genpc_chamfer_backward(const float *xyz1, const float *xyz2, cons
 // Which scan genpc_chamfer_forward would queue for this shape with the current knobs (host logic only, no device call):
 // 0 = exhaustive (symmetric or per-direction), 1 = Hilbert-sorted pruned scan (nn_prune.cuh), 2 = two-level pruned scan for large
 // clouds (nn_grid.cuh).  The device may still hand a pruned launch back to the exhaustive kernels (range / overlap / probe).
+extern "C" int genpc_chamfer_sort_layout(int B, int N, int M, int sms, int *mixed, int *grid) {
+    if (B <= 0 || N <= 0 || M <= 0 || mixed == nullptr || grid == nullptr) return GENPC_ERR_SHAPE;
+    return sort_layout(B, N > M ? N : M, N > M ? M : N, sms > 0 ? sms : GENPC_NUM_SMS_B200, mixed, grid);
+}
+
 extern "C" int genpc_chamfer_scan_kind(int B, int N, int M) {
     if (B <= 0 || N <= 0 || M <= 0) return GENPC_ERR_SHAPE;
     if (!takes_sym_path(N, M)) return 0;

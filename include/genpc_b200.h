@@ -68,6 +68,11 @@ int genpc_chamfer_prune_stats(unsigned *stats4);
  * 1 = Hilbert-sorted pruned exact scan (batches of >= 2^30 evaluations, 2048 .. 32768 points per cloud), 2 = two-level pruned
  * exact scan for large clouds (>= 2^32 evaluations, more than 32768 points on a side, B <= 8).  Same outputs in every case. */
 int genpc_chamfer_scan_kind(int B, int N, int M);
+/* How the pruned scan's sort kernel would be laid out for B cloud pairs on a part with `sms` SMs (<= 0: 148; host logic only):
+ * returns the CTAs per cloud of the larger side (1, or the thread-block cluster size 2 / 3 / 4 / 8), *mixed = 1 when the
+ * smaller side's clouds take one CTA each, *grid = CTAs launched (whole clusters).  The rule keeps the grid inside one wave of
+ * one 1024-thread CTA per SM; GENPC_SORT_CLUSTER overrides it. */
+int genpc_chamfer_sort_layout(int B, int N, int M, int sms, int *mixed, int *grid);
 int genpc_tc_probe(const float *rows128, const float *cols256, float *e_out, genpc_stream_t stream);
 
 /* Host-fed forward: the same result as genpc_chamfer_forward, but the clouds start in HOST memory

@@ -74,3 +74,39 @@ def test_scan_selection_host_logic():
         assert kind(2, 700, 1300) == 2
     assert L.genpc_emd_workspace_bytes_n(32, 8192) > L.genpc_emd_workspace_bytes(32) + 32 * 8192 * 16
     assert L.genpc_emd_workspace_bytes_n(1, 65536) == L.genpc_emd_workspace_bytes(1)   # beyond the pruned Bid's range
+
+
+def test_sort_layout_host_logic():
+    """Layout of the pruned scan's sort kernel (host logic, no device): clusters only for clouds of >= 8192 points, the largest
+    cluster size whose grid is one wave of one CTA per SM, the mixed layout when one side is >= 4x smaller, knob overrides."""
+    import ctypes
+
+    from genpc_b200 import _lib
+
+    L = _lib.lib()
+
+    def layout(B, N, M, sms=148):
+        mixed, grid = ctypes.c_int(-1), ctypes.c_int(-1)
+        cs = L.genpc_chamfer_sort_layout(B, N, M, sms, ctypes.byref(mixed), ctypes.byref(grid))
+        return cs, mixed.value, grid.value
+
+    assert layout(32, 2048, 16384) == (3, 1, 129) == layout(32, 16384, 2048)      # BASELINE C2: 32 x 3 + 33 CTAs
+    assert layout(32, 8192, 8192) == (2, 0, 128) and layout(16, 16384, 16384) == (4, 0, 128)
+    assert layout(64, 16384, 16384) == (1, 0, 128)                                  # 128 clouds: no room for clusters
+    assert layout(32, 2048, 4096) == (1, 0, 64)                                     # small clouds: one CTA each
+    assert layout(5, 2048, 16384) == (4, 1, 28) and layout(2, 32768, 32768) == (8, 0, 32)
+    assert layout(40, 2048, 16384) == (2, 1, 120) and layout(60, 2048, 16384) == (1, 0, 120)
+    assert layout(32, 2048, 16384, sms=132) == (3, 1, 129) and layout(32, 2048, 16384, sms=100) == (2, 1, 96)
+    for B in (1, 3, 7, 16, 31, 32, 33, 50):                                         # never more CTAs than SMs once clusters are used
+        for (N, M) in ((2048, 16384), (8192, 8192), (16384, 16384), (4096, 32768)):
+            cs, mixed, grid = layout(B, N, M)
+            assert grid % cs == 0 and (cs == 1 or grid <= 148), (B, N, M, cs, mixed, grid)
+            assert grid >= (B * cs + B if mixed else 2 * B * cs)
+    with _lib.tunable(GENPC_SORT_CLUSTER="m4"):
+        assert layout(32, 2048, 16384) == (4, 1, 160)
+    with _lib.tunable(GENPC_SORT_CLUSTER="8"):
+        assert layout(2, 700, 1300) == (8, 0, 32)
+    with _lib.tunable(GENPC_SORT_CLUSTER="1"):
+        assert layout(32, 2048, 16384) == (1, 0, 64)
+    mixed, grid = ctypes.c_int(), ctypes.c_int()
+    assert L.genpc_chamfer_sort_layout(0, 5, 5, 148, ctypes.byref(mixed), ctypes.byref(grid)) < 0
