@@ -107,8 +107,9 @@ static __global__ void prune_rearm_kernel(unsigned long long *words, size_t n, c
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) words[i] = ~0ull;
 }
 
-// grid = 2 * B * CS CTAs: cloud = blockIdx.x / CS = side * B + b (or the mixed layout below).  CS > 1 (launched as thread-block clusters of CS CTAs): the CTAs of
-// a cluster share one cloud -- every CTA takes each CS-th slab of 1024 points, keeps its own histogram, and reads its siblings'
+// grid = 2 * B * CS CTAs: cloud = blockIdx.x / CS = side * B + b (or the mixed layout below).  CS > 1 (launched as thread-block
+// clusters of CS CTAs): the CTAs of a cluster share one cloud -- every CTA takes each CS-th slab of 1024 points, keeps its own
+// histogram, and reads its siblings'
 // bounding boxes and histograms through distributed shared memory (a point's slot = cells before it + the same cell's counts in
 // the lower-ranked CTAs + the CTA's own atomic counter); the block boxes are split between the CTAs after the last cluster
 // barrier.  One CTA per 16384-point cloud was 55 us of C2's 170 us forward with 84 of the 148 SMs idle.
